@@ -1,0 +1,267 @@
+"""ctypes binding of the C ABI in include/gcs_b200.h.
+
+This is plumbing for bench.py and the tests: the product is the CUDA library
+(`libgcs_b200.so`, built from csrc/) and the C++ host mirror (host/).  There is no CPU
+fallback here: if the library is missing, `load()` raises; if no CUDA device is present every
+compute entry point returns GCS_E_NO_DEVICE and `check()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+MAX_IN_COLS = 13
+MAX_OUT_COLS = 4
+MAX_SEEDS = 8
+
+KIND_PP, KIND_SDD, KIND_PPL, KIND_PLL, KIND_ANG = 1, 2, 3, 4, 5
+KIND_NAMES = {1: "K1_PP", 2: "K2_SDD", 3: "K3_PPL", 4: "K4_PLL", 5: "K5_ANG"}
+IN_COLS = {1: 6, 2: 9, 3: 10, 4: 12, 5: 13}
+OUT_COLS = {1: 2, 2: 4, 3: 2, 4: 2, 5: 4}
+IN_COL_NAMES = {
+    1: ["ax", "ay", "ra", "bx", "by", "rb"],
+    2: ["p1x", "p1y", "p2x", "p2y", "s1", "s2", "gnx", "gny", "canvas_len"],
+    3: ["px", "py", "r", "xa", "ya", "xb", "yb", "s", "cfx", "cfy"],
+    4: ["xa1", "ya1", "xb1", "yb1", "s1", "xa2", "ya2", "xb2", "yb2", "s2", "cfx", "cfy"],
+    5: ["fdx", "fdy", "cosA", "gnx", "gny", "cfdx", "cfdy", "px", "py", "s", "r2x", "r2y",
+        "canvas_len"],
+}
+
+MEM_HOST, MEM_DEVICE = 0, 1
+VARIANT_DEFAULT, VARIANT_STATIC, VARIANT_REFILL = 0, 1, 2
+
+CODE_COLLINEAR = 0x10
+CODE_CANVAS_PARALLEL = 0x20
+
+GCS_OK, GCS_E_INVALID, GCS_E_NO_DEVICE, GCS_E_CUDA, GCS_E_NOT_INIT, GCS_E_NOMEM = 0, -1, -2, -3, -4, -5
+
+CONVERGENCE_THRESHOLD = 0.00001
+MAXIMUM_ITERATIONS = 1000
+
+
+def make_code(sign0, sign1=0, flags=0):
+    """GCS_MAKE_CODE of gcs_b200.h, vectorised."""
+    s0 = (np.asarray(sign0).astype(np.int64) + 1) & 3
+    s1 = (np.asarray(sign1).astype(np.int64) + 1) & 3
+    return (s0 | (s1 << 2) | np.asarray(flags).astype(np.int64)).astype(np.uint8)
+
+
+class CBatch(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("n_seeds", C.c_int32),
+        ("n", C.c_int64),
+        ("mem", C.c_int32),
+        ("variant", C.c_int32),
+        ("in_", C.c_void_p * MAX_IN_COLS),
+        ("code", C.c_void_p),
+        ("guesses", C.c_void_p),
+        ("out", C.c_void_p * MAX_OUT_COLS),
+        ("cand", C.c_void_p),
+        ("iters", C.c_void_p),
+        ("converged", C.c_void_p),
+        ("root_index", C.c_void_p),
+    ]
+
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libgcs_b200.so")
+_lib = None
+
+EXPORTS = [
+    "gcs_b200_kind_in_cols", "gcs_b200_kind_out_cols", "gcs_b200_device_count", "gcs_b200_init",
+    "gcs_b200_shutdown", "gcs_b200_last_error", "gcs_b200_version", "gcs_b200_solve",
+    "gcs_b200_solve_host", "gcs_b200_solve_sharded", "gcs_b200_launch_count",
+    "gcs_b200_fp64_probe", "gcs_b200_synth_pp",
+]
+
+
+def load():
+    """Load libgcs_b200.so (built in-tree by __graft_entry__.build()).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension was not built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.gcs_b200_kind_in_cols.argtypes = [C.c_int]
+    lib.gcs_b200_kind_out_cols.argtypes = [C.c_int]
+    lib.gcs_b200_init.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    lib.gcs_b200_last_error.restype = C.c_char_p
+    lib.gcs_b200_version.restype = C.c_char_p
+    lib.gcs_b200_solve.argtypes = [C.POINTER(CBatch), C.c_int, C.c_void_p]
+    lib.gcs_b200_solve_host.argtypes = [C.POINTER(CBatch), C.c_int]
+    lib.gcs_b200_solve_sharded.argtypes = [C.POINTER(CBatch), C.c_int]
+    lib.gcs_b200_launch_count.restype = C.c_int64
+    lib.gcs_b200_fp64_probe.argtypes = [C.c_int, C.c_int]
+    lib.gcs_b200_fp64_probe.restype = C.c_double
+    lib.gcs_b200_synth_pp.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_int64, C.c_int64,
+                                      C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
+    _lib = lib
+    return lib
+
+
+class GcsError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "gcs_b200"):
+    if rc != 0:
+        msg = load().gcs_b200_last_error()
+        raise GcsError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")
+
+
+def init(devices=None):
+    lib = load()
+    if devices is None:
+        check(lib.gcs_b200_init(0, None), "gcs_b200_init")
+    else:
+        arr = (C.c_int * len(devices))(*devices)
+        check(lib.gcs_b200_init(len(devices), arr), "gcs_b200_init")
+
+
+@dataclass
+class HostBatch:
+    """A batch whose columns are numpy arrays (GCS_MEM_HOST).  Keeps the arrays alive."""
+    kind: int
+    n_seeds: int
+    cols: list                      # kind-specific input columns, float64[n]
+    code: np.ndarray                # uint8[n]
+    guesses: np.ndarray | None = None   # float64[n_seeds, 2, n]
+    variant: int = VARIANT_DEFAULT
+    want_cand: bool = True
+    out: list = field(default_factory=list)
+    cand: np.ndarray | None = None
+    iters: np.ndarray | None = None
+    converged: np.ndarray | None = None
+    root_index: np.ndarray | None = None
+
+    @property
+    def n(self):
+        return int(self.code.shape[0])
+
+    def alloc_outputs(self):
+        n = self.n
+        self.out = [np.full(n, np.nan) for _ in range(OUT_COLS[self.kind])]
+        self.cand = np.full((self.n_seeds, 2, n), np.nan) if self.want_cand else None
+        self.iters = np.full((self.n_seeds, n), -1, dtype=np.int16)
+        self.converged = np.full((self.n_seeds, n), 255, dtype=np.uint8)
+        self.root_index = np.full(n, 255, dtype=np.uint8)
+        return self
+
+    def slice(self, lo, hi):
+        """Contiguous index range [lo, hi) as a new HostBatch (inputs are views)."""
+        g = None if self.guesses is None else np.ascontiguousarray(self.guesses[:, :, lo:hi])
+        return HostBatch(self.kind, self.n_seeds, [c[lo:hi] for c in self.cols], self.code[lo:hi],
+                         g, self.variant, self.want_cand)
+
+    def cbatch(self) -> CBatch:
+        assert len(self.cols) == IN_COLS[self.kind], (len(self.cols), self.kind)
+        b = CBatch()
+        b.kind, b.n_seeds, b.n, b.mem, b.variant = self.kind, self.n_seeds, self.n, MEM_HOST, self.variant
+        n = self.n
+        for i, c in enumerate(self.cols):
+            assert c.dtype == np.float64 and c.flags["C_CONTIGUOUS"] and c.shape == (n,)
+            b.in_[i] = c.ctypes.data
+        assert self.code.dtype == np.uint8 and self.code.flags["C_CONTIGUOUS"]
+        b.code = self.code.ctypes.data
+        if self.guesses is not None:
+            assert self.guesses.dtype == np.float64 and self.guesses.flags["C_CONTIGUOUS"]
+            assert self.guesses.shape == (self.n_seeds, 2, n)
+            b.guesses = self.guesses.ctypes.data
+        for i, o in enumerate(self.out):
+            b.out[i] = o.ctypes.data
+        b.cand = self.cand.ctypes.data if self.cand is not None else None
+        b.iters = self.iters.ctypes.data if self.iters is not None else None
+        b.converged = self.converged.ctypes.data if self.converged is not None else None
+        b.root_index = self.root_index.ctypes.data if self.root_index is not None else None
+        return b
+
+
+def solve_host(batch: HostBatch, device: int = 0) -> HostBatch:
+    """gcs_b200_solve_host: H2D, kernel, D2H, synchronised."""
+    if not batch.out:
+        batch.alloc_outputs()
+    cb = batch.cbatch()
+    check(load().gcs_b200_solve_host(C.byref(cb), device), "gcs_b200_solve_host")
+    return batch
+
+
+def solve_sharded(batch: HostBatch, n_dev: int) -> HostBatch:
+    if not batch.out:
+        batch.alloc_outputs()
+    cb = batch.cbatch()
+    check(load().gcs_b200_solve_sharded(C.byref(cb), n_dev), "gcs_b200_solve_sharded")
+    return batch
+
+
+class DeviceBatch:
+    """A batch resident in HBM as torch tensors (torch is only the allocator / stream owner)."""
+
+    def __init__(self, host: HostBatch, device, want_cand=False, variant=None):
+        import torch
+        self.torch = torch
+        self.device = torch.device(device)
+        self.kind, self.n_seeds = host.kind, host.n_seeds
+        self.variant = host.variant if variant is None else variant
+        self.n = host.n
+        dev = self.device
+        self.cols = [torch.from_numpy(c).to(dev) for c in host.cols]
+        self.code = torch.from_numpy(host.code).to(dev)
+        self.guesses = None if host.guesses is None else torch.from_numpy(host.guesses).to(dev)
+        n = self.n
+        self.out = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(OUT_COLS[self.kind])]
+        self.cand = torch.empty((self.n_seeds, 2, n), dtype=torch.float64, device=dev) if want_cand else None
+        self.iters = torch.empty((self.n_seeds, n), dtype=torch.int16, device=dev)
+        self.converged = torch.empty((self.n_seeds, n), dtype=torch.uint8, device=dev)
+        self.root_index = torch.empty(n, dtype=torch.uint8, device=dev)
+        self._cb = self._make_cbatch()
+
+    def _make_cbatch(self):
+        b = CBatch()
+        b.kind, b.n_seeds, b.n, b.mem, b.variant = self.kind, self.n_seeds, self.n, MEM_DEVICE, self.variant
+        for i, c in enumerate(self.cols):
+            b.in_[i] = c.data_ptr()
+        b.code = self.code.data_ptr()
+        b.guesses = self.guesses.data_ptr() if self.guesses is not None else None
+        for i, o in enumerate(self.out):
+            b.out[i] = o.data_ptr()
+        b.cand = self.cand.data_ptr() if self.cand is not None else None
+        b.iters = self.iters.data_ptr()
+        b.converged = self.converged.data_ptr()
+        b.root_index = self.root_index.data_ptr()
+        return b
+
+    def set_variant(self, variant):
+        self.variant = variant
+        self._cb.variant = variant
+
+    def solve(self, stream=None):
+        """Enqueue gcs_b200_solve on `stream` (default: torch's current stream)."""
+        torch = self.torch
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        check(load().gcs_b200_solve(C.byref(self._cb), idx, C.c_void_p(s.cuda_stream)), "gcs_b200_solve")
+
+    def to_host(self, host: HostBatch) -> HostBatch:
+        host.out = [o.cpu().numpy() for o in self.out]
+        host.cand = self.cand.cpu().numpy() if self.cand is not None else None
+        host.iters = self.iters.cpu().numpy()
+        host.converged = self.converged.cpu().numpy()
+        host.root_index = self.root_index.cpu().numpy()
+        return host
+
+    def algorithmic_bytes(self):
+        """Minimum HBM traffic of one launch: inputs + code + outputs + per-seed flags."""
+        n, ns = self.n, self.n_seeds
+        b = IN_COLS[self.kind] * 8 + 1 + OUT_COLS[self.kind] * 8 + ns * 3 + 1
+        if self.cand is not None:
+            b += ns * 16
+        if self.guesses is not None:
+            b += ns * 16
+        return n * b

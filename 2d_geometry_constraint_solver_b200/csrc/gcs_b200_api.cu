@@ -1,0 +1,531 @@
+// gcs_b200_api.cu — C ABI (include/gcs_b200.h) over the sm_100a kernels.
+//
+// No torch types, no exceptions across the boundary, no CPU fallback: every compute entry point
+// needs a CUDA device and reports GCS_E_NO_DEVICE otherwise.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/gcs_b200.h"
+#include "newton_kernels.cuh"
+
+using namespace gcsk;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(GCS_E_CUDA, "%s -> %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                __LINE__);                                                                     \
+    } while (0)
+
+constexpr int kTicketSlots = 64;
+constexpr int kRefillCH = 64;
+constexpr int kRefillWarps = 4;
+
+struct DeviceState {
+    int device = -1;
+    int sm_count = 0;
+    unsigned* tickets = nullptr;  // kTicketSlots x 2 counters, zero between launches
+    std::atomic<unsigned> ticket_rr { 0 };
+    // staging arena for the host-buffer entry points
+    std::mutex arena_mu;
+    unsigned char* arena = nullptr;
+    size_t arena_bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+std::mutex g_mu;
+std::vector<DeviceState*> g_devs;  // indexed by position in the init list
+std::atomic<long long> g_launches { 0 };
+
+DeviceState* find_dev(int device)
+{
+    for (auto* d : g_devs)
+        if (d->device == device) return d;
+    return nullptr;
+}
+
+int ensure_init()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_devs.empty()) return GCS_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(GCS_E_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback",
+            e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    for (int i = 0; i < n; ++i) {
+        auto* d = new DeviceState();
+        d->device = i;
+        g_devs.push_back(d);
+    }
+    return GCS_OK;
+}
+
+int prepare_device(DeviceState* d)
+{
+    if (d->tickets) return GCS_OK;
+    CUDA_TRY(cudaSetDevice(d->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
+    d->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaMalloc(&d->tickets, sizeof(unsigned) * 2 * kTicketSlots));
+    CUDA_TRY(cudaMemset(d->tickets, 0, sizeof(unsigned) * 2 * kTicketSlots));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    return GCS_OK;
+}
+
+int validate(const gcs_b200_batch* b)
+{
+    if (!b) return fail(GCS_E_INVALID, "null batch");
+    if (b->kind < 1 || b->kind > GCS_KIND_COUNT) return fail(GCS_E_INVALID, "unknown kind %d", b->kind);
+    if (b->n < 0) return fail(GCS_E_INVALID, "negative n");
+    const bool column_guess = (b->kind == GCS_KIND_SDD || b->kind == GCS_KIND_ANG);
+    if (column_guess) {
+        if (b->n_seeds != 2) return fail(GCS_E_INVALID, "kind %d takes exactly 2 seeds", b->kind);
+    } else if (b->n_seeds != 2 && b->n_seeds != 8) {
+        return fail(GCS_E_INVALID, "n_seeds must be 2 or 8 (got %d)", b->n_seeds);
+    }
+    if (b->n == 0) return GCS_OK;
+    const int nin = gcs_b200_kind_in_cols(b->kind);
+    for (int c = 0; c < nin; ++c)
+        if (!b->in[c]) return fail(GCS_E_INVALID, "input column %d is null", c);
+    if (!b->code) return fail(GCS_E_INVALID, "code column is null");
+    const int nout = gcs_b200_kind_out_cols(b->kind);
+    for (int c = 0; c < nout; ++c)
+        if (!b->out[c]) return fail(GCS_E_INVALID, "output column %d is null", c);
+    return GCS_OK;
+}
+
+BatchDev to_dev(const gcs_b200_batch* b)
+{
+    BatchDev p;
+    memset(&p, 0, sizeof(p));
+    for (int c = 0; c < GCS_MAX_IN_COLS; ++c) p.in[c] = b->in[c];
+    p.code = b->code;
+    p.guesses = b->guesses;
+    for (int c = 0; c < GCS_MAX_OUT_COLS; ++c) p.out[c] = b->out[c];
+    p.cand = b->cand;
+    p.iters = b->iters;
+    p.converged = b->converged;
+    p.root = b->root_index;
+    p.n = b->n;
+    return p;
+}
+
+template <int KIND, int NS>
+int launch_static(const BatchDev& p, cudaStream_t st)
+{
+    const long long threads = p.n * NS;
+    const int block = 128;
+    const long long grid = (threads + block - 1) / block;
+    if (grid > 0x7fffffffLL) return fail(GCS_E_INVALID, "batch too large for one launch");
+    newton_static_kernel<KIND, NS><<<(unsigned)grid, block, 0, st>>>(p);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCS_OK;
+}
+
+template <int KIND, int NS>
+int launch_refill(DeviceState* d, const BatchDev& p, cudaStream_t st)
+{
+    constexpr int CH = kRefillCH, W = kRefillWarps;
+    auto kern = newton_refill_kernel<KIND, NS, CH, W>;
+    const size_t smem = refill_smem_bytes<KIND, NS, CH>(W);
+    static thread_local int configured_dev[GCS_KIND_COUNT + 1][GCS_MAX_SEEDS + 1] = {};
+    static thread_local int blocks_per_sm[GCS_KIND_COUNT + 1][GCS_MAX_SEEDS + 1] = {};
+    if (configured_dev[KIND][NS] != d->device + 1) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int bps = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, W * 32, smem));
+        if (bps < 1) return fail(GCS_E_CUDA, "refill kernel does not fit on an SM");
+        blocks_per_sm[KIND][NS] = bps;
+        configured_dev[KIND][NS] = d->device + 1;
+    }
+    const long long nchunks = (p.n + CH - 1) / CH;
+    long long grid = (long long)d->sm_count * blocks_per_sm[KIND][NS];
+    const long long need = (nchunks + W - 1) / W;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    bool aligned = p.code != nullptr && ((reinterpret_cast<uintptr_t>(p.code) & 15) == 0);
+    for (int c = 0; c < Sys<KIND>::kCols; ++c)
+        aligned = aligned && ((reinterpret_cast<uintptr_t>(p.in[c]) & 15) == 0);
+    unsigned* tk = d->tickets + 2 * (d->ticket_rr.fetch_add(1) % kTicketSlots);
+    kern<<<(unsigned)grid, W * 32, smem, st>>>(p, tk, aligned ? 1 : 0);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCS_OK;
+}
+
+template <int KIND>
+int launch_kind(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cudaStream_t st)
+{
+    int variant = b->variant;
+    if (variant == GCS_VARIANT_DEFAULT) variant = GCS_VARIANT_REFILL;
+    constexpr bool column_guess = (KIND == GCS_KIND_SDD || KIND == GCS_KIND_ANG);
+    if (b->n_seeds == 2) {
+        return variant == GCS_VARIANT_REFILL ? launch_refill<KIND, 2>(d, p, st) : launch_static<KIND, 2>(p, st);
+    }
+    if constexpr (!column_guess) {
+        return variant == GCS_VARIANT_REFILL ? launch_refill<KIND, 8>(d, p, st) : launch_static<KIND, 8>(p, st);
+    }
+    return fail(GCS_E_INVALID, "unsupported seed count");
+}
+
+int solve_on(DeviceState* d, const gcs_b200_batch* b, cudaStream_t st)
+{
+    if (b->n == 0) return GCS_OK;
+    const BatchDev p = to_dev(b);
+    switch (b->kind) {
+    case GCS_KIND_PP: return launch_kind<GCS_KIND_PP>(d, b, p, st);
+    case GCS_KIND_SDD: return launch_kind<GCS_KIND_SDD>(d, b, p, st);
+    case GCS_KIND_PPL: return launch_kind<GCS_KIND_PPL>(d, b, p, st);
+    case GCS_KIND_PLL: return launch_kind<GCS_KIND_PLL>(d, b, p, st);
+    case GCS_KIND_ANG: return launch_kind<GCS_KIND_ANG>(d, b, p, st);
+    }
+    return fail(GCS_E_INVALID, "unknown kind");
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- FP64 probes --------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double seed)
+{
+    // 8 independent chains per thread; MODE 0: DFMA, MODE 1: alternating DADD / DMUL
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        if (MODE == 0) {
+            a0 = __fma_rn(a0, m, c), a1 = __fma_rn(a1, m, c), a2 = __fma_rn(a2, m, c), a3 = __fma_rn(a3, m, c);
+            a4 = __fma_rn(a4, m, c), a5 = __fma_rn(a5, m, c), a6 = __fma_rn(a6, m, c), a7 = __fma_rn(a7, m, c);
+        } else {
+            a0 = __dadd_rn(a0, c), a1 = __dmul_rn(a1, m), a2 = __dadd_rn(a2, c), a3 = __dmul_rn(a3, m);
+            a4 = __dadd_rn(a4, c), a5 = __dmul_rn(a5, m), a6 = __dadd_rn(a6, c), a7 = __dmul_rn(a7, m);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+__global__ void fp64_latency_kernel(double* out, long long* cycles, int iters, double seed)
+{
+    double a = seed;
+    const double m = 1.0000000001, c = 1e-9;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+        a = __fma_rn(a, m, c), a = __fma_rn(a, m, c), a = __fma_rn(a, m, c), a = __fma_rn(a, m, c);
+        a = __fma_rn(a, m, c), a = __fma_rn(a, m, c), a = __fma_rn(a, m, c), a = __fma_rn(a, m, c);
+    }
+    const long long t1 = clock64();
+    out[threadIdx.x] = a;
+    if (threadIdx.x == 0) *cycles = t1 - t0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcs_b200_kind_in_cols(int kind)
+{
+    static const int t[GCS_KIND_COUNT + 1] = { 0, 6, 9, 10, 12, 13 };
+    return (kind >= 1 && kind <= GCS_KIND_COUNT) ? t[kind] : 0;
+}
+
+int gcs_b200_kind_out_cols(int kind)
+{
+    static const int t[GCS_KIND_COUNT + 1] = { 0, 2, 4, 2, 2, 4 };
+    return (kind >= 1 && kind <= GCS_KIND_COUNT) ? t[kind] : 0;
+}
+
+int gcs_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int gcs_b200_init(int device_count, const int* devices)
+{
+    int rc = ensure_init();
+    if (rc != GCS_OK) return rc;
+    const int avail = (int)g_devs.size();
+    if (device_count <= 0) device_count = avail;
+    for (int i = 0; i < device_count; ++i) {
+        const int dev = devices ? devices[i] : i;
+        if (dev < 0 || dev >= avail) return fail(GCS_E_NO_DEVICE, "device %d out of range (%d present)", dev, avail);
+        rc = prepare_device(g_devs[dev]);
+        if (rc != GCS_OK) return rc;
+    }
+    return GCS_OK;
+}
+
+void gcs_b200_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto* d : g_devs) {
+        if (d->tickets || d->arena || d->stream) {
+            cudaSetDevice(d->device);
+            if (d->stream) cudaStreamSynchronize(d->stream), cudaStreamDestroy(d->stream);
+            if (d->tickets) cudaFree(d->tickets);
+            if (d->arena) cudaFree(d->arena);
+        }
+        delete d;
+    }
+    g_devs.clear();
+}
+
+const char* gcs_b200_last_error(void) { return g_err; }
+
+const char* gcs_b200_version(void) { return "gcs_b200 0.1.0 (sm_100a, fp64, fmad=false)"; }
+
+int64_t gcs_b200_launch_count(void) { return g_launches.load(); }
+
+int gcs_b200_solve(const gcs_b200_batch* b, int device, void* cuda_stream)
+{
+    int rc = validate(b);
+    if (rc != GCS_OK) return rc;
+    if (b->mem != GCS_MEM_DEVICE) return fail(GCS_E_INVALID, "gcs_b200_solve needs device pointers (mem=GCS_MEM_DEVICE)");
+    rc = ensure_init();
+    if (rc != GCS_OK) return rc;
+    DeviceState* d = find_dev(device);
+    if (!d) return fail(GCS_E_NO_DEVICE, "device %d not present", device);
+    rc = prepare_device(d);
+    if (rc != GCS_OK) return rc;
+    int cur = -1;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != device) CUDA_TRY(cudaSetDevice(device));
+    rc = solve_on(d, b, static_cast<cudaStream_t>(cuda_stream));
+    if (cur != device && cur >= 0) cudaSetDevice(cur);
+    return rc;
+}
+
+int gcs_b200_solve_host(const gcs_b200_batch* b, int device)
+{
+    int rc = validate(b);
+    if (rc != GCS_OK) return rc;
+    if (b->mem != GCS_MEM_HOST) return fail(GCS_E_INVALID, "gcs_b200_solve_host needs host pointers (mem=GCS_MEM_HOST)");
+    rc = ensure_init();
+    if (rc != GCS_OK) return rc;
+    DeviceState* d = find_dev(device);
+    if (!d) return fail(GCS_E_NO_DEVICE, "device %d not present", device);
+    rc = prepare_device(d);
+    if (rc != GCS_OK) return rc;
+    if (b->n == 0) return GCS_OK;
+
+    std::lock_guard<std::mutex> lk(d->arena_mu);
+    int cur = -1;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != device) CUDA_TRY(cudaSetDevice(device));
+
+    const size_t n = (size_t)b->n;
+    const int ns = b->n_seeds;
+    const int nin = gcs_b200_kind_in_cols(b->kind), nout = gcs_b200_kind_out_cols(b->kind);
+    const size_t colb = align_up(n * 8, 256);
+    size_t need = colb * (nin + nout) + align_up(n, 256) * 2;  // code + root
+    if (b->guesses) need += align_up(n * 8 * 2 * ns, 256);
+    if (b->cand) need += align_up(n * 8 * 2 * ns, 256);
+    if (b->iters) need += align_up(n * 2 * ns, 256);
+    if (b->converged) need += align_up(n * ns, 256);
+    if (need > d->arena_bytes) {
+        if (d->arena) CUDA_TRY(cudaFree(d->arena));
+        d->arena = nullptr, d->arena_bytes = 0;
+        const size_t grow = need + need / 4;
+        if (cudaMalloc(&d->arena, grow) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(GCS_E_NOMEM, "cudaMalloc(%zu) for the staging arena failed", grow);
+        }
+        d->arena_bytes = grow;
+    }
+    unsigned char* cur_p = d->arena;
+    auto take = [&](size_t bytes) {
+        unsigned char* r = cur_p;
+        cur_p += align_up(bytes, 256);
+        return r;
+    };
+    gcs_b200_batch db = *b;
+    db.mem = GCS_MEM_DEVICE;
+    cudaStream_t st = d->stream;
+    for (int c = 0; c < nin; ++c) {
+        double* p = reinterpret_cast<double*>(take(n * 8));
+        CUDA_TRY(cudaMemcpyAsync(p, b->in[c], n * 8, cudaMemcpyHostToDevice, st));
+        db.in[c] = p;
+    }
+    {
+        uint8_t* p = take(n);
+        CUDA_TRY(cudaMemcpyAsync(p, b->code, n, cudaMemcpyHostToDevice, st));
+        db.code = p;
+    }
+    if (b->guesses) {
+        double* p = reinterpret_cast<double*>(take(n * 8 * 2 * ns));
+        CUDA_TRY(cudaMemcpyAsync(p, b->guesses, n * 8 * 2 * ns, cudaMemcpyHostToDevice, st));
+        db.guesses = p;
+    }
+    for (int c = 0; c < nout; ++c) db.out[c] = reinterpret_cast<double*>(take(n * 8));
+    if (b->cand) db.cand = reinterpret_cast<double*>(take(n * 8 * 2 * ns));
+    if (b->iters) db.iters = reinterpret_cast<int16_t*>(take(n * 2 * ns));
+    if (b->converged) db.converged = take(n * ns);
+    db.root_index = take(n);
+
+    rc = solve_on(d, &db, st);
+    if (rc == GCS_OK) {
+        for (int c = 0; c < nout; ++c)
+            CUDA_TRY(cudaMemcpyAsync(b->out[c], db.out[c], n * 8, cudaMemcpyDeviceToHost, st));
+        if (b->cand) CUDA_TRY(cudaMemcpyAsync(b->cand, db.cand, n * 8 * 2 * ns, cudaMemcpyDeviceToHost, st));
+        if (b->iters) CUDA_TRY(cudaMemcpyAsync(b->iters, db.iters, n * 2 * ns, cudaMemcpyDeviceToHost, st));
+        if (b->converged) CUDA_TRY(cudaMemcpyAsync(b->converged, db.converged, n * ns, cudaMemcpyDeviceToHost, st));
+        if (b->root_index) CUDA_TRY(cudaMemcpyAsync(b->root_index, db.root_index, n, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    if (cur != device && cur >= 0) cudaSetDevice(cur);
+    return rc;
+}
+
+int gcs_b200_solve_sharded(const gcs_b200_batch* b, int n_dev)
+{
+    int rc = validate(b);
+    if (rc != GCS_OK) return rc;
+    if (b->mem != GCS_MEM_HOST) return fail(GCS_E_INVALID, "gcs_b200_solve_sharded needs host pointers");
+    rc = ensure_init();
+    if (rc != GCS_OK) return rc;
+    const int avail = (int)g_devs.size();
+    if (n_dev <= 0) n_dev = avail;
+    if (n_dev > avail) return fail(GCS_E_NO_DEVICE, "%d devices requested, %d present", n_dev, avail);
+    if (n_dev == 1) return gcs_b200_solve_host(b, 0);
+    if (b->guesses || b->cand) {
+        // [seed][2][n] planes are not contiguous per shard
+        return fail(GCS_E_INVALID, "sharded solve does not take explicit guesses / cand planes");
+    }
+    std::vector<int> rcs(n_dev, GCS_OK);
+    std::vector<std::string> msgs(n_dev);
+    std::vector<std::thread> th;
+    const int64_t n = b->n;
+    for (int g = 0; g < n_dev; ++g) {
+        th.emplace_back([&, g]() {
+            const int64_t lo = n * g / n_dev, hi = n * (g + 1) / n_dev;
+            gcs_b200_batch s = *b;
+            s.n = hi - lo;
+            const int nin = gcs_b200_kind_in_cols(b->kind), nout = gcs_b200_kind_out_cols(b->kind);
+            for (int c = 0; c < nin; ++c) s.in[c] = b->in[c] + lo;
+            s.code = b->code + lo;
+            for (int c = 0; c < nout; ++c) s.out[c] = b->out[c] + lo;
+            if (b->root_index) s.root_index = b->root_index + lo;
+            // per-seed planes [seed][n]: solve into shard-local temporaries, then scatter
+            std::vector<int16_t> its;
+            std::vector<uint8_t> cvs;
+            if (b->iters) its.resize((size_t)s.n * b->n_seeds), s.iters = its.data();
+            if (b->converged) cvs.resize((size_t)s.n * b->n_seeds), s.converged = cvs.data();
+            rcs[g] = gcs_b200_solve_host(&s, g);
+            if (rcs[g] != GCS_OK) {
+                msgs[g] = g_err;
+                return;
+            }
+            for (int k = 0; k < b->n_seeds; ++k) {
+                if (b->iters) memcpy(b->iters + (size_t)k * n + lo, its.data() + (size_t)k * s.n, (size_t)s.n * 2);
+                if (b->converged) memcpy(b->converged + (size_t)k * n + lo, cvs.data() + (size_t)k * s.n, (size_t)s.n);
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int g = 0; g < n_dev; ++g)
+        if (rcs[g] != GCS_OK) return fail(rcs[g], "shard %d: %s", g, msgs[g].c_str());
+    return GCS_OK;
+}
+
+double gcs_b200_fp64_probe(int device, int what)
+{
+    int rc = ensure_init();
+    if (rc != GCS_OK) return (double)rc;
+    DeviceState* d = find_dev(device);
+    if (!d) return (double)fail(GCS_E_NO_DEVICE, "device %d not present", device);
+    rc = prepare_device(d);
+    if (rc != GCS_OK) return (double)rc;
+    if (cudaSetDevice(device) != cudaSuccess) return (double)GCS_E_CUDA;
+    double* out = nullptr;
+    const int blocks = d->sm_count * 8, threads = 256, iters = 20000;
+    if (cudaMalloc(&out, sizeof(double) * blocks * threads + 64) != cudaSuccess) return (double)GCS_E_NOMEM;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    double result = 0.0;
+    if (what == 0 || what == 1) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(e0, d->stream);
+            if (what == 0)
+                fp64_probe_kernel<0><<<blocks, threads, 0, d->stream>>>(out, iters, 1.0);
+            else
+                fp64_probe_kernel<1><<<blocks, threads, 0, d->stream>>>(out, iters, 1.0);
+            cudaEventRecord(e1, d->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double ops = (double)blocks * threads * (double)iters * 8.0;
+        const double flops = ops * (what == 0 ? 2.0 : 1.0);
+        result = flops / (best * 1e-3) / 1e12;
+    } else {
+        long long* cyc = reinterpret_cast<long long*>(out + (size_t)blocks * threads);
+        fp64_latency_kernel<<<1, 32, 0, d->stream>>>(out, cyc, 4096, 1.0);
+        fp64_latency_kernel<<<1, 32, 0, d->stream>>>(out, cyc, 4096, 1.0);
+        cudaStreamSynchronize(d->stream);
+        long long h = 0;
+        cudaMemcpy(&h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+        result = (double)h / (4096.0 * 8.0);
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    cudaFree(out);
+    if (e != cudaSuccess) return (double)fail(GCS_E_CUDA, "fp64 probe: %s", cudaGetErrorString(e));
+    return result;
+}
+
+int gcs_b200_synth_pp_launch(void* cuda_stream, uint64_t seed, int64_t first, int64_t n,
+    int perturb_of, double* const cols[6], uint8_t* code);  // synth.cu
+
+int gcs_b200_synth_pp(int device, void* cuda_stream, uint64_t seed, int64_t first, int64_t n,
+    int perturb_of, double* const cols[6], uint8_t* code)
+{
+    if (n < 0 || !cols || !code) return fail(GCS_E_INVALID, "bad synth arguments");
+    for (int c = 0; c < 6; ++c)
+        if (!cols[c]) return fail(GCS_E_INVALID, "synth column %d is null", c);
+    int rc = ensure_init();
+    if (rc != GCS_OK) return rc;
+    if (!find_dev(device)) return fail(GCS_E_NO_DEVICE, "device %d not present", device);
+    int cur = -1;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != device) CUDA_TRY(cudaSetDevice(device));
+    rc = gcs_b200_synth_pp_launch(cuda_stream, seed, first, n, perturb_of, cols, code);
+    g_launches.fetch_add(1);
+    if (cur != device && cur >= 0) cudaSetDevice(cur);
+    if (rc != 0) return fail(GCS_E_CUDA, "synth launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return GCS_OK;
+}
+
+}  // extern "C"

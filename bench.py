@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — sub-system Newton solves/sec on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, host cores
+
+Workload (config.workload): BASELINE.json configs[1] — 2^20 independent synthetic triangle
+clusters per GPU, half K1 (distance+distance, ZeroFixedPoints/TwoFixedPointsDistance shapes) and
+half K5 (angle+unit normal), one solve2D-equivalent each (2 seeds, reference defaults) + root
+selection (+ line reconstruction for K5).  A step = one pass over that batch = two kernel
+launches.  Weak scaling: every rank owns its own 2^20 instances (index range rank*2^20...), no
+data-path collective.
+
+`value`  : whole-job solves/s, inputs resident in HBM, per-step CUDA-event time, max over ranks.
+`e2e`    : same metric through gcs_b200_solve_host with pinned HOST buffers (H2D + kernels + D2H
+           inside the timed region).
+`roofline`: dominant kernel (K1 refill kernel): algorithmic FP64 flops (work model of
+           BASELINE.md section 5, from the MEASURED iteration counts) / its event-timed duration,
+           against the DFMA peak measured live by gcs_b200_fp64_probe (MEASURED_PEAKS.json
+           carries no FP64 figure); the HBM side is reported beside it.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU = 1 << 20
+METRIC = "subsystem Newton solves/sec"
+UNIT = "solves/s"
+WORKLOAD = "configs[1]: 2^20 synthetic triangle clusters per GPU (2^19 K1 distance-distance + 2^19 K5 angle-normal), 2 seeds each, FP64"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", type=int, default=0, help="0 default, 1 static, 2 refill")
+    ap.add_argument("--n", type=int, default=N_PER_GPU, help="solves per GPU (default 2^20)")
+    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Polls NVML for SM clock + throttle reasons while a region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._in_region = False
+        self.region = []
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {}
+        if nv:
+            for k in dir(nv):
+                if k.startswith("nvmlClocksEventReason") or k.startswith("nvmlClocksThrottleReason"):
+                    v = getattr(nv, k)
+                    if isinstance(v, int) and v not in (0,):
+                        names.setdefault(v, k.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+        while not self._stop.is_set():
+            if nv:
+                try:
+                    mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.samples.append(mhz)
+                    if self._in_region:
+                        self.region.append(mhz)
+                        for bit, nm in names.items():
+                            if r & bit and nm not in ("GpuIdle", "None", "All"):
+                                self.reasons.add(nm)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def start(self):
+        self.t.start()
+
+    def enter(self):
+        self._in_region = True
+
+    def leave(self):
+        self._in_region = False
+
+    def stop(self):
+        self._stop.set()
+        self.t.join(timeout=1.0)
+        src = self.region if self.region else self.samples
+        return {
+            "sm_mhz": float(np.median(src)) if src else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples_in_timed_region": len(self.region),
+        }
+
+
+def make_batches(synth, n, rank):
+    half = n // 2
+    first = rank * half
+    return [synth.make_pp(half, first=first), synth.make_ang(half, first=first)]
+
+
+def cpu_rate(gcs, seconds, threads=0):
+    """Time the CPU implementation of the path on a bounded sample of the same workload.
+    Returns (solves/s, cores, kind, sample description)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import __graft_entry__ as g
+    g.build_oracle()
+    import oracle_lib as O
+    synth = gcs.synth
+    cores = O.max_threads() if threads < 1 else threads
+    # calibrate on 2^13 of each kind, then size the sample for ~`seconds` of wall time
+    def run(m):
+        bs = [synth.make_pp(m).alloc_outputs(), synth.make_ang(m).alloc_outputs()]
+        t0 = time.perf_counter()
+        for b in bs:
+            O.solve(b, threads)
+        return time.perf_counter() - t0
+    run(1 << 10)
+    t = run(1 << 13)
+    rate = 2 * (1 << 13) / t
+    m = int(min(max(rate * seconds / 2, 1 << 13), 1 << 19))
+    t = run(m)
+    return 2 * m / t, cores, "port", f"{m} K1 + {m} K5 solves (same generators), OpenMP static, {cores} threads, {t:.2f} s"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    gcs = importlib.import_module("2d_geometry_constraint_solver_b200")
+    per_step = max(args.cpu_seconds / max(args.steps + args.warmup, 1), 0.5)
+    rates = []
+    desc = cores = kind = None
+    for i in range(args.warmup + args.steps):
+        r, cores, kind, desc = cpu_rate(gcs, per_step)
+        if i >= args.warmup:
+            rates.append(r)
+    v = float(np.mean(rates))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference CPU path on the box's host cores: the restated oracle "
+                   "(oracle/gcs_oracle.c; the reference itself needs GCC>=15, Eigen, autodiff and cannot be built here)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    gcs = importlib.import_module("2d_geometry_constraint_solver_b200")
+    capi, synth = gcs.capi, gcs.synth
+    capi.init([local_rank])
+    lib = capi.load()
+
+    n = args.n
+    host = make_batches(synth, n, rank)
+    for h in host:
+        h.variant = args.variant
+    devb = [capi.DeviceBatch(h, dev, want_cand=False, variant=args.variant) for h in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    stream = torch.cuda.current_stream(dev)
+
+    def step(events=None):
+        if events:
+            events[0].record(stream)
+        devb[0].solve()
+        if events:
+            events[1].record(stream)
+        devb[1].solve()
+        if events:
+            events[2].record(stream)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        step()
+    barrier()
+
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    l0 = lib.gcs_b200_launch_count()
+    sampler.enter()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)  # evict the batch from L2 between timed steps (outside the events)
+        step(evs[k])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.leave()
+    launches = lib.gcs_b200_launch_count() - l0
+
+    ms_k1 = np.array([e[0].elapsed_time(e[1]) for e in evs])
+    ms_k5 = np.array([e[1].elapsed_time(e[2]) for e in evs])
+    ms_step = ms_k1 + ms_k5
+    t_sum = torch.tensor([float(ms_step.sum())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_sum, op=dist.ReduceOp.MAX)
+    total_ms = float(t_sum.item())
+    value = (n * world * args.steps) / (total_ms * 1e-3)
+
+    # ---- iteration histogram -> algorithmic work of the dominant kernel ----
+    it1 = devb[0].iters.cpu().numpy()
+    it5 = devb[1].iters.cpu().numpy()
+    w_k1 = synth.algorithmic_flops(1, it1)
+    w_k5 = synth.algorithmic_flops(5, it5)
+    dfma_peak = lib.gcs_b200_fp64_probe(local_rank, 0)
+    mix_peak = lib.gcs_b200_fp64_probe(local_rank, 1)
+    peaks, peak_src = load_peaks()
+    k1_ms = float(np.mean(ms_k1))
+    k5_ms = float(np.mean(ms_k5))
+    ach_tf = w_k1 / (k1_ms * 1e-3) / 1e12
+    b_k1 = devb[0].algorithmic_bytes()
+    b_k5 = devb[1].algorithmic_bytes()
+    roofline = {
+        "kernel": "newton_refill_kernel<K1,2 seeds>" if args.variant != 1 else "newton_static_kernel<K1,2 seeds>",
+        "bound": "fp64",
+        "achieved": ach_tf, "peak": dfma_peak, "unit": "TFLOP/s", "frac": ach_tf / dfma_peak if dfma_peak > 0 else None,
+        "peak_source": "measured live: gcs_b200_fp64_probe DFMA micro-benchmark (FMA = 2 flops); MEASURED_PEAKS.json has no FP64 entry",
+        "non_fma_peak": mix_peak,
+        "frac_of_non_fma_peak": ach_tf / mix_peak if mix_peak > 0 else None,
+        "traffic": None,
+        "algorithmic_flops_per_launch": w_k1,
+        "flops_per_solve": w_k1 / devb[0].n,
+        "mean_iters_per_seed": float(it1.mean()),
+        "launch_ms": k1_ms,
+        "share_of_step": k1_ms / (k1_ms + k5_ms),
+        "hbm": {"achieved": b_k1 / (k1_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": b_k1 / (k1_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 1.0), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_k1},
+        "second_kernel": {"kernel": "K5", "launch_ms": k5_ms, "achieved_tflops": w_k5 / (k5_ms * 1e-3) / 1e12,
+                          "hbm_gbs": b_k5 / (k5_ms * 1e-3) / 1e9, "mean_iters_per_seed": float(it5.mean())},
+    }
+
+    # ---- end to end through the host-buffer C-ABI call, pinned host memory ----
+    def pin_like(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].copy()).dtype, pin_memory=True)
+        v = t.numpy()
+        v[...] = a
+        return t, v
+
+    keep = []
+    e2e_batches = []
+    for h in host:
+        cols = []
+        for c in h.cols:
+            t, v = pin_like(c); keep.append(t); cols.append(v)
+        t, code = pin_like(h.code); keep.append(t)
+        hb = capi.HostBatch(h.kind, h.n_seeds, cols, code, None, args.variant, want_cand=False)
+        m = hb.n
+        outs = []
+        for _ in range(capi.OUT_COLS[h.kind]):
+            t, v = pin_like(np.zeros(m)); keep.append(t); outs.append(v)
+        hb.out = outs
+        t, hb.iters = pin_like(np.zeros((h.n_seeds, m), np.int16)); keep.append(t)
+        t, hb.converged = pin_like(np.zeros((h.n_seeds, m), np.uint8)); keep.append(t)
+        t, hb.root_index = pin_like(np.zeros(m, np.uint8)); keep.append(t)
+        hb.cand = None
+        e2e_batches.append(hb)
+    h2d = sum(capi.IN_COLS[b.kind] * 8 * b.n + b.n for b in e2e_batches)
+    d2h = sum(capi.OUT_COLS[b.kind] * 8 * b.n + b.n_seeds * 3 * b.n + b.n for b in e2e_batches)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        for b in e2e_batches:
+            capi.solve_host(b, local_rank)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        for b in e2e_batches:
+            capi.solve_host(b, local_rank)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = n * world * e2e_steps / float(e2e_t.item())
+    # the e2e results must equal the device-resident ones (same inputs)
+    assert np.array_equal(e2e_batches[0].iters, it1) and np.array_equal(e2e_batches[1].iters, it5)
+
+    clocks = sampler.stop()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, kind, desc = cpu_rate(gcs, args.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "solves_per_gpu": n, "l2": "256 MiB flush write between timed steps",
+                       "variant": {0: "default(refill)", 1: "static", 2: "refill"}[args.variant],
+                       "timing": "per-step CUDA events on the launching stream, sum over steps, max over ranks",
+                       "wall_s_timed_region_incl_flush": t_wall},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "gcs_b200_solve_host (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,198 @@
+/*
+ * gcs_b200.h — C ABI of the B200-native batched Newton-Raphson sub-system solver.
+ *
+ * This is the drop-in boundary for ONE path of the reference
+ * (SolyomBalint/2D_geometry_constraint_solver): the 2-unknown Newton-Raphson root finder
+ *   src/constraint_solver/src/solving/equations/newton_raphson.hpp:41-102   (solve2D)
+ * fed by the equation primitives
+ *   src/constraint_solver/src/solving/equations/equation_primitives.hpp:23-199
+ * and followed by the root-selection heuristics
+ *   src/constraint_solver/src/solving/solvers/heuristics.hpp:22-335
+ * and the line write-back helper `reconstructLineEndpoints`
+ *   src/constraint_solver/src/solving/solvers/point_line_solvers.cpp:74-106.
+ *
+ * The reference has no FFI of its own (it is one C++ shared library); this header is what a
+ * binding for that path binds.  One "solve" = one `solve2D` call (all seeds) + the heuristic that
+ * picks the root (+ line reconstruction where the unknown is a line).  The host packer (the C++
+ * layer in 2d_geometry_constraint_solver_b200/host, mirroring the reference's eight
+ * `Solvers::*::solve` functions) turns matched 3-element components into the
+ * structure-of-arrays batches described below.
+ *
+ * Conventions
+ *   - plain C, no exceptions, every entry point returns 0 on success or a negative GCS_E_* code;
+ *     `gcs_b200_last_error()` returns a thread-local message for the last failure.
+ *   - all pointers are caller-owned; the library retains nothing after a call returns, except
+ *     the internal per-device staging arena used by the host-buffer entry points.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     GCS_E_NO_DEVICE.
+ *   - arithmetic is IEEE-754 binary64 without contraction; constants below equal the reference's
+ *     (newton_raphson.hpp:17, :20, :105-107; heuristics.hpp:173, :209).
+ */
+#ifndef GCS_B200_H
+#define GCS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define GCS_B200_API
+#else
+#define GCS_B200_API __attribute__((visibility("default")))
+#endif
+
+/* ---- constants of the path (reference file:line in the comment) ---- */
+#define GCS_CONVERGENCE_THRESHOLD 0.00001 /* newton_raphson.hpp:17 */
+#define GCS_MAXIMUM_ITERATIONS 1000       /* newton_raphson.hpp:20 */
+#define GCS_DEFAULT_GUESS 20000.0         /* newton_raphson.hpp:105-107: (+g,+g), (-g,-g) */
+#define GCS_PARALLEL_EPSILON 1e-10        /* heuristics.hpp:173 */
+#define GCS_COLLINEAR_EPSILON 1e-8        /* heuristics.hpp:209 */
+
+/* ---- error codes ---- */
+#define GCS_OK 0
+#define GCS_E_INVALID (-1)   /* bad descriptor (kind, n_seeds, null column, ...) */
+#define GCS_E_NO_DEVICE (-2) /* no CUDA device / device index out of range */
+#define GCS_E_CUDA (-3)      /* a CUDA runtime call failed; see gcs_b200_last_error() */
+#define GCS_E_NOT_INIT (-4)
+#define GCS_E_NOMEM (-5)
+
+/* ---- equation-pair kinds (what the kernels are specialised on) ----
+ * K1 PP   : point-to-point distance x2                 (equation_primitives.hpp:23-28)
+ *           used by ZeroFixedPointsTriangleSolver / TwoFixedPointsDistanceSolver
+ *           (point_point_solvers.cpp:56-65, :136-145); selection pickByTriangleOrientation.
+ * K2 SDD  : lineNormalSignedDistanceDiff + unitNormalConstraint (equation_primitives.hpp:176-199)
+ *           used by ZeroFixedPPLTriangleSolver / TwoFixedPointsLineSolver
+ *           (point_line_solvers.cpp:205-222, :349-367); selection pickLineBySignedDistances;
+ *           output = line endpoints via reconstructLineEndpoints.
+ * K3 PPL  : pointToPointDistance + pointToLineDistance (equation_primitives.hpp:23-28, :70-76)
+ *           used by FixedPointAndLineFreePointSolver (point_line_solvers.cpp:500-512);
+ *           selection pickByTriangleOrientationWithFallback with perpendicular feet.
+ * K4 PLL  : pointToLineDistance x2, used by TwoFixedLinesFreePointSolver
+ *           (point_line_solvers.cpp:636-649); selection via line intersection (:656-682).
+ * K5 ANG  : lineNormalAngleConstraint + unitNormalConstraint (equation_primitives.hpp:141-149,
+ *           :196-199), used by ZeroFixedLLPAngleTriangleSolver / FixedLineAndPointFreeLineSolver
+ *           (line_angle_solvers.cpp:293-311, :483-501); selection
+ *           pickLineNormalByAngleOrientation; output = line endpoints.
+ */
+#define GCS_KIND_PP 1
+#define GCS_KIND_SDD 2
+#define GCS_KIND_PPL 3
+#define GCS_KIND_PLL 4
+#define GCS_KIND_ANG 5
+#define GCS_KIND_COUNT 5
+
+/* Input columns (each `const double[n]`, SoA, 16-byte aligned base recommended).
+ * "solver space" = coordinates already solved by earlier components; "canvas" = the sketch.
+ *
+ * K1 PP (6):  0 ax  1 ay  2 ra  3 bx  4 by  5 rb
+ *     fixed point A, |free-A|, fixed point B, |free-B|.
+ * K2 SDD (9): 0 p1x 1 p1y 2 p2x 3 p2y 4 s1 5 s2 6 gnx 7 gny 8 canvas_len
+ *     fixed points P1,P2 (solver space), signed distances s_i = signOf(canvas side)*d_i,
+ *     canvas unit normal of the free line (guess 0; guess 1 is its negation),
+ *     canvas length of the free line.
+ * K3 PPL (10): 0 px 1 py 2 r 3 xa 4 ya 5 xb 6 yb 7 s 8 cfx 9 cfy
+ *     fixed point + distance, fixed line endpoints (solver space), signed line distance,
+ *     canvas position of the free point (read only when GCS_CODE_COLLINEAR is set).
+ * K4 PLL (12): 0 xa1 1 ya1 2 xb1 3 yb1 4 s1  5 xa2 6 ya2 7 xb2 8 yb2 9 s2  10 cfx 11 cfy
+ * K5 ANG (13): 0 fdx 1 fdy 2 cosA 3 gnx 4 gny 5 cfdx 6 cfdy 7 px 8 py 9 s 10 r2x 11 r2y
+ *              12 canvas_len
+ *     fixed line direction (solver space), cos(angle), canvas unit normal of the free line,
+ *     canvas direction of the fixed line, the constraining point (solver space) and its signed
+ *     distance to the free line, second reference point for reconstruction, canvas length.
+ */
+#define GCS_MAX_IN_COLS 13
+#define GCS_MAX_OUT_COLS 4
+#define GCS_MAX_SEEDS 8
+
+/* Orientation code column (`const uint8_t[n]`): the canvas-side facts the heuristics need,
+ * reduced by the packer to a few bits ("orientation signs" of the north-star batch layout).
+ *   bits 1:0  sign0 + 1, sign0 in {-1,0,+1} (three-valued sign(x) = (x>0)-(x<0))
+ *             K1: sign(triangleOrientation(canvasA, canvasB, canvasFree))   heuristics.hpp:52
+ *             K2: sign(canvas signed distance of P1 to the line)            heuristics.hpp:261
+ *             K3/K4: sign(canvas reference-triangle orientation)            heuristics.hpp:220-223
+ *             K5: sign(canvasFixedDir x canvasFreeDir) after flipOrientation heuristics.hpp:310-312
+ *   bits 3:2  sign1 + 1 (K2 only: canvas signed distance of P2)             heuristics.hpp:262
+ *   bit  4    GCS_CODE_COLLINEAR: |canvasOri| < 1e-8 -> nearest-to-canvas   heuristics.hpp:212-217
+ *   bit  5    GCS_CODE_CANVAS_PARALLEL (K4): the canvas lines do not intersect,
+ *             point_line_solvers.cpp:674-682
+ */
+#define GCS_CODE_SIGN0(code) ((int)((code) & 3) - 1)
+#define GCS_CODE_SIGN1(code) ((int)(((code) >> 2) & 3) - 1)
+#define GCS_CODE_COLLINEAR 0x10
+#define GCS_CODE_CANVAS_PARALLEL 0x20
+#define GCS_MAKE_CODE(sign0, sign1, flags) \
+    ((uint8_t)((((sign0) + 1) & 3) | ((((sign1) + 1) & 3) << 2) | (flags)))
+
+/* where the column pointers of a batch live */
+#define GCS_MEM_HOST 0
+#define GCS_MEM_DEVICE 1
+
+/* kernel selection (0 = library default). Both produce bit-identical results. */
+#define GCS_VARIANT_DEFAULT 0
+#define GCS_VARIANT_STATIC 1 /* one lane per (sub-system, seed), static mapping */
+#define GCS_VARIANT_REFILL 2 /* persistent CTAs, TMA-staged tiles, warp-level lane refill */
+
+typedef struct gcs_b200_batch {
+    int32_t kind;    /* GCS_KIND_* */
+    int32_t n_seeds; /* 2 = reference semantics; 8 = multi-start (kinds with default guesses) */
+    int64_t n;       /* sub-systems in this batch */
+    int32_t mem;     /* GCS_MEM_HOST or GCS_MEM_DEVICE for every pointer below */
+    int32_t variant; /* GCS_VARIANT_* */
+    const double* in[GCS_MAX_IN_COLS]; /* kind-specific input columns, each length n */
+    const uint8_t* code;               /* [n] orientation codes */
+    const double* guesses;             /* NULL = kind default; else [n_seeds][2][n] */
+    double* out[GCS_MAX_OUT_COLS];     /* point kinds: x,y ; line kinds: p1x,p1y,p2x,p2y */
+    double* cand;                      /* optional [n_seeds][2][n]: every seed's end point */
+    int16_t* iters;                    /* optional [n_seeds][n]: updates applied per seed */
+    uint8_t* converged;                /* optional [n_seeds][n]: 1 iff loop left via break */
+    uint8_t* root_index;               /* optional [n]: index of the candidate chosen */
+} gcs_b200_batch;
+
+/* number of input / output columns of a kind (0 for an unknown kind) */
+GCS_B200_API int gcs_b200_kind_in_cols(int kind);
+GCS_B200_API int gcs_b200_kind_out_cols(int kind);
+
+/* library / device management */
+GCS_B200_API int gcs_b200_device_count(void);
+GCS_B200_API int gcs_b200_init(int device_count, const int* devices); /* NULL = 0..count-1 */
+GCS_B200_API void gcs_b200_shutdown(void);
+GCS_B200_API const char* gcs_b200_last_error(void);
+GCS_B200_API const char* gcs_b200_version(void);
+
+/* Solve one batch on one device, asynchronously on `cuda_stream` (a cudaStream_t, NULL = the
+ * default stream).  batch->mem must be GCS_MEM_DEVICE.  Replaces a loop of
+ * `Equations::solve2D` + `pickBy*` calls (newton_raphson.hpp:41-102, heuristics.hpp). */
+GCS_B200_API int gcs_b200_solve(const gcs_b200_batch* batch, int device, void* cuda_stream);
+
+/* Same with HOST buffers: copies inputs H2D, solves, copies outputs D2H and synchronises.
+ * This is the call the host-side solver mirror makes. */
+GCS_B200_API int gcs_b200_solve_host(const gcs_b200_batch* batch, int device);
+
+/* Host buffers, sharded by batch index over the first n_dev initialised devices
+ * (contiguous ranges [g*n/G, (g+1)*n/G)); no collective, per-device D2H into disjoint slices. */
+GCS_B200_API int gcs_b200_solve_sharded(const gcs_b200_batch* batch, int n_dev);
+
+/* number of kernel launches issued by this process so far (bench bookkeeping) */
+GCS_B200_API int64_t gcs_b200_launch_count(void);
+
+/* FP64 pipe micro-benchmarks used as roofline denominators (seconds-scale, device `device`):
+ *   what = 0: dependent-free DFMA throughput, returns TFLOP/s counting FMA = 2 flops
+ *   what = 1: DADD/DMUL mix throughput (1 flop per instruction), TFLOP/s
+ *   what = 2: DFMA dependent-issue latency in SM clocks
+ * Returns a negative GCS_E_* code as a double on failure. */
+GCS_B200_API double gcs_b200_fp64_probe(int device, int what);
+
+/* On-device synthetic instance generator for the parametric sweep (BASELINE config 5) and the
+ * 1M-cluster configs: fills K1 columns for indices [first, first+n) with the counter-based
+ * splitmix64 stream documented in DESIGN.md.  All pointers are device pointers. */
+GCS_B200_API int gcs_b200_synth_pp(int device, void* cuda_stream, uint64_t seed, int64_t first,
+    int64_t n, int perturb_of, double* const cols[6], uint8_t* code);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* GCS_B200_H */

@@ -1,0 +1,71 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/gcs_b200.h declares, and fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gcs_b200.h")).read()
+    return sorted(set(re.findall(r"GCS_B200_API\s+[\w\s\*]+?\b(gcs_b200_\w+)\s*\(", text)))
+
+
+def test_header_symbols_are_all_exported(gcs, built):
+    lib = gcs.capi.load()
+    names = _declared_symbols()
+    assert len(names) >= 12
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in gcs_b200.h but not exported"
+    assert set(names) == set(gcs.capi.EXPORTS)
+
+
+def test_kind_tables_match_python_mirror(gcs, built):
+    lib, capi = gcs.capi.load(), gcs.capi
+    for k in range(0, 8):
+        assert lib.gcs_b200_kind_in_cols(k) == capi.IN_COLS.get(k, 0)
+        assert lib.gcs_b200_kind_out_cols(k) == capi.OUT_COLS.get(k, 0)
+    assert b"sm_100a" in lib.gcs_b200_version()
+
+
+def test_batch_struct_layout_matches_header(gcs):
+    capi = gcs.capi
+    # int32 x2, int64, int32 x2, 13 ptr, ptr, ptr, 4 ptr, 4 ptr
+    assert C.sizeof(capi.CBatch) == 4 + 4 + 8 + 4 + 4 + 8 * (13 + 1 + 1 + 4 + 4)
+    assert capi.CBatch.in_.offset == 24 and capi.CBatch.code.offset == 24 + 13 * 8
+
+
+def test_no_cpu_fallback_without_a_device(gcs, built):
+    """In the CPU container the compute entry points must refuse, not compute."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the refusal path is for CPU-only hosts")
+    capi = gcs.capi
+    lib = capi.load()
+    assert lib.gcs_b200_device_count() == 0
+    hb = gcs.synth.make_pp(8).alloc_outputs()
+    cb = hb.cbatch()
+    assert lib.gcs_b200_solve_host(C.byref(cb), 0) == capi.GCS_E_NO_DEVICE
+    assert b"no CPU fallback" in lib.gcs_b200_last_error()
+    assert np.isnan(hb.out[0]).all()  # nothing was written
+    with pytest.raises(capi.GcsError):
+        capi.solve_host(hb, 0)
+    assert lib.gcs_b200_fp64_probe(0, 0) < 0
+
+
+def test_product_does_not_reference_the_oracle():
+    """The oracle is test infrastructure: nothing under the package or include/ may name it."""
+    pkg = os.path.join(ROOT, "2d_geometry_constraint_solver_b200")
+    bad = []
+    for base in (pkg, os.path.join(ROOT, "include")):
+        for dp, _, files in os.walk(base):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".c")) or f == "Makefile":
+                    t = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"gcs_oracle|oracle_lib|libgcs_oracle|/oracle/|\.\./oracle", t):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
