@@ -284,10 +284,23 @@ __global__ void __launch_bounds__(WARPS * 32)
                             default_seed(slot_seed, x, y);
                         }
                         px = 0.0, py = 0.0, it = 0;
-                        active = true;
+                        // iteration 0 of the reference loop compares the guess with prev = (0,0)
+                        // (newton_raphson.hpp:58, :83-88): a guess inside the tolerance box leaves
+                        // at once, unchanged
+                        if (fabs(px - x) < kTol && fabs(py - y) < kTol) {
+                            sl.cx[slot_seed][slot_sub] = x;
+                            sl.cy[slot_seed][slot_sub] = y;
+                            sl.it[slot_seed][slot_sub] = 0;
+                            sl.cv[slot_seed][slot_sub] = 1;
+                        } else {
+                            active = true;
+                        }
                     }
                 }
-                if (!__any_sync(kFull, active)) break;
+                if (!__any_sync(kFull, active)) {
+                    if (next >= runs) break;
+                    continue;  // every fresh run left at iteration 0; hand out the next ones
+                }
             }
             double f, g, a, b, c, d, s0, s1;
             sys.eval(x, y, f, g, a, b, c, d);
