@@ -15,7 +15,10 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <memory>
 #include <vector>
 
@@ -84,11 +87,15 @@ void run_solve2d(const F& f, const G& g, const std::array<Vector2d, 2>* guesses,
     }
 }
 
+// index of the candidate the reference's heuristic returned; 2 = unobservable (both candidates
+// carry the same bits, e.g. both seeds reached the same root)
 int which(const Vector2d& chosen, const std::array<Vector2d, 2>& cand)
 {
     auto same = [](double a, double b) { return std::memcmp(&a, &b, 8) == 0 || (a != a && b != b); };
-    if (same(chosen.x(), cand[0].x()) && same(chosen.y(), cand[0].y())) return 0;
-    return 1;
+    const bool is0 = same(chosen.x(), cand[0].x()) && same(chosen.y(), cand[0].y());
+    const bool is1 = same(chosen.x(), cand[1].x()) && same(chosen.y(), cand[1].y());
+    if (is0 && is1) return 2;
+    return is0 ? 0 : 1;
 }
 
 void solve_one(const gcs_b200_batch* b, int64_t i, bool count)
@@ -323,6 +330,9 @@ __attribute__((visibility("default"))) int gcs_ref_component_solve(
             }
         }
         return (int)r.status;
+    } catch (const std::exception& ex) {
+        if (std::getenv("GCS_REF_DEBUG")) std::fprintf(stderr, "[gcs_ref] exception: %s\n", ex.what());
+        return -1;
     } catch (...) {
         return -1;
     }

@@ -1,0 +1,73 @@
+"""ctypes binding of oracle/_ref/libgcs_ref.so: the reference's own solve2D / primitives /
+heuristics / solver translation units compiled against stand-in third-party headers
+(oracle/build_ref.sh).  Exists only where it was built (the container with /root/reference, and
+the GPU box, to which the built .so travels).  Test infrastructure only."""
+import ctypes as C
+import importlib
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libgcs_ref.so")
+gcs = importlib.import_module("2d_geometry_constraint_solver_b200")
+capi = gcs.capi
+
+_lib = None
+
+
+class RefElement(C.Structure):
+    _fields_ = [("type", C.c_int32), ("is_set", C.c_int32), ("canvas", C.c_double * 4), ("pos", C.c_double * 4)]
+
+
+class RefEdge(C.Structure):
+    _fields_ = [("a", C.c_int32), ("b", C.c_int32), ("type", C.c_int32), ("flip", C.c_int32), ("value", C.c_double)]
+
+
+def available():
+    return os.path.exists(REF_SO)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        lib = C.CDLL(REF_SO)
+        lib.gcs_ref_solve_batch.argtypes = [C.POINTER(capi.CBatch), C.c_int, C.c_int]
+        lib.gcs_ref_component_solve.argtypes = [C.c_int, C.POINTER(RefElement), C.c_int, C.POINTER(RefEdge)]
+        _lib = lib
+    return _lib
+
+
+def solve_batch(batch, count_iters=True, threads=0):
+    if not batch.out:
+        batch.alloc_outputs()
+    cb = batch.cbatch()
+    rc = load().gcs_ref_solve_batch(C.byref(cb), 1 if count_iters else 0, threads)
+    if rc != 0:
+        raise RuntimeError(f"gcs_ref_solve_batch -> {rc}")
+    return batch
+
+
+def component_solve(elements, edges):
+    """elements: list of dicts {type, canvas, pos?, is_set?}; edges: list of dicts {a, b, type, value, flip}.
+    Returns (status, elements-with-positions).  stderr of the reference (its per-solve prints) is
+    left alone."""
+    els = (RefElement * len(elements))()
+    for i, e in enumerate(elements):
+        els[i].type = e["type"]
+        els[i].is_set = 1 if e.get("is_set") else 0
+        for j, v in enumerate(e["canvas"]):
+            els[i].canvas[j] = v
+        for j, v in enumerate(e.get("pos", [])):
+            els[i].pos[j] = v
+    eds = (RefEdge * len(edges))()
+    for i, e in enumerate(edges):
+        eds[i].a, eds[i].b, eds[i].type = e["a"], e["b"], e["type"]
+        eds[i].flip = 1 if e.get("flip") else 0
+        eds[i].value = e.get("value", 0.0)
+    status = load().gcs_ref_component_solve(len(elements), els, len(edges), eds)
+    out = []
+    for i, e in enumerate(elements):
+        k = 2 if e["type"] == 0 else 4
+        out.append({"type": e["type"], "is_set": bool(els[i].is_set), "pos": [els[i].pos[j] for j in range(k)]})
+    return status, out
