@@ -75,7 +75,7 @@ EXPORTS = [
     "gcs_b200_kind_in_cols", "gcs_b200_kind_out_cols", "gcs_b200_device_count", "gcs_b200_init",
     "gcs_b200_shutdown", "gcs_b200_last_error", "gcs_b200_version", "gcs_b200_solve",
     "gcs_b200_solve_host", "gcs_b200_solve_sharded", "gcs_b200_launch_count",
-    "gcs_b200_fp64_probe", "gcs_b200_synth_pp",
+    "gcs_b200_fp64_probe", "gcs_b200_synth_pp", "gcs_b200_selftest",
 ]
 
 
@@ -100,6 +100,7 @@ def load():
     lib.gcs_b200_launch_count.restype = C.c_int64
     lib.gcs_b200_fp64_probe.argtypes = [C.c_int, C.c_int]
     lib.gcs_b200_fp64_probe.restype = C.c_double
+    lib.gcs_b200_selftest.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.POINTER(C.c_uint64)]
     lib.gcs_b200_synth_pp.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_int64, C.c_int64,
                                       C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
     _lib = lib

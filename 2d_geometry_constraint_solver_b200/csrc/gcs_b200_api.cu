@@ -245,6 +245,32 @@ __global__ void fp64_latency_kernel(double* out, long long* cycles, int iters, d
     if (threadIdx.x == 0) *cycles = t1 - t0;
 }
 
+// DFMA lanes per SM per clock as a function of resident warps and per-thread ILP (one block per SM)
+template <int ILP>
+__global__ void fp64_curve_kernel(double* out, long long* cycles, int iters, double seed)
+{
+    double a[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) a[k] = seed + k + threadIdx.x;
+    const double m = 1.0000000001, c = 1e-9;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) a[k] = __fma_rn(a[k], m, c);
+        }
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) s += a[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -490,6 +516,30 @@ double gcs_b200_fp64_probe(int device, int what)
         const double ops = (double)blocks * threads * (double)iters * 8.0;
         const double flops = ops * (what == 0 ? 2.0 : 1.0);
         result = flops / (best * 1e-3) / 1e12;
+    } else if (what >= 1000) {
+        // what = 1000 + 100*ILP + warps per SM  -> DFMA lanes per SM per clock
+        const int ilp = (what / 100) % 10, warps = what % 100;
+        if (warps < 1 || warps > 32) {
+            cudaFree(out);
+            return (double)fail(GCS_E_INVALID, "probe: warps per SM must be 1..32");
+        }
+        long long* cyc = nullptr;
+        cudaMalloc(&cyc, sizeof(long long) * d->sm_count);
+        const int it = 2000;
+        for (int rep = 0; rep < 2; ++rep) {
+            switch (ilp) {
+            case 1: fp64_curve_kernel<1><<<d->sm_count, warps * 32, 0, d->stream>>>(out, cyc, it, 1.0); break;
+            case 2: fp64_curve_kernel<2><<<d->sm_count, warps * 32, 0, d->stream>>>(out, cyc, it, 1.0); break;
+            case 4: fp64_curve_kernel<4><<<d->sm_count, warps * 32, 0, d->stream>>>(out, cyc, it, 1.0); break;
+            default: fp64_curve_kernel<8><<<d->sm_count, warps * 32, 0, d->stream>>>(out, cyc, it, 1.0); break;
+            }
+        }
+        cudaStreamSynchronize(d->stream);
+        long long h = 0;
+        cudaMemcpy(&h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(cyc);
+        const int eff_ilp = (ilp == 1 || ilp == 2 || ilp == 4) ? ilp : 8;
+        result = (double)warps * 32.0 * it * 8.0 * eff_ilp / (double)h;
     } else {
         long long* cyc = reinterpret_cast<long long*>(out + (size_t)blocks * threads);
         fp64_latency_kernel<<<1, 32, 0, d->stream>>>(out, cyc, 4096, 1.0);
@@ -504,6 +554,32 @@ double gcs_b200_fp64_probe(int device, int what)
     cudaFree(out);
     if (e != cudaSuccess) return (double)fail(GCS_E_CUDA, "fp64 probe: %s", cudaGetErrorString(e));
     return result;
+}
+
+int gcs_b200_selftest_launch(uint64_t seed, long long n, unsigned long long* dev_counts, int sm_count);  // selftest.cu
+
+int gcs_b200_selftest(int device, uint64_t seed, int64_t n, uint64_t counts[8])
+{
+    if (!counts || n < 0) return fail(GCS_E_INVALID, "bad selftest arguments");
+    int rc = ensure_init();
+    if (rc != GCS_OK) return rc;
+    DeviceState* d = find_dev(device);
+    if (!d) return fail(GCS_E_NO_DEVICE, "device %d not present", device);
+    rc = prepare_device(d);
+    if (rc != GCS_OK) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    unsigned long long* dc = nullptr;
+    CUDA_TRY(cudaMalloc(&dc, 8 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(dc, 0, 8 * sizeof(unsigned long long)));
+    rc = gcs_b200_selftest_launch(seed, (long long)n, dc, d->sm_count);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaDeviceSynchronize();
+    unsigned long long h[8] = {};
+    if (e == cudaSuccess) e = cudaMemcpy(h, dc, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(dc);
+    if (rc != 0 || e != cudaSuccess) return fail(GCS_E_CUDA, "selftest: %s", cudaGetErrorString(e));
+    for (int k = 0; k < 8; ++k) counts[k] = h[k];
+    return GCS_OK;
 }
 
 int gcs_b200_synth_pp_launch(void* cuda_stream, uint64_t seed, int64_t first, int64_t n,

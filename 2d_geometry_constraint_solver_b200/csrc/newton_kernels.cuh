@@ -304,7 +304,10 @@ __global__ void __launch_bounds__(WARPS * 32)
             }
             double f, g, a, b, c, d, s0, s1;
             sys.eval(x, y, f, g, a, b, c, d);
-            qr_solve_2x2(a, b, c, d, -f, -g, s0, s1);
+            if (!qr_solve_fast(a, b, c, d, -f, -g, s0, s1)) {
+                const double2 s = qr_solve_generic(a, b, c, d, -f, -g);
+                s0 = s.x, s1 = s.y;
+            }
             if (active) {
                 px = x, py = y;
                 x += s0, y += s1;

@@ -191,6 +191,14 @@ GCS_B200_API double gcs_b200_fp64_probe(int device, int what);
 GCS_B200_API int gcs_b200_synth_pp(int device, void* cuda_stream, uint64_t seed, int64_t first,
     int64_t n, int perturb_of, double* const cols[6], uint8_t* code);
 
+/* Test hook: on-device self check of the hand-written division / square root / 2x2 QR fast paths
+ * against the generic IEEE code (csrc/selftest.cu).  Fills counts[8]:
+ *   [0] divisions on the fast path, [1] of those differing from a/b,
+ *   [2] square roots on the fast path, [3] of those differing from sqrt(a),
+ *   [4] 2x2 systems accepted by the fast solver, [5] of those differing from the generic solver,
+ *   [6] systems tried, [7] operand pairs tried.   [1], [3], [5] must be 0. */
+GCS_B200_API int gcs_b200_selftest(int device, uint64_t seed, int64_t n, uint64_t counts[8]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -223,3 +223,18 @@ def test_fp64_probe_reports_a_plausible_peak(gpu):
     mix = lib.gcs_b200_fp64_probe(0, 1)
     lat = lib.gcs_b200_fp64_probe(0, 2)
     assert 5.0 < dfma < 80.0 and 2.0 < mix < 45.0 and 2.0 < lat < 64.0
+
+
+def test_fast_division_sqrt_and_qr_equal_the_generic_ieee_path(gpu):
+    """2^26 operand pairs / 2x2 systems per seed, compared in-kernel (csrc/selftest.cu): the
+    hand-written fast paths may only return the bits the built-in operators return."""
+    import ctypes as C
+    lib = gpu.load()
+    for seed in (1, 0xC0FFEE):
+        counts = (C.c_uint64 * 8)()
+        assert lib.gcs_b200_selftest(0, seed, 1 << 26, counts) == 0
+        c = list(counts)
+        assert c[7] == 1 << 26 and c[6] == 1 << 26
+        assert c[1] == 0 and c[3] == 0 and c[5] == 0, c
+        # the fast paths are actually exercised
+        assert c[0] > 0.4 * c[7] and c[2] > 0.6 * c[7] and c[4] > 0.3 * c[6], c
