@@ -68,7 +68,8 @@ class CBatch(C.Structure):
 
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libgcs_b200.so")
+# GCS_B200_LIB: developer override to A/B an experimental build of the same library
+LIB_PATH = os.environ.get("GCS_B200_LIB") or os.path.join(_PKG_DIR, "libgcs_b200.so")
 _lib = None
 
 EXPORTS = [

@@ -41,8 +41,11 @@ constexpr unsigned kFull = 0xffffffffu;
 // ------------------------------------------------------------------------------------------
 // static variant
 // ------------------------------------------------------------------------------------------
+#ifndef GCS_STATIC_MINB
+#define GCS_STATIC_MINB 1
+#endif
 template <int KIND, int NS>
-__global__ void __launch_bounds__(128) newton_static_kernel(const BatchDev p)
+__global__ void __launch_bounds__(128, GCS_STATIC_MINB) newton_static_kernel(const BatchDev p)
 {
     using S = Sys<KIND>;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -302,12 +305,8 @@ __global__ void __launch_bounds__(WARPS * 32)
                     continue;  // every fresh run left at iteration 0; hand out the next ones
                 }
             }
-            double f, g, a, b, c, d, s0, s1;
-            sys.eval(x, y, f, g, a, b, c, d);
-            if (!qr_solve_fast(a, b, c, d, -f, -g, s0, s1)) {
-                const double2 s = qr_solve_generic(a, b, c, d, -f, -g);
-                s0 = s.x, s1 = s.y;
-            }
+            double s0, s1;
+            newton_step<KIND>(sys, x, y, s0, s1);
             if (active) {
                 px = x, py = y;
                 x += s0, y += s1;
