@@ -1,0 +1,39 @@
+// DeficitStreeBasedTopDownStrategy (reference:
+// includes/gcs/decomposition/top_down/stree_top_down_strategy.hpp:15-31,
+// src/decomposition/top_down/stree_top_down_strategy.cpp:12-79).
+//
+// solveGcs is the accelerated entry point: the reference's sequential
+// `for_each(leaves, classifyAndSolve)` becomes Gcs::B200::solveLeaves (same final element state,
+// one kernel launch per equation kind per dependency wave).  The S-tree decomposition itself is
+// host graph work on OGDF and out of scope for this path; decomposeConstraintGraph accepts what
+// needs no splitting (a single 3-element component) and otherwise asks the caller to supply the
+// leaves (e.g. from the reference's own decomposition).
+#pragma once
+
+#include <vector>
+
+#include <gcs/b200/leaf_batch.hpp>
+#include <gcs/export.hpp>
+#include <gcs/model/gcs_data_structures.hpp>
+#include <gcs/orchestration/solving_strategy.hpp>
+
+namespace Gcs {
+
+class GCS_API DeficitStreeBasedTopDownStrategy : public GcsSolvingStrategy {
+public:
+    Constrainedness checkConstraintGraphConstrainedness(const ConstraintGraph& gcs) override;
+    bool resolve(ConstraintGraph& gcs) override;
+    std::vector<ConstraintGraph> decomposeConstraintGraph(ConstraintGraph& gcs) override;
+    void solveGcs(std::vector<ConstraintGraph>& splitComponents) override;
+    ~DeficitStreeBasedTopDownStrategy() override = default;
+
+    // what the last solveGcs did (leaves, waves, launches, per-leaf results)
+    const B200::BatchReport& lastReport() const { return m_report; }
+    void setDevice(int device) { m_device = device; }
+
+private:
+    B200::BatchReport m_report;
+    int m_device = 0;
+};
+
+}  // namespace Gcs

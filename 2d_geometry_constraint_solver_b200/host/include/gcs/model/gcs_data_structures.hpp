@@ -1,0 +1,71 @@
+// ConstraintGraph: graph + element / constraint property maps + virtual-edge set, with the
+// accessor surface the sub-problem solvers use (reference:
+// includes/gcs/model/gcs_data_structures.hpp:31-148).  Graph splitting (getSeparatingGraphs,
+// OGDF triconnectivity) is decomposition work outside the accelerated path and is not provided.
+#pragma once
+
+#include <cstddef>
+#include <expected>
+#include <memory>
+#include <unordered_set>
+#include <vector>
+
+#include <gcs/export.hpp>
+#include <gcs/model/constraints.hpp>
+#include <gcs/model/elements.hpp>
+#include <structures/property_map.hpp>
+#include <structures/simple_graph.hpp>
+
+namespace Gcs {
+
+enum class ConstraintGraphError { OK, NodeNotFound, EdgeNotFound };
+
+class GCS_API ConstraintGraph final {
+public:
+    using Graph = MathUtils::SimpleGraph;
+    using NodeIdType = Graph::NodeIdType;
+    using EdgeIdType = Graph::EdgeIdType;
+
+    ConstraintGraphError addElement(NodeIdType node, std::shared_ptr<Element> element);
+    ConstraintGraphError addConstraint(EdgeIdType edge, std::shared_ptr<Constraint> constraint);
+    std::expected<EdgeIdType, ConstraintGraphError> getEdgeBetween(NodeIdType s, NodeIdType t) const;
+    EdgeIdType addVirtualEdge(NodeIdType s, NodeIdType t);
+    ConstraintGraphError removeVirtualEdge(EdgeIdType virtualEdge);
+    ConstraintGraphError removeElement(NodeIdType node);
+    ConstraintGraphError removeConstraintEdge(EdgeIdType edge);
+
+    std::shared_ptr<Element> getElement(NodeIdType node) const;
+    std::shared_ptr<Constraint> getConstraintForEdge(EdgeIdType edge) const;
+    // Throws std::bad_expected_access like the reference when there is no edge, or the edge is a
+    // virtual one that carries no constraint (gcs_data_structures.hpp:66-71).
+    std::shared_ptr<Constraint> getConstraintBetweenNodes(NodeIdType s, NodeIdType t) const;
+
+    const MathUtils::NodePropertyMap<std::shared_ptr<Element>>& getElementMap() const { return m_elementNodeMap; }
+    const MathUtils::EdgePropertyMap<std::shared_ptr<Constraint>>& getConstraintMap() const { return m_constraintEdgeMap; }
+
+    bool hasVirtualEdge() const { return !m_virtualEdges.empty(); }
+    bool isVirtualEdge(EdgeIdType edge) const { return m_virtualEdges.count(edge) != 0; }
+    const std::unordered_set<EdgeIdType>& getVirtualEdges() const { return m_virtualEdges; }
+
+    std::size_t nodeCount() const { return m_constraintGraph.nodeCount(); }
+    std::size_t edgeCount() const { return m_constraintGraph.edgeCount(); }
+    int numberOfSolvedElements() const;
+    int getDeficit() const
+    {
+        return (2 * static_cast<int>(nodeCount()) - 3) - static_cast<int>(edgeCount());
+    }
+
+    Graph& getGraph() { return m_constraintGraph; }
+    const Graph& getGraph() const { return m_constraintGraph; }
+
+    std::vector<std::shared_ptr<Element>> getElements() const;
+    std::vector<std::shared_ptr<Constraint>> getConstraints() const;
+
+private:
+    Graph m_constraintGraph;
+    MathUtils::NodePropertyMap<std::shared_ptr<Element>> m_elementNodeMap;
+    MathUtils::EdgePropertyMap<std::shared_ptr<Constraint>> m_constraintEdgeMap;
+    std::unordered_set<EdgeIdType> m_virtualEdges;
+};
+
+}  // namespace Gcs

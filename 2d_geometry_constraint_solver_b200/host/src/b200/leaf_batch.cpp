@@ -1,0 +1,668 @@
+// leaf_batch.cpp — classification, role assignment, packing, write-back and the batched leaf
+// scheduler behind the reference-shaped solver entry points (see gcs/b200/leaf_batch.hpp).
+//
+// What each piece restates (all paths relative to src/constraint_solver/src/solving/):
+//   matches()      the eight predicates           solvers/point_point_solvers.cpp:14-24, :87-95
+//                                                 solvers/point_line_solvers.cpp:114-133, :261-289,
+//                                                 :405-443, :547-575
+//                                                 solvers/line_angle_solvers.cpp:169-185, :377-415
+//   classify()     first-match dispatch order     component_solver.hpp:31-66
+//   assignRoles()  ascending-NodeId role loops    point_point_solvers.cpp:28-45, :110-123, ...
+//   packNumeric()  anchoring, signed distances, canvas normals, canvas-side signs: everything
+//                  the reference's solve() does before and around solve2D that is not a function
+//                  of the Newton candidates.  The candidate-dependent rest runs in the kernels.
+// Numerics on this side are plain IEEE doubles evaluated in the reference's order (one rounding
+// per operation; the host build uses -ffp-contract=off like the reference's baseline x86-64 build).
+#include <algorithm>
+#include <cmath>
+#include <exception>
+#include <stdexcept>
+#include <unordered_map>
+#include <unordered_set>
+
+#include <gcs/b200/leaf_batch.hpp>
+#include <gcs/model/constraints.hpp>
+#include <gcs/model/elements.hpp>
+
+#include "solving/solvers/heuristics.hpp"
+
+namespace Gcs::B200 {
+
+using Eigen::Vector2d;
+using NodeId = ConstraintGraph::NodeIdType;
+
+namespace {
+
+bool querySet(const SetQuery& q, const Element* e) { return q ? q(e) : e->isElementSet(); }
+
+int sign3(double x) { return (x > 0) - (x < 0); }            // heuristics.hpp:54 (three-valued)
+double signOf(double x) { return (x > 0.0) ? 1.0 : -1.0; }   // point_line_solvers.cpp:195 (zero -> -1)
+
+struct Census {
+    int points = 0, lines = 0;
+    int solved = 0, solvedPoints = 0, unsolvedPoints = 0, solvedLines = 0, unsolvedLines = 0;
+};
+
+Census census(const ConstraintGraph& g, const SetQuery& q)
+{
+    Census c;
+    for (const auto& [node, e] : g.getElementMap()) {
+        const bool set = querySet(q, e.get());
+        c.solved += set ? 1 : 0;
+        if (e->isElementType<Point>()) {
+            ++c.points;
+            ++(set ? c.solvedPoints : c.unsolvedPoints);
+        } else if (e->isElementType<Line>()) {
+            ++c.lines;
+            ++(set ? c.solvedLines : c.unsolvedLines);
+        }
+    }
+    return c;
+}
+
+struct ConstraintCensus {
+    int total = 0, distance = 0, angle = 0;
+};
+
+ConstraintCensus constraintCensus(const ConstraintGraph& g)
+{
+    // the constraint map holds real constraints only: virtual edges carry none
+    ConstraintCensus c;
+    for (const auto& [edge, k] : g.getConstraintMap()) {
+        if (g.isVirtualEdge(edge)) continue;
+        ++c.total;
+        if (k->isConstraintType<DistanceConstraint>())
+            ++c.distance;
+        else if (k->isConstraintType<AngleConstraint>())
+            ++c.angle;
+    }
+    return c;
+}
+
+// Who plays which part in a leaf, plus the constraint values the solver reads.  Filled without
+// touching any position, so it can run ahead of the numeric solve (on predicted solved flags).
+struct Roles {
+    SolverId id = SolverId::None;
+    // a, b: the two "known" elements in the solver's own naming order; c: the element solved for
+    //  1 ZeroFixedPoints      a=P1 b=P2 c=P3            v0=d12 v1=d13 v2=d23
+    //  2 ZeroFixedPPL         a=P1 b=P2 c=line          v0=d12 v1=d(P1,line) v2=d(P2,line)
+    //  3 ZeroFixedLLPAngle    a=line1 b=point c=line2   v0=angle v1=d(P,line1) v2=d(P,line2)
+    //  4 TwoFixedPointsDist   a=fixed1 b=fixed2 c=free  v1=d(f1,free) v2=d(f2,free)
+    //  5 TwoFixedPointsLine   a=fixed1 b=fixed2 c=line  v1=d(f1,line) v2=d(f2,line)
+    //  6 FixedPointAndLine    a=fixedPt b=line c=free   v1=d(fixedPt,free) v2=d(line,free)
+    //  7 TwoFixedLines        a=line1 b=line2 c=free    v1=d(l1,free) v2=d(l2,free)
+    //  8 FixedLineAndPoint    a=fixedLine b=point c=freeLine  v0=angle v2=d(point,freeLine)
+    Element* a = nullptr;
+    Element* b = nullptr;
+    Element* c = nullptr;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+    bool flip = false;  // AngleConstraint::flipOrientation of the line-line constraint
+};
+
+double valueBetween(const ConstraintGraph& g, NodeId s, NodeId t, bool* flip = nullptr)
+{
+    // getConstraintBetweenNodes throws std::bad_expected_access for a missing / virtual edge,
+    // getConstraintValue().value() for a constraint without a value - as in the reference
+    const auto k = g.getConstraintBetweenNodes(s, t);
+    if (flip) {
+        const auto* ang = k->getConstraintAs<AngleConstraint>();
+        *flip = ang != nullptr && ang->flipOrientation;  // line_angle_solvers.cpp:322-326
+    }
+    return k->getConstraintValue().value();
+}
+
+Roles assignRoles(SolverId id, const ConstraintGraph& g, const SetQuery& q)
+{
+    Roles r;
+    r.id = id;
+    NodeId na {}, nb {}, nc {};
+    bool haveA = false;
+    const auto& map = g.getElementMap();
+    switch (id) {
+    case SolverId::ZeroFixedPointsTriangle: {  // point_point_solvers.cpp:28-45
+        int i = 0;
+        for (const auto& [node, e] : map) {
+            if (i == 0) r.a = e.get(), na = node;
+            if (i == 1) r.b = e.get(), nb = node;
+            if (i == 2) r.c = e.get(), nc = node;
+            ++i;
+        }
+        r.v0 = valueBetween(g, na, nb);
+        r.v1 = valueBetween(g, na, nc);
+        r.v2 = valueBetween(g, nb, nc);
+        break;
+    }
+    case SolverId::ZeroFixedPPLTriangle:  // point_line_solvers.cpp:148-161
+    case SolverId::TwoFixedPointsLine: {  // point_line_solvers.cpp:304-317
+        for (const auto& [node, e] : map) {
+            if (e->isElementType<Line>()) {
+                r.c = e.get(), nc = node;
+            } else if (e->isElementType<Point>()) {
+                if (!haveA)
+                    r.a = e.get(), na = node, haveA = true;
+                else
+                    r.b = e.get(), nb = node;
+            }
+        }
+        if (id == SolverId::ZeroFixedPPLTriangle) r.v0 = valueBetween(g, na, nb);
+        r.v1 = valueBetween(g, na, nc);
+        r.v2 = valueBetween(g, nb, nc);
+        break;
+    }
+    case SolverId::ZeroFixedLLPAngleTriangle: {  // line_angle_solvers.cpp:202-215
+        for (const auto& [node, e] : map) {
+            if (e->isElementType<Point>()) {
+                r.b = e.get(), nb = node;
+            } else if (e->isElementType<Line>()) {
+                if (!haveA)
+                    r.a = e.get(), na = node, haveA = true;
+                else
+                    r.c = e.get(), nc = node;
+            }
+        }
+        r.v0 = valueBetween(g, na, nc, &r.flip);
+        r.v1 = valueBetween(g, nb, na);
+        r.v2 = valueBetween(g, nb, nc);
+        break;
+    }
+    case SolverId::TwoFixedPointsDistance: {  // point_point_solvers.cpp:110-123
+        for (const auto& [node, e] : map) {
+            if (querySet(q, e.get())) {
+                if (!haveA)
+                    r.a = e.get(), na = node, haveA = true;
+                else
+                    r.b = e.get(), nb = node;
+            } else {
+                r.c = e.get(), nc = node;
+            }
+        }
+        if (!r.c)
+            throw std::logic_error("TwoFixedPointsDistanceSolver: all three points are already solved; the reference "
+                                   "dereferences a null free point here (point_point_solvers.cpp:89, :110-127)");
+        r.v1 = valueBetween(g, na, nc);
+        r.v2 = valueBetween(g, nb, nc);
+        break;
+    }
+    case SolverId::FixedPointAndLineFreePoint: {  // point_line_solvers.cpp:458-471
+        for (const auto& [node, e] : map) {
+            if (e->isElementType<Line>()) {
+                r.b = e.get(), nb = node;
+            } else if (e->isElementType<Point>()) {
+                if (querySet(q, e.get()))
+                    r.a = e.get(), na = node;
+                else
+                    r.c = e.get(), nc = node;
+            }
+        }
+        r.v1 = valueBetween(g, na, nc);
+        r.v2 = valueBetween(g, nb, nc);
+        break;
+    }
+    case SolverId::TwoFixedLinesFreePoint: {  // point_line_solvers.cpp:590-603
+        for (const auto& [node, e] : map) {
+            if (e->isElementType<Point>()) {
+                r.c = e.get(), nc = node;
+            } else if (e->isElementType<Line>()) {
+                if (!haveA)
+                    r.a = e.get(), na = node, haveA = true;
+                else
+                    r.b = e.get(), nb = node;
+            }
+        }
+        r.v1 = valueBetween(g, na, nc);
+        r.v2 = valueBetween(g, nb, nc);
+        break;
+    }
+    case SolverId::FixedLineAndPointFreeLine: {  // line_angle_solvers.cpp:432-445
+        for (const auto& [node, e] : map) {
+            if (e->isElementType<Point>()) {
+                r.b = e.get(), nb = node;
+            } else if (e->isElementType<Line>()) {
+                if (querySet(q, e.get()))
+                    r.a = e.get(), na = node;
+                else
+                    r.c = e.get(), nc = node;
+            }
+        }
+        r.v0 = valueBetween(g, na, nc, &r.flip);
+        r.v2 = valueBetween(g, nb, nc);
+        break;
+    }
+    case SolverId::None: break;
+    }
+    return r;
+}
+
+bool zeroFixed(SolverId id)
+{
+    return id == SolverId::ZeroFixedPointsTriangle || id == SolverId::ZeroFixedPPLTriangle
+        || id == SolverId::ZeroFixedLLPAngleTriangle;
+}
+
+Footprint footprintOf(const Roles& r)
+{
+    Footprint f;
+    if (r.id == SolverId::None) return f;
+    if (zeroFixed(r.id)) {
+        f.writes = { r.a, r.b, r.c };
+        f.nWrites = 3;
+    } else {
+        f.writes[0] = r.c;
+        f.nWrites = 1;
+        f.reads = { r.a, r.b, nullptr };
+        f.nReads = 2;
+    }
+    return f;
+}
+
+// canvas unit normal of a line: (-dir.y / len, dir.x / len), two separate divisions
+// (point_line_solvers.cpp:213-216, line_angle_solvers.cpp:300-305)
+void canvasNormal(const Line& l, double& nx, double& ny, double& len)
+{
+    const Vector2d dir = l.canvasP2 - l.canvasP1;
+    len = dir.norm();
+    nx = -dir.y() / len;
+    ny = dir.x() / len;
+}
+
+// Numeric half of pack(): reads solved positions, places anchors, fills the batch row.
+PackedLeaf packNumeric(const Roles& r)
+{
+    PackedLeaf p;
+    p.solver = r.id;
+    p.kind = kindOf(r.id);
+    p.target = r.c;
+    double* in = p.in;
+    switch (r.id) {
+    case SolverId::ZeroFixedPointsTriangle: {
+        // point_point_solvers.cpp:48-71
+        r.a->updateElementPosition(Vector2d { 0.0, 0.0 });
+        r.b->updateElementPosition(Vector2d { r.v0, 0.0 });
+        const auto& p1 = r.a->getElement<Point>();
+        const auto& p2 = r.b->getElement<Point>();
+        const auto& p3 = r.c->getElement<Point>();
+        in[0] = p1.position.x(), in[1] = p1.position.y(), in[2] = r.v1;
+        in[3] = p2.position.x(), in[4] = p2.position.y(), in[5] = r.v2;
+        const double ori = Solvers::triangleOrientation(p1.canvasPosition, p2.canvasPosition, p3.canvasPosition);
+        p.code = GCS_MAKE_CODE(sign3(ori), 0, 0);
+        break;
+    }
+    case SolverId::TwoFixedPointsDistance: {
+        // point_point_solvers.cpp:136-151
+        const auto& f1 = r.a->getElement<Point>();
+        const auto& f2 = r.b->getElement<Point>();
+        const auto& fr = r.c->getElement<Point>();
+        in[0] = f1.position.x(), in[1] = f1.position.y(), in[2] = r.v1;
+        in[3] = f2.position.x(), in[4] = f2.position.y(), in[5] = r.v2;
+        const double ori = Solvers::triangleOrientation(f1.canvasPosition, f2.canvasPosition, fr.canvasPosition);
+        p.code = GCS_MAKE_CODE(sign3(ori), 0, 0);
+        break;
+    }
+    case SolverId::ZeroFixedPPLTriangle:
+    case SolverId::TwoFixedPointsLine: {
+        // point_line_solvers.cpp:179-219 / :335-364
+        if (r.id == SolverId::ZeroFixedPPLTriangle) {
+            r.a->updateElementPosition(Vector2d { 0.0, 0.0 });
+            r.b->updateElementPosition(Vector2d { r.v0, 0.0 });
+        }
+        const auto& p1 = r.a->getElement<Point>();
+        const auto& p2 = r.b->getElement<Point>();
+        const auto& ln = r.c->getElement<Line>();
+        const double c1 = Solvers::signedDistanceToLine(p1.canvasPosition, ln.canvasP1, ln.canvasP2);
+        const double c2 = Solvers::signedDistanceToLine(p2.canvasPosition, ln.canvasP1, ln.canvasP2);
+        in[0] = p1.position.x(), in[1] = p1.position.y();
+        in[2] = p2.position.x(), in[3] = p2.position.y();
+        in[4] = signOf(c1) * r.v1;
+        in[5] = signOf(c2) * r.v2;
+        canvasNormal(ln, in[6], in[7], in[8]);
+        p.code = GCS_MAKE_CODE(sign3(c1), sign3(c2), 0);
+        break;
+    }
+    case SolverId::FixedPointAndLineFreePoint: {
+        // point_line_solvers.cpp:485-529
+        const auto& fp = r.a->getElement<Point>();
+        const auto& ln = r.b->getElement<Line>();
+        const auto& fr = r.c->getElement<Point>();
+        const double cs = Solvers::signedDistanceToLine(fr.canvasPosition, ln.canvasP1, ln.canvasP2);
+        in[0] = fp.position.x(), in[1] = fp.position.y(), in[2] = r.v1;
+        in[3] = ln.p1.x(), in[4] = ln.p1.y(), in[5] = ln.p2.x(), in[6] = ln.p2.y();
+        in[7] = signOf(cs) * r.v2;
+        in[8] = fr.canvasPosition.x(), in[9] = fr.canvasPosition.y();
+        const Vector2d canvasFoot = Solvers::perpendicularFoot(fp.canvasPosition, ln.canvasP1, ln.canvasP2);
+        const double ori = Solvers::triangleOrientation(fp.canvasPosition, canvasFoot, fr.canvasPosition);
+        const int flags = (std::abs(ori) < GCS_COLLINEAR_EPSILON) ? GCS_CODE_COLLINEAR : 0;  // heuristics.hpp:209-217
+        p.code = GCS_MAKE_CODE(sign3(ori), 0, flags);
+        break;
+    }
+    case SolverId::TwoFixedLinesFreePoint: {
+        // point_line_solvers.cpp:617-682
+        const auto& l1 = r.a->getElement<Line>();
+        const auto& l2 = r.b->getElement<Line>();
+        const auto& fr = r.c->getElement<Point>();
+        const double c1 = Solvers::signedDistanceToLine(fr.canvasPosition, l1.canvasP1, l1.canvasP2);
+        const double c2 = Solvers::signedDistanceToLine(fr.canvasPosition, l2.canvasP1, l2.canvasP2);
+        in[0] = l1.p1.x(), in[1] = l1.p1.y(), in[2] = l1.p2.x(), in[3] = l1.p2.y(), in[4] = signOf(c1) * r.v1;
+        in[5] = l2.p1.x(), in[6] = l2.p1.y(), in[7] = l2.p2.x(), in[8] = l2.p2.y(), in[9] = signOf(c2) * r.v2;
+        in[10] = fr.canvasPosition.x(), in[11] = fr.canvasPosition.y();
+        const auto ci = Solvers::lineLineIntersection(l1.canvasP1, l1.canvasP2, l2.canvasP1, l2.canvasP2);
+        if (!ci) {
+            p.code = GCS_MAKE_CODE(0, 0, GCS_CODE_CANVAS_PARALLEL);
+        } else {
+            const Vector2d canvasDir = (l1.canvasP2 - l1.canvasP1).normalized();
+            const Vector2d canvasRef = *ci + canvasDir;
+            const double ori = Solvers::triangleOrientation(*ci, canvasRef, fr.canvasPosition);
+            const int flags = (std::abs(ori) < GCS_COLLINEAR_EPSILON) ? GCS_CODE_COLLINEAR : 0;
+            p.code = GCS_MAKE_CODE(sign3(ori), 0, flags);
+        }
+        break;
+    }
+    case SolverId::ZeroFixedLLPAngleTriangle: {
+        // line_angle_solvers.cpp:245-361
+        auto& l1e = *r.a;
+        const Vector2d canvasDir1 = l1e.getElement<Line>().canvasP2 - l1e.getElement<Line>().canvasP1;
+        const double len1 = canvasDir1.norm();
+        const Vector2d a1 { -len1 / 2.0, 0.0 }, a2 { len1 / 2.0, 0.0 };
+        l1e.updateElementPosition(a1, a2);
+        const auto& l1 = l1e.getElement<Line>();
+        const auto& pt = r.b->getElement<Point>();
+        const auto& l2 = r.c->getElement<Line>();
+        const double cs1 = Solvers::signedDistanceToLine(pt.canvasPosition, l1.canvasP1, l1.canvasP2);
+        const double sd1 = signOf(cs1) * r.v1;
+        const Vector2d anchorPoint { 0.0, sd1 };
+        r.b->updateElementPosition(anchorPoint);
+        const Vector2d anchorDir = a2 - a1;
+        in[0] = anchorDir.x(), in[1] = anchorDir.y();
+        in[2] = std::cos(r.v0);
+        canvasNormal(l2, in[3], in[4], in[12]);
+        in[5] = canvasDir1.x(), in[6] = canvasDir1.y();
+        Vector2d canvasFree = l2.canvasP2 - l2.canvasP1;
+        if (r.flip) canvasFree = -canvasFree;
+        const double cross = (canvasDir1.x() * canvasFree.y()) - (canvasDir1.y() * canvasFree.x());  // heuristics.hpp:310-312
+        const double cs2 = Solvers::signedDistanceToLine(pt.canvasPosition, l2.canvasP1, l2.canvasP2);
+        in[7] = anchorPoint.x(), in[8] = anchorPoint.y();
+        in[9] = signOf(cs2) * r.v2;
+        in[10] = 0.0, in[11] = 0.0;  // second reference point: the origin (line_angle_solvers.cpp:353)
+        p.code = GCS_MAKE_CODE(sign3(cross), 0, 0);
+        break;
+    }
+    case SolverId::FixedLineAndPointFreeLine: {
+        // line_angle_solvers.cpp:474-557
+        const auto& fl = r.a->getElement<Line>();
+        const auto& pt = r.b->getElement<Point>();
+        const auto& fr = r.c->getElement<Line>();
+        const Vector2d fd = fl.p2 - fl.p1;
+        in[0] = fd.x(), in[1] = fd.y();
+        in[2] = std::cos(r.v0);
+        canvasNormal(fr, in[3], in[4], in[12]);
+        const Vector2d canvasFixed = fl.canvasP2 - fl.canvasP1;
+        in[5] = canvasFixed.x(), in[6] = canvasFixed.y();
+        Vector2d canvasFree = fr.canvasP2 - fr.canvasP1;
+        if (r.flip) canvasFree = -canvasFree;
+        const double cross = (canvasFixed.x() * canvasFree.y()) - (canvasFixed.y() * canvasFree.x());
+        const double cs = Solvers::signedDistanceToLine(pt.canvasPosition, fr.canvasP1, fr.canvasP2);
+        in[7] = pt.position.x(), in[8] = pt.position.y();
+        in[9] = signOf(cs) * r.v2;
+        const Vector2d mid = fl.midpoint();
+        in[10] = mid.x(), in[11] = mid.y();
+        p.code = GCS_MAKE_CODE(sign3(cross), 0, 0);
+        break;
+    }
+    case SolverId::None: break;
+    }
+    return p;
+}
+
+void solveBatchOnDevice(KindBatch& batch, int device)
+{
+    gcs_b200_batch d = batch.descriptor();
+    const int rc = gcs_b200_solve_host(&d, device);
+    if (rc != GCS_OK)
+        throw std::runtime_error(std::string("gcs_b200_solve_host failed (") + std::to_string(rc) + "): " + gcs_b200_last_error()
+            + " - the sub-problem solvers run on the CUDA path only");
+    batch.applyAll();
+}
+
+struct Plan {
+    BatchReport report;
+    std::vector<Roles> roles;          // per leaf (id None = unsupported)
+    std::size_t stop = 0;              // leaves [0, stop) are solved; == leaves.size() when no leaf throws
+    std::exception_ptr error;          // what the reference's loop would have thrown at leaf `stop`
+};
+
+Plan makePlan(const std::vector<ConstraintGraph>& leaves)
+{
+    Plan plan;
+    const std::size_t n = leaves.size();
+    plan.report.leaves = n;
+    plan.report.level.assign(n, -1);
+    plan.report.solver.assign(n, SolverId::None);
+    plan.report.results.assign(n, SolveResult::unsupported("No solver matches this component configuration"));
+    plan.roles.resize(n);
+    plan.stop = n;
+
+    std::unordered_set<const Element*> predicted;  // solved once the leaves so far have run
+    std::unordered_map<const Element*, int> lastWrite, lastRead;
+    const SetQuery q = [&](const Element* e) { return e->isElementSet() || predicted.count(e) != 0; };
+    auto levelOf = [](const std::unordered_map<const Element*, int>& m, const Element* e) {
+        const auto it = m.find(e);
+        return it == m.end() ? -1 : it->second;
+    };
+    int top = -1;
+    for (std::size_t i = 0; i < n; ++i) {
+        const SolverId id = classify(leaves[i], q);
+        plan.report.solver[i] = id;
+        if (id == SolverId::None) {
+            ++plan.report.unsupported;
+            continue;
+        }
+        try {
+            plan.roles[i] = assignRoles(id, leaves[i], q);
+        } catch (...) {
+            plan.error = std::current_exception();
+            plan.stop = i;
+            plan.report.solver[i] = SolverId::None;
+            break;
+        }
+        const Footprint f = footprintOf(plan.roles[i]);
+        int lvl = -1;
+        for (int k = 0; k < f.nReads; ++k) lvl = std::max(lvl, levelOf(lastWrite, f.reads[k]));
+        for (int k = 0; k < f.nWrites; ++k)
+            lvl = std::max({ lvl, levelOf(lastWrite, f.writes[k]), levelOf(lastRead, f.writes[k]) });
+        ++lvl;
+        plan.report.level[i] = lvl;
+        top = std::max(top, lvl);
+        for (int k = 0; k < f.nReads; ++k) lastRead[f.reads[k]] = std::max(levelOf(lastRead, f.reads[k]), lvl);
+        for (int k = 0; k < f.nWrites; ++k) {
+            lastWrite[f.writes[k]] = lvl;
+            predicted.insert(f.writes[k]);
+        }
+        plan.report.results[i] = SolveResult::success();
+        ++plan.report.solved;
+    }
+    for (std::size_t i = plan.stop; i < n; ++i) {
+        plan.report.level[i] = -1;
+        if (i > plan.stop) plan.report.solver[i] = SolverId::None;
+    }
+    plan.report.waves = static_cast<std::size_t>(top + 1);
+    return plan;
+}
+
+}  // namespace
+
+const char* solverName(SolverId id)
+{
+    switch (id) {
+    case SolverId::ZeroFixedPointsTriangle: return "ZeroFixedPointsTriangleSolver";
+    case SolverId::ZeroFixedPPLTriangle: return "ZeroFixedPPLTriangleSolver";
+    case SolverId::ZeroFixedLLPAngleTriangle: return "ZeroFixedLLPAngleTriangleSolver";
+    case SolverId::TwoFixedPointsDistance: return "TwoFixedPointsDistanceSolver";
+    case SolverId::TwoFixedPointsLine: return "TwoFixedPointsLineSolver";
+    case SolverId::FixedPointAndLineFreePoint: return "FixedPointAndLineFreePointSolver";
+    case SolverId::TwoFixedLinesFreePoint: return "TwoFixedLinesFreePointSolver";
+    case SolverId::FixedLineAndPointFreeLine: return "FixedLineAndPointFreeLineSolver";
+    case SolverId::None: break;
+    }
+    return "None";
+}
+
+int kindOf(SolverId id)
+{
+    switch (id) {
+    case SolverId::ZeroFixedPointsTriangle:
+    case SolverId::TwoFixedPointsDistance: return GCS_KIND_PP;
+    case SolverId::ZeroFixedPPLTriangle:
+    case SolverId::TwoFixedPointsLine: return GCS_KIND_SDD;
+    case SolverId::FixedPointAndLineFreePoint: return GCS_KIND_PPL;
+    case SolverId::TwoFixedLinesFreePoint: return GCS_KIND_PLL;
+    case SolverId::ZeroFixedLLPAngleTriangle:
+    case SolverId::FixedLineAndPointFreeLine: return GCS_KIND_ANG;
+    case SolverId::None: break;
+    }
+    return 0;
+}
+
+bool matches(SolverId id, const ConstraintGraph& g, const SetQuery& q)
+{
+    if (g.nodeCount() != 3) return false;
+    const Census c = census(g, q);
+    const ConstraintCensus k = constraintCensus(g);
+    const bool allDistance = k.distance == k.total;
+    switch (id) {
+    case SolverId::ZeroFixedPointsTriangle:
+        return g.edgeCount() == 3 && c.solved == 0 && c.points == 3 && allDistance;
+    case SolverId::ZeroFixedPPLTriangle:
+        return g.edgeCount() == 3 && c.solved == 0 && c.points == 2 && c.lines == 1 && allDistance;
+    case SolverId::ZeroFixedLLPAngleTriangle:
+        return g.edgeCount() == 3 && c.solved == 0 && c.points == 1 && c.lines == 2 && k.angle == 1 && k.distance == 2;
+    case SolverId::TwoFixedPointsDistance:
+        return c.solved >= 2 && c.points == 3 && allDistance;
+    case SolverId::TwoFixedPointsLine:
+        return c.solved >= 2 && c.points == 2 && c.lines == 1 && c.unsolvedPoints == 0 && c.solvedLines == 0 && allDistance;
+    case SolverId::FixedPointAndLineFreePoint:
+        return c.solved >= 2 && c.points == 2 && c.lines == 1 && c.solvedPoints == 1 && c.unsolvedPoints == 1
+            && c.solvedLines == 1 && allDistance;
+    case SolverId::TwoFixedLinesFreePoint:
+        return c.solved >= 2 && c.points == 1 && c.lines == 2 && c.solvedPoints == 0 && c.unsolvedLines == 0 && allDistance;
+    case SolverId::FixedLineAndPointFreeLine:
+        return c.solved >= 2 && c.points == 1 && c.lines == 2 && c.solvedLines == 1 && c.unsolvedLines == 1
+            && c.solvedPoints == 1 && k.angle == 1 && k.distance == 1;
+    case SolverId::None: break;
+    }
+    return false;
+}
+
+SolverId classify(const ConstraintGraph& g, const SetQuery& q)
+{
+    // component_solver.hpp:35-60: fully unsolved shapes first, then the partially solved ones
+    static constexpr SolverId order[] = { SolverId::ZeroFixedPointsTriangle, SolverId::ZeroFixedPPLTriangle,
+        SolverId::ZeroFixedLLPAngleTriangle, SolverId::TwoFixedPointsDistance, SolverId::TwoFixedPointsLine,
+        SolverId::FixedPointAndLineFreePoint, SolverId::TwoFixedLinesFreePoint, SolverId::FixedLineAndPointFreeLine };
+    for (SolverId id : order)
+        if (matches(id, g, q)) return id;
+    return SolverId::None;
+}
+
+Footprint footprint(SolverId id, const ConstraintGraph& g, const SetQuery& q) { return footprintOf(assignRoles(id, g, q)); }
+
+PackedLeaf pack(SolverId id, ConstraintGraph& g) { return packNumeric(assignRoles(id, g, {})); }
+
+void apply(const PackedLeaf& leaf, const double out[GCS_MAX_OUT_COLS])
+{
+    if (!leaf.target) return;
+    if (gcs_b200_kind_out_cols(leaf.kind) == 2)
+        leaf.target->updateElementPosition(Vector2d { out[0], out[1] });
+    else
+        leaf.target->updateElementPosition(Vector2d { out[0], out[1] }, Vector2d { out[2], out[3] });
+}
+
+KindBatch::KindBatch(int kind) : m_kind(kind) {}
+
+void KindBatch::clear()
+{
+    for (auto& c : m_in) c.clear();
+    for (auto& c : m_out) c.clear();
+    m_code.clear(), m_iters.clear(), m_conv.clear(), m_root.clear(), m_leaves.clear();
+}
+
+void KindBatch::push(const PackedLeaf& leaf)
+{
+    if (m_kind == 0) m_kind = leaf.kind;
+    if (leaf.kind != m_kind) throw std::invalid_argument("KindBatch::push: leaf of another kind");
+    const int nin = gcs_b200_kind_in_cols(m_kind);
+    for (int c = 0; c < nin; ++c) m_in[static_cast<std::size_t>(c)].push_back(leaf.in[c]);
+    m_code.push_back(leaf.code);
+    m_leaves.push_back(leaf);
+}
+
+gcs_b200_batch KindBatch::descriptor()
+{
+    gcs_b200_batch d {};
+    const std::size_t n = size();
+    d.kind = m_kind;
+    d.n_seeds = 2;  // Equations::solve2D runs exactly two guesses (newton_raphson.hpp:42-53)
+    d.n = static_cast<std::int64_t>(n);
+    d.mem = GCS_MEM_HOST;
+    d.variant = GCS_VARIANT_DEFAULT;
+    const int nin = gcs_b200_kind_in_cols(m_kind), nout = gcs_b200_kind_out_cols(m_kind);
+    for (int c = 0; c < nin; ++c) d.in[c] = m_in[static_cast<std::size_t>(c)].data();
+    d.code = m_code.data();
+    d.guesses = nullptr;
+    for (int c = 0; c < nout; ++c) {
+        m_out[static_cast<std::size_t>(c)].assign(n, 0.0);
+        d.out[c] = m_out[static_cast<std::size_t>(c)].data();
+    }
+    m_iters.assign(2 * n, 0), m_conv.assign(2 * n, 0), m_root.assign(n, 0);
+    d.cand = nullptr;
+    d.iters = m_iters.data();
+    d.converged = m_conv.data();
+    d.root_index = m_root.data();
+    return d;
+}
+
+void KindBatch::applyAll()
+{
+    const int nout = gcs_b200_kind_out_cols(m_kind);
+    for (std::size_t i = 0; i < m_leaves.size(); ++i) {
+        double o[GCS_MAX_OUT_COLS] = {};
+        for (int c = 0; c < nout; ++c) o[c] = m_out[static_cast<std::size_t>(c)][i];
+        apply(m_leaves[i], o);
+    }
+}
+
+SolveResult solveSingle(SolverId id, ConstraintGraph& component, int device)
+{
+    if (id == SolverId::None) return SolveResult::unsupported("No solver matches this component configuration");
+    KindBatch batch(kindOf(id));
+    batch.push(pack(id, component));
+    solveBatchOnDevice(batch, device);
+    return SolveResult::success();  // every reference solver returns success() (e.g. point_point_solvers.cpp:163)
+}
+
+BatchReport planLeaves(const std::vector<ConstraintGraph>& leaves) { return makePlan(leaves).report; }
+
+BatchReport solveLeaves(std::vector<ConstraintGraph>& leaves, int device)
+{
+    Plan plan = makePlan(leaves);
+    BatchReport& rep = plan.report;
+    // leaves of a wave, in input order
+    std::vector<std::vector<std::size_t>> byWave(rep.waves);
+    for (std::size_t i = 0; i < plan.stop; ++i)
+        if (rep.level[i] >= 0) byWave[static_cast<std::size_t>(rep.level[i])].push_back(i);
+    KindBatch batches[GCS_KIND_COUNT + 1];
+    for (const auto& wave : byWave) {
+        for (int k = 1; k <= GCS_KIND_COUNT; ++k) batches[k] = KindBatch(k);
+        for (std::size_t i : wave) {
+            const PackedLeaf row = packNumeric(plan.roles[i]);
+            batches[row.kind].push(row);
+        }
+        for (int k = 1; k <= GCS_KIND_COUNT; ++k) {
+            if (batches[k].size() == 0) continue;
+            solveBatchOnDevice(batches[k], device);
+            ++rep.launches;
+        }
+    }
+    if (plan.error) std::rethrow_exception(plan.error);
+    return rep;
+}
+
+}  // namespace Gcs::B200

@@ -1,0 +1,275 @@
+// capi_host.cpp — plain-C entry points over the C++ host mirror, for bindings and tests
+// (ctypes in tests/host_lib.py).  The element / edge records have the layout of the records in
+// oracle/ref_driver.cpp, so the same fixture drives the reference build and this library.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <exception>
+#include <memory>
+#include <vector>
+
+#include <gcs/b200/leaf_batch.hpp>
+#include <gcs/decomposition/top_down/stree_top_down_strategy.hpp>
+#include <gcs/model/constraints.hpp>
+#include <gcs/model/elements.hpp>
+#include <gcs/model/gcs_data_structures.hpp>
+#include <gcs/orchestration/geometric_constraint_system.hpp>
+
+#include "solving/component_solver.hpp"
+#include "solving/equations/newton_raphson.hpp"
+
+using Eigen::Vector2d;
+
+extern "C" {
+
+typedef struct gcs_host_element {
+    int32_t type;      // 0 = Point, 1 = Line
+    int32_t is_set;    // in: already solved (pos valid); out: Element::isElementSet() afterwards
+    double canvas[4];  // point: x,y ; line: x1,y1,x2,y2
+    double pos[4];     // solver-space position, same layout
+} gcs_host_element;
+
+typedef struct gcs_host_edge {
+    int32_t a, b;  // element indices
+    int32_t type;  // 0 = Distance, 1 = Angle, 2 = virtual edge (no constraint)
+    int32_t flip;  // AngleConstraint::flipOrientation
+    double value;  // distance, or angle in radians
+} gcs_host_edge;
+
+}  // extern "C"
+
+namespace {
+
+thread_local char g_msg[512] = "";
+
+std::shared_ptr<Gcs::Element> makeElement(const gcs_host_element& e)
+{
+    std::shared_ptr<Gcs::Element> el;
+    if (e.type == 0) {
+        el = std::make_shared<Gcs::Element>(Gcs::Point(Vector2d(e.canvas[0], e.canvas[1])));
+        if (e.is_set) el->updateElementPosition(Vector2d(e.pos[0], e.pos[1]));
+    } else {
+        el = std::make_shared<Gcs::Element>(Gcs::Line(Vector2d(e.canvas[0], e.canvas[1]), Vector2d(e.canvas[2], e.canvas[3])));
+        if (e.is_set) el->updateElementPosition(Vector2d(e.pos[0], e.pos[1]), Vector2d(e.pos[2], e.pos[3]));
+    }
+    return el;
+}
+
+void readBack(const Gcs::Element& el, gcs_host_element& e)
+{
+    e.is_set = el.isElementSet() ? 1 : 0;
+    if (e.type == 0) {
+        const auto& p = el.getElement<Gcs::Point>();
+        e.pos[0] = p.position.x(), e.pos[1] = p.position.y();
+    } else {
+        const auto& l = el.getElement<Gcs::Line>();
+        e.pos[0] = l.p1.x(), e.pos[1] = l.p1.y(), e.pos[2] = l.p2.x(), e.pos[3] = l.p2.y();
+    }
+}
+
+// one leaf graph over (a subset of) shared elements; `local[i]` = index into `elems` of node i
+Gcs::ConstraintGraph makeLeaf(const std::vector<std::shared_ptr<Gcs::Element>>& elems, const int32_t* local, int n_local,
+    const gcs_host_edge* edges, int n_edges)
+{
+    Gcs::ConstraintGraph g;
+    std::vector<Gcs::ConstraintGraph::NodeIdType> nodes;
+    std::vector<int> globalOf;
+    for (int i = 0; i < n_local; ++i) {
+        const auto node = g.getGraph().addNode();
+        g.addElement(node, elems[static_cast<std::size_t>(local[i])]);
+        nodes.push_back(node);
+        globalOf.push_back(local[i]);
+    }
+    auto nodeOf = [&](int global) {
+        for (std::size_t i = 0; i < globalOf.size(); ++i)
+            if (globalOf[i] == global) return nodes[i];
+        throw std::runtime_error("edge endpoint is not an element of the leaf");
+    };
+    for (int k = 0; k < n_edges; ++k) {
+        const auto& ed = edges[k];
+        if (ed.type == 2) {
+            g.addVirtualEdge(nodeOf(ed.a), nodeOf(ed.b));
+            continue;
+        }
+        const auto eid = g.getGraph().addEdge(nodeOf(ed.a), nodeOf(ed.b)).value();
+        if (ed.type == 0)
+            g.addConstraint(eid, std::make_shared<Gcs::Constraint>(Gcs::DistanceConstraint(ed.value)));
+        else
+            g.addConstraint(eid, std::make_shared<Gcs::Constraint>(Gcs::AngleConstraint(ed.value, ed.flip != 0)));
+    }
+    return g;
+}
+
+int fail(const std::exception& ex)
+{
+    std::snprintf(g_msg, sizeof(g_msg), "%s", ex.what());
+    return -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+GCS_API const char* gcs_host_last_error(void) { return g_msg; }
+
+// A 3-element leaf through classifyAndSolve (batch of one on the device).
+// Returns SolveStatus (0 Success, 1 Unsupported, 2 Failed) or -1 on an exception.
+GCS_API int gcs_host_component_solve(int n_el, gcs_host_element* el, int n_edges, const gcs_host_edge* edges)
+{
+    try {
+        std::vector<std::shared_ptr<Gcs::Element>> elems;
+        std::vector<int32_t> local;
+        for (int i = 0; i < n_el; ++i) elems.push_back(makeElement(el[i])), local.push_back(i);
+        Gcs::ConstraintGraph g = makeLeaf(elems, local.data(), n_el, edges, n_edges);
+        const Gcs::SolveResult r = Gcs::classifyAndSolve(g);
+        for (int i = 0; i < n_el; ++i) readBack(*elems[static_cast<std::size_t>(i)], el[i]);
+        return static_cast<int>(r.status);
+    } catch (const std::exception& ex) {
+        return fail(ex);
+    } catch (...) {
+        std::snprintf(g_msg, sizeof(g_msg), "unknown exception");
+        return -1;
+    }
+}
+
+// Packer only (no device): classify the leaf, assign roles, place anchors, and return the batch
+// row the kernel would receive plus the index of the element that receives the result.
+// Returns the SolverId (0 = unsupported) or -1 on an exception.
+GCS_API int gcs_host_component_pack(int n_el, gcs_host_element* el, int n_edges, const gcs_host_edge* edges, int32_t* kind,
+    double in[GCS_MAX_IN_COLS], uint8_t* code, int32_t* target)
+{
+    try {
+        std::vector<std::shared_ptr<Gcs::Element>> elems;
+        std::vector<int32_t> local;
+        for (int i = 0; i < n_el; ++i) elems.push_back(makeElement(el[i])), local.push_back(i);
+        Gcs::ConstraintGraph g = makeLeaf(elems, local.data(), n_el, edges, n_edges);
+        const Gcs::B200::SolverId id = Gcs::B200::classify(g);
+        *kind = 0, *target = -1;
+        if (id == Gcs::B200::SolverId::None) return 0;
+        const Gcs::B200::PackedLeaf row = Gcs::B200::pack(id, g);
+        *kind = row.kind;
+        *code = row.code;
+        for (int c = 0; c < GCS_MAX_IN_COLS; ++c) in[c] = row.in[c];
+        for (int i = 0; i < n_el; ++i) {
+            if (elems[static_cast<std::size_t>(i)].get() == row.target) *target = i;
+            readBack(*elems[static_cast<std::size_t>(i)], el[i]);
+        }
+        return static_cast<int>(id);
+    } catch (const std::exception& ex) {
+        return fail(ex);
+    } catch (...) {
+        std::snprintf(g_msg, sizeof(g_msg), "unknown exception");
+        return -1;
+    }
+}
+
+// Many leaves over shared elements (what DeficitStreeBasedTopDownStrategy::solveGcs receives).
+//   leaf_elems   [3 * n_leaves] element indices, node order of each leaf
+//   edge_offsets [n_leaves + 1] range of each leaf's edges in `edges` (a, b = element indices)
+//   mode 0: the reference's loop, one classifyAndSolve per leaf (a launch per leaf)
+//        1: DeficitStreeBasedTopDownStrategy::solveGcs (dependency waves, a launch per kind per wave)
+//        2: plan only (no device): solver + wave per leaf
+//   status/level/solver [n_leaves] (may be NULL); stats[0] = waves, stats[1] = launches, stats[2] = solved
+// Returns 0, or -1 after an exception (elements solved before it are still written back).
+GCS_API int gcs_host_leaves_solve(int n_el, gcs_host_element* el, int n_leaves, const int32_t* leaf_elems,
+    const int32_t* edge_offsets, const gcs_host_edge* edges, int mode, int32_t* status, int32_t* level, int32_t* solver,
+    int64_t* stats)
+{
+    std::vector<std::shared_ptr<Gcs::Element>> elems;
+    int rc = 0;
+    try {
+        for (int i = 0; i < n_el; ++i) elems.push_back(makeElement(el[i]));
+        std::vector<Gcs::ConstraintGraph> leaves;
+        for (int l = 0; l < n_leaves; ++l)
+            leaves.push_back(makeLeaf(elems, leaf_elems + 3 * l, 3, edges + edge_offsets[l], edge_offsets[l + 1] - edge_offsets[l]));
+        if (stats) stats[0] = stats[1] = stats[2] = 0;
+        if (mode == 0) {
+            for (int l = 0; l < n_leaves; ++l) {
+                const Gcs::B200::SolverId id = Gcs::B200::classify(leaves[static_cast<std::size_t>(l)]);
+                if (solver) solver[l] = static_cast<int32_t>(id);
+                const Gcs::SolveResult r = Gcs::classifyAndSolve(leaves[static_cast<std::size_t>(l)]);
+                if (status) status[l] = static_cast<int32_t>(r.status);
+                if (level) level[l] = l;
+                if (stats && r.status == Gcs::SolveStatus::Success) ++stats[1], ++stats[2];
+            }
+        } else {
+            Gcs::B200::BatchReport rep;
+            if (mode == 1) {
+                Gcs::DeficitStreeBasedTopDownStrategy strategy;
+                try {
+                    strategy.solveGcs(leaves);
+                    rep = strategy.lastReport();
+                } catch (const std::exception& ex) {
+                    rc = fail(ex);
+                    rep = Gcs::B200::planLeaves(leaves);  // not reached by the solved prefix; reporting only
+                }
+            } else {
+                rep = Gcs::B200::planLeaves(leaves);
+            }
+            for (int l = 0; l < n_leaves; ++l) {
+                const auto i = static_cast<std::size_t>(l);
+                if (status) status[l] = static_cast<int32_t>(rep.results[i].status);
+                if (level) level[l] = rep.level[i];
+                if (solver) solver[l] = static_cast<int32_t>(rep.solver[i]);
+            }
+            if (stats) stats[0] = static_cast<int64_t>(rep.waves), stats[1] = static_cast<int64_t>(rep.launches), stats[2] = static_cast<int64_t>(rep.solved);
+        }
+    } catch (const std::exception& ex) {
+        rc = fail(ex);
+    } catch (...) {
+        std::snprintf(g_msg, sizeof(g_msg), "unknown exception");
+        rc = -1;
+    }
+    for (std::size_t i = 0; i < elems.size(); ++i) readBack(*elems[i], el[i]);
+    return rc;
+}
+
+// Equations::solve2D through the mirror.  pair: 1 P2P+P2P (6 params: x0,y0,d, x0,y0,d);
+// 2 SDD+unit (dx,dy,s1,s2); 3 P2P+P2L (x0,y0,d, xa,ya,xb,yb,d,L); 4 P2L+P2L (2 x (xa,ya,xb,yb,d,L));
+// 5 angle+unit (fdx,fdy,L,cosA).  guesses: 4 doubles (g0x,g0y,g1x,g1y) or NULL for the defaults.
+GCS_API int gcs_host_solve2d(int pair, const double* p, const double* guesses, double* cand4, int32_t* iters2, int32_t* conv2)
+{
+    namespace Eq = Gcs::Equations;
+    try {
+        std::array<Vector2d, 2> gs = Eq::DEFAULT_SPATIAL_GUESSES;
+        if (guesses) gs = { Vector2d(guesses[0], guesses[1]), Vector2d(guesses[2], guesses[3]) };
+        Eq::Solve2DInfo info;
+        std::array<Vector2d, 2> r;
+        switch (pair) {
+        case 1: r = Eq::solve2D(Eq::pointToPointDistance(p[0], p[1], p[2]), Eq::pointToPointDistance(p[3], p[4], p[5]), gs, &info); break;
+        case 2: r = Eq::solve2D(Eq::lineNormalSignedDistanceDiff(p[0], p[1], p[2], p[3]), Eq::unitNormalConstraint(), gs, &info); break;
+        case 3: r = Eq::solve2D(Eq::pointToPointDistance(p[0], p[1], p[2]), Eq::pointToLineDistance(p[3], p[4], p[5], p[6], p[7], p[8]), gs, &info); break;
+        case 4: r = Eq::solve2D(Eq::pointToLineDistance(p[0], p[1], p[2], p[3], p[4], p[5]), Eq::pointToLineDistance(p[6], p[7], p[8], p[9], p[10], p[11]), gs, &info); break;
+        case 5: r = Eq::solve2D(Eq::lineNormalAngleConstraint(p[0], p[1], p[2], p[3]), Eq::unitNormalConstraint(), gs, &info); break;
+        default: std::snprintf(g_msg, sizeof(g_msg), "unknown equation pair %d", pair); return -1;
+        }
+        cand4[0] = r[0].x(), cand4[1] = r[0].y(), cand4[2] = r[1].x(), cand4[3] = r[1].y();
+        for (int s = 0; s < 2; ++s) {
+            if (iters2) iters2[s] = info.iterations[s];
+            if (conv2) conv2[s] = info.converged[s] ? 1 : 0;
+        }
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(ex);
+    }
+}
+
+// GeometricConstraintSystem with the top-down strategy on a single 3-element sketch
+// (BASELINE config 1: the whole pipeline check -> decompose -> solveGcs).
+GCS_API int gcs_host_system_solve(int n_el, gcs_host_element* el, int n_edges, const gcs_host_edge* edges)
+{
+    try {
+        std::vector<std::shared_ptr<Gcs::Element>> elems;
+        std::vector<int32_t> local;
+        for (int i = 0; i < n_el; ++i) elems.push_back(makeElement(el[i])), local.push_back(i);
+        Gcs::ConstraintGraph g = makeLeaf(elems, local.data(), n_el, edges, n_edges);
+        Gcs::GeometricConstraintSystem sys(std::make_unique<Gcs::DeficitStreeBasedTopDownStrategy>());
+        sys.solveGeometricConstraintSystem(g);
+        for (int i = 0; i < n_el; ++i) readBack(*elems[static_cast<std::size_t>(i)], el[i]);
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(ex);
+    }
+}
+
+}  // extern "C"

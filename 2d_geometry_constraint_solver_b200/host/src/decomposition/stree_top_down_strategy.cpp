@@ -1,0 +1,35 @@
+// DeficitStreeBasedTopDownStrategy (reference:
+// src/constraint_solver/src/decomposition/top_down/stree_top_down_strategy.cpp:12-45).
+#include <stdexcept>
+
+#include <gcs/decomposition/top_down/stree_top_down_strategy.hpp>
+
+namespace Gcs {
+
+Constrainedness DeficitStreeBasedTopDownStrategy::checkConstraintGraphConstrainedness(const ConstraintGraph& gcs)
+{
+    // The reference computes the deficit in std::size_t (stree_top_down_strategy.cpp:16): it can
+    // never be negative, an over-constrained graph wraps around and reports UNDER_CONSTRAINED.
+    const std::size_t deficit = (2 * gcs.nodeCount() - 3) - gcs.edgeCount();
+    if (deficit == 0) return Constrainedness::WELL_CONSTRAINED;
+    return Constrainedness::UNDER_CONSTRAINED;
+}
+
+bool DeficitStreeBasedTopDownStrategy::resolve(ConstraintGraph& /*gcs*/) { return false; }
+
+std::vector<ConstraintGraph> DeficitStreeBasedTopDownStrategy::decomposeConstraintGraph(ConstraintGraph& gcs)
+{
+    // A triconnected 3-element graph is its own single leaf (stree_top_down_strategy.cpp:54-57).
+    if (gcs.nodeCount() == 3) return { gcs };
+    throw std::runtime_error("DeficitStreeBasedTopDownStrategy::decomposeConstraintGraph: the S-tree decomposition "
+                             "(OGDF separation pairs) is host graph work outside the accelerated path; pass the leaf "
+                             "components to solveGcs directly");
+}
+
+void DeficitStreeBasedTopDownStrategy::solveGcs(std::vector<ConstraintGraph>& splitComponents)
+{
+    // reference: std::ranges::for_each(splitComponents, classifyAndSolve), results discarded
+    m_report = B200::solveLeaves(splitComponents, m_device);
+}
+
+}  // namespace Gcs

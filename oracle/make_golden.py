@@ -213,7 +213,25 @@ def components():
     print("components:", sorted(by.items()))
 
 
+def sketches():
+    """Multi-leaf sketches (shared elements, dependency chains) through the reference's
+    sequential leaf loop: pins the batched scheduler's final element state."""
+    import sketch_gen as S
+    items = []
+    for seed, n, first, loc in ((11, 300, 1, None), (12, 300, 2, None), (13, 300, 3, None), (14, 120, 1, 6)):
+        el, lv = S.make_sketch(n, seed=seed, first_shape=first, locality=loc)
+        rc, status, out = R.leaves_solve(el, lv)
+        items.append({"seed": seed, "first_shape": first, "locality": loc, "elements": el, "leaves": lv, "rc": rc,
+                      "status": status, "expected": out})
+        print("sketch", seed, "leaves", n, "rc", rc, "statuses", sorted(set(status)),
+              "set", sum(e["is_set"] for e in out), "of", len(out))
+    with open(os.path.join(GOLD, "sketch_leaves.json"), "w") as f:
+        json.dump({"generator": "oracle/make_golden.py", "items": items}, f)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    numeric()
-    components()
+    if "--sketches-only" not in sys.argv:
+        numeric()
+        components()
+    sketches()

@@ -338,4 +338,70 @@ __attribute__((visibility("default"))) int gcs_ref_component_solve(
     }
 }
 
+// ---- leaf list level: the reference's sequential loop over leaves that share elements -------
+// (DeficitStreeBasedTopDownStrategy::solveGcs = for_each(leaves, classifyAndSolve),
+// stree_top_down_strategy.cpp:41-45).  leaf_elems: 3 element indices per leaf (node order);
+// edge_offsets: n_leaves + 1 offsets into edges (a, b = element indices).  status[l] = SolveStatus
+// of leaf l, or -1 from the leaf that threw on (the loop stops there, as an exception would).
+__attribute__((visibility("default"))) int gcs_ref_leaves_solve(int n_el, gcs_ref_element* el, int n_leaves,
+    const int32_t* leaf_elems, const int32_t* edge_offsets, const gcs_ref_edge* edges, int32_t* status)
+{
+    std::vector<std::shared_ptr<Gcs::Element>> elems;
+    for (int i = 0; i < n_el; ++i) {
+        std::shared_ptr<Gcs::Element> e;
+        if (el[i].type == 0) {
+            e = std::make_shared<Gcs::Element>(Gcs::Point(Vector2d(el[i].canvas[0], el[i].canvas[1])));
+            if (el[i].is_set) e->updateElementPosition(Vector2d(el[i].pos[0], el[i].pos[1]));
+        } else {
+            e = std::make_shared<Gcs::Element>(Gcs::Line(Vector2d(el[i].canvas[0], el[i].canvas[1]), Vector2d(el[i].canvas[2], el[i].canvas[3])));
+            if (el[i].is_set) e->updateElementPosition(Vector2d(el[i].pos[0], el[i].pos[1]), Vector2d(el[i].pos[2], el[i].pos[3]));
+        }
+        elems.push_back(e);
+    }
+    int rc = 0;
+    for (int l = 0; l < n_leaves; ++l) status[l] = -2;  // not reached
+    for (int l = 0; l < n_leaves && rc == 0; ++l) {
+        try {
+            Gcs::ConstraintGraph g;
+            Gcs::ConstraintGraph::NodeIdType nodes[3];
+            for (int i = 0; i < 3; ++i) {
+                nodes[i] = g.getGraph().addNode();
+                g.addElement(nodes[i], elems[leaf_elems[3 * l + i]]);
+            }
+            auto nodeOf = [&](int global) {
+                for (int i = 0; i < 3; ++i)
+                    if (leaf_elems[3 * l + i] == global) return nodes[i];
+                throw std::runtime_error("edge endpoint outside the leaf");
+            };
+            for (int k = edge_offsets[l]; k < edge_offsets[l + 1]; ++k) {
+                const auto& ed = edges[k];
+                if (ed.type == 2) {
+                    g.addVirtualEdge(nodeOf(ed.a), nodeOf(ed.b));
+                    continue;
+                }
+                auto eid = g.getGraph().addEdge(nodeOf(ed.a), nodeOf(ed.b)).value();
+                if (ed.type == 0)
+                    g.addConstraint(eid, std::make_shared<Gcs::Constraint>(Gcs::DistanceConstraint(ed.value)));
+                else
+                    g.addConstraint(eid, std::make_shared<Gcs::Constraint>(Gcs::AngleConstraint(ed.value, ed.flip != 0)));
+            }
+            status[l] = (int32_t)Gcs::classifyAndSolve(g).status;
+        } catch (...) {
+            status[l] = -1;
+            rc = -1;
+        }
+    }
+    for (int i = 0; i < n_el; ++i) {
+        el[i].is_set = elems[i]->isElementSet() ? 1 : 0;
+        if (el[i].type == 0) {
+            const auto& p = elems[i]->getElement<Gcs::Point>();
+            el[i].pos[0] = p.position.x(), el[i].pos[1] = p.position.y();
+        } else {
+            const auto& ln = elems[i]->getElement<Gcs::Line>();
+            el[i].pos[0] = ln.p1.x(), el[i].pos[1] = ln.p1.y(), el[i].pos[2] = ln.p2.x(), el[i].pos[3] = ln.p2.y();
+        }
+    }
+    return rc;
+}
+
 }  // extern "C"

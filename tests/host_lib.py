@@ -1,0 +1,125 @@
+"""ctypes binding of the C entry points of the host mirror
+(2d_geometry_constraint_solver_b200/host/libgcs_host.so, src/capi_host.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_DIR = os.path.join(ROOT, "2d_geometry_constraint_solver_b200", "host")
+HOST_SO = os.path.join(HOST_DIR, "libgcs_host.so")
+
+_lib = None
+
+
+class Element(C.Structure):
+    _fields_ = [("type", C.c_int32), ("is_set", C.c_int32), ("canvas", C.c_double * 4), ("pos", C.c_double * 4)]
+
+
+class Edge(C.Structure):
+    _fields_ = [("a", C.c_int32), ("b", C.c_int32), ("type", C.c_int32), ("flip", C.c_int32), ("value", C.c_double)]
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(HOST_SO):
+            subprocess.check_call(["make", "-C", HOST_DIR, "-s"])
+        lib = C.CDLL(HOST_SO)
+        lib.gcs_host_last_error.restype = C.c_char_p
+        lib.gcs_host_component_solve.argtypes = [C.c_int, C.POINTER(Element), C.c_int, C.POINTER(Edge)]
+        lib.gcs_host_system_solve.argtypes = [C.c_int, C.POINTER(Element), C.c_int, C.POINTER(Edge)]
+        lib.gcs_host_component_pack.argtypes = [C.c_int, C.POINTER(Element), C.c_int, C.POINTER(Edge), C.POINTER(C.c_int32),
+                                                C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)]
+        lib.gcs_host_leaves_solve.argtypes = [C.c_int, C.POINTER(Element), C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                              C.POINTER(Edge), C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                              C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+        lib.gcs_host_solve2d.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().gcs_host_last_error().decode()
+
+
+def to_c(elements, edges, el_type=Element, ed_type=Edge):
+    els = (el_type * max(len(elements), 1))()
+    for i, e in enumerate(elements):
+        els[i].type = e["type"]
+        els[i].is_set = 1 if e.get("is_set") else 0
+        for j, v in enumerate(e["canvas"]):
+            els[i].canvas[j] = v
+        for j, v in enumerate(e.get("pos", [])):
+            els[i].pos[j] = v
+    eds = (ed_type * max(len(edges), 1))()
+    for i, e in enumerate(edges):
+        eds[i].a, eds[i].b, eds[i].type = e["a"], e["b"], e["type"]
+        eds[i].flip = 1 if e.get("flip") else 0
+        eds[i].value = e.get("value", 0.0)
+    return els, eds
+
+
+def from_c(elements, els):
+    out = []
+    for i, e in enumerate(elements):
+        k = 2 if e["type"] == 0 else 4
+        out.append({"type": e["type"], "is_set": bool(els[i].is_set), "pos": [els[i].pos[j] for j in range(k)]})
+    return out
+
+
+def component_solve(elements, edges):
+    """classifyAndSolve on one leaf (CUDA path).  Returns (status, elements)."""
+    els, eds = to_c(elements, edges)
+    status = load().gcs_host_component_solve(len(elements), els, len(edges), eds)
+    return status, from_c(elements, els)
+
+
+def system_solve(elements, edges):
+    els, eds = to_c(elements, edges)
+    rc = load().gcs_host_system_solve(len(elements), els, len(edges), eds)
+    return rc, from_c(elements, els)
+
+
+def component_pack(elements, edges):
+    """Packer only.  Returns (solver_id, kind, in[13], code, target_index, elements-with-anchors)."""
+    els, eds = to_c(elements, edges)
+    kind, target, code = C.c_int32(), C.c_int32(), C.c_uint8()
+    row = (C.c_double * 13)()
+    sid = load().gcs_host_component_pack(len(elements), els, len(edges), eds, C.byref(kind), row, C.byref(code), C.byref(target))
+    return sid, kind.value, np.array(list(row)), code.value, target.value, from_c(elements, els)
+
+
+def leaves_solve(elements, leaves, mode):
+    """leaves: list of {"elems": [i, j, k], "edges": [edge dicts with element indices]}.
+    mode 0 sequential classifyAndSolve, 1 batched solveGcs, 2 plan only.
+    Returns dict(rc, status, level, solver, waves, launches, solved, elements)."""
+    els, _ = to_c(elements, [])
+    flat = []
+    offs = [0]
+    for lf in leaves:
+        flat += lf["edges"]
+        offs.append(len(flat))
+    _, eds = to_c([], flat)
+    n = len(leaves)
+    le = (C.c_int32 * max(3 * n, 1))(*[i for lf in leaves for i in lf["elems"]])
+    eo = (C.c_int32 * (n + 1))(*offs)
+    status = (C.c_int32 * max(n, 1))()
+    level = (C.c_int32 * max(n, 1))()
+    solver = (C.c_int32 * max(n, 1))()
+    stats = (C.c_int64 * 3)()
+    rc = load().gcs_host_leaves_solve(len(elements), els, n, le, eo, eds, mode, status, level, solver, stats)
+    return {"rc": rc, "status": list(status)[:n], "level": list(level)[:n], "solver": list(solver)[:n],
+            "waves": stats[0], "launches": stats[1], "solved": stats[2], "elements": from_c(elements, els)}
+
+
+def solve2d(pair, params, guesses=None):
+    p = (C.c_double * len(params))(*params)
+    g = None if guesses is None else (C.c_double * 4)(*guesses)
+    cand = (C.c_double * 4)()
+    it = (C.c_int32 * 2)()
+    cv = (C.c_int32 * 2)()
+    rc = load().gcs_host_solve2d(pair, p, g, cand, it, cv)
+    return rc, np.array(list(cand)).reshape(2, 2), list(it), list(cv)

@@ -34,6 +34,9 @@ def load():
         lib = C.CDLL(REF_SO)
         lib.gcs_ref_solve_batch.argtypes = [C.POINTER(capi.CBatch), C.c_int, C.c_int]
         lib.gcs_ref_component_solve.argtypes = [C.c_int, C.POINTER(RefElement), C.c_int, C.POINTER(RefEdge)]
+        if hasattr(lib, "gcs_ref_leaves_solve"):
+            lib.gcs_ref_leaves_solve.argtypes = [C.c_int, C.POINTER(RefElement), C.c_int, C.POINTER(C.c_int32),
+                                                 C.POINTER(C.c_int32), C.POINTER(RefEdge), C.POINTER(C.c_int32)]
         _lib = lib
     return _lib
 
@@ -71,3 +74,21 @@ def component_solve(elements, edges):
         k = 2 if e["type"] == 0 else 4
         out.append({"type": e["type"], "is_set": bool(els[i].is_set), "pos": [els[i].pos[j] for j in range(k)]})
     return status, out
+
+
+def leaves_solve(elements, leaves):
+    """The reference's sequential for_each(leaves, classifyAndSolve) over shared elements.
+    Returns (rc, per-leaf status, elements-with-positions)."""
+    import host_lib as H
+    els, _ = H.to_c(elements, [], RefElement, RefEdge)
+    flat, offs = [], [0]
+    for lf in leaves:
+        flat += lf["edges"]
+        offs.append(len(flat))
+    _, eds = H.to_c([], flat, RefElement, RefEdge)
+    n = len(leaves)
+    le = (C.c_int32 * max(3 * n, 1))(*[i for lf in leaves for i in lf["elems"]])
+    eo = (C.c_int32 * (n + 1))(*offs)
+    status = (C.c_int32 * max(n, 1))()
+    rc = load().gcs_ref_leaves_solve(len(elements), els, n, le, eo, eds, status)
+    return rc, list(status)[:n], H.from_c(elements, els)

@@ -1,0 +1,153 @@
+"""Host mirror on the GPU: the reference-shaped entry points (classifyAndSolve, the solver
+structs, Equations::solve2D, DeficitStreeBasedTopDownStrategy::solveGcs,
+GeometricConstraintSystem) run through the CUDA path and must leave the element state the
+reference's own code leaves (golden fixtures made from the reference sources)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import host_lib as H
+import oracle_lib as O
+import sketch_gen as S
+from test_host_packer import GOLD, same_pos
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def host(gpu, built):
+    built.build_host()
+    return H.load()
+
+
+def test_classify_and_solve_matches_reference_components(host):
+    items = json.load(open(os.path.join(GOLD, "components.json")))["items"]
+    for it in items:
+        status, els = H.component_solve(it["elements"], it["edges"])
+        assert status == it["status"], (it["shape"], status, H.last_error())
+        if status != 0:
+            continue
+        for got, exp in zip(els, it["expected"]):
+            assert got["is_set"] == exp["is_set"]
+            if exp["is_set"]:
+                assert same_pos(got["pos"], exp["pos"]), (it["shape"], got, exp)
+
+
+def test_baseline_config_1_single_triangle_through_the_whole_pipeline(host):
+    """BASELINE configs[0]: points (100,100), (200,100), (150,200), distances 3-4-5, through
+    GeometricConstraintSystem -> DeficitStreeBasedTopDownStrategy -> solveGcs."""
+    el = [{"type": 0, "canvas": [100.0, 100.0]}, {"type": 0, "canvas": [200.0, 100.0]}, {"type": 0, "canvas": [150.0, 200.0]}]
+    ed = [{"a": 0, "b": 1, "type": 0, "value": 3.0}, {"a": 0, "b": 2, "type": 0, "value": 4.0}, {"a": 1, "b": 2, "type": 0, "value": 5.0}]
+    rc, out = H.system_solve(el, ed)
+    assert rc == 0, H.last_error()
+    assert out[0]["pos"] == [0.0, 0.0] and out[1]["pos"] == [3.0, 0.0]
+    assert out[2]["pos"][1] == 4.0 and abs(out[2]["pos"][0]) < 1e-12
+    # under-constrained (an edge missing): the driver throws like the reference
+    rc, _ = H.system_solve(el, ed[:2])
+    assert rc == -1 and "not well-constrained" in H.last_error()
+
+
+@pytest.mark.parametrize("pair,kind", [(1, 1), (2, 2), (3, 3), (4, 4), (5, 5)])
+def test_solve2d_mirror_equals_the_oracle(host, gcs, pair, kind):
+    rng = np.random.default_rng(pair)
+    for _ in range(40):
+        if pair == 1:
+            params = [*rng.uniform(-50, 50, 2), rng.uniform(60, 90), *rng.uniform(-50, 50, 2), rng.uniform(60, 90)]
+            consts, guesses = params, None
+        elif pair == 2:
+            th = rng.uniform(0, 6.28)
+            params = [*rng.uniform(-80, 80, 2), *rng.uniform(-30, 30, 2)]
+            guesses = [np.cos(th), np.sin(th), -np.cos(th), -np.sin(th)]
+            consts = [0.0, 0.0, params[0], params[1], params[2], params[3]]
+        elif pair == 3:
+            xa, ya, xb, yb = rng.uniform(-100, 100, 4)
+            ln = float(np.sqrt((xb - xa) * (xb - xa) + (yb - ya) * (yb - ya)))
+            params = [*rng.uniform(-50, 50, 2), rng.uniform(150, 250), xa, ya, xb, yb, rng.uniform(-20, 20), ln]
+            consts, guesses = params[:8], None
+        elif pair == 4:
+            l = rng.uniform(-100, 100, 8)
+            l1 = float(np.sqrt((l[2] - l[0]) ** 2 + (l[3] - l[1]) ** 2))
+            l2 = float(np.sqrt((l[6] - l[4]) ** 2 + (l[7] - l[5]) ** 2))
+            s1, s2 = rng.uniform(-30, 30, 2)
+            params = [*l[:4], s1, l1, *l[4:], s2, l2]
+            consts, guesses = [*l[:4], s1, *l[4:], s2], None
+        else:
+            fd = rng.uniform(-100, 100, 2)
+            th = rng.uniform(0, 6.28)
+            ln = float(np.sqrt(fd[0] * fd[0] + fd[1] * fd[1]))
+            params = [fd[0], fd[1], ln, np.cos(rng.uniform(0.2, 2.9))]
+            guesses = [np.cos(th), np.sin(th), -np.cos(th), -np.sin(th)]
+            consts = [fd[0], fd[1], params[3]]
+        rc, cand, it, cv = H.solve2d(pair, params, guesses)
+        assert rc == 0, H.last_error()
+        g = guesses if guesses is not None else [20000.0, 20000.0, -20000.0, -20000.0]
+        for s in range(2):
+            x, y, oit, ocv = O.newton2d(kind, consts, g[2 * s], g[2 * s + 1])
+            assert (it[s], cv[s]) == (oit, ocv)
+            assert same_pos([cand[s, 0], cand[s, 1]], [x, y])
+    # a length that is not the direction's length is refused, not silently recomputed
+    if pair == 3:
+        params[8] *= 1.5
+        rc, *_ = H.solve2d(pair, params, None)
+        assert rc == -1 and "length" in H.last_error()
+
+
+def test_solve_gcs_batched_equals_the_reference_loop_on_golden_sketches(host):
+    data = json.load(open(os.path.join(GOLD, "sketch_leaves.json")))["items"]
+    for sk in data:
+        for mode in (0, 1):
+            r = H.leaves_solve(sk["elements"], sk["leaves"], mode)
+            assert r["rc"] == 0, H.last_error()
+            assert r["status"] == sk["status"]
+            for got, exp in zip(r["elements"], sk["expected"]):
+                assert got["is_set"] == exp["is_set"] and same_pos(got["pos"], exp["pos"])
+            if mode == 1:
+                assert r["launches"] <= 5 * r["waves"] and r["waves"] < len(sk["leaves"])
+
+
+def test_solve_gcs_batched_equals_sequential_at_scale(host):
+    """20k leaves: one launch per kind per wave (a few hundred launches) against one launch per
+    leaf; the final element state must be bit-identical."""
+    el, lv = S.make_sketch(20000, seed=5, first_shape=2)
+    a = H.leaves_solve(el, lv, 1)
+    assert a["rc"] == 0 and a["solved"] == len(lv)
+    sub_el, sub_lv = S.make_sketch(1500, seed=6, first_shape=3, locality=40)
+    b0 = H.leaves_solve(sub_el, sub_lv, 0)
+    b1 = H.leaves_solve(sub_el, sub_lv, 1)
+    assert b0["rc"] == 0 and b1["rc"] == 0
+    for x, y in zip(b0["elements"], b1["elements"]):
+        assert x["is_set"] and y["is_set"] and same_pos(x["pos"], y["pos"])
+    assert a["launches"] < 0.05 * len(lv)
+    # every constraint of the big sketch holds in the solved layout (distances only checked)
+    pos = a["elements"]
+    worst = 0.0
+    for lf in lv:
+        for e in lf["edges"]:
+            if e["type"] != 0:
+                continue
+            pa, pb = pos[e["a"]], pos[e["b"]]
+            if pa["type"] == 0 and pb["type"] == 0:
+                d = np.hypot(pa["pos"][0] - pb["pos"][0], pa["pos"][1] - pb["pos"][1])
+            else:
+                pt, ln = (pa, pb) if pa["type"] == 0 else (pb, pa)
+                ex, ey = ln["pos"][2] - ln["pos"][0], ln["pos"][3] - ln["pos"][1]
+                d = abs(ex * (pt["pos"][1] - ln["pos"][1]) - ey * (pt["pos"][0] - ln["pos"][0])) / np.hypot(ex, ey)
+            worst = max(worst, abs(d - e["value"]) / max(1.0, e["value"]))
+    assert worst < 1e-6
+
+
+def test_an_exception_mid_list_stops_the_loop_like_the_reference(host):
+    el, lv = S.make_sketch(60, seed=9, p_line=0.0)
+    bad = {"elems": lv[30]["elems"], "edges": [dict(e) for e in lv[30]["edges"] if e["type"] != 2]}
+    # remove one of the two real constraints of leaf 30: getConstraintBetweenNodes throws there
+    real = [e for e in bad["edges"] if e["type"] == 0 and max(e["a"], e["b"]) == max(bad["elems"])]
+    bad["edges"].remove(real[0])
+    lv2 = lv[:30] + [bad] + lv[31:]
+    seq = H.leaves_solve(el, lv2, 0)
+    bat = H.leaves_solve(el, lv2, 1)
+    assert seq["rc"] == -1 and bat["rc"] == -1
+    for x, y in zip(seq["elements"], bat["elements"]):
+        assert x["is_set"] == y["is_set"] and (not x["is_set"] or same_pos(x["pos"], y["pos"]))
+    assert sum(e["is_set"] for e in bat["elements"]) == 32  # leaves 0..29 only
