@@ -75,7 +75,7 @@ _lib = None
 EXPORTS = [
     "gcs_b200_kind_in_cols", "gcs_b200_kind_out_cols", "gcs_b200_device_count", "gcs_b200_init",
     "gcs_b200_shutdown", "gcs_b200_last_error", "gcs_b200_version", "gcs_b200_solve",
-    "gcs_b200_solve_host", "gcs_b200_solve_sharded", "gcs_b200_launch_count",
+    "gcs_b200_solve_host", "gcs_b200_solve_host_async", "gcs_b200_wait", "gcs_b200_solve_sharded", "gcs_b200_launch_count", "gcs_b200_kernel_name",
     "gcs_b200_fp64_probe", "gcs_b200_synth_pp", "gcs_b200_selftest",
 ]
 
@@ -98,7 +98,11 @@ def load():
     lib.gcs_b200_solve.argtypes = [C.POINTER(CBatch), C.c_int, C.c_void_p]
     lib.gcs_b200_solve_host.argtypes = [C.POINTER(CBatch), C.c_int]
     lib.gcs_b200_solve_sharded.argtypes = [C.POINTER(CBatch), C.c_int]
+    lib.gcs_b200_solve_host_async.argtypes = [C.POINTER(CBatch), C.c_int]
+    lib.gcs_b200_wait.argtypes = [C.c_int]
     lib.gcs_b200_launch_count.restype = C.c_int64
+    lib.gcs_b200_kernel_name.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.gcs_b200_kernel_name.restype = C.c_char_p
     lib.gcs_b200_fp64_probe.argtypes = [C.c_int, C.c_int]
     lib.gcs_b200_fp64_probe.restype = C.c_double
     lib.gcs_b200_selftest.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.POINTER(C.c_uint64)]
@@ -192,6 +196,19 @@ def solve_host(batch: HostBatch, device: int = 0) -> HostBatch:
     cb = batch.cbatch()
     check(load().gcs_b200_solve_host(C.byref(cb), device), "gcs_b200_solve_host")
     return batch
+
+
+def solve_host_async(batch: HostBatch, device: int = 0) -> HostBatch:
+    """gcs_b200_solve_host_async: enqueue only; results are valid after wait(device)."""
+    if not batch.out:
+        batch.alloc_outputs()
+    cb = batch.cbatch()
+    check(load().gcs_b200_solve_host_async(C.byref(cb), device), "gcs_b200_solve_host_async")
+    return batch
+
+
+def wait(device: int = 0):
+    check(load().gcs_b200_wait(device), "gcs_b200_wait")
 
 
 def solve_sharded(batch: HostBatch, n_dev: int) -> HostBatch:

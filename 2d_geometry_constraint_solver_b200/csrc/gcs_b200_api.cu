@@ -39,6 +39,7 @@ int fail(int code, const char* fmt, ...)
                 __LINE__);                                                                     \
     } while (0)
 
+constexpr int kDefaultVariant = GCS_VARIANT_STATIC;  // measured faster on every kind (profiles/)
 constexpr int kTicketSlots = 64;
 constexpr int kRefillCH = 64;
 constexpr int kRefillWarps = 4;
@@ -52,7 +53,13 @@ struct DeviceState {
     std::mutex arena_mu;
     unsigned char* arena = nullptr;
     size_t arena_bytes = 0;
-    cudaStream_t stream = nullptr;
+    size_t arena_used = 0;        // bump pointer; reset when the device is drained
+    bool in_flight = false;       // host-buffer work enqueued and not yet waited for
+    cudaStream_t stream = nullptr;  // kernels
+    cudaStream_t h2d = nullptr;     // input copies  (own copy engine)
+    cudaStream_t d2h = nullptr;     // output copies (the other copy engine)
+    std::vector<cudaEvent_t> events;
+    size_t ev_next = 0;
 };
 
 std::mutex g_mu;
@@ -95,6 +102,8 @@ int prepare_device(DeviceState* d)
     CUDA_TRY(cudaMalloc(&d->tickets, sizeof(unsigned) * 2 * kTicketSlots));
     CUDA_TRY(cudaMemset(d->tickets, 0, sizeof(unsigned) * 2 * kTicketSlots));
     CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->d2h, cudaStreamNonBlocking));
     return GCS_OK;
 }
 
@@ -133,6 +142,7 @@ BatchDev to_dev(const gcs_b200_batch* b)
     p.converged = b->converged;
     p.root = b->root_index;
     p.n = b->n;
+    p.stride = b->n;
     return p;
 }
 
@@ -184,7 +194,7 @@ template <int KIND>
 int launch_kind(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cudaStream_t st)
 {
     int variant = b->variant;
-    if (variant == GCS_VARIANT_DEFAULT) variant = GCS_VARIANT_REFILL;
+    if (variant == GCS_VARIANT_DEFAULT) variant = kDefaultVariant;
     constexpr bool column_guess = (KIND == GCS_KIND_SDD || KIND == GCS_KIND_ANG);
     if (b->n_seeds == 2) {
         return variant == GCS_VARIANT_REFILL ? launch_refill<KIND, 2>(d, p, st) : launch_static<KIND, 2>(p, st);
@@ -195,10 +205,9 @@ int launch_kind(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cuda
     return fail(GCS_E_INVALID, "unsupported seed count");
 }
 
-int solve_on(DeviceState* d, const gcs_b200_batch* b, cudaStream_t st)
+int solve_dev(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cudaStream_t st)
 {
-    if (b->n == 0) return GCS_OK;
-    const BatchDev p = to_dev(b);
+    if (p.n == 0) return GCS_OK;
     switch (b->kind) {
     case GCS_KIND_PP: return launch_kind<GCS_KIND_PP>(d, b, p, st);
     case GCS_KIND_SDD: return launch_kind<GCS_KIND_SDD>(d, b, p, st);
@@ -207,6 +216,12 @@ int solve_on(DeviceState* d, const gcs_b200_batch* b, cudaStream_t st)
     case GCS_KIND_ANG: return launch_kind<GCS_KIND_ANG>(d, b, p, st);
     }
     return fail(GCS_E_INVALID, "unknown kind");
+}
+
+int solve_on(DeviceState* d, const gcs_b200_batch* b, cudaStream_t st)
+{
+    if (b->n == 0) return GCS_OK;
+    return solve_dev(d, b, to_dev(b), st);
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -319,6 +334,9 @@ void gcs_b200_shutdown(void)
         if (d->tickets || d->arena || d->stream) {
             cudaSetDevice(d->device);
             if (d->stream) cudaStreamSynchronize(d->stream), cudaStreamDestroy(d->stream);
+            if (d->h2d) cudaStreamSynchronize(d->h2d), cudaStreamDestroy(d->h2d);
+            if (d->d2h) cudaStreamSynchronize(d->d2h), cudaStreamDestroy(d->d2h);
+            for (cudaEvent_t e : d->events) cudaEventDestroy(e);
             if (d->tickets) cudaFree(d->tickets);
             if (d->arena) cudaFree(d->arena);
         }
@@ -332,6 +350,15 @@ const char* gcs_b200_last_error(void) { return g_err; }
 const char* gcs_b200_version(void) { return "gcs_b200 0.1.0 (sm_100a, fp64, fmad=false)"; }
 
 int64_t gcs_b200_launch_count(void) { return g_launches.load(); }
+
+const char* gcs_b200_kernel_name(int kind, int n_seeds, int variant)
+{
+    static thread_local char name[96];
+    if (variant == GCS_VARIANT_DEFAULT) variant = kDefaultVariant;
+    snprintf(name, sizeof(name), "%s<K%d,%d seeds>", variant == GCS_VARIANT_REFILL ? "newton_refill_kernel" : "newton_static_kernel",
+        kind, n_seeds);
+    return name;
+}
 
 int gcs_b200_solve(const gcs_b200_batch* b, int device, void* cuda_stream)
 {
@@ -352,24 +379,49 @@ int gcs_b200_solve(const gcs_b200_batch* b, int device, void* cuda_stream)
     return rc;
 }
 
-int gcs_b200_solve_host(const gcs_b200_batch* b, int device)
+// ---- host-buffer path: chunked three-stage pipeline -------------------------------------
+// A batch is cut into index ranges; range c+1 is on its way up (h2d stream, one copy engine)
+// while range c is being solved (kernel stream) and range c-1 is on its way down (d2h stream,
+// the other copy engine).  With pinned host buffers the three overlap and the call costs about
+// max(H2D, D2H) instead of H2D + kernel + D2H; with pageable buffers the copies stage through
+// the driver and the result is the same, only slower.
+namespace {
+
+int next_event(DeviceState* d, cudaEvent_t* ev)
 {
-    int rc = validate(b);
-    if (rc != GCS_OK) return rc;
-    if (b->mem != GCS_MEM_HOST) return fail(GCS_E_INVALID, "gcs_b200_solve_host needs host pointers (mem=GCS_MEM_HOST)");
-    rc = ensure_init();
-    if (rc != GCS_OK) return rc;
-    DeviceState* d = find_dev(device);
-    if (!d) return fail(GCS_E_NO_DEVICE, "device %d not present", device);
-    rc = prepare_device(d);
-    if (rc != GCS_OK) return rc;
-    if (b->n == 0) return GCS_OK;
+    if (d->ev_next == d->events.size()) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        d->events.push_back(e);
+    }
+    *ev = d->events[d->ev_next++];
+    return GCS_OK;
+}
 
-    std::lock_guard<std::mutex> lk(d->arena_mu);
-    int cur = -1;
-    CUDA_TRY(cudaGetDevice(&cur));
-    if (cur != device) CUDA_TRY(cudaSetDevice(device));
+int drain(DeviceState* d)
+{
+    CUDA_TRY(cudaStreamSynchronize(d->h2d));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->d2h));
+    d->arena_used = 0;
+    d->ev_next = 0;
+    d->in_flight = false;
+    return GCS_OK;
+}
 
+int64_t chunk_len(int64_t n)
+{
+    // 8 ranges for the bench-sized batches, never below 32 Ki sub-systems (launch + copy latency)
+    // nor above 256 Ki (pipeline ramp); multiples of 128 keep every slice 16-byte aligned
+    int64_t c = (n + 7) / 8;
+    if (c < 32768) c = 32768;
+    if (c > 262144) c = 262144;
+    return (c + 127) / 128 * 128;
+}
+
+// arena_mu held, device current
+int enqueue_host(DeviceState* d, const gcs_b200_batch* b)
+{
     const size_t n = (size_t)b->n;
     const int ns = b->n_seeds;
     const int nin = gcs_b200_kind_in_cols(b->kind), nout = gcs_b200_kind_out_cols(b->kind);
@@ -377,58 +429,141 @@ int gcs_b200_solve_host(const gcs_b200_batch* b, int device)
     size_t need = colb * (nin + nout) + align_up(n, 256) * 2;  // code + root
     if (b->guesses) need += align_up(n * 8 * 2 * ns, 256);
     if (b->cand) need += align_up(n * 8 * 2 * ns, 256);
-    if (b->iters) need += align_up(n * 2 * ns, 256);
-    if (b->converged) need += align_up(n * ns, 256);
-    if (need > d->arena_bytes) {
-        if (d->arena) CUDA_TRY(cudaFree(d->arena));
-        d->arena = nullptr, d->arena_bytes = 0;
-        const size_t grow = need + need / 4;
-        if (cudaMalloc(&d->arena, grow) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(GCS_E_NOMEM, "cudaMalloc(%zu) for the staging arena failed", grow);
+    need += align_up(n * 2 * ns, 256) + align_up(n * ns, 256);  // iters + converged
+    if (d->arena_used + need > d->arena_bytes) {
+        if (d->in_flight) {
+            const int rc = drain(d);
+            if (rc != GCS_OK) return rc;
         }
-        d->arena_bytes = grow;
+        if (need > d->arena_bytes) {
+            if (d->arena) CUDA_TRY(cudaFree(d->arena));
+            d->arena = nullptr, d->arena_bytes = 0;
+            const size_t grow = need + need / 4;
+            if (cudaMalloc(&d->arena, grow) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(GCS_E_NOMEM, "cudaMalloc(%zu) for the staging arena failed", grow);
+            }
+            d->arena_bytes = grow;
+        }
     }
-    unsigned char* cur_p = d->arena;
+    unsigned char* cur_p = d->arena + d->arena_used;
     auto take = [&](size_t bytes) {
         unsigned char* r = cur_p;
         cur_p += align_up(bytes, 256);
         return r;
     };
-    gcs_b200_batch db = *b;
-    db.mem = GCS_MEM_DEVICE;
-    cudaStream_t st = d->stream;
-    for (int c = 0; c < nin; ++c) {
-        double* p = reinterpret_cast<double*>(take(n * 8));
-        CUDA_TRY(cudaMemcpyAsync(p, b->in[c], n * 8, cudaMemcpyHostToDevice, st));
-        db.in[c] = p;
-    }
-    {
-        uint8_t* p = take(n);
-        CUDA_TRY(cudaMemcpyAsync(p, b->code, n, cudaMemcpyHostToDevice, st));
-        db.code = p;
-    }
-    if (b->guesses) {
-        double* p = reinterpret_cast<double*>(take(n * 8 * 2 * ns));
-        CUDA_TRY(cudaMemcpyAsync(p, b->guesses, n * 8 * 2 * ns, cudaMemcpyHostToDevice, st));
-        db.guesses = p;
-    }
-    for (int c = 0; c < nout; ++c) db.out[c] = reinterpret_cast<double*>(take(n * 8));
-    if (b->cand) db.cand = reinterpret_cast<double*>(take(n * 8 * 2 * ns));
-    if (b->iters) db.iters = reinterpret_cast<int16_t*>(take(n * 2 * ns));
-    if (b->converged) db.converged = take(n * ns);
-    db.root_index = take(n);
+    double* din[GCS_MAX_IN_COLS] = {};
+    double* dout[GCS_MAX_OUT_COLS] = {};
+    for (int c = 0; c < nin; ++c) din[c] = reinterpret_cast<double*>(take(n * 8));
+    uint8_t* dcode = take(n);
+    double* dguess = b->guesses ? reinterpret_cast<double*>(take(n * 8 * 2 * ns)) : nullptr;
+    for (int c = 0; c < nout; ++c) dout[c] = reinterpret_cast<double*>(take(n * 8));
+    double* dcand = b->cand ? reinterpret_cast<double*>(take(n * 8 * 2 * ns)) : nullptr;
+    int16_t* diters = reinterpret_cast<int16_t*>(take(n * 2 * ns));
+    uint8_t* dconv = take(n * ns);
+    uint8_t* droot = take(n);
+    d->arena_used = (size_t)(cur_p - d->arena);
+    d->in_flight = true;
 
-    rc = solve_on(d, &db, st);
-    if (rc == GCS_OK) {
+    const int64_t step = chunk_len(b->n);
+    for (int64_t lo = 0; lo < b->n; lo += step) {
+        const int64_t len = (b->n - lo < step) ? (b->n - lo) : step;
+        const size_t m = (size_t)len;
+        // up
+        for (int c = 0; c < nin; ++c)
+            CUDA_TRY(cudaMemcpyAsync(din[c] + lo, b->in[c] + lo, m * 8, cudaMemcpyHostToDevice, d->h2d));
+        CUDA_TRY(cudaMemcpyAsync(dcode + lo, b->code + lo, m, cudaMemcpyHostToDevice, d->h2d));
+        if (b->guesses)
+            for (int pl = 0; pl < 2 * ns; ++pl)
+                CUDA_TRY(cudaMemcpyAsync(dguess + (size_t)pl * n + lo, b->guesses + (size_t)pl * n + lo, m * 8,
+                    cudaMemcpyHostToDevice, d->h2d));
+        cudaEvent_t up, done;
+        int rc = next_event(d, &up);
+        if (rc != GCS_OK) return rc;
+        CUDA_TRY(cudaEventRecord(up, d->h2d));
+        // solve
+        CUDA_TRY(cudaStreamWaitEvent(d->stream, up, 0));
+        BatchDev p;
+        memset(&p, 0, sizeof(p));
+        for (int c = 0; c < nin; ++c) p.in[c] = din[c] + lo;
+        p.code = dcode + lo;
+        p.guesses = dguess ? dguess + lo : nullptr;
+        for (int c = 0; c < nout; ++c) p.out[c] = dout[c] + lo;
+        p.cand = dcand ? dcand + lo : nullptr;
+        p.iters = diters + lo;
+        p.converged = dconv + lo;
+        p.root = droot + lo;
+        p.n = len;
+        p.stride = b->n;
+        rc = solve_dev(d, b, p, d->stream);
+        if (rc != GCS_OK) return rc;
+        rc = next_event(d, &done);
+        if (rc != GCS_OK) return rc;
+        CUDA_TRY(cudaEventRecord(done, d->stream));
+        // down
+        CUDA_TRY(cudaStreamWaitEvent(d->d2h, done, 0));
         for (int c = 0; c < nout; ++c)
-            CUDA_TRY(cudaMemcpyAsync(b->out[c], db.out[c], n * 8, cudaMemcpyDeviceToHost, st));
-        if (b->cand) CUDA_TRY(cudaMemcpyAsync(b->cand, db.cand, n * 8 * 2 * ns, cudaMemcpyDeviceToHost, st));
-        if (b->iters) CUDA_TRY(cudaMemcpyAsync(b->iters, db.iters, n * 2 * ns, cudaMemcpyDeviceToHost, st));
-        if (b->converged) CUDA_TRY(cudaMemcpyAsync(b->converged, db.converged, n * ns, cudaMemcpyDeviceToHost, st));
-        if (b->root_index) CUDA_TRY(cudaMemcpyAsync(b->root_index, db.root_index, n, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaMemcpyAsync(b->out[c] + lo, dout[c] + lo, m * 8, cudaMemcpyDeviceToHost, d->d2h));
+        if (b->cand)
+            for (int pl = 0; pl < 2 * ns; ++pl)
+                CUDA_TRY(cudaMemcpyAsync(b->cand + (size_t)pl * n + lo, dcand + (size_t)pl * n + lo, m * 8,
+                    cudaMemcpyDeviceToHost, d->d2h));
+        for (int k = 0; k < ns; ++k) {
+            if (b->iters)
+                CUDA_TRY(cudaMemcpyAsync(b->iters + (size_t)k * n + lo, diters + (size_t)k * n + lo, m * 2,
+                    cudaMemcpyDeviceToHost, d->d2h));
+            if (b->converged)
+                CUDA_TRY(cudaMemcpyAsync(b->converged + (size_t)k * n + lo, dconv + (size_t)k * n + lo, m,
+                    cudaMemcpyDeviceToHost, d->d2h));
+        }
+        if (b->root_index) CUDA_TRY(cudaMemcpyAsync(b->root_index + lo, droot + lo, m, cudaMemcpyDeviceToHost, d->d2h));
     }
+    return GCS_OK;
+}
+
+int host_entry(const gcs_b200_batch* b, int device, bool wait)
+{
+    int rc = validate(b);
+    if (rc != GCS_OK) return rc;
+    if (b->mem != GCS_MEM_HOST) return fail(GCS_E_INVALID, "this entry point needs host pointers (mem=GCS_MEM_HOST)");
+    rc = ensure_init();
+    if (rc != GCS_OK) return rc;
+    DeviceState* d = find_dev(device);
+    if (!d) return fail(GCS_E_NO_DEVICE, "device %d not present", device);
+    rc = prepare_device(d);
+    if (rc != GCS_OK) return rc;
+    std::lock_guard<std::mutex> lk(d->arena_mu);
+    int cur = -1;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != device) CUDA_TRY(cudaSetDevice(device));
+    if (b->n > 0) rc = enqueue_host(d, b);
+    if (rc != GCS_OK) {
+        drain(d);  // leave nothing behind a failed call
+    } else if (wait && d->in_flight) {
+        rc = drain(d);
+    }
+    if (cur != device && cur >= 0) cudaSetDevice(cur);
+    return rc;
+}
+
+}  // namespace
+
+int gcs_b200_solve_host(const gcs_b200_batch* b, int device) { return host_entry(b, device, true); }
+
+int gcs_b200_solve_host_async(const gcs_b200_batch* b, int device) { return host_entry(b, device, false); }
+
+int gcs_b200_wait(int device)
+{
+    int rc = ensure_init();
+    if (rc != GCS_OK) return rc;
+    DeviceState* d = find_dev(device);
+    if (!d) return fail(GCS_E_NO_DEVICE, "device %d not present", device);
+    if (!d->tickets) return GCS_OK;  // never used
+    std::lock_guard<std::mutex> lk(d->arena_mu);
+    int cur = -1;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != device) CUDA_TRY(cudaSetDevice(device));
+    rc = drain(d);
     if (cur != device && cur >= 0) cudaSetDevice(cur);
     return rc;
 }

@@ -34,6 +34,7 @@ struct BatchDev {
     uint8_t* converged; // [NS][n] or null
     uint8_t* root;      // [n] or null
     long long n;
+    long long stride;  // distance between per-seed planes (== n unless this launch is a slice of a larger batch)
 };
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -63,8 +64,8 @@ __global__ void __launch_bounds__(128, GCS_STATIC_MINB) newton_static_kernel(con
     sys.load(k);
     double x, y;
     if (p.guesses) {
-        x = __ldg(p.guesses + ((long long)seed * 2 + 0) * p.n + i);
-        y = __ldg(p.guesses + ((long long)seed * 2 + 1) * p.n + i);
+        x = __ldg(p.guesses + ((long long)seed * 2 + 0) * p.stride + i);
+        y = __ldg(p.guesses + ((long long)seed * 2 + 1) * p.stride + i);
     } else if constexpr (S::kGuessFromCols) {
         column_seed<KIND>(k, seed, x, y);
     } else {
@@ -83,11 +84,11 @@ __global__ void __launch_bounds__(128, GCS_STATIC_MINB) newton_static_kernel(con
         cy[s] = __shfl_sync(kFull, y, lead + s);
     }
     if (valid) {
-        if (p.iters) p.iters[(long long)seed * p.n + sub] = (int16_t)it;
-        if (p.converged) p.converged[(long long)seed * p.n + sub] = (uint8_t)conv;
+        if (p.iters) p.iters[(long long)seed * p.stride + sub] = (int16_t)it;
+        if (p.converged) p.converged[(long long)seed * p.stride + sub] = (uint8_t)conv;
         if (p.cand) {
-            p.cand[((long long)seed * 2 + 0) * p.n + sub] = x;
-            p.cand[((long long)seed * 2 + 1) * p.n + sub] = y;
+            p.cand[((long long)seed * 2 + 0) * p.stride + sub] = x;
+            p.cand[((long long)seed * 2 + 1) * p.stride + sub] = y;
         }
         if (seed == 0) {
             double out[4];
@@ -279,8 +280,8 @@ __global__ void __launch_bounds__(WARPS * 32)
                         for (int c = 0; c < S::kCols; ++c) k[c] = sl.in[buf][c][slot_sub];
                         sys.load(k);
                         if (p.guesses) {
-                            x = __ldg(p.guesses + ((long long)slot_seed * 2 + 0) * p.n + base + slot_sub);
-                            y = __ldg(p.guesses + ((long long)slot_seed * 2 + 1) * p.n + base + slot_sub);
+                            x = __ldg(p.guesses + ((long long)slot_seed * 2 + 0) * p.stride + base + slot_sub);
+                            y = __ldg(p.guesses + ((long long)slot_seed * 2 + 1) * p.stride + base + slot_sub);
                         } else if constexpr (S::kGuessFromCols) {
                             column_seed<KIND>(k, slot_seed, x, y);
                         } else {
@@ -335,11 +336,11 @@ __global__ void __launch_bounds__(WARPS * 32)
             if (p.root) p.root[gi] = (uint8_t)root;
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                if (p.iters) p.iters[(long long)s * p.n + gi] = sl.it[s][j];
-                if (p.converged) p.converged[(long long)s * p.n + gi] = sl.cv[s][j];
+                if (p.iters) p.iters[(long long)s * p.stride + gi] = sl.it[s][j];
+                if (p.converged) p.converged[(long long)s * p.stride + gi] = sl.cv[s][j];
                 if (p.cand) {
-                    p.cand[((long long)s * 2 + 0) * p.n + gi] = cx[s];
-                    p.cand[((long long)s * 2 + 1) * p.n + gi] = cy[s];
+                    p.cand[((long long)s * 2 + 0) * p.stride + gi] = cx[s];
+                    p.cand[((long long)s * 2 + 1) * p.stride + gi] = cy[s];
                 }
             }
         }

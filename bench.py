@@ -5,19 +5,23 @@
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, host cores
 
 Workload (config.workload): BASELINE.json configs[1] — 2^20 independent synthetic triangle
-clusters per GPU, half K1 (distance+distance, ZeroFixedPoints/TwoFixedPointsDistance shapes) and
-half K5 (angle+unit normal), one solve2D-equivalent each (2 seeds, reference defaults) + root
-selection (+ line reconstruction for K5).  A step = one pass over that batch = two kernel
-launches.  Weak scaling: every rank owns its own 2^20 instances (index range rank*2^20...), no
-data-path collective.
+clusters per GPU, half K1 (distance+distance: ZeroFixedPoints / TwoFixedPointsDistance shapes),
+half K5 (angle + unit normal), one solve2D-equivalent each (2 seeds, reference defaults) + root
+selection (+ line reconstruction for K5).  A step = one pass over that batch = one K1 launch +
+one K5 launch.  Weak scaling: rank r owns instances [r*2^19, (r+1)*2^19) of each kind's index
+space; no data-path collective (NCCL only carries the barrier and the max-over-ranks of the time).
 
-`value`  : whole-job solves/s, inputs resident in HBM, per-step CUDA-event time, max over ranks.
-`e2e`    : same metric through gcs_b200_solve_host with pinned HOST buffers (H2D + kernels + D2H
-           inside the timed region).
-`roofline`: dominant kernel (K1 refill kernel): algorithmic FP64 flops (work model of
-           BASELINE.md section 5, from the MEASURED iteration counts) / its event-timed duration,
-           against the DFMA peak measured live by gcs_b200_fp64_probe (MEASURED_PEAKS.json
-           carries no FP64 figure); the HBM side is reported beside it.
+`value`   whole-job solves/s with the batch resident in HBM; per-launch CUDA events on the
+          launching stream, summed over the steps, max over ranks; L2 flushed between steps.
+`e2e`     the same metric through the host-buffer C-ABI calls (gcs_b200_solve_host_async per kind
+          + gcs_b200_wait): pinned HOST inputs and outputs, H2D + kernels + D2H inside the region.
+`roofline` the dominant kernel (K1): algorithmic FP64 flops (work model of DESIGN.md section 3,
+          from the MEASURED iteration counts) / its event-timed duration, against the DFMA peak
+          measured live by gcs_b200_fp64_probe (MEASURED_PEAKS.json has no FP64 figure); the HBM
+          side is reported beside it against MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`  the reference's own solve2D + primitives + heuristics sources
+          (oracle/_ref, built from /root/reference against stand-in Eigen/autodiff headers) where
+          that library is present, else the restated C oracle; all host threads, bounded sample.
 """
 from __future__ import annotations
 
@@ -37,7 +41,8 @@ sys.path.insert(0, ROOT)
 N_PER_GPU = 1 << 20
 METRIC = "subsystem Newton solves/sec"
 UNIT = "solves/s"
-WORKLOAD = "configs[1]: 2^20 synthetic triangle clusters per GPU (2^19 K1 distance-distance + 2^19 K5 angle-normal), 2 seeds each, FP64"
+WORKLOAD = ("configs[1]: 2^20 synthetic triangle clusters per GPU (2^19 K1 distance-distance + 2^19 K5 "
+            "angle-normal), 2 seeds each, FP64")
 
 
 def parse():
@@ -46,9 +51,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", type=int, default=0, help="0 default, 1 static, 2 refill")
+    ap.add_argument("--variant", type=int, default=0, help="0 library default, 1 static, 2 refill")
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="solves per GPU (default 2^20)")
-    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -61,6 +66,16 @@ def load_peaks():
         except Exception:
             pass
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the last committed `ncu --set full`
+    capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -106,7 +121,7 @@ class ClockSampler:
                                 self.reasons.add(nm)
                 except Exception:
                     pass
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def start(self):
         self.t.start()
@@ -135,48 +150,68 @@ def make_batches(synth, n, rank):
     return [synth.make_pp(half, first=first), synth.make_ang(half, first=first)]
 
 
-def cpu_rate(gcs, seconds, threads=0):
-    """Time the CPU implementation of the path on a bounded sample of the same workload.
-    Returns (solves/s, cores, kind, sample description)."""
+# --------------------------------------------------------------------------------------------
+# CPU leg: the reference's own sources where oracle/_ref exists, else the restated oracle
+# --------------------------------------------------------------------------------------------
+def cpu_backend():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import __graft_entry__ as g
     g.build_oracle()
+    try:
+        import ref_lib as R
+        if R.available():
+            R.load()
+            return ("reference", lambda b, t: R.solve_batch(b, count_iters=False, threads=t), R.load().gcs_ref_max_threads(),
+                    "the reference's solve2D / equation primitives / heuristics sources compiled from /root/reference "
+                    "(oracle/_ref; Eigen and autodiff are the stand-in headers of oracle/ref_shim)")
+    except Exception:
+        pass
     import oracle_lib as O
+    return ("port", lambda b, t: O.solve(b, t), O.max_threads(),
+            "restated C oracle (oracle/gcs_oracle.c): oracle/_ref is not present on this box")
+
+
+def cpu_rate(gcs, seconds, threads=0):
+    """Solves/s of the CPU path on a bounded sample of the same workload (same generators, same
+    K1/K5 mix), repeated until about `seconds` of wall time have been spent."""
     synth = gcs.synth
-    cores = O.max_threads() if threads < 1 else threads
-    # calibrate on 2^13 of each kind, then size the sample for ~`seconds` of wall time
-    def run(m):
-        bs = [synth.make_pp(m).alloc_outputs(), synth.make_ang(m).alloc_outputs()]
+    kind, solve, cores, what = cpu_backend()
+    if threads > 0:
+        cores = threads
+    m = 1 << 15
+    bs = [synth.make_pp(m).alloc_outputs(), synth.make_ang(m).alloc_outputs()]
+    for b in bs:  # warm the threads and the pages
+        solve(b, threads)
+    done, t_total, reps = 0, 0.0, 0
+    while t_total < seconds or reps < 2:
         t0 = time.perf_counter()
         for b in bs:
-            O.solve(b, threads)
-        return time.perf_counter() - t0
-    run(1 << 10)
-    t = run(1 << 13)
-    rate = 2 * (1 << 13) / t
-    m = int(min(max(rate * seconds / 2, 1 << 13), 1 << 19))
-    t = run(m)
-    return 2 * m / t, cores, "port", f"{m} K1 + {m} K5 solves (same generators), OpenMP static, {cores} threads, {t:.2f} s"
+            solve(b, threads)
+        t_total += time.perf_counter() - t0
+        done += 2 * m
+        reps += 1
+    sample = f"{reps} x ({m} K1 + {m} K5) solves of the bench generators, {cores} threads, {t_total:.1f} s; {what}"
+    return done / t_total, cores, kind, sample
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank):
     if rank != 0:
         return
     gcs = importlib.import_module("2d_geometry_constraint_solver_b200")
-    per_step = max(args.cpu_seconds / max(args.steps + args.warmup, 1), 0.5)
+    n_steps = max(args.steps, 1)
+    per_step = min(max(args.cpu_seconds / (n_steps + args.warmup), 0.25), 20.0)
     rates = []
     desc = cores = kind = None
-    for i in range(args.warmup + args.steps):
+    for i in range(args.warmup + n_steps):
         r, cores, kind, desc = cpu_rate(gcs, per_step)
         if i >= args.warmup:
             rates.append(r)
     v = float(np.mean(rates))
     out = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CPU path on the box's host cores: the restated oracle "
-                   "(oracle/gcs_oracle.c; the reference itself needs GCC>=15, Eigen, autodiff and cannot be built here)"},
+        "config": {"workload": WORKLOAD, "note": "CPU path on the box's host cores, rank 0 only; each step is a bounded sample"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -184,13 +219,14 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+# --------------------------------------------------------------------------------------------
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
 
     import torch
@@ -209,6 +245,7 @@ def main():
     lib = capi.load()
 
     n = args.n
+    warmup = max(args.warmup, 3)
     host = make_batches(synth, n, rank)
     for h in host:
         h.variant = args.variant
@@ -234,7 +271,7 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         flush.fill_(1)
         step()
     barrier()
@@ -249,7 +286,6 @@ def main():
         step(evs[k])
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    sampler.leave()
     launches = lib.gcs_b200_launch_count() - l0
 
     ms_k1 = np.array([e[0].elapsed_time(e[1]) for e in evs])
@@ -266,35 +302,12 @@ def main():
     it5 = devb[1].iters.cpu().numpy()
     w_k1 = synth.algorithmic_flops(1, it1)
     w_k5 = synth.algorithmic_flops(5, it5)
-    dfma_peak = lib.gcs_b200_fp64_probe(local_rank, 0)
-    mix_peak = lib.gcs_b200_fp64_probe(local_rank, 1)
-    peaks, peak_src = load_peaks()
     k1_ms = float(np.mean(ms_k1))
     k5_ms = float(np.mean(ms_k5))
-    ach_tf = w_k1 / (k1_ms * 1e-3) / 1e12
     b_k1 = devb[0].algorithmic_bytes()
     b_k5 = devb[1].algorithmic_bytes()
-    roofline = {
-        "kernel": "newton_refill_kernel<K1,2 seeds>" if args.variant != 1 else "newton_static_kernel<K1,2 seeds>",
-        "bound": "fp64",
-        "achieved": ach_tf, "peak": dfma_peak, "unit": "TFLOP/s", "frac": ach_tf / dfma_peak if dfma_peak > 0 else None,
-        "peak_source": "measured live: gcs_b200_fp64_probe DFMA micro-benchmark (FMA = 2 flops); MEASURED_PEAKS.json has no FP64 entry",
-        "non_fma_peak": mix_peak,
-        "frac_of_non_fma_peak": ach_tf / mix_peak if mix_peak > 0 else None,
-        "traffic": None,
-        "algorithmic_flops_per_launch": w_k1,
-        "flops_per_solve": w_k1 / devb[0].n,
-        "mean_iters_per_seed": float(it1.mean()),
-        "launch_ms": k1_ms,
-        "share_of_step": k1_ms / (k1_ms + k5_ms),
-        "hbm": {"achieved": b_k1 / (k1_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                "frac": b_k1 / (k1_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 1.0), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": b_k1},
-        "second_kernel": {"kernel": "K5", "launch_ms": k5_ms, "achieved_tflops": w_k5 / (k5_ms * 1e-3) / 1e12,
-                          "hbm_gbs": b_k5 / (k5_ms * 1e-3) / 1e9, "mean_iters_per_seed": float(it5.mean())},
-    }
 
-    # ---- end to end through the host-buffer C-ABI call, pinned host memory ----
+    # ---- end to end through the host-buffer C-ABI calls, pinned host memory ----
     def pin_like(a):
         t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].copy()).dtype, pin_memory=True)
         v = t.numpy()
@@ -321,25 +334,64 @@ def main():
         e2e_batches.append(hb)
     h2d = sum(capi.IN_COLS[b.kind] * 8 * b.n + b.n for b in e2e_batches)
     d2h = sum(capi.OUT_COLS[b.kind] * 8 * b.n + b.n_seeds * 3 * b.n + b.n for b in e2e_batches)
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step():
         for b in e2e_batches:
-            capi.solve_host(b, local_rank)
+            capi.solve_host_async(b, local_rank)
+        capi.wait(local_rank)
+
+    for _ in range(3):
+        e2e_step()
+    l1 = lib.gcs_b200_launch_count()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        for b in e2e_batches:
-            capi.solve_host(b, local_rank)
+        e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    sampler.leave()
+    e2e_launches = lib.gcs_b200_launch_count() - l1
     e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = n * world * e2e_steps / float(e2e_t.item())
     # the e2e results must equal the device-resident ones (same inputs)
     assert np.array_equal(e2e_batches[0].iters, it1) and np.array_equal(e2e_batches[1].iters, it5)
+    assert np.array_equal(e2e_batches[0].out[0], devb[0].out[0].cpu().numpy())
 
     clocks = sampler.stop()
+
+    # ---- peaks (after the timed regions: the probe heats the chip) ----
+    dfma_peak = lib.gcs_b200_fp64_probe(local_rank, 0)
+    mix_peak = lib.gcs_b200_fp64_probe(local_rank, 1)
+    peaks, peak_src = load_peaks()
+    ach_tf = w_k1 / (k1_ms * 1e-3) / 1e12
+    traffic = load_traffic()
+    vname = {0: "default", 1: "static", 2: "refill"}[args.variant]
+    kernel_name = lib.gcs_b200_kernel_name(1, 2, args.variant).decode() if hasattr(lib, "gcs_b200_kernel_name") else vname
+    roofline = {
+        "kernel": kernel_name,
+        "bound": "fp64",
+        "bound_note": "FP64 CUDA-core pipe (no tensor-core work on this path); the HBM side is under 'hbm'",
+        "achieved": ach_tf, "peak": dfma_peak, "unit": "TFLOP/s", "frac": ach_tf / dfma_peak if dfma_peak > 0 else None,
+        "peak_source": "measured live: gcs_b200_fp64_probe DFMA micro-benchmark (FMA = 2 flops); MEASURED_PEAKS.json has no FP64 entry",
+        "non_fma_peak": mix_peak,
+        "frac_of_non_fma_peak": ach_tf / mix_peak if mix_peak > 0 else None,
+        "traffic": traffic.get(kernel_name, {}).get("dram_bytes_per_launch"),
+        "traffic_source": traffic.get(kernel_name, {}).get("source"),
+        "algorithmic_flops_per_launch": w_k1,
+        "flops_per_solve": w_k1 / devb[0].n,
+        "mean_iters_per_seed": float(it1.mean()),
+        "launch_ms": k1_ms,
+        "share_of_step": k1_ms / (k1_ms + k5_ms),
+        "hbm": {"achieved": b_k1 / (k1_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": b_k1 / (k1_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 1.0), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_k1},
+        "second_kernel": {"kernel": "K5", "launch_ms": k5_ms, "achieved_tflops": w_k5 / (k5_ms * 1e-3) / 1e12,
+                          "hbm_gbs": b_k5 / (k5_ms * 1e-3) / 1e9, "mean_iters_per_seed": float(it5.mean()),
+                          "algorithmic_flops_per_launch": w_k5, "algorithmic_bytes_per_launch": b_k5},
+    }
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -349,15 +401,16 @@ def main():
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "solves_per_gpu": n, "l2": "256 MiB flush write between timed steps",
-                       "variant": {0: "default(refill)", 1: "static", 2: "refill"}[args.variant],
-                       "timing": "per-step CUDA events on the launching stream, sum over steps, max over ranks",
+                       "variant": vname,
+                       "timing": "per-launch CUDA events on the launching stream, sum over steps, max over ranks",
                        "wall_s_timed_region_incl_flush": t_wall},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "gcs_b200_solve_host (pinned host buffers)"},
+                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "gpu_launches": int(e2e_launches),
+                    "api": "gcs_b200_solve_host_async x2 + gcs_b200_wait (pinned host buffers, wall clock incl. copies)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -171,12 +171,21 @@ GCS_B200_API int gcs_b200_solve(const gcs_b200_batch* batch, int device, void* c
  * This is the call the host-side solver mirror makes. */
 GCS_B200_API int gcs_b200_solve_host(const gcs_b200_batch* batch, int device);
 
+/* The same without the final synchronisation: the batch is cut into index ranges that move up,
+ * are solved and move down on three streams (pinned host buffers overlap fully); several batches
+ * can be queued back to back, e.g. one per equation kind of a dependency wave.  Inputs must stay
+ * valid and outputs are undefined until gcs_b200_wait(device) returns. */
+GCS_B200_API int gcs_b200_solve_host_async(const gcs_b200_batch* batch, int device);
+GCS_B200_API int gcs_b200_wait(int device);
+
 /* Host buffers, sharded by batch index over the first n_dev initialised devices
  * (contiguous ranges [g*n/G, (g+1)*n/G)); no collective, per-device D2H into disjoint slices. */
 GCS_B200_API int gcs_b200_solve_sharded(const gcs_b200_batch* batch, int n_dev);
 
 /* number of kernel launches issued by this process so far (bench bookkeeping) */
 GCS_B200_API int64_t gcs_b200_launch_count(void);
+/* name of the kernel a batch of this kind / seed count / variant is solved by (thread-local string) */
+GCS_B200_API const char* gcs_b200_kernel_name(int kind, int n_seeds, int variant);
 
 /* FP64 pipe micro-benchmarks used as roofline denominators (seconds-scale, device `device`):
  *   what = 0: dependent-free DFMA throughput, returns TFLOP/s counting FMA = 2 flops

@@ -238,3 +238,47 @@ def test_fast_division_sqrt_and_qr_equal_the_generic_ieee_path(gpu):
         assert c[1] == 0 and c[3] == 0 and c[5] == 0, c
         # the fast paths are actually exercised
         assert c[0] > 0.4 * c[7] and c[2] > 0.6 * c[7] and c[4] > 0.3 * c[6], c
+
+
+def test_device_generator_matches_the_host_generator(gpu, gcs):
+    """gcs_b200_synth_pp (csrc/synth.cu) fills K1 columns on the device with the same
+    counter-based stream as synth.make_pp, incl. the perturbed sweep of BASELINE config 5."""
+    import ctypes as C
+    import torch
+    synth, capi = gcs.synth, gcs.capi
+    lib = capi.load()
+    for first, n, perturb in ((0, 5000, 0), (123456, 4097, 0), (1 << 20, 8192, 4096)):
+        cols = [torch.empty(n, dtype=torch.float64, device="cuda:0") for _ in range(6)]
+        code = torch.empty(n, dtype=torch.uint8, device="cuda:0")
+        ptrs = (C.c_void_p * 6)(*[c.data_ptr() for c in cols])
+        rc = lib.gcs_b200_synth_pp(0, None, synth.BASE_SEED, first, n, perturb, ptrs, C.c_void_p(code.data_ptr()))
+        assert rc == 0, lib.gcs_b200_last_error()
+        torch.cuda.synchronize()
+        hb = synth.make_pp(n, first=first, perturb_of=perturb)
+        for c in range(6):
+            assert np.array_equal(bits(cols[c].cpu().numpy()), bits(hb.cols[c])), (first, perturb, c)
+        assert np.array_equal(code.cpu().numpy(), hb.code)
+
+
+def test_async_host_calls_pipeline_and_match(gpu, gcs):
+    """Two kinds queued back to back (gcs_b200_solve_host_async) then one wait: same bits as the
+    synchronous call; batch sizes straddle the chunk length of the three-stage pipeline."""
+    synth, capi = gcs.synth, gcs.capi
+    for n in (1, 32768, 32769, 300001):
+        a = synth.make_pp(n).alloc_outputs()
+        b = synth.make_ang(n).alloc_outputs()
+        g = np.ascontiguousarray(np.random.default_rng(n).uniform(-3000, 3000, size=(2, 2, n)))
+        c = synth.make_ppl(n)
+        c.guesses = g
+        c.alloc_outputs()
+        for h in (a, b, c):
+            capi.solve_host_async(h, 0)
+        capi.wait(0)
+        for h, mk in ((a, synth.make_pp), (b, synth.make_ang)):
+            r = mk(n).alloc_outputs()
+            capi.solve_host(r, 0)
+            assert_batches_identical(h, r, f"async n {n}")
+        r = synth.make_ppl(n)
+        r.guesses = g
+        O.solve(r.alloc_outputs())
+        assert_batches_identical(c, r, f"async explicit guesses n {n}")
