@@ -7,10 +7,12 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/gcs_b200.h"
@@ -385,17 +387,56 @@ int gcs_b200_solve(const gcs_b200_batch* b, int device, void* cuda_stream)
 // the other copy engine).  With pinned host buffers the three overlap and the call costs about
 // max(H2D, D2H) instead of H2D + kernel + D2H; with pageable buffers the copies stage through
 // the driver and the result is the same, only slower.
+//
+// (Recording the same calls as a CUDA graph and replaying it was measured too: 1.80 ms per bench
+// step against 1.77 ms for plain stream calls - the enqueue cost, ~0.1 ms, already hides behind
+// the transfers - so the plain form stayed.)
 namespace {
 
-int next_event(DeviceState* d, cudaEvent_t* ev)
+// GCS_B200_TRACE=1: timing events at the stage boundaries of the (non-graph) pipeline, printed at drain
+struct TraceMark {
+    cudaEvent_t ev;
+    const char* what;
+    int batch_kind;
+    long long lo;
+};
+std::vector<TraceMark> g_trace;
+cudaEvent_t g_trace_origin = nullptr;
+bool trace_on()
 {
-    if (d->ev_next == d->events.size()) {
-        cudaEvent_t e;
-        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        d->events.push_back(e);
-    }
-    *ev = d->events[d->ev_next++];
-    return GCS_OK;
+    static const bool on = getenv("GCS_B200_TRACE") != nullptr;
+    return on;
+}
+void trace_mark(cudaStream_t st, const char* what, int kind, long long lo)
+{
+    if (!trace_on()) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    g_trace.push_back({ e, what, kind, lo });
+}
+void trace_dump()
+{
+    if (!trace_on() || g_trace.empty()) return;
+    for (auto& m : g_trace) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g_trace[0].ev, m.ev);
+        fprintf(stderr, "[trace] K%d lo=%-8lld %-10s %8.3f ms\n", m.batch_kind, m.lo, m.what, ms);
+        }
+    for (auto& m : g_trace) cudaEventDestroy(m.ev);
+    g_trace.clear();
+}
+
+size_t arena_need(const gcs_b200_batch* b)
+{
+    const size_t n = (size_t)b->n;
+    const int ns = b->n_seeds;
+    const int nin = gcs_b200_kind_in_cols(b->kind), nout = gcs_b200_kind_out_cols(b->kind);
+    size_t need = align_up(n * 8, 256) * (size_t)(nin + nout) + align_up(n, 256) * 2;  // columns, code, root
+    if (b->guesses) need += align_up(n * 8 * 2 * ns, 256);
+    if (b->cand) need += align_up(n * 8 * 2 * ns, 256);
+    need += align_up(n * 2 * ns, 256) + align_up(n * ns, 256);  // iters + converged
+    return need;
 }
 
 int drain(DeviceState* d)
@@ -403,50 +444,72 @@ int drain(DeviceState* d)
     CUDA_TRY(cudaStreamSynchronize(d->h2d));
     CUDA_TRY(cudaStreamSynchronize(d->stream));
     CUDA_TRY(cudaStreamSynchronize(d->d2h));
+    trace_dump();
     d->arena_used = 0;
     d->ev_next = 0;
     d->in_flight = false;
     return GCS_OK;
 }
 
-int64_t chunk_len(int64_t n)
+// makes room for `need` more arena bytes (may drain the device and grow the arena)
+int reserve_arena(DeviceState* d, size_t need)
 {
-    // 8 ranges for the bench-sized batches, never below 32 Ki sub-systems (launch + copy latency)
-    // nor above 256 Ki (pipeline ramp); multiples of 128 keep every slice 16-byte aligned
-    int64_t c = (n + 7) / 8;
+    if (d->arena_used + need <= d->arena_bytes) return GCS_OK;
+    // Not enough room behind the batches already in flight: finish those, then size the arena
+    // for what was asked for in total so that the same sequence of calls overlaps next time.
+    const size_t want = d->arena_used + need;
+    if (d->in_flight) {
+        const int rc = drain(d);
+        if (rc != GCS_OK) return rc;
+    }
+    if (d->arena) CUDA_TRY(cudaFree(d->arena));
+    d->arena = nullptr, d->arena_bytes = 0;
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    size_t grow = want + want / 4;
+    if (grow > free_b / 2) grow = want;
+    if (grow > free_b / 2) grow = need;
+    if (cudaMalloc(&d->arena, grow) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(GCS_E_NOMEM, "cudaMalloc(%zu) for the staging arena failed", grow);
+    }
+    d->arena_bytes = grow;
+    return GCS_OK;
+}
+
+int ensure_events(DeviceState* d, size_t count)
+{
+    while (d->events.size() < d->ev_next + count) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        d->events.push_back(e);
+    }
+    return GCS_OK;
+}
+
+int64_t chunk_len(int64_t n, bool slabs)
+{
+    // Ranges per batch: 4 when every range moves with a handful of strided copies, 3 when each
+    // column needs its own call; never below 32 Ki sub-systems nor above 256 Ki (pipeline ramp);
+    // multiples of 128 keep every slice 16-byte aligned
+    static const int forced = getenv("GCS_B200_PARTS") ? atoi(getenv("GCS_B200_PARTS")) : 0;  // tuning knob
+    const int parts = forced > 0 ? forced : (slabs ? 4 : 3);
+    int64_t c = (n + parts - 1) / parts;
     if (c < 32768) c = 32768;
     if (c > 262144) c = 262144;
     return (c + 127) / 128 * 128;
 }
 
-// arena_mu held, device current
-int enqueue_host(DeviceState* d, const gcs_b200_batch* b)
+// Issues the whole pipeline of one batch on (h2d, stream, d2h), device buffers at arena + off.
+// Nothing joins the streams here: the next batch's upload may start at once (its buffers are a
+// different arena region); gcs_b200_wait / drain synchronises all three.
+int record_pipeline(DeviceState* d, const gcs_b200_batch* b, size_t off)
 {
     const size_t n = (size_t)b->n;
     const int ns = b->n_seeds;
     const int nin = gcs_b200_kind_in_cols(b->kind), nout = gcs_b200_kind_out_cols(b->kind);
     const size_t colb = align_up(n * 8, 256);
-    size_t need = colb * (nin + nout) + align_up(n, 256) * 2;  // code + root
-    if (b->guesses) need += align_up(n * 8 * 2 * ns, 256);
-    if (b->cand) need += align_up(n * 8 * 2 * ns, 256);
-    need += align_up(n * 2 * ns, 256) + align_up(n * ns, 256);  // iters + converged
-    if (d->arena_used + need > d->arena_bytes) {
-        if (d->in_flight) {
-            const int rc = drain(d);
-            if (rc != GCS_OK) return rc;
-        }
-        if (need > d->arena_bytes) {
-            if (d->arena) CUDA_TRY(cudaFree(d->arena));
-            d->arena = nullptr, d->arena_bytes = 0;
-            const size_t grow = need + need / 4;
-            if (cudaMalloc(&d->arena, grow) != cudaSuccess) {
-                cudaGetLastError();
-                return fail(GCS_E_NOMEM, "cudaMalloc(%zu) for the staging arena failed", grow);
-            }
-            d->arena_bytes = grow;
-        }
-    }
-    unsigned char* cur_p = d->arena + d->arena_used;
+    unsigned char* cur_p = d->arena + off;
     auto take = [&](size_t bytes) {
         unsigned char* r = cur_p;
         cur_p += align_up(bytes, 256);
@@ -462,25 +525,59 @@ int enqueue_host(DeviceState* d, const gcs_b200_batch* b)
     int16_t* diters = reinterpret_cast<int16_t*>(take(n * 2 * ns));
     uint8_t* dconv = take(n * ns);
     uint8_t* droot = take(n);
-    d->arena_used = (size_t)(cur_p - d->arena);
-    d->in_flight = true;
 
-    const int64_t step = chunk_len(b->n);
-    for (int64_t lo = 0; lo < b->n; lo += step) {
-        const int64_t len = (b->n - lo < step) ? (b->n - lo) : step;
+    // runs of columns at one constant positive spacing (bytes) in host memory
+    int in_runs[GCS_MAX_IN_COLS] = {}, out_runs[GCS_MAX_OUT_COLS] = {};
+    size_t in_pitch = 0, out_pitch = 0;
+    auto find_runs = [&](auto* const* cols, int count, int* runs, size_t* pitch) {
+        for (int c = 0; c < count; ++c) runs[c] = 1;
+        if (count < 2 || getenv("GCS_B200_NOSLAB")) return;
+        const ptrdiff_t sp = reinterpret_cast<const char*>(cols[1]) - reinterpret_cast<const char*>(cols[0]);
+        if (sp < (ptrdiff_t)(n * 8)) return;
+        for (int c = 2; c < count; ++c)
+            if (reinterpret_cast<const char*>(cols[c]) - reinterpret_cast<const char*>(cols[c - 1]) != sp) return;
+        runs[0] = count;
+        *pitch = (size_t)sp;
+    };
+    find_runs(b->in, nin, in_runs, &in_pitch);
+    find_runs(b->out, nout, out_runs, &out_pitch);
+    const bool slabs = in_runs[0] == nin && out_runs[0] == nout;
+
+    // index ranges: equal steps, the last one halved so that less work trails the final upload
+    const int64_t step = chunk_len(b->n, slabs);
+    std::vector<std::pair<int64_t, int64_t>> ranges;
+    for (int64_t lo = 0; lo < b->n; lo += step) ranges.push_back({ lo, (b->n - lo < step) ? (b->n - lo) : step });
+    if (ranges.size() >= 2 && ranges.back().second >= 65536) {
+        const auto last = ranges.back();
+        const int64_t half = (last.second / 2 + 127) / 128 * 128;
+        ranges.back() = { last.first, half };
+        ranges.push_back({ last.first + half, last.second - half });
+    }
+    int rc = ensure_events(d, 2 * ranges.size());
+    if (rc != GCS_OK) return rc;
+    for (const auto& range : ranges) {
+        const int64_t lo = range.first, len = range.second;
         const size_t m = (size_t)len;
-        // up
-        for (int c = 0; c < nin; ++c)
-            CUDA_TRY(cudaMemcpyAsync(din[c] + lo, b->in[c] + lo, m * 8, cudaMemcpyHostToDevice, d->h2d));
+        trace_mark(d->h2d, "up-begin", b->kind, lo);
+        // up: columns that sit at a constant spacing in host memory (one [cols][n] slab) go up as
+        // one strided copy, anything else column by column
+        for (int c = 0; c < nin;) {
+            const int run = in_runs[c];
+            if (run > 1) {
+                CUDA_TRY(cudaMemcpy2DAsync(din[c] + lo, colb, b->in[c] + lo, in_pitch, m * 8, (size_t)run,
+                    cudaMemcpyHostToDevice, d->h2d));
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(din[c] + lo, b->in[c] + lo, m * 8, cudaMemcpyHostToDevice, d->h2d));
+            }
+            c += run;
+        }
         CUDA_TRY(cudaMemcpyAsync(dcode + lo, b->code + lo, m, cudaMemcpyHostToDevice, d->h2d));
         if (b->guesses)
-            for (int pl = 0; pl < 2 * ns; ++pl)
-                CUDA_TRY(cudaMemcpyAsync(dguess + (size_t)pl * n + lo, b->guesses + (size_t)pl * n + lo, m * 8,
-                    cudaMemcpyHostToDevice, d->h2d));
-        cudaEvent_t up, done;
-        int rc = next_event(d, &up);
-        if (rc != GCS_OK) return rc;
+            CUDA_TRY(cudaMemcpy2DAsync(dguess + lo, n * 8, b->guesses + lo, n * 8, m * 8, (size_t)(2 * ns),
+                cudaMemcpyHostToDevice, d->h2d));
+        cudaEvent_t up = d->events[d->ev_next++], done = d->events[d->ev_next++];
         CUDA_TRY(cudaEventRecord(up, d->h2d));
+        trace_mark(d->h2d, "up-end", b->kind, lo);
         // solve
         CUDA_TRY(cudaStreamWaitEvent(d->stream, up, 0));
         BatchDev p;
@@ -497,28 +594,44 @@ int enqueue_host(DeviceState* d, const gcs_b200_batch* b)
         p.stride = b->n;
         rc = solve_dev(d, b, p, d->stream);
         if (rc != GCS_OK) return rc;
-        rc = next_event(d, &done);
-        if (rc != GCS_OK) return rc;
         CUDA_TRY(cudaEventRecord(done, d->stream));
+        trace_mark(d->stream, "solved", b->kind, lo);
         // down
         CUDA_TRY(cudaStreamWaitEvent(d->d2h, done, 0));
-        for (int c = 0; c < nout; ++c)
-            CUDA_TRY(cudaMemcpyAsync(b->out[c] + lo, dout[c] + lo, m * 8, cudaMemcpyDeviceToHost, d->d2h));
-        if (b->cand)
-            for (int pl = 0; pl < 2 * ns; ++pl)
-                CUDA_TRY(cudaMemcpyAsync(b->cand + (size_t)pl * n + lo, dcand + (size_t)pl * n + lo, m * 8,
+        for (int c = 0; c < nout;) {
+            const int run = out_runs[c];
+            if (run > 1) {
+                CUDA_TRY(cudaMemcpy2DAsync(b->out[c] + lo, out_pitch, dout[c] + lo, colb, m * 8, (size_t)run,
                     cudaMemcpyDeviceToHost, d->d2h));
-        for (int k = 0; k < ns; ++k) {
-            if (b->iters)
-                CUDA_TRY(cudaMemcpyAsync(b->iters + (size_t)k * n + lo, diters + (size_t)k * n + lo, m * 2,
-                    cudaMemcpyDeviceToHost, d->d2h));
-            if (b->converged)
-                CUDA_TRY(cudaMemcpyAsync(b->converged + (size_t)k * n + lo, dconv + (size_t)k * n + lo, m,
-                    cudaMemcpyDeviceToHost, d->d2h));
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(b->out[c] + lo, dout[c] + lo, m * 8, cudaMemcpyDeviceToHost, d->d2h));
+            }
+            c += run;
         }
+        if (b->cand)
+            CUDA_TRY(cudaMemcpy2DAsync(b->cand + lo, n * 8, dcand + lo, n * 8, m * 8, (size_t)(2 * ns),
+                cudaMemcpyDeviceToHost, d->d2h));
+        if (b->iters)
+            CUDA_TRY(cudaMemcpy2DAsync(b->iters + lo, n * 2, diters + lo, n * 2, m * 2, (size_t)ns, cudaMemcpyDeviceToHost, d->d2h));
+        if (b->converged)
+            CUDA_TRY(cudaMemcpy2DAsync(b->converged + lo, n, dconv + lo, n, m, (size_t)ns, cudaMemcpyDeviceToHost, d->d2h));
         if (b->root_index) CUDA_TRY(cudaMemcpyAsync(b->root_index + lo, droot + lo, m, cudaMemcpyDeviceToHost, d->d2h));
     }
+    trace_mark(d->d2h, "flags-end", b->kind, -1);
     return GCS_OK;
+}
+
+// arena_mu held, device current
+int enqueue_host(DeviceState* d, const gcs_b200_batch* b)
+{
+    const size_t need = arena_need(b);
+    int rc = reserve_arena(d, need);
+    if (rc != GCS_OK) return rc;
+    const size_t off = d->arena_used;
+    rc = record_pipeline(d, b, off);
+    d->arena_used = off + need;
+    d->in_flight = true;
+    return rc;
 }
 
 int host_entry(const gcs_b200_batch* b, int device, bool wait)

@@ -317,16 +317,14 @@ def main():
     keep = []
     e2e_batches = []
     for h in host:
-        cols = []
-        for c in h.cols:
-            t, v = pin_like(c); keep.append(t); cols.append(v)
+        # one pinned [columns][n] slab per direction: the library moves such slabs with strided copies
+        t, slab = pin_like(np.stack(h.cols)); keep.append(t)
+        cols = [slab[c] for c in range(slab.shape[0])]
         t, code = pin_like(h.code); keep.append(t)
         hb = capi.HostBatch(h.kind, h.n_seeds, cols, code, None, args.variant, want_cand=False)
         m = hb.n
-        outs = []
-        for _ in range(capi.OUT_COLS[h.kind]):
-            t, v = pin_like(np.zeros(m)); keep.append(t); outs.append(v)
-        hb.out = outs
+        t, oslab = pin_like(np.zeros((capi.OUT_COLS[h.kind], m))); keep.append(t)
+        hb.out = [oslab[c] for c in range(oslab.shape[0])]
         t, hb.iters = pin_like(np.zeros((h.n_seeds, m), np.int16)); keep.append(t)
         t, hb.converged = pin_like(np.zeros((h.n_seeds, m), np.uint8)); keep.append(t)
         t, hb.root_index = pin_like(np.zeros(m, np.uint8)); keep.append(t)
