@@ -152,7 +152,7 @@ template <int KIND, int NS>
 int launch_static(const BatchDev& p, cudaStream_t st)
 {
     const long long threads = p.n * NS;
-    const int block = 128;
+    static const int block = getenv("GCS_STATIC_BLOCK") ? atoi(getenv("GCS_STATIC_BLOCK")) : 128;  // tuning knob (multiple of 32)
     const long long grid = (threads + block - 1) / block;
     if (grid > 0x7fffffffLL) return fail(GCS_E_INVALID, "batch too large for one launch");
     newton_static_kernel<KIND, NS><<<(unsigned)grid, block, 0, st>>>(p);

@@ -244,9 +244,9 @@ __global__ void __launch_bounds__(WARPS * 32)
 
         // ---- Newton phase with lane refill ----
         int next = 0;  // warp-uniform
-        bool active = false;
+        bool active = false, cv = false;
         int slot_seed = 0, slot_sub = 0, it = 0;
-        double x = 1.0, y = 1.0, px = 1.0, py = 1.0;
+        double x = 1.0, y = 1.0;
         S sys;
         {
             double z[S::kCols];
@@ -256,16 +256,12 @@ __global__ void __launch_bounds__(WARPS * 32)
         }
 #pragma unroll 1
         for (;;) {
-            if (active) {
-                const bool hit_cap = it >= kMaxIt;
-                const bool conv = !hit_cap && fabs(px - x) < kTol && fabs(py - y) < kTol;
-                if (hit_cap || conv) {
-                    sl.cx[slot_seed][slot_sub] = x;
-                    sl.cy[slot_seed][slot_sub] = y;
-                    sl.it[slot_seed][slot_sub] = (int16_t)it;
-                    sl.cv[slot_seed][slot_sub] = (uint8_t)conv;
-                    active = false;
-                }
+            if (active && (cv || it >= kMaxIt)) {
+                sl.cx[slot_seed][slot_sub] = x;
+                sl.cy[slot_seed][slot_sub] = y;
+                sl.it[slot_seed][slot_sub] = (int16_t)it;
+                sl.cv[slot_seed][slot_sub] = (uint8_t)(cv && it < kMaxIt);
+                active = false;
             }
             const unsigned need = __ballot_sync(kFull, !active);
             if (need) {
@@ -287,11 +283,12 @@ __global__ void __launch_bounds__(WARPS * 32)
                         } else {
                             default_seed(slot_seed, x, y);
                         }
-                        px = 0.0, py = 0.0, it = 0;
+                        it = 0;
                         // iteration 0 of the reference loop compares the guess with prev = (0,0)
                         // (newton_raphson.hpp:58, :83-88): a guess inside the tolerance box leaves
                         // at once, unchanged
-                        if (fabs(px - x) < kTol && fabs(py - y) < kTol) {
+                        cv = fabs(0.0 - x) < kTol && fabs(0.0 - y) < kTol;
+                        if (cv) {
                             sl.cx[slot_seed][slot_sub] = x;
                             sl.cy[slot_seed][slot_sub] = y;
                             sl.it[slot_seed][slot_sub] = 0;
@@ -306,11 +303,11 @@ __global__ void __launch_bounds__(WARPS * 32)
                     continue;  // every fresh run left at iteration 0; hand out the next ones
                 }
             }
-            double s0, s1;
-            newton_step<KIND>(sys, x, y, s0, s1);
+            double nx, ny;
+            newton_update<KIND>(sys, x, y, nx, ny);
             if (active) {
-                px = x, py = y;
-                x += s0, y += s1;
+                cv = fabs(x - nx) < kTol && fabs(y - ny) < kTol;
+                x = nx, y = ny;
                 ++it;
             }
         }

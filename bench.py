@@ -176,8 +176,11 @@ def cpu_rate(gcs, seconds, threads=0):
     K1/K5 mix), repeated until about `seconds` of wall time have been spent."""
     synth = gcs.synth
     kind, solve, cores, what = cpu_backend()
-    if threads > 0:
-        cores = threads
+    if threads < 1:
+        # every core this process may run on (torchrun exports OMP_NUM_THREADS=1; the CPU arm is
+        # meant to use the whole host)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = threads
     m = 1 << 15
     bs = [synth.make_pp(m).alloc_outputs(), synth.make_ang(m).alloc_outputs()]
     for b in bs:  # warm the threads and the pages

@@ -1,2 +1,3 @@
-for p in 1 4 8; do echo "PARTS $p"; GCS_B200_PARTS=$p python scratch/e2e_probe.py; done
-echo NOGRAPH; GCS_B200_NOGRAPH=1 GCS_B200_PARTS=4 python scratch/e2e_probe.py
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python scratch/kbench.py 1 1,2,3,4,5
+python scratch/kbench.py 2 1,5
