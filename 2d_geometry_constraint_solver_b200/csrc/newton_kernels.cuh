@@ -71,8 +71,10 @@ __global__ void __launch_bounds__(128, GCS_STATIC_MINB) newton_static_kernel(con
     } else {
         default_seed(seed, x, y);
     }
+    FastConsts fc;
+    fc.init((double)(p.n >> 62));  // 0.0 for every valid n, opaque to the compiler
     int it, conv;
-    newton_run<KIND>(sys, x, y, it, conv);
+    newton_run<KIND>(sys, fc, x, y, it, conv);
 
     // exchange candidates inside the NS-lane group
     const int lane = threadIdx.x & 31;
@@ -244,6 +246,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 
         // ---- Newton phase with lane refill ----
         int next = 0;  // warp-uniform
+        FastConsts fc;
+        fc.init((double)(p.n >> 62));
         bool active = false, cv = false;
         int slot_seed = 0, slot_sub = 0, it = 0;
         double x = 1.0, y = 1.0;
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(WARPS * 32)
                 }
             }
             double nx, ny;
-            newton_update<KIND>(sys, x, y, nx, ny);
+            newton_update<KIND>(sys, fc, x, y, nx, ny);
             if (active) {
                 cv = fabs(x - nx) < kTol && fabs(y - ny) < kTol;
                 x = nx, y = ny;
