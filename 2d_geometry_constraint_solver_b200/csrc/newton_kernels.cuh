@@ -308,11 +308,12 @@ __global__ void __launch_bounds__(WARPS * 32)
                 }
             }
             double nx, ny;
-            newton_update<KIND>(sys, fc, x, y, nx, ny);
+            int it_next = it;
+            newton_update<KIND>(sys, fc, x, y, nx, ny, it_next);
             if (active) {
                 cv = fabs(x - nx) < kTol && fabs(y - ny) < kTol;
                 x = nx, y = ny;
-                ++it;
+                it = it_next;
             }
         }
         __syncwarp();
