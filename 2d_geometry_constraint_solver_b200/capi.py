@@ -241,6 +241,26 @@ class DeviceBatch:
         self.root_index = torch.empty(n, dtype=torch.uint8, device=dev)
         self._cb = self._make_cbatch()
 
+    @classmethod
+    def empty(cls, kind, n_seeds, n, device, variant=VARIANT_DEFAULT, want_cand=False):
+        """Uninitialised device-resident batch (columns to be filled on the device)."""
+        import torch
+        self = cls.__new__(cls)
+        self.torch = torch
+        self.device = torch.device(device)
+        self.kind, self.n_seeds, self.variant, self.n = kind, n_seeds, variant, n
+        dev = self.device
+        self.cols = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(IN_COLS[kind])]
+        self.code = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.guesses = None
+        self.out = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(OUT_COLS[kind])]
+        self.cand = torch.empty((n_seeds, 2, n), dtype=torch.float64, device=dev) if want_cand else None
+        self.iters = torch.empty((n_seeds, n), dtype=torch.int16, device=dev)
+        self.converged = torch.empty((n_seeds, n), dtype=torch.uint8, device=dev)
+        self.root_index = torch.empty(n, dtype=torch.uint8, device=dev)
+        self._cb = self._make_cbatch()
+        return self
+
     def _make_cbatch(self):
         b = CBatch()
         b.kind, b.n_seeds, b.n, b.mem, b.variant = self.kind, self.n_seeds, self.n, MEM_DEVICE, self.variant

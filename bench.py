@@ -55,6 +55,10 @@ def parse():
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="solves per GPU (default 2^20)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="configs1", choices=["configs1", "multistart8", "sweep64m"],
+                    help="configs1 = the bench line (BASELINE configs[1]); multistart8 = configs[2] (2^20 K1 x 8 seeds per "
+                         "GPU, weak); sweep64m = configs[4] (2^26 perturbed K1 instances generated on the device, sharded "
+                         "over the ranks, strong)")
     return ap.parse_args()
 
 
@@ -223,6 +227,140 @@ def run_reference(args, rank):
 
 
 # --------------------------------------------------------------------------------------------
+# the other BASELINE configs that are benchmarks (not the driver's bench line)
+# --------------------------------------------------------------------------------------------
+def run_extra(args, rank, local_rank, world):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    gcs = importlib.import_module("2d_geometry_constraint_solver_b200")
+    capi, synth = gcs.capi, gcs.synth
+    shard = importlib.import_module("2d_geometry_constraint_solver_b200.shard")
+    capi.init([local_rank])
+    lib = capi.load()
+    warmup = max(args.warmup, 3)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    if args.workload == "multistart8":
+        n_total, scaling = (1 << 20) * world, "weak"
+        n = 1 << 20
+        hb = synth.make_pp(n, first=rank * n, n_seeds=8)
+        hb.variant = args.variant
+        db = capi.DeviceBatch(hb, dev, want_cand=False, variant=args.variant)
+        name = "configs[2]: 2^20 K1 clusters per GPU x 8 initial guesses, orientation-based root selection"
+        gen = None
+    else:
+        n_total, scaling = 1 << 26, "strong"
+        lo, hi = shard.shard_range(n_total, rank, world)
+        n = hi - lo
+        hb = synth.make_pp(1)  # descriptor template; the columns are generated on the device
+        db = capi.DeviceBatch.empty(capi.KIND_PP, 2, n, dev, variant=args.variant)
+        ptrs = (C.c_void_p * 6)(*[c.data_ptr() for c in db.cols])
+
+        def gen():
+            capi.check(lib.gcs_b200_synth_pp(local_rank, C.c_void_p(stream.cuda_stream), synth.BASE_SEED, lo, n, 4096, ptrs,
+                                             C.c_void_p(db.code.data_ptr())), "gcs_b200_synth_pp")
+        gen()
+        name = ("configs[4]: parametric sweep, 2^26 K1 instances = 4096 base clusters x 16384 perturbations (+-5% on ra, rb, d), "
+                "generated on the device, sharded by index over the ranks")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        flush.fill_(1)
+        db.solve()
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = lib.gcs_b200_launch_count()
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        evs[k][0].record(stream)
+        db.solve()
+        evs[k][1].record(stream)
+    barrier()
+    launches = lib.gcs_b200_launch_count() - l0
+    ms = np.array([a.elapsed_time(b) for a, b in evs])
+    t = torch.tensor([float(ms.sum())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = n_total * args.steps / (total_ms * 1e-3)
+    # work of this rank's launch from its measured iteration counts (device-side reduction)
+    it = db.iters
+    w = float((it.to(torch.int64) + 1).sum().item()) * synth.F_EVAL[1] + n * synth.F_SELECT[1]
+    ach = w / (float(ms.mean()) * 1e-3) / 1e12
+    conv = float(db.converged.to(torch.float32).mean().item())
+    # end to end: generation (sweep) or pinned H2D (multi-start), solve, results back to pinned host memory
+    e2e_steps = max(3, min(args.steps, 10))
+    if gen is None:
+        keep = []
+        slab = torch.empty((6, n), dtype=torch.float64, pin_memory=True); slab.numpy()[...] = np.stack(hb.cols)
+        code = torch.empty(n, dtype=torch.uint8, pin_memory=True); code.numpy()[...] = hb.code
+        oslab = torch.empty((2, n), dtype=torch.float64, pin_memory=True)
+        its = torch.empty((8, n), dtype=torch.int16, pin_memory=True)
+        cvs = torch.empty((8, n), dtype=torch.uint8, pin_memory=True)
+        root = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        keep += [slab, code, oslab, its, cvs, root]
+        eb = capi.HostBatch(1, 8, [slab.numpy()[c] for c in range(6)], code.numpy(), None, args.variant, want_cand=False)
+        eb.out = [oslab.numpy()[c] for c in range(2)]
+        eb.iters, eb.converged, eb.root_index, eb.cand = its.numpy(), cvs.numpy(), root.numpy(), None
+
+        def e2e_step():
+            capi.solve_host(eb, local_rank)
+        h2d, d2h = 6 * 8 * n + n, 2 * 8 * n + 8 * 3 * n + n
+    else:
+        outs = [torch.empty(n, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        roots = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+
+        def e2e_step():
+            gen()
+            db.solve()
+            for o, dcol in zip(outs, db.out):
+                o.copy_(dcol, non_blocking=True)
+            roots.copy_(db.root_index, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        h2d, d2h = 0, 17 * n
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    et = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        dfma = lib.gcs_b200_fp64_probe(local_rank, 0)
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "solves_total": n_total, "solves_rank0": n, "l2": "256 MiB flush write between timed steps",
+                       "converged_fraction_rank0": conv, "mean_iters_per_seed_rank0": float(it.to(torch.float32).mean().item())},
+            "e2e": {"value": n_total * e2e_steps / float(et.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "gcs_b200_solve_host (pinned)" if gen is None else "gcs_b200_synth_pp + gcs_b200_solve + D2H of (x, y, root) to pinned memory"},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": lib.gcs_b200_kernel_name(1, 8 if gen is None else 2, args.variant).decode(), "bound": "fp64",
+                         "achieved": ach, "peak": dfma, "unit": "TFLOP/s", "frac": ach / dfma if dfma > 0 else None, "traffic": None,
+                         "algorithmic_flops_per_launch_rank0": w},
+            "cpu_baseline": None,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -230,6 +368,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload != "configs1":
+        run_extra(args, rank, local_rank, world)
         return
 
     import torch

@@ -382,10 +382,13 @@ static const double k_default_seeds[GCS_MAX_SEEDS][2] = {
     { -20000.0, -20000.0 },
     { 20000.0, -20000.0 },
     { -20000.0, 20000.0 },
-    { 28284.271247461902, 0.0 },
-    { 0.0, 28284.271247461902 },
-    { -28284.271247461902, 0.0 },
-    { 0.0, -28284.271247461902 },
+    /* multi-start extension: radius ~20000*sqrt(2) at 22.5 deg + k*90 deg.  Off the axes on
+     * purpose: an anchored triangle has both fixed points on y = 0, where the distance-distance
+     * Jacobian is singular, and a seed on that line crawls for hundreds of iterations */
+    { 26131.0, 10824.0 },
+    { -10824.0, 26131.0 },
+    { -26131.0, -10824.0 },
+    { 10824.0, -26131.0 },
 };
 
 /* nearest-to-canvas among the candidates; with two candidates this is
