@@ -1,11 +1,14 @@
 // capi_host.cpp — plain-C entry points over the C++ host mirror, for bindings and tests
 // (ctypes in tests/host_lib.py).  The element / edge records have the layout of the records in
 // oracle/ref_driver.cpp, so the same fixture drives the reference build and this library.
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <exception>
 #include <memory>
+#include <stdexcept>
+#include <unordered_map>
 #include <vector>
 
 #include <gcs/b200/leaf_batch.hpp>
@@ -254,19 +257,122 @@ GCS_API int gcs_host_solve2d(int pair, const double* p, const double* guesses, d
     }
 }
 
-// GeometricConstraintSystem with the top-down strategy on a single 3-element sketch
-// (BASELINE config 1: the whole pipeline check -> decompose -> solveGcs).
-GCS_API int gcs_host_system_solve(int n_el, gcs_host_element* el, int n_edges, const gcs_host_edge* edges)
+// GeometricConstraintSystem with the top-down strategy on a whole sketch: constrainedness check,
+// decomposition (a 3-element sketch is its own leaf - BASELINE config 1; larger Henneberg-style
+// sketches go through the degree-2 peeling of gcs/b200/peel_decomposition.hpp - config 4), then
+// the batched solveGcs.  stats (may be NULL): [0] leaves, [1] waves, [2] launches, [3] solved,
+// [4] microseconds in check + decomposition, [5] microseconds in solveGcs.
+GCS_API int gcs_host_system_solve_ex(int n_el, gcs_host_element* el, int n_edges, const gcs_host_edge* edges, int64_t* stats)
 {
     try {
         std::vector<std::shared_ptr<Gcs::Element>> elems;
-        std::vector<int32_t> local;
-        for (int i = 0; i < n_el; ++i) elems.push_back(makeElement(el[i])), local.push_back(i);
-        Gcs::ConstraintGraph g = makeLeaf(elems, local.data(), n_el, edges, n_edges);
-        Gcs::GeometricConstraintSystem sys(std::make_unique<Gcs::DeficitStreeBasedTopDownStrategy>());
-        sys.solveGeometricConstraintSystem(g);
+        Gcs::ConstraintGraph g;
+        std::vector<Gcs::ConstraintGraph::NodeIdType> nodes;
+        elems.reserve(static_cast<std::size_t>(n_el));
+        for (int i = 0; i < n_el; ++i) {
+            elems.push_back(makeElement(el[i]));
+            nodes.push_back(g.getGraph().addNode());
+            g.addElement(nodes.back(), elems.back());
+        }
+        for (int k = 0; k < n_edges; ++k) {
+            const auto& ed = edges[k];
+            const auto a = nodes.at(static_cast<std::size_t>(ed.a)), b = nodes.at(static_cast<std::size_t>(ed.b));
+            if (ed.type == 2) {
+                g.addVirtualEdge(a, b);
+                continue;
+            }
+            const auto eid = g.getGraph().addEdge(a, b).value();
+            if (ed.type == 0)
+                g.addConstraint(eid, std::make_shared<Gcs::Constraint>(Gcs::DistanceConstraint(ed.value)));
+            else
+                g.addConstraint(eid, std::make_shared<Gcs::Constraint>(Gcs::AngleConstraint(ed.value, ed.flip != 0)));
+        }
+        // the three steps of GeometricConstraintSystem::solveGeometricConstraintSystem, timed apart
+        auto strategy = std::make_unique<Gcs::DeficitStreeBasedTopDownStrategy>();
+        Gcs::DeficitStreeBasedTopDownStrategy* st = strategy.get();
+        const auto t0 = std::chrono::steady_clock::now();
+        if (st->checkConstraintGraphConstrainedness(g) != Gcs::Constrainedness::WELL_CONSTRAINED && !st->resolve(g))
+            throw std::runtime_error("Gcs is not well-constrained, current algorithms do not support such inputs");
+        auto leaves = st->decomposeConstraintGraph(g);
+        const auto t1 = std::chrono::steady_clock::now();
+        st->solveGcs(leaves);
+        const auto t2 = std::chrono::steady_clock::now();
+        if (stats) {
+            const auto& rep = st->lastReport();
+            stats[0] = static_cast<int64_t>(rep.leaves), stats[1] = static_cast<int64_t>(rep.waves);
+            stats[2] = static_cast<int64_t>(rep.launches), stats[3] = static_cast<int64_t>(rep.solved);
+            stats[4] = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+            stats[5] = std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
+        }
         for (int i = 0; i < n_el; ++i) readBack(*elems[static_cast<std::size_t>(i)], el[i]);
         return 0;
+    } catch (const std::exception& ex) {
+        return fail(ex);
+    }
+}
+
+GCS_API int gcs_host_system_solve(int n_el, gcs_host_element* el, int n_edges, const gcs_host_edge* edges)
+{
+    // through the class itself (the timed variant above repeats its three calls)
+    if (n_el == 3) {
+        try {
+            std::vector<std::shared_ptr<Gcs::Element>> elems;
+            std::vector<int32_t> local;
+            for (int i = 0; i < n_el; ++i) elems.push_back(makeElement(el[i])), local.push_back(i);
+            Gcs::ConstraintGraph g = makeLeaf(elems, local.data(), n_el, edges, n_edges);
+            Gcs::GeometricConstraintSystem sys(std::make_unique<Gcs::DeficitStreeBasedTopDownStrategy>());
+            sys.solveGeometricConstraintSystem(g);
+            for (int i = 0; i < n_el; ++i) readBack(*elems[static_cast<std::size_t>(i)], el[i]);
+            return 0;
+        } catch (const std::exception& ex) {
+            return fail(ex);
+        }
+    }
+    return gcs_host_system_solve_ex(n_el, el, n_edges, edges, nullptr);
+}
+
+// Decomposition only (no device): leaf count and, per leaf, its three element indices in node
+// order (leaf_elems, 3 per leaf, capacity given in leaves) - for tests.  Returns the number of
+// leaves or -1.
+GCS_API int gcs_host_decompose(int n_el, const gcs_host_element* el, int n_edges, const gcs_host_edge* edges, int32_t* leaf_elems,
+    int32_t* leaf_virtual, int32_t* leaf_real, int capacity)
+{
+    try {
+        std::vector<std::shared_ptr<Gcs::Element>> elems;
+        Gcs::ConstraintGraph g;
+        std::vector<Gcs::ConstraintGraph::NodeIdType> nodes;
+        std::unordered_map<const Gcs::Element*, int32_t> indexOf;
+        for (int i = 0; i < n_el; ++i) {
+            elems.push_back(makeElement(el[i]));
+            indexOf[elems.back().get()] = i;
+            nodes.push_back(g.getGraph().addNode());
+            g.addElement(nodes.back(), elems.back());
+        }
+        for (int k = 0; k < n_edges; ++k) {
+            const auto& ed = edges[k];
+            const auto a = nodes.at(static_cast<std::size_t>(ed.a)), b = nodes.at(static_cast<std::size_t>(ed.b));
+            if (ed.type == 2) {
+                g.addVirtualEdge(a, b);
+                continue;
+            }
+            const auto eid = g.getGraph().addEdge(a, b).value();
+            if (ed.type == 0)
+                g.addConstraint(eid, std::make_shared<Gcs::Constraint>(Gcs::DistanceConstraint(ed.value)));
+            else
+                g.addConstraint(eid, std::make_shared<Gcs::Constraint>(Gcs::AngleConstraint(ed.value, ed.flip != 0)));
+        }
+        Gcs::DeficitStreeBasedTopDownStrategy st;
+        const auto leaves = st.decomposeConstraintGraph(g);
+        int l = 0;
+        for (const auto& leaf : leaves) {
+            if (l >= capacity) break;
+            int k = 0;
+            for (const auto& [node, e] : leaf.getElementMap()) leaf_elems[3 * l + k++] = indexOf.at(e.get());
+            leaf_virtual[l] = static_cast<int32_t>(leaf.getVirtualEdges().size());
+            leaf_real[l] = static_cast<int32_t>(leaf.getConstraintMap().size());
+            ++l;
+        }
+        return static_cast<int>(leaves.size());
     } catch (const std::exception& ex) {
         return fail(ex);
     }

@@ -2,6 +2,7 @@
 // src/constraint_solver/src/decomposition/top_down/stree_top_down_strategy.cpp:12-45).
 #include <stdexcept>
 
+#include <gcs/b200/peel_decomposition.hpp>
 #include <gcs/decomposition/top_down/stree_top_down_strategy.hpp>
 
 namespace Gcs {
@@ -21,9 +22,9 @@ std::vector<ConstraintGraph> DeficitStreeBasedTopDownStrategy::decomposeConstrai
 {
     // A triconnected 3-element graph is its own single leaf (stree_top_down_strategy.cpp:54-57).
     if (gcs.nodeCount() == 3) return { gcs };
-    throw std::runtime_error("DeficitStreeBasedTopDownStrategy::decomposeConstraintGraph: the S-tree decomposition "
-                             "(OGDF separation pairs) is host graph work outside the accelerated path; pass the leaf "
-                             "components to solveGcs directly");
+    // Otherwise: the reference's split rules applied to degree-2 separation pairs (no OGDF here);
+    // throws for graphs that need general separation pairs.
+    return B200::decomposeByPeeling(gcs);
 }
 
 void DeficitStreeBasedTopDownStrategy::solveGcs(std::vector<ConstraintGraph>& splitComponents)
