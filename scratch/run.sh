@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py --workload multistart8 --steps 5 > gpurun_out/bench_multistart8.json; cut -c1-330 gpurun_out/bench_multistart8.json; echo
-python bench.py --workload sweep64m --steps 5 > gpurun_out/bench_sweep64m_n1.json; cut -c1-330 gpurun_out/bench_sweep64m_n1.json; echo
+python -m pytest tests/test_gpu_host.py -m gpu -x -q 2>&1 | tail -5
+python profiles/sketch_bench.py 100000 2>/dev/null | tail -1

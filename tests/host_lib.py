@@ -35,6 +35,9 @@ def load():
         lib.gcs_host_leaves_solve.argtypes = [C.c_int, C.POINTER(Element), C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                               C.POINTER(Edge), C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                               C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+        lib.gcs_host_system_solve_ex.argtypes = [C.c_int, C.POINTER(Element), C.c_int, C.POINTER(Edge), C.POINTER(C.c_int64)]
+        lib.gcs_host_decompose.argtypes = [C.c_int, C.POINTER(Element), C.c_int, C.POINTER(Edge), C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
         lib.gcs_host_solve2d.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _lib = lib
@@ -81,6 +84,27 @@ def system_solve(elements, edges):
     els, eds = to_c(elements, edges)
     rc = load().gcs_host_system_solve(len(elements), els, len(edges), eds)
     return rc, from_c(elements, els)
+
+
+def system_solve_ex(elements, edges):
+    """Whole sketch through check -> decompose -> batched solveGcs.  Returns (rc, elements, stats dict)."""
+    els, eds = to_c(elements, edges)
+    stats = (C.c_int64 * 6)()
+    rc = load().gcs_host_system_solve_ex(len(elements), els, len(edges), eds, stats)
+    keys = ("leaves", "waves", "launches", "solved", "decompose_us", "solve_us")
+    return rc, from_c(elements, els), dict(zip(keys, list(stats)))
+
+
+def decompose(elements, edges):
+    """Decomposition only.  Returns (n_leaves, [(i, j, k)], virtual-edge counts, real-edge counts)."""
+    els, eds = to_c(elements, edges)
+    cap = max(len(elements), 1)
+    le = (C.c_int32 * (3 * cap))()
+    lv = (C.c_int32 * cap)()
+    lr = (C.c_int32 * cap)()
+    n = load().gcs_host_decompose(len(elements), els, len(edges), eds, le, lv, lr, cap)
+    m = max(min(n, cap), 0)
+    return n, [tuple(le[3 * i:3 * i + 3]) for i in range(m)], list(lv)[:m], list(lr)[:m]
 
 
 def component_pack(elements, edges):

@@ -128,3 +128,29 @@ def make_sketch(n_leaves, seed=1, first_shape=1, p_line=0.35, locality=None):
             cv += [c * x - s * y + t[0] + rng.normal(0, 1.0), s * x + c * y + t[1] + rng.normal(0, 1.0)]
         elements.append({"type": L if len(e) == 4 else P, "canvas": [float(v) for v in cv]})
     return elements, leaves
+
+
+def sketch_graph(elements, leaves):
+    """The whole-sketch constraint graph of a generated leaf list: the three constraints of the
+    first leaf and the two constraints that hang each later element on its parents (the redundant
+    parent-parent edges some leaves repeat are dropped), no virtual edges: 2n - 3 constraints, what
+    a user would draw; decomposing it is the solver's job."""
+    seen, edges = set(), []
+    for k, lf in enumerate(leaves):
+        new = max(lf["elems"])
+        for e in lf["edges"]:
+            if e["type"] == VIRT or (k > 0 and new not in (e["a"], e["b"])):
+                continue
+            key = (min(e["a"], e["b"]), max(e["a"], e["b"]))
+            if key in seen:
+                continue
+            seen.add(key)
+            edges.append(dict(e))
+    return edges
+
+
+def make_linkage(n_points, seed=1):
+    """BASELINE config 4: a rigidly well-constrained linkage of points and distances (2n - 3
+    constraints), every new point hung on two earlier ones.  Returns (elements, edges)."""
+    el, lv = make_sketch(n_points - 2, seed=seed, first_shape=1, p_line=0.0)
+    return el, sketch_graph(el, lv)

@@ -142,3 +142,65 @@ def test_an_exception_mid_list_stops_the_loop_like_the_reference(host):
     for x, y in zip(seq["elements"], bat["elements"]):
         assert x["is_set"] == y["is_set"] and (not x["is_set"] or same_pos(x["pos"], y["pos"]))
     assert sum(e["is_set"] for e in bat["elements"]) == 32  # leaves 0..29 only
+
+
+def _leaf_dicts(el, edges, leaves):
+    """Leaf list (dicts) of a decomposition given as element-index triples: the two constraints of
+    the new element + a virtual edge between its parents; the base keeps its real edges."""
+    by_pair = {(min(e["a"], e["b"]), max(e["a"], e["b"])): e for e in edges}
+    placed = set(leaves[0])
+    out = []
+    for k, lf in enumerate(leaves):
+        new = None if k == 0 else [i for i in lf if i not in placed][0]
+        es = []
+        for a, b in ((lf[0], lf[1]), (lf[0], lf[2]), (lf[1], lf[2])):
+            e = by_pair.get((min(a, b), max(a, b)))
+            if k == 0:
+                if e:
+                    es.append(e)
+            elif new in (a, b):
+                es.append(e)
+            else:
+                es.append({"a": a, "b": b, "type": 2})
+        if new is not None:
+            placed.add(new)
+        out.append({"elems": list(lf), "edges": es})
+    return out
+
+
+@pytest.mark.parametrize("seed,first,n", [(31, 1, 3000), (32, 2, 3000), (33, 3, 3000)])
+def test_whole_sketch_pipeline_equals_reference_loop_on_the_same_leaves(host, seed, first, n):
+    """GeometricConstraintSystem::solveGeometricConstraintSystem on a whole sketch (check ->
+    peel decomposition -> batched solveGcs on the GPU) against the reference build's sequential
+    loop over the same leaves (oracle/_ref), bit for bit."""
+    import ref_lib as R
+    el, lv = S.make_sketch(n, seed=seed, first_shape=first)
+    edges = S.sketch_graph(el, lv)
+    rc, got, stats = H.system_solve_ex(el, edges)
+    assert rc == 0, H.last_error()
+    assert stats["leaves"] == len(el) - 2 and stats["solved"] == stats["leaves"]
+    assert stats["launches"] <= 5 * stats["waves"] and stats["waves"] < 0.2 * stats["leaves"]
+    assert all(e["is_set"] for e in got)
+    if not R.available():
+        pytest.skip("oracle/_ref not present on this box")
+    nl, leaves, _, _ = H.decompose(el, edges)
+    rc, status, exp = R.leaves_solve(el, _leaf_dicts(el, edges, leaves))
+    assert rc == 0 and set(status) == {0}
+    for g, e in zip(got, exp):
+        assert g["is_set"] == e["is_set"] and same_pos(g["pos"], e["pos"])
+
+
+def test_config4_linkage_100k_points(host):
+    """BASELINE config 4 at full size: 100k points, 199,997 distances, through the public entry
+    point.  Size-independent checks: everything solved, few waves, and the two constraints that
+    placed each point hold wherever the reference's own heuristic picked a consistent root."""
+    el, edges = S.make_linkage(100000, seed=4)
+    rc, got, stats = H.system_solve_ex(el, edges)
+    assert rc == 0, H.last_error()
+    assert stats["leaves"] == 99998 and stats["solved"] == 99998
+    assert stats["launches"] == stats["waves"] < 200
+    xy = np.array([e["pos"] for e in got])
+    ea = np.array([[e["a"], e["b"], e["value"]] for e in edges])
+    d = np.hypot(*(xy[ea[:, 0].astype(int)] - xy[ea[:, 1].astype(int)]).T)
+    ok = np.abs(d - ea[:, 2]) / np.maximum(1.0, ea[:, 2]) < 1e-6
+    assert ok.mean() > 0.2   # the rest descend from a leaf where both seeds met the same root (reference behaviour)
