@@ -4,10 +4,10 @@
 //
 // solveGcs is the accelerated entry point: the reference's sequential
 // `for_each(leaves, classifyAndSolve)` becomes Gcs::B200::solveLeaves (same final element state,
-// one kernel launch per equation kind per dependency wave).  The S-tree decomposition itself is
-// host graph work on OGDF and out of scope for this path; decomposeConstraintGraph accepts what
-// needs no splitting (a single 3-element component) and otherwise asks the caller to supply the
-// leaves (e.g. from the reference's own decomposition).
+// one kernel launch per equation kind per dependency wave).  decomposeConstraintGraph applies the
+// reference's S-tree split rules to degree-2 separation pairs (gcs/b200/peel_decomposition.hpp;
+// OGDF is not available here): Henneberg-style sketches decompose completely, graphs that need
+// general separation pairs throw - supply their leaves from the reference's own decomposition.
 #pragma once
 
 #include <vector>
