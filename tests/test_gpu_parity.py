@@ -344,3 +344,20 @@ def test_multistart_full_size_1m_x_8(gpu, gcs):
     O.solve(sub.alloc_outputs())
     assert np.array_equal(sub.iters, db.iters.cpu().numpy()[:, idx])
     assert np.array_equal(sub.root_index, db.root_index.cpu().numpy()[idx])
+
+
+def test_sharded_solve_over_all_devices_matches_single_device(gpu, gcs):
+    """gcs_b200_solve_sharded: one host thread + stream per device, contiguous index ranges,
+    D2H into disjoint slices.  On a one-GPU box this is the n_dev == 1 path; with more devices
+    (gpurun --gpus N) the shards really run on different GPUs."""
+    synth, capi = gcs.synth, gcs.capi
+    ndev = capi.load().gcs_b200_device_count()
+    capi.init(list(range(ndev)))
+    for kind, n in ((1, 100003), (5, 65537), (4, 7)):
+        a = synth.make(kind, n)
+        a.want_cand = False
+        capi.solve_sharded(a.alloc_outputs(), ndev)
+        b = synth.make(kind, n)
+        b.want_cand = False
+        capi.solve_host(b.alloc_outputs(), 0)
+        assert_batches_identical(a, b, f"sharded kind {kind} over {ndev} devices")
