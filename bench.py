@@ -87,6 +87,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.period = float(os.environ.get("GCS_BENCH_CLOCK_PERIOD", "0.001"))
         self._stop = threading.Event()
         self._in_region = False
         self.region = []
@@ -125,7 +126,7 @@ class ClockSampler:
                                 self.reasons.add(nm)
                 except Exception:
                     pass
-            time.sleep(0.001)
+            time.sleep(self.period)
 
     def start(self):
         self.t.start()
