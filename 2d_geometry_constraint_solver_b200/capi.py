@@ -31,7 +31,7 @@ IN_COL_NAMES = {
 }
 
 MEM_HOST, MEM_DEVICE = 0, 1
-VARIANT_DEFAULT, VARIANT_STATIC, VARIANT_REFILL = 0, 1, 2
+VARIANT_DEFAULT, VARIANT_STATIC, VARIANT_REFILL, VARIANT_SORTED, VARIANT_PAIR = 0, 1, 2, 3, 4
 
 CODE_COLLINEAR = 0x10
 CODE_CANVAS_PARALLEL = 0x20

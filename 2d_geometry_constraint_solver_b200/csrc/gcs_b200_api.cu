@@ -161,6 +161,29 @@ int launch_static(const BatchDev& p, cudaStream_t st)
     return GCS_OK;
 }
 
+template <int KIND>
+int launch_pair(const BatchDev& p, cudaStream_t st)
+{
+    const long long grid = (p.n + 127) / 128;
+    if (grid > 0x7fffffffLL) return fail(GCS_E_INVALID, "batch too large for one launch");
+    newton_pair_kernel<KIND><<<(unsigned)grid, 128, 0, st>>>(p);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCS_OK;
+}
+
+template <int KIND, int NS>
+int launch_sorted(const BatchDev& p, cudaStream_t st)
+{
+    constexpr int T = GCS_SORTED_THREADS, TILE = 2 * T / NS;  // two runs per lane
+    const long long grid = (p.n + TILE - 1) / TILE;
+    if (grid > 0x7fffffffLL) return fail(GCS_E_INVALID, "batch too large for one launch");
+    newton_sorted_kernel<KIND, NS, TILE, T><<<(unsigned)grid, T, 0, st>>>(p);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCS_OK;
+}
+
 template <int KIND, int NS>
 int launch_refill(DeviceState* d, const BatchDev& p, cudaStream_t st)
 {
@@ -199,9 +222,12 @@ int launch_kind(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cuda
     if (variant == GCS_VARIANT_DEFAULT) variant = kDefaultVariant;
     constexpr bool column_guess = (KIND == GCS_KIND_SDD || KIND == GCS_KIND_ANG);
     if (b->n_seeds == 2) {
+        if (variant == GCS_VARIANT_SORTED) return launch_sorted<KIND, 2>(p, st);
+        if (variant == GCS_VARIANT_PAIR) return launch_pair<KIND>(p, st);
         return variant == GCS_VARIANT_REFILL ? launch_refill<KIND, 2>(d, p, st) : launch_static<KIND, 2>(p, st);
     }
     if constexpr (!column_guess) {
+        if (variant == GCS_VARIANT_SORTED) return launch_sorted<KIND, 8>(p, st);
         return variant == GCS_VARIANT_REFILL ? launch_refill<KIND, 8>(d, p, st) : launch_static<KIND, 8>(p, st);
     }
     return fail(GCS_E_INVALID, "unsupported seed count");
@@ -357,8 +383,11 @@ const char* gcs_b200_kernel_name(int kind, int n_seeds, int variant)
 {
     static thread_local char name[96];
     if (variant == GCS_VARIANT_DEFAULT) variant = kDefaultVariant;
-    snprintf(name, sizeof(name), "%s<K%d,%d seeds>", variant == GCS_VARIANT_REFILL ? "newton_refill_kernel" : "newton_static_kernel",
-        kind, n_seeds);
+    const char* base = variant == GCS_VARIANT_REFILL ? "newton_refill_kernel"
+        : variant == GCS_VARIANT_SORTED              ? "newton_sorted_kernel"
+        : (variant == GCS_VARIANT_PAIR && n_seeds == 2) ? "newton_pair_kernel"
+                                                     : "newton_static_kernel";
+    snprintf(name, sizeof(name), "%s<K%d,%d seeds>", base, kind, n_seeds);
     return name;
 }
 

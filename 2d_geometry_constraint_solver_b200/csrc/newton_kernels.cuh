@@ -1,4 +1,4 @@
-// newton_kernels.cuh — the two kernel variants of the batched Newton-Raphson path (sm_100a).
+// newton_kernels.cuh — the kernel variants of the batched Newton-Raphson path (sm_100a).
 //
 //  newton_static_kernel : one lane per (sub-system, seed); the seeds of a sub-system sit in
 //      adjacent lanes, candidates are exchanged with warp shuffles and the group leader applies
@@ -15,10 +15,16 @@
 //      are parked in shared memory; after the chunk's runs drain, each lane selects the root for
 //      its sub-systems and writes all outputs with coalesced stores.
 //
-// Both produce bit-identical results (same device functions, same operation order per run).
+//  newton_sorted_kernel : one CTA per tile; after three updates every run's remaining updates are
+//      predicted from its step lengths, the tile's runs are sorted by the prediction and each
+//      lane finishes one run, so the lanes of a warp stop (almost) together.  See the kernel.
+//
+// All produce bit-identical results (same device functions, same operation order per run).
 #pragma once
 
 #include <cuda_runtime.h>
+
+#include <cstring>
 
 #include "newton_core.cuh"
 
@@ -38,6 +44,13 @@ struct BatchDev {
 };
 
 constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
 
 // ------------------------------------------------------------------------------------------
 // static variant
@@ -103,6 +116,293 @@ __global__ void __launch_bounds__(128, GCS_STATIC_MINB) newton_static_kernel(con
 }
 
 // ------------------------------------------------------------------------------------------
+// pair variant: one lane per sub-system, its two seeds iterated in lockstep (newton_run2)
+// ------------------------------------------------------------------------------------------
+#ifndef GCS_PAIR_MINB
+#define GCS_PAIR_MINB 1
+#endif
+template <int KIND>
+__global__ void __launch_bounds__(128, GCS_PAIR_MINB) newton_pair_kernel(const BatchDev p)
+{
+    using S = Sys<KIND>;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    double k[S::kCols];
+#pragma unroll
+    for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + i);
+    const uint8_t code = p.code ? __ldg(p.code + i) : (uint8_t)GCS_MAKE_CODE(0, 0, 0);
+    S sys;
+    sys.load(k);
+    double cx[2], cy[2];
+    if (p.guesses) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            cx[s] = __ldg(p.guesses + ((long long)s * 2 + 0) * p.stride + i);
+            cy[s] = __ldg(p.guesses + ((long long)s * 2 + 1) * p.stride + i);
+        }
+    } else if constexpr (S::kGuessFromCols) {
+        column_seed<KIND>(k, 0, cx[0], cy[0]);
+        column_seed<KIND>(k, 1, cx[1], cy[1]);
+    } else {
+        default_seed(0, cx[0], cy[0]);
+        default_seed(1, cx[1], cy[1]);
+    }
+    FastConsts fc;
+    fc.init((double)(p.n >> 62));
+    // iteration 0 compares the guess with prev = (0,0) (newton_raphson.hpp:58, :83-88)
+    bool cva = fabs(0.0 - cx[0]) < fc.tol && fabs(0.0 - cy[0]) < fc.tol;
+    bool cvb = fabs(0.0 - cx[1]) < fc.tol && fabs(0.0 - cy[1]) < fc.tol;
+    int ita = 0, itb = 0;
+    newton_run2<KIND>(sys, sys, fc, cx[0], cy[0], ita, cva, !cva, cx[1], cy[1], itb, cvb, !cvb);
+    if (p.iters) p.iters[i] = (int16_t)ita, p.iters[p.stride + i] = (int16_t)itb;
+    if (p.converged) p.converged[i] = (uint8_t)cva, p.converged[p.stride + i] = (uint8_t)cvb;
+    if (p.cand) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            p.cand[((long long)s * 2 + 0) * p.stride + i] = cx[s];
+            p.cand[((long long)s * 2 + 1) * p.stride + i] = cy[s];
+        }
+    }
+    double out[4];
+    const int root = select_and_finish<KIND, 2>(k, code, cx, cy, out);
+#pragma unroll
+    for (int c = 0; c < S::kOut; ++c) p.out[c][i] = out[c];
+    if (p.root) p.root[i] = (uint8_t)root;
+}
+
+// ------------------------------------------------------------------------------------------
+// sorted variant
+//
+// The static kernel loses lanes to the spread of iteration counts: a warp lasts as long as its
+// slowest run (K1 from the default guesses: mean 12.5 updates, mean warp maximum 16.2; K5: 5.3 vs
+// 10.3).  Re-packing the live runs after every update (tried: run state in shared memory, one
+// barrier per update) costs more than it recovers in an issue-bound kernel.  This kernel instead
+// PREDICTS each run's remaining updates once, sorts the runs of a CTA tile by the prediction and
+// lets every lane finish one run in registers, so the 32 runs of a warp need (almost) the same
+// number of updates and nothing is paid per update.
+//
+// Prediction.  Every equation pair of this path is one quadratic (a circle) plus an equation that
+// is linear (K2-K5) or becomes linear after subtracting the two (K1).  Newton's method is affine
+// covariant, so the first update lands on that line and from then on the run is the scalar
+// iteration w <- (w^2 + h^2) / (2w) for the coordinate w along the line, measured from the foot
+// point, with +-h the two roots.  In t = w/h = coth(theta) this is theta <- 2 theta: the step
+// after j more updates is h / sinh(2^(j+1) theta).  Two consecutive step lengths identify the
+// state: with s2, s3 the lengths of updates 2 and 3,  w2 = s2^2 / (2 s3),  h^2 = w2^2 - s2^2,
+// w3 = w2 - s3,  theta = ln((w3 + h) / s3),  and the run needs
+//         ceil(log2( ln(2h / tol) / theta ))
+// more updates.  Measured on the bench inputs: exact for 99.6 % of the runs, off by one for the
+// rest.  A wrong prediction costs time only: every run still iterates to the reference's own
+// convergence test, so results are bit-identical to the other variants.
+//
+// Phases, per CTA tile: (A) lane = run does the iteration-0 test and up to three updates (hardly
+// any run converges earlier, so nothing idles) and predicts; (B) counting sort of the live runs by
+// predicted updates (32 bins, warp-aggregated shared-memory atomics); (C) every lane takes runs in
+// sorted order and iterates each to the end in registers; (D) selection + write-back, coalesced.
+// ------------------------------------------------------------------------------------------
+constexpr int kSortBins = 32;
+
+// Remaining updates of a run from the squared lengths of its 2nd and 3rd update (see above).
+// d2 - 4 d3 is taken in FP64 (far from the root s3 ~ s2/2 and the difference carries h); the rest
+// is FP32 on the SFU.  Garbage in (a run that is not on its line yet, overflow) gives some bin:
+// harmless.
+__device__ __forceinline__ int predict_remaining(double d2, double d3)
+{
+    const float t = (float)__fma_rn(-4.0, d3, d2);
+    const float f2 = (float)d2, f3 = (float)d3;
+    const float r3 = rsqrtf(f3);
+    const float s3 = f3 * r3;         // |update 3|
+    const float w2 = 0.5f * f2 * r3;  // s2^2 / (2 s3)
+    const float hsq = 0.25f * (f2 * t) * (r3 * r3);
+    const float h = hsq * rsqrtf(hsq);
+    const float w3 = w2 - s3;
+    const float theta = __log2f((w3 + h) * r3);
+    const float span = __log2f(h * (float)(2.0 / kTol));
+    const float k = ceilf(__log2f(__fdividef(span, theta)));
+    int key = (k >= 1.0f) ? (int)fminf(k, (float)(kSortBins - 1)) : 1;
+    if (!(hsq > 0.0f)) key = kSortBins - 1;  // no real root in sight: put it with the long runs
+    return key;
+}
+
+#ifndef GCS_SORTED_THREADS
+#define GCS_SORTED_THREADS 128
+#endif
+#ifndef GCS_SORTED_MINB
+#define GCS_SORTED_MINB 6
+#endif
+
+// One CTA of THREADS lanes owns a tile of TILE sub-systems = RUNS = TILE*NS = 2*THREADS runs: two
+// runs per lane in every phase, so a CTA is as short-lived as two static warps and the grid stays
+// fine grained (many CTAs per SM slot), while the sort still sees 2*THREADS runs.  Inputs are not
+// staged: phase A reads the columns coalesced, phases C and D read them again through L1/L2 (C: a
+// gather inside the tile's 8*TILE bytes per column), which keeps shared memory at 22 bytes per run
+// and the occupancy where the register file puts it.  In phase C the sorted runs form 2*W blocks
+// of 32, longest first; warp w takes blocks w and 2W-1-w (a long one and a short one), so the
+// warps of the CTA reach the last barrier at about the same time.
+template <int KIND, int NS, int TILE, int THREADS>
+__global__ void __launch_bounds__(THREADS, GCS_SORTED_MINB) newton_sorted_kernel(const BatchDev p)
+{
+    using S = Sys<KIND>;
+    constexpr int RUNS = TILE * NS;
+    constexpr int W = THREADS / 32;
+    static_assert(RUNS == 2 * THREADS && THREADS % TILE == 0 && TILE % 32 == 0, "tile shape");
+    __shared__ double s_x[RUNS], s_y[RUNS];  // run state, then the candidates; run = seed*TILE + sub
+    __shared__ short s_it[RUNS];
+    __shared__ unsigned short s_order[RUNS];
+    __shared__ unsigned char s_cv[RUNS];
+    __shared__ int s_bin[kSortBins + 1];  // counts, then offsets; [kSortBins] = live runs
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const long long base = (long long)blockIdx.x * TILE;
+    const int cnt = (int)((p.n - base < TILE) ? (p.n - base) : TILE);
+    FastConsts fc;
+    fc.init((double)(p.n >> 62));  // 0.0 for every valid n, opaque to the compiler
+    if (tid <= kSortBins) s_bin[tid] = 0;
+    __syncthreads();
+
+    // ---- (A) iteration-0 test, three updates, prediction; this lane's runs: tid and tid + THREADS,
+    //      two seeds of one sub-system ----
+    int key[2] = { -1, -1 };  // sort key = kSortBins-1 - predicted updates; -1: finished / no run
+    {
+        const int sub = tid & (TILE - 1);
+        if (sub < cnt) {
+            const long long gi = base + sub;
+            double k[S::kCols];
+#pragma unroll
+            for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + gi);
+            S sys;
+            sys.load(k);
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {
+                const int r = tid + q * THREADS;
+                const int seed = r / TILE;
+                double x, y;
+                if (p.guesses) {
+                    x = __ldg(p.guesses + ((long long)seed * 2 + 0) * p.stride + gi);
+                    y = __ldg(p.guesses + ((long long)seed * 2 + 1) * p.stride + gi);
+                } else if constexpr (S::kGuessFromCols) {
+                    column_seed<KIND>(k, seed, x, y);
+                } else {
+                    default_seed(seed, x, y);
+                }
+                // iteration 0 compares the guess with prev = (0,0) (newton_raphson.hpp:58, :83-88)
+                bool conv = fabs(0.0 - x) < fc.tol && fabs(0.0 - y) < fc.tol;
+                int it = 0;
+                double d2 = 0.0, d3 = 0.0;
+#pragma unroll 1
+                for (int j = 0; j < 3 && !conv && it < kMaxIt; ++j) {
+                    double nx, ny;
+                    newton_update<KIND>(sys, fc, x, y, nx, ny, it);
+                    const double ex = x - nx, ey = y - ny;
+                    conv = fabs(ex) < fc.tol && fabs(ey) < fc.tol;
+                    d2 = d3;
+                    d3 = ex * ex + ey * ey;
+                    x = nx, y = ny;
+                }
+                s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
+                s_cv[r] = (conv && it < kMaxIt) ? 1 : 0;
+                if (!conv && it < kMaxIt) {
+                    const int kk = kSortBins - 1 - predict_remaining(d2, d3);
+                    atomicAdd(&s_bin[kk], 1);
+                    if (q == 0) key[0] = kk; else key[1] = kk;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- (B) counting sort of the live runs, longest predicted first ----
+    if (tid < 32) {
+        const int c = s_bin[lane];
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+        }
+        s_bin[lane] = incl - c;
+        if (lane == 31) s_bin[kSortBins] = incl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int kk = key[q];
+        const unsigned live = __ballot_sync(kFull, kk >= 0);
+        if (kk >= 0) {
+            const unsigned peers = __match_any_sync(live, kk);
+            const int leader = __ffs(peers) - 1;
+            int o = 0;
+            if (lane == leader) o = atomicAdd(&s_bin[kk], __popc(peers));
+            o = __shfl_sync(peers, o, leader);
+            s_order[o + __popc(peers & lanemask_lt())] = (unsigned short)(tid + q * THREADS);
+        }
+    }
+    __syncthreads();
+
+    // ---- (C) the rest of every live run: warp w takes sorted blocks w and 2W-1-w ----
+    {
+        const int n_live = s_bin[kSortBins];
+        const int w = tid >> 5;
+#pragma unroll 1
+        for (int q = 0; q < 2; ++q) {
+            const int j = (q == 0 ? w : 2 * W - 1 - w) * 32 + lane;
+            if (j < n_live) {
+                const int r = s_order[j];
+                const int sub = r & (TILE - 1);
+                double k[S::kCols];
+#pragma unroll
+                for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + base + sub);  // only what load() reads survives
+                S sys;
+                sys.load(k);
+                double x = s_x[r], y = s_y[r];
+                int it = s_it[r];
+                bool conv = false;
+#pragma unroll 1
+                while (!conv && it < kMaxIt) {
+                    double nx, ny;
+                    newton_update<KIND>(sys, fc, x, y, nx, ny, it);
+                    conv = fabs(x - nx) < fc.tol && fabs(y - ny) < fc.tol;
+                    x = nx, y = ny;
+                }
+                s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
+                s_cv[r] = (conv && it < kMaxIt) ? 1 : 0;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- (D) selection + write-back, coalesced, every lane busy ----
+#pragma unroll 1
+    for (int sub = tid; sub < cnt; sub += THREADS) {
+        const long long gi = base + sub;
+        double k[S::kCols];
+#pragma unroll
+        for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + gi);
+        const uint8_t code = p.code ? __ldg(p.code + gi) : (uint8_t)GCS_MAKE_CODE(0, 0, 0);
+        double cx[NS], cy[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            cx[s] = s_x[s * TILE + sub];
+            cy[s] = s_y[s * TILE + sub];
+        }
+        double out[4];
+        const int root = select_and_finish<KIND, NS>(k, code, cx, cy, out);
+#pragma unroll
+        for (int c = 0; c < S::kOut; ++c) p.out[c][gi] = out[c];
+        if (p.root) p.root[gi] = (uint8_t)root;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const long long pi = (long long)s * p.stride + gi;
+            if (p.iters) p.iters[pi] = s_it[s * TILE + sub];
+            if (p.converged) p.converged[pi] = s_cv[s * TILE + sub];
+            if (p.cand) {
+                p.cand[((long long)s * 2 + 0) * p.stride + gi] = cx[s];
+                p.cand[((long long)s * 2 + 1) * p.stride + gi] = cy[s];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA bulk copy (global -> shared::cta)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -143,12 +443,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ unsigned lanemask_lt()
-{
-    unsigned m;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-    return m;
 }
 
 // ------------------------------------------------------------------------------------------

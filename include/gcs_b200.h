@@ -134,6 +134,8 @@ extern "C" {
 #define GCS_VARIANT_DEFAULT 0
 #define GCS_VARIANT_STATIC 1 /* one lane per (sub-system, seed), static mapping */
 #define GCS_VARIANT_REFILL 2 /* persistent CTAs, TMA-staged tiles, warp-level lane refill */
+#define GCS_VARIANT_SORTED 3 /* CTA tiles; runs sorted by predicted update count, one lane finishes one run */
+#define GCS_VARIANT_PAIR 4 /* one lane per sub-system, its two seeds iterated in lockstep (2 seeds only; else static) */
 
 typedef struct gcs_b200_batch {
     int32_t kind;    /* GCS_KIND_* */

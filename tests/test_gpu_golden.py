@@ -7,7 +7,7 @@ from test_golden import check_against_golden, load_numeric
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("kind", [1, 2, 3, 4, 5])
 def test_cuda_matches_reference_golden(gpu, gcs, kind, variant):
     hb, z = load_numeric(gcs.capi, kind)

@@ -14,7 +14,7 @@ from util import assert_batches_identical, bits, rel_err
 pytestmark = pytest.mark.gpu
 
 KINDS = [1, 2, 3, 4, 5]
-VARIANTS = [1, 2]  # static, refill
+VARIANTS = [1, 2, 3, 4]  # static, refill, sorted, pair
 
 
 def _solve_pair(gpu, synth, kind, n, variant, **kw):
@@ -149,7 +149,7 @@ def test_device_resident_batch_on_torch_stream(gpu, gcs):
     db = capi.DeviceBatch(hb, "cuda:0", want_cand=True)
     s = torch.cuda.Stream(device="cuda:0")
     with torch.cuda.stream(s):
-        for variant in (1, 2):
+        for variant in (1, 2, 3, 4):
             db.set_variant(variant)
             db.solve()
             s.synchronize()
