@@ -75,7 +75,7 @@ _lib = None
 EXPORTS = [
     "gcs_b200_kind_in_cols", "gcs_b200_kind_out_cols", "gcs_b200_device_count", "gcs_b200_init",
     "gcs_b200_shutdown", "gcs_b200_last_error", "gcs_b200_version", "gcs_b200_solve",
-    "gcs_b200_solve_host", "gcs_b200_solve_host_async", "gcs_b200_wait", "gcs_b200_solve_sharded", "gcs_b200_launch_count", "gcs_b200_kernel_name",
+    "gcs_b200_solve_host", "gcs_b200_solve_host_async", "gcs_b200_wait", "gcs_b200_solve_sharded", "gcs_b200_launch_count", "gcs_b200_kernel_name", "gcs_b200_default_variant",
     "gcs_b200_fp64_probe", "gcs_b200_synth_pp", "gcs_b200_selftest",
 ]
 
@@ -103,6 +103,7 @@ def load():
     lib.gcs_b200_launch_count.restype = C.c_int64
     lib.gcs_b200_kernel_name.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.gcs_b200_kernel_name.restype = C.c_char_p
+    lib.gcs_b200_default_variant.argtypes = [C.c_int64, C.c_int]
     lib.gcs_b200_fp64_probe.argtypes = [C.c_int, C.c_int]
     lib.gcs_b200_fp64_probe.restype = C.c_double
     lib.gcs_b200_selftest.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.POINTER(C.c_uint64)]

@@ -41,7 +41,15 @@ int fail(int code, const char* fmt, ...)
                 __LINE__);                                                                     \
     } while (0)
 
-constexpr int kDefaultVariant = GCS_VARIANT_STATIC;  // measured faster on every kind (profiles/)
+// GCS_VARIANT_DEFAULT: the sorted kernel from kSortedMinRuns Newton runs per launch (measured faster
+// on every kind and seed count there, profiles/), the static kernel below (a sorted CTA lives
+// twice as long as a static one, which shows while the launch does not fill the device)
+constexpr long long kSortedMinRuns = 1ll << 18;
+inline int resolve_variant(int variant, long long n, int n_seeds)
+{
+    if (variant != GCS_VARIANT_DEFAULT) return variant;
+    return n * n_seeds >= kSortedMinRuns ? GCS_VARIANT_SORTED : GCS_VARIANT_STATIC;
+}
 constexpr int kTicketSlots = 64;
 constexpr int kRefillCH = 64;
 constexpr int kRefillWarps = 4;
@@ -218,8 +226,7 @@ int launch_refill(DeviceState* d, const BatchDev& p, cudaStream_t st)
 template <int KIND>
 int launch_kind(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cudaStream_t st)
 {
-    int variant = b->variant;
-    if (variant == GCS_VARIANT_DEFAULT) variant = kDefaultVariant;
+    const int variant = resolve_variant(b->variant, p.n, b->n_seeds);
     constexpr bool column_guess = (KIND == GCS_KIND_SDD || KIND == GCS_KIND_ANG);
     if (b->n_seeds == 2) {
         if (variant == GCS_VARIANT_SORTED) return launch_sorted<KIND, 2>(p, st);
@@ -379,10 +386,12 @@ const char* gcs_b200_version(void) { return "gcs_b200 0.1.0 (sm_100a, fp64, fmad
 
 int64_t gcs_b200_launch_count(void) { return g_launches.load(); }
 
+int gcs_b200_default_variant(int64_t n, int n_seeds) { return resolve_variant(GCS_VARIANT_DEFAULT, n, n_seeds); }
+
 const char* gcs_b200_kernel_name(int kind, int n_seeds, int variant)
 {
     static thread_local char name[96];
-    if (variant == GCS_VARIANT_DEFAULT) variant = kDefaultVariant;
+    variant = resolve_variant(variant, kSortedMinRuns, 1);  // default: named for a launch that fills the device
     const char* base = variant == GCS_VARIANT_REFILL ? "newton_refill_kernel"
         : variant == GCS_VARIANT_SORTED              ? "newton_sorted_kernel"
         : (variant == GCS_VARIANT_PAIR && n_seeds == 2) ? "newton_pair_kernel"

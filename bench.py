@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", type=int, default=0, help="0 library default, 1 static, 2 refill")
+    ap.add_argument("--variant", type=int, default=0, help="0 library default (sorted for device-filling launches), 1 static, 2 refill, 3 sorted, 4 pair")
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="solves per GPU (default 2^20)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -511,7 +511,7 @@ def main():
     peaks, peak_src = load_peaks()
     ach_tf = w_k1 / (k1_ms * 1e-3) / 1e12
     traffic = load_traffic()
-    vname = {0: "default", 1: "static", 2: "refill"}[args.variant]
+    vname = {0: "default", 1: "static", 2: "refill", 3: "sorted", 4: "pair"}[args.variant]
     kernel_name = lib.gcs_b200_kernel_name(1, 2, args.variant).decode() if hasattr(lib, "gcs_b200_kernel_name") else vname
     roofline = {
         "kernel": kernel_name,

@@ -188,6 +188,8 @@ GCS_B200_API int gcs_b200_solve_sharded(const gcs_b200_batch* batch, int n_dev);
 GCS_B200_API int64_t gcs_b200_launch_count(void);
 /* name of the kernel a batch of this kind / seed count / variant is solved by (thread-local string) */
 GCS_B200_API const char* gcs_b200_kernel_name(int kind, int n_seeds, int variant);
+/* the variant GCS_VARIANT_DEFAULT resolves to for a launch of n sub-systems x n_seeds seeds */
+GCS_B200_API int gcs_b200_default_variant(int64_t n, int n_seeds);
 
 /* FP64 pipe micro-benchmarks used as roofline denominators (seconds-scale, device `device`):
  *   what = 0: dependent-free DFMA throughput, returns TFLOP/s counting FMA = 2 flops
