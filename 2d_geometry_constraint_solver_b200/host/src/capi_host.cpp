@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 #include <exception>
+#include <limits>
+#include <optional>
 #include <memory>
 #include <stdexcept>
 #include <unordered_map>
@@ -18,6 +20,7 @@
 #include <gcs/model/gcs_data_structures.hpp>
 #include <gcs/orchestration/geometric_constraint_system.hpp>
 
+#include "solving/bottom_up/merge3_solver_common.hpp"
 #include "solving/component_solver.hpp"
 #include "solving/equations/newton_raphson.hpp"
 
@@ -376,6 +379,124 @@ GCS_API int gcs_host_decompose(int n_el, const gcs_host_element* el, int n_edges
     } catch (const std::exception& ex) {
         return fail(ex);
     }
+}
+
+// ---- bottom-up Merge3 numeric helpers (solving/bottom_up/merge3_solver_common.hpp) ----
+// kase 1: point from two fixed points   rows of 12: fixedA(2) fixedB(2) distA distB canvasA(2) canvasB(2) canvasFree(2) -> 2
+//      2: line from two fixed points    rows of 14: fixedA(2) fixedB(2) distA distB canvasA(2) canvasB(2) canvasFreeLine(4) -> 4
+//      3: point from point and line     rows of 16: fixedPoint(2) fixedLine(4) distP distL canvasPoint(2) canvasLine(4) canvasFree(2) -> 2
+//      4: point from two lines          rows of 20: lineA(4) lineB(4) distA distB canvasA(4) canvasB(4) canvasFree(2) -> 2
+// mode 0: pack only (no device): packed[i][13] + code[i] = the kernel row, ok[i] = 0 where the
+//         reference answers nullopt without numerics;
+//      1: all rows as ONE Merge3Batch (one launch); 2: row by row through the single-call functions.
+// stats (may be NULL): [0] launches.  Returns 0 or -1 after an exception.
+GCS_API int gcs_host_m3_solve(int kase, int64_t n, const double* rows, double* out, uint8_t* ok, int mode, double* packed,
+    uint8_t* code, int64_t* stats)
+{
+    namespace Bu = Gcs::Solvers::BottomUp;
+    auto v2 = [](const double* p) { return Vector2d(p[0], p[1]); };
+    auto ln = [&](const double* p) { return Bu::LinePose { v2(p), v2(p + 2) }; };
+    static const int width[5] = { 0, 12, 14, 16, 20 }, nout[5] = { 0, 2, 4, 2, 2 };
+    try {
+        if (kase < 1 || kase > 4) throw std::invalid_argument("unknown Merge3 case");
+        const int w = width[kase], no = nout[kase];
+        auto add = [&](Gcs::B200::Merge3Batch& b, const double* r) {
+            switch (kase) {
+            case 1: return b.addFreePointFromFixedPoints(v2(r), v2(r + 2), r[4], r[5], v2(r + 6), v2(r + 8), v2(r + 10));
+            case 2: return b.addFreeLineFromFixedPoints(v2(r), v2(r + 2), r[4], r[5], v2(r + 6), v2(r + 8), ln(r + 10));
+            case 3: return b.addFreePointFromFixedPointAndLine(v2(r), ln(r + 2), r[6], r[7], v2(r + 8), ln(r + 10), v2(r + 14));
+            default: return b.addFreePointFromFixedLines(ln(r), ln(r + 4), r[8], r[9], ln(r + 10), ln(r + 14), v2(r + 18));
+            }
+        };
+        auto store = [&](int64_t i, const std::optional<Vector2d>& p, const std::optional<Bu::LinePose>& l) {
+            ok[i] = (no == 2) ? p.has_value() : l.has_value();
+            for (int c = 0; c < no; ++c) out[no * i + c] = std::numeric_limits<double>::quiet_NaN();
+            if (no == 2 && p) out[2 * i] = p->x(), out[2 * i + 1] = p->y();
+            if (no == 4 && l) out[4 * i] = l->p1.x(), out[4 * i + 1] = l->p1.y(), out[4 * i + 2] = l->p2.x(), out[4 * i + 3] = l->p2.y();
+        };
+        if (stats) stats[0] = 0;
+        if (mode == 2) {
+            for (int64_t i = 0; i < n; ++i) {
+                const double* r = rows + w * i;
+                switch (kase) {
+                case 1: store(i, Bu::solveFreePointFromFixedPoints(v2(r), v2(r + 2), r[4], r[5], v2(r + 6), v2(r + 8), v2(r + 10)), {}); break;
+                case 2: store(i, {}, Bu::solveFreeLineFromFixedPoints(v2(r), v2(r + 2), r[4], r[5], v2(r + 6), v2(r + 8), ln(r + 10))); break;
+                case 3: store(i, Bu::solveFreePointFromFixedPointAndLine(v2(r), ln(r + 2), r[6], r[7], v2(r + 8), ln(r + 10), v2(r + 14)), {}); break;
+                default: store(i, Bu::solveFreePointFromFixedLines(ln(r), ln(r + 4), r[8], r[9], ln(r + 10), ln(r + 14), v2(r + 18)), {}); break;
+                }
+                if (stats) ++stats[0];
+            }
+            return 0;
+        }
+        Gcs::B200::Merge3Batch batch;
+        std::vector<Gcs::B200::Merge3Batch::Handle> h;
+        for (int64_t i = 0; i < n; ++i) h.push_back(add(batch, rows + w * i));
+        if (mode == 0) {
+            for (int64_t i = 0; i < n; ++i) {
+                const int kind = batch.kindOf(h[static_cast<std::size_t>(i)]);
+                ok[i] = kind != 0;
+                for (int c = 0; c < GCS_MAX_IN_COLS; ++c) packed[GCS_MAX_IN_COLS * i + c] = 0.0;
+                code[i] = 0;
+                if (kind == 0) continue;
+                const auto& kb = batch.rows(kind);
+                const std::size_t row = batch.rowOf(h[static_cast<std::size_t>(i)]);
+                for (int c = 0; c < gcs_b200_kind_in_cols(kind); ++c) packed[GCS_MAX_IN_COLS * i + c] = kb.column(c)[row];
+                code[i] = kb.codes()[row];
+            }
+            return 0;
+        }
+        batch.solve();
+        if (stats) stats[0] = static_cast<int64_t>(batch.launches());
+        for (int64_t i = 0; i < n; ++i) {
+            if (no == 2)
+                store(i, batch.point(h[static_cast<std::size_t>(i)]), {});
+            else
+                store(i, {}, batch.line(h[static_cast<std::size_t>(i)]));
+        }
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(ex);
+    }
+}
+
+// estimateRigidTransform on npts point pairs; out6 = R00 R01 R10 R11 tx ty.  Returns 1, 0 (nullopt) or -1.
+GCS_API int gcs_host_m3_rigid_transform(int npts, const double* src, const double* dst, double* out6)
+{
+    try {
+        std::vector<Vector2d> s, t;
+        for (int i = 0; i < npts; ++i) s.emplace_back(src[2 * i], src[2 * i + 1]), t.emplace_back(dst[2 * i], dst[2 * i + 1]);
+        const auto tr = Gcs::Solvers::BottomUp::estimateRigidTransform(s, t);
+        if (!tr) return 0;
+        out6[0] = tr->rotation(0, 0), out6[1] = tr->rotation(0, 1), out6[2] = tr->rotation(1, 0), out6[3] = tr->rotation(1, 1);
+        out6[4] = tr->translation.x(), out6[5] = tr->translation.y();
+        return 1;
+    } catch (const std::exception& ex) {
+        return fail(ex);
+    }
+}
+
+// scoreMergedPose over a graph of n_el elements (type 0 point / 1 line; canvas4 and pose4: x,y or
+// x1,y1,x2,y2); in_pose[i] != 0 puts element i into the merged pose, inserted in index order.
+GCS_API double gcs_host_m3_score(int n_el, const int32_t* type, const double* canvas4, const double* pose4, const uint8_t* in_pose)
+{
+    namespace Bu = Gcs::Solvers::BottomUp;
+    Gcs::ConstraintGraph g;
+    Bu::ClusterPose merged;
+    for (int i = 0; i < n_el; ++i) {
+        const double* c = canvas4 + 4 * i;
+        const double* p = pose4 + 4 * i;
+        const auto node = g.getGraph().addNode();
+        if (type[i] == 0)
+            g.addElement(node, std::make_shared<Gcs::Element>(Gcs::Point(Vector2d(c[0], c[1]))));
+        else
+            g.addElement(node, std::make_shared<Gcs::Element>(Gcs::Line(Vector2d(c[0], c[1]), Vector2d(c[2], c[3]))));
+        if (!in_pose[i]) continue;
+        if (type[i] == 0)
+            merged.emplace(node, Bu::PointPose { Vector2d(p[0], p[1]) });
+        else
+            merged.emplace(node, Bu::LinePose { Vector2d(p[0], p[1]), Vector2d(p[2], p[3]) });
+    }
+    return Bu::scoreMergedPose(g, merged);
 }
 
 }  // extern "C"

@@ -40,6 +40,13 @@ def load():
                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
         lib.gcs_host_solve2d.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        if hasattr(lib, "gcs_host_m3_solve"):
+            lib.gcs_host_m3_solve.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint8),
+                                              C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int64)]
+            lib.gcs_host_m3_rigid_transform.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+            lib.gcs_host_m3_score.argtypes = [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                              C.POINTER(C.c_uint8)]
+            lib.gcs_host_m3_score.restype = C.c_double
         _lib = lib
     return _lib
 
@@ -147,3 +154,54 @@ def solve2d(pair, params, guesses=None):
     cv = (C.c_int32 * 2)()
     rc = load().gcs_host_solve2d(pair, p, g, cand, it, cv)
     return rc, np.array(list(cand)).reshape(2, 2), list(it), list(cv)
+
+
+# ---- bottom-up Merge3 numeric helpers ----
+M3_WIDTH = {1: 12, 2: 14, 3: 16, 4: 20}
+M3_OUT = {1: 2, 2: 4, 3: 2, 4: 2}
+M3_KIND = {1: 1, 2: 2, 3: 3, 4: 4}  # equation-pair kind each case packs into
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def m3_solve(kase, rows, mode):
+    """mode 1: one Merge3Batch; 2: single-call functions.  Returns (rc, out[n][M3_OUT], ok[n], launches)."""
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    n = rows.shape[0]
+    out = np.zeros((n, M3_OUT[kase]))
+    ok = np.zeros(n, dtype=np.uint8)
+    stats = (C.c_int64 * 1)()
+    rc = load().gcs_host_m3_solve(kase, n, _dp(rows), _dp(out), ok.ctypes.data_as(C.POINTER(C.c_uint8)), mode, None, None, stats)
+    return rc, out, ok, stats[0]
+
+
+def m3_pack(kase, rows):
+    """Pack only (no device).  Returns (rc, packed[n][13], code[n], needs_numerics[n])."""
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    n = rows.shape[0]
+    out = np.zeros((n, M3_OUT[kase]))
+    ok = np.zeros(n, dtype=np.uint8)
+    packed = np.zeros((n, 13))
+    code = np.zeros(n, dtype=np.uint8)
+    rc = load().gcs_host_m3_solve(kase, n, _dp(rows), _dp(out), ok.ctypes.data_as(C.POINTER(C.c_uint8)), 0, _dp(packed),
+                                  code.ctypes.data_as(C.POINTER(C.c_uint8)), None)
+    return rc, packed, code, ok
+
+
+def m3_rigid_transform(src, dst):
+    src = np.ascontiguousarray(src, dtype=np.float64)
+    dst = np.ascontiguousarray(dst, dtype=np.float64)
+    out = np.zeros(6)
+    rc = load().gcs_host_m3_rigid_transform(src.shape[0], _dp(src), _dp(dst), _dp(out))
+    return rc, out
+
+
+def m3_score(types, canvas4, pose4, in_pose):
+    types = np.ascontiguousarray(types, dtype=np.int32)
+    canvas4 = np.ascontiguousarray(canvas4, dtype=np.float64)
+    pose4 = np.ascontiguousarray(pose4, dtype=np.float64)
+    in_pose = np.ascontiguousarray(in_pose, dtype=np.uint8)
+    return load().gcs_host_m3_score(len(types), types.ctypes.data_as(C.POINTER(C.c_int32)), _dp(canvas4), _dp(pose4),
+                                    in_pose.ctypes.data_as(C.POINTER(C.c_uint8)))

@@ -37,6 +37,14 @@ def load():
         if hasattr(lib, "gcs_ref_leaves_solve"):
             lib.gcs_ref_leaves_solve.argtypes = [C.c_int, C.POINTER(RefElement), C.c_int, C.POINTER(C.c_int32),
                                                  C.POINTER(C.c_int32), C.POINTER(RefEdge), C.POINTER(C.c_int32)]
+        if hasattr(lib, "gcs_ref_m3_free_line"):
+            dp, bp = C.POINTER(C.c_double), C.POINTER(C.c_uint8)
+            lib.gcs_ref_m3_point_pp.argtypes = [C.c_int64, dp, dp]
+            for f in (lib.gcs_ref_m3_free_line, lib.gcs_ref_m3_point_pl, lib.gcs_ref_m3_point_ll):
+                f.argtypes = [C.c_int64, dp, dp, bp]
+            lib.gcs_ref_m3_rigid_transform.argtypes = [C.c_int, dp, dp, dp]
+            lib.gcs_ref_m3_score.argtypes = [C.c_int, C.POINTER(C.c_int32), dp, dp, bp]
+            lib.gcs_ref_m3_score.restype = C.c_double
         _lib = lib
     return _lib
 
@@ -92,3 +100,42 @@ def leaves_solve(elements, leaves):
     status = (C.c_int32 * max(n, 1))()
     rc = load().gcs_ref_leaves_solve(len(elements), els, n, le, eo, eds, status)
     return rc, list(status)[:n], H.from_c(elements, els)
+
+
+# ---- the reference's bottom-up Merge3 numeric helpers (oracle/ref_merge3_driver.cpp) ----
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def m3_solve(kase, rows):
+    """kase 1 point from two points, 2 line from two points, 3 point from point+line, 4 point from two
+    lines (row layouts: oracle/ref_merge3_driver.cpp).  Returns (out, ok)."""
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    n = rows.shape[0]
+    nout = {1: 2, 2: 4, 3: 2, 4: 2}[kase]
+    out = np.zeros((n, nout))
+    ok = np.ones(n, dtype=np.uint8)
+    okp = ok.ctypes.data_as(C.POINTER(C.c_uint8))
+    lib = load()
+    if kase == 1:
+        lib.gcs_ref_m3_point_pp(n, _dp(rows), _dp(out))
+    else:
+        {2: lib.gcs_ref_m3_free_line, 3: lib.gcs_ref_m3_point_pl, 4: lib.gcs_ref_m3_point_ll}[kase](n, _dp(rows), _dp(out), okp)
+    return out, ok
+
+
+def m3_rigid_transform(src, dst):
+    src = np.ascontiguousarray(src, dtype=np.float64)
+    dst = np.ascontiguousarray(dst, dtype=np.float64)
+    out = np.zeros(6)
+    rc = load().gcs_ref_m3_rigid_transform(src.shape[0], _dp(src), _dp(dst), _dp(out))
+    return rc, out
+
+
+def m3_score(types, canvas4, pose4, in_pose):
+    types = np.ascontiguousarray(types, dtype=np.int32)
+    canvas4 = np.ascontiguousarray(canvas4, dtype=np.float64)
+    pose4 = np.ascontiguousarray(pose4, dtype=np.float64)
+    in_pose = np.ascontiguousarray(in_pose, dtype=np.uint8)
+    return load().gcs_ref_m3_score(len(types), types.ctypes.data_as(C.POINTER(C.c_int32)), _dp(canvas4), _dp(pose4),
+                                   in_pose.ctypes.data_as(C.POINTER(C.c_uint8)))
