@@ -1,1 +1,1 @@
-python -m pytest tests/test_merge3.py -m gpu -x -q 2>&1 | tail -5
+python profiles/merge3_bench.py 20000 | tail -1 > gpurun_out/merge3_bench.json; cat gpurun_out/merge3_bench.json
