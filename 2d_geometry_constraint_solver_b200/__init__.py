@@ -7,6 +7,6 @@ benchmark and the tests.  Import as
     gcs = importlib.import_module("2d_geometry_constraint_solver_b200")
 (the directory name starts with a digit, so the `import` statement cannot spell it).
 """
-from . import capi, synth  # noqa: F401
+from . import capi, sketch_io, synth  # noqa: F401
 
 __version__ = "0.1.0"

@@ -13,6 +13,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include <gcs/b200/canvas_transform.hpp>
 #include <gcs/b200/leaf_batch.hpp>
 #include <gcs/decomposition/top_down/stree_top_down_strategy.hpp>
 #include <gcs/model/constraints.hpp>
@@ -497,6 +498,35 @@ GCS_API double gcs_host_m3_score(int n_el, const int32_t* type, const double* ca
             merged.emplace(node, Bu::LinePose { Vector2d(p[0], p[1]), Vector2d(p[2], p[3]) });
     }
     return Bu::scoreMergedPose(g, merged);
+}
+
+// The step after the solve (gcs/b200/canvas_transform.hpp): elements with is_set != 0 carry solver
+// positions in pos; on return canvas holds the transformed sketch.  Returns 0 or -1.
+GCS_API int gcs_host_canvas_transform(int n_el, gcs_host_element* el)
+{
+    try {
+        std::vector<std::shared_ptr<Gcs::Element>> elems;
+        Gcs::ConstraintGraph g;
+        for (int i = 0; i < n_el; ++i) {
+            elems.push_back(makeElement(el[i]));
+            g.addElement(g.getGraph().addNode(), elems.back());
+        }
+        Gcs::B200::applySolverToCanvasTransform(g);
+        for (int i = 0; i < n_el; ++i) {
+            const auto& e = *elems[static_cast<std::size_t>(i)];
+            if (el[i].type == 0) {
+                const auto& p = e.getElement<Gcs::Point>();
+                el[i].canvas[0] = p.canvasPosition.x(), el[i].canvas[1] = p.canvasPosition.y();
+            } else {
+                const auto& l = e.getElement<Gcs::Line>();
+                el[i].canvas[0] = l.canvasP1.x(), el[i].canvas[1] = l.canvasP1.y();
+                el[i].canvas[2] = l.canvasP2.x(), el[i].canvas[3] = l.canvasP2.y();
+            }
+        }
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(ex);
+    }
 }
 
 }  // extern "C"

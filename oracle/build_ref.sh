@@ -19,7 +19,9 @@ CXX="${GCS_REF_CXX:-/usr/bin/g++}"
   -fvisibility=hidden -include format -include tuple -include iostream \
   -I "$here/ref_shim" -I "$cs/includes" -I "$cs/src" -I "$ref/src/structures/include" \
   -o "$here/_ref/libgcs_ref.so" \
-  "$here/ref_driver.cpp" "$here/ref_merge3_driver.cpp" "$here/ref_graph_members.cpp" \
+  -I "$ref/gui/src" \
+  "$here/ref_driver.cpp" "$here/ref_merge3_driver.cpp" "$here/ref_model_driver.cpp" "$here/ref_graph_members.cpp" \
+  "$ref/gui/src/constraint_model.cpp" \
   "$cs/src/solving/bottom_up/merge3_solver_common.cpp" \
   "$cs/src/model/elements.cpp" "$cs/src/model/constraints.cpp" \
   "$cs/src/solving/solvers/point_point_solvers.cpp" \

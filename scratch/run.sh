@@ -1,1 +1,2 @@
-python profiles/merge3_bench.py 20000 | tail -1 > gpurun_out/merge3_bench.json; cat gpurun_out/merge3_bench.json
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

@@ -40,6 +40,8 @@ def load():
                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
         lib.gcs_host_solve2d.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        if hasattr(lib, "gcs_host_canvas_transform"):
+            lib.gcs_host_canvas_transform.argtypes = [C.c_int, C.POINTER(Element)]
         if hasattr(lib, "gcs_host_m3_solve"):
             lib.gcs_host_m3_solve.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint8),
                                               C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int64)]
@@ -205,3 +207,10 @@ def m3_score(types, canvas4, pose4, in_pose):
     in_pose = np.ascontiguousarray(in_pose, dtype=np.uint8)
     return load().gcs_host_m3_score(len(types), types.ctypes.data_as(C.POINTER(C.c_int32)), _dp(canvas4), _dp(pose4),
                                     in_pose.ctypes.data_as(C.POINTER(C.c_uint8)))
+
+
+def canvas_transform(elements):
+    """Solver -> canvas rigid motion over elements carrying is_set/pos.  Returns (rc, canvas list)."""
+    els, _ = to_c(elements, [])
+    rc = load().gcs_host_canvas_transform(len(elements), els)
+    return rc, [[els[i].canvas[j] for j in range(2 if e["type"] == 0 else 4)] for i, e in enumerate(elements)]

@@ -45,6 +45,9 @@ def load():
             lib.gcs_ref_m3_rigid_transform.argtypes = [C.c_int, dp, dp, dp]
             lib.gcs_ref_m3_score.argtypes = [C.c_int, C.POINTER(C.c_int32), dp, dp, bp]
             lib.gcs_ref_m3_score.restype = C.c_double
+        if hasattr(lib, "gcs_ref_model_solve_transform"):
+            dp, bp, ip = C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
+            lib.gcs_ref_model_solve_transform.argtypes = [C.c_int, ip, dp, dp, bp, C.c_int, ip, dp, dp, dp]
         _lib = lib
     return _lib
 
@@ -139,3 +142,22 @@ def m3_score(types, canvas4, pose4, in_pose):
     in_pose = np.ascontiguousarray(in_pose, dtype=np.uint8)
     return load().gcs_ref_m3_score(len(types), types.ctypes.data_as(C.POINTER(C.c_int32)), _dp(canvas4), _dp(pose4),
                                    in_pose.ctypes.data_as(C.POINTER(C.c_uint8)))
+
+
+def model_solve_transform(types, canvas4, pos4, solved, con4, value):
+    """The reference GUI model: build it (add* calls), install the given solver positions in place
+    of the solve, run solveConstraintSystem() -> applySolverToCanvasTransform.
+    Returns (accepted constraints, canvas4 afterwards, stored constraint values)."""
+    types = np.ascontiguousarray(types, dtype=np.int32)
+    canvas4 = np.ascontiguousarray(canvas4, dtype=np.float64)
+    pos4 = np.ascontiguousarray(pos4, dtype=np.float64)
+    solved = np.ascontiguousarray(solved, dtype=np.uint8)
+    con4 = np.ascontiguousarray(con4, dtype=np.int32).reshape(-1, 4)
+    value = np.ascontiguousarray(value, dtype=np.float64)
+    out = np.zeros_like(canvas4)
+    stored = np.zeros(max(len(value), 1))
+    ip = C.POINTER(C.c_int32)
+    n = load().gcs_ref_model_solve_transform(len(types), types.ctypes.data_as(ip), _dp(canvas4), _dp(pos4),
+                                             solved.ctypes.data_as(C.POINTER(C.c_uint8)), len(value),
+                                             con4.ctypes.data_as(ip), _dp(value), _dp(out), _dp(stored))
+    return n, out, stored[:len(value)]
