@@ -1,2 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+GCS_B200_TRACE=1 python scratch/trace.py 2> gpurun_out/trace_e2e.log; tail -40 gpurun_out/trace_e2e.log
+python scratch/e2e_probe.py
+for p in 3 6 8; do echo parts $p; GCS_B200_PARTS=$p python scratch/e2e_probe.py | grep both; done
