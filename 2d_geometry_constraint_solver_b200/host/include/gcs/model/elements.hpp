@@ -1,7 +1,11 @@
 // Geometry element value types kept at the boundary (reference:
-// includes/gcs/model/elements.hpp:24-158, src/model/elements.cpp).  Same names, members and
-// semantics: `canvas*` is the user's sketch, `position` / `p1,p2` the solver-space result;
-// Element::updateElementPosition stores the result and marks the element solved (m_isSet).
+// includes/gcs/model/elements.hpp:24-158, src/model/elements.cpp).  Same type names, member names
+// and semantics, because host code written against the reference must compile unchanged:
+//   canvas*            where the user drew the element (never touched by the solver path; the
+//                      solver->canvas transform of gcs/b200/canvas_transform.hpp rewrites it)
+//   position / p1,p2   the solver-space result
+//   Element            a variant over the shapes + the "already solved" flag (m_isSet), which
+//                      Element::updateElementPosition sets and the eight matches() predicates read.
 #pragma once
 
 #include <string>
@@ -14,78 +18,85 @@
 namespace Gcs {
 
 struct GCS_API Point {
+    Point();
+    explicit Point(const Eigen::Vector2d& canvasPos);
+
     Eigen::Vector2d canvasPosition;
     Eigen::Vector2d position;
 
-    Point();
-    explicit Point(const Eigen::Vector2d& canvasPos);
-    std::string getTypeName() const;
-    std::string toString() const;
     void updateElementPosition(const Eigen::Vector2d& newPosition);
+    std::string getTypeName() const;  // "Point"
+    std::string toString() const;
 };
 
+// Part of the variant in the reference; no sub-problem solver reads or writes it.
 struct GCS_API FixedRadiusCircle {
+    FixedRadiusCircle();
+    explicit FixedRadiusCircle(const Eigen::Vector2d& centerPos, double r);
+
     Eigen::Vector2d position;
     double fixedRadius;
 
-    FixedRadiusCircle();
-    explicit FixedRadiusCircle(const Eigen::Vector2d& centerPos, double r);
-    std::string getTypeName() const;
-    std::string toString() const;
     void updateElementPosition(const Eigen::Vector2d& newPosition);
+    std::string getTypeName() const;  // "FixedRadiusCircle"
+    std::string toString() const;
 };
 
 struct GCS_API Line {
+    Line();
+    explicit Line(const Eigen::Vector2d& canvasEndpoint1, const Eigen::Vector2d& canvasEndpoint2);
+
     Eigen::Vector2d canvasP1;
     Eigen::Vector2d canvasP2;
     Eigen::Vector2d p1;
     Eigen::Vector2d p2;
 
-    Line();
-    explicit Line(const Eigen::Vector2d& canvasEndpoint1, const Eigen::Vector2d& canvasEndpoint2);
-    std::string getTypeName() const;
-    std::string toString() const;
     void updateElementPosition(const Eigen::Vector2d& newP1, const Eigen::Vector2d& newP2);
+    std::string getTypeName() const;  // "Line"
+    std::string toString() const;
 
+    // solver-space helpers (the packer reads length() and midpoint(); operation order in elements.cpp)
     Eigen::Vector2d direction() const;      // p2 - p1
-    Eigen::Vector2d unitDirection() const;  // (p2 - p1).normalized()
-    Eigen::Vector2d normal() const;         // (-dir.y, dir.x)
-    double length() const;                  // (p2 - p1).norm()
-    Eigen::Vector2d midpoint() const;       // (p1 + p2) / 2.0
+    double length() const;                  // |p2 - p1|
+    Eigen::Vector2d unitDirection() const;  // direction / length, or direction itself when it is zero
+    Eigen::Vector2d normal() const;         // (-direction.y, direction.x), not normalised
+    Eigen::Vector2d midpoint() const;       // (p1 + p2) / 2
 };
 
 using ElementVariant = std::variant<Point, FixedRadiusCircle, Line>;
 
 class GCS_API Element final {
 public:
-    template <typename T>
-    explicit Element(const T& e) : m_element { e } {}
+    template <typename Shape>
+    explicit Element(const Shape& shape) : m_element(shape) {}
 
-    template <typename T>
-    bool isElementType() const { return std::holds_alternative<T>(m_element); }
-    template <typename T>
-    T& getElement() { return std::get<T>(m_element); }
-    template <typename T>
-    const T& getElement() const { return std::get<T>(m_element); }
-
-    std::string getElementName() const;
-    std::string toString() const;
     bool isElementSet() const { return m_isSet; }
 
-    // Point / circle: one vector; Line: two vectors.  A call whose arguments do not fit the
-    // active alternative is ignored (the reference asserts), the element stays unset.
-    template <typename... Parameters>
-    void updateElementPosition(Parameters&&... params)
+    template <typename Shape>
+    bool isElementType() const { return std::holds_alternative<Shape>(m_element); }
+    template <typename Shape>
+    const Shape& getElement() const { return std::get<Shape>(m_element); }
+    template <typename Shape>
+    Shape& getElement() { return std::get<Shape>(m_element); }
+
+    // One vector for a point / circle, two for a line; marks the element solved.  Arguments that
+    // do not fit the active alternative leave the element untouched and unset (the reference
+    // asserts there).
+    template <typename... Args>
+    void updateElementPosition(Args&&... args)
     {
         std::visit(
-            [&](auto& elem) {
-                if constexpr (requires { elem.updateElementPosition(std::forward<Parameters>(params)...); }) {
-                    elem.updateElementPosition(std::forward<Parameters>(params)...);
+            [&](auto& shape) {
+                if constexpr (requires { shape.updateElementPosition(std::forward<Args>(args)...); }) {
+                    shape.updateElementPosition(std::forward<Args>(args)...);
                     m_isSet = true;
                 }
             },
             m_element);
     }
+
+    std::string getElementName() const;
+    std::string toString() const;
 
 private:
     ElementVariant m_element;

@@ -25,46 +25,48 @@ public:
     using Graph = MathUtils::SimpleGraph;
     using NodeIdType = Graph::NodeIdType;
     using EdgeIdType = Graph::EdgeIdType;
+    using ElementMap = MathUtils::NodePropertyMap<std::shared_ptr<Element>>;
+    using ConstraintMap = MathUtils::EdgePropertyMap<std::shared_ptr<Constraint>>;
 
-    ConstraintGraphError addElement(NodeIdType node, std::shared_ptr<Element> element);
-    ConstraintGraphError addConstraint(EdgeIdType edge, std::shared_ptr<Constraint> constraint);
+    // ---- the underlying graph (nodes and edges are created there, then decorated here) ----
+    Graph& getGraph() { return m_constraintGraph; }
+    const Graph& getGraph() const { return m_constraintGraph; }
+    std::size_t nodeCount() const { return m_constraintGraph.nodeCount(); }
+    std::size_t edgeCount() const { return m_constraintGraph.edgeCount(); }  // virtual edges included
     std::expected<EdgeIdType, ConstraintGraphError> getEdgeBetween(NodeIdType s, NodeIdType t) const;
-    EdgeIdType addVirtualEdge(NodeIdType s, NodeIdType t);
-    ConstraintGraphError removeVirtualEdge(EdgeIdType virtualEdge);
-    ConstraintGraphError removeElement(NodeIdType node);
-    ConstraintGraphError removeConstraintEdge(EdgeIdType edge);
 
-    std::shared_ptr<Element> getElement(NodeIdType node) const;
-    std::shared_ptr<Constraint> getConstraintForEdge(EdgeIdType edge) const;
-    // Throws std::bad_expected_access like the reference when there is no edge, or the edge is a
+    // ---- elements on nodes ----
+    ConstraintGraphError addElement(NodeIdType node, std::shared_ptr<Element> element);
+    ConstraintGraphError removeElement(NodeIdType node);
+    std::shared_ptr<Element> getElement(NodeIdType node) const;  // null when absent
+    std::vector<std::shared_ptr<Element>> getElements() const;
+    const ElementMap& getElementMap() const { return m_elementNodeMap; }  // ascending node id
+    int numberOfSolvedElements() const;
+
+    // ---- constraints on edges ----
+    ConstraintGraphError addConstraint(EdgeIdType edge, std::shared_ptr<Constraint> constraint);
+    ConstraintGraphError removeConstraintEdge(EdgeIdType edge);
+    std::shared_ptr<Constraint> getConstraintForEdge(EdgeIdType edge) const;  // null when absent
+    // Throws std::bad_expected_access, like the reference, when there is no edge or the edge is a
     // virtual one that carries no constraint (gcs_data_structures.hpp:66-71).
     std::shared_ptr<Constraint> getConstraintBetweenNodes(NodeIdType s, NodeIdType t) const;
+    std::vector<std::shared_ptr<Constraint>> getConstraints() const;  // real constraints only
+    const ConstraintMap& getConstraintMap() const { return m_constraintEdgeMap; }
 
-    const MathUtils::NodePropertyMap<std::shared_ptr<Element>>& getElementMap() const { return m_elementNodeMap; }
-    const MathUtils::EdgePropertyMap<std::shared_ptr<Constraint>>& getConstraintMap() const { return m_constraintEdgeMap; }
-
+    // ---- virtual edges: the separation-pair edge a split leaves behind; no constraint on it ----
+    EdgeIdType addVirtualEdge(NodeIdType s, NodeIdType t);
+    ConstraintGraphError removeVirtualEdge(EdgeIdType virtualEdge);
     bool hasVirtualEdge() const { return !m_virtualEdges.empty(); }
     bool isVirtualEdge(EdgeIdType edge) const { return m_virtualEdges.count(edge) != 0; }
     const std::unordered_set<EdgeIdType>& getVirtualEdges() const { return m_virtualEdges; }
 
-    std::size_t nodeCount() const { return m_constraintGraph.nodeCount(); }
-    std::size_t edgeCount() const { return m_constraintGraph.edgeCount(); }
-    int numberOfSolvedElements() const;
-    int getDeficit() const
-    {
-        return (2 * static_cast<int>(nodeCount()) - 3) - static_cast<int>(edgeCount());
-    }
-
-    Graph& getGraph() { return m_constraintGraph; }
-    const Graph& getGraph() const { return m_constraintGraph; }
-
-    std::vector<std::shared_ptr<Element>> getElements() const;
-    std::vector<std::shared_ptr<Constraint>> getConstraints() const;
+    // 2n - 3 - edges, in int (the reference's strategy computes it in size_t and wraps)
+    int getDeficit() const { return (2 * static_cast<int>(nodeCount()) - 3) - static_cast<int>(edgeCount()); }
 
 private:
     Graph m_constraintGraph;
-    MathUtils::NodePropertyMap<std::shared_ptr<Element>> m_elementNodeMap;
-    MathUtils::EdgePropertyMap<std::shared_ptr<Constraint>> m_constraintEdgeMap;
+    ElementMap m_elementNodeMap;
+    ConstraintMap m_constraintEdgeMap;
     std::unordered_set<EdgeIdType> m_virtualEdges;
 };
 

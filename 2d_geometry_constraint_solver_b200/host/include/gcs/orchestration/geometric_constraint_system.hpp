@@ -12,16 +12,23 @@
 
 namespace Gcs {
 
+// Owns one strategy and runs its three steps on a sketch.  With
+// DeficitStreeBasedTopDownStrategy the last step is the batched wave scheduler of
+// gcs/b200/leaf_batch.hpp: one kernel launch per equation-pair kind per dependency wave.
 class GCS_API GeometricConstraintSystem final {
+    std::unique_ptr<GcsSolvingStrategy> m_strategy;
+
 public:
     explicit GeometricConstraintSystem(std::unique_ptr<GcsSolvingStrategy> strategy) : m_strategy(std::move(strategy)) {}
-    // throws std::runtime_error when the graph is not well-constrained and resolve() fails
-    void solveGeometricConstraintSystem(ConstraintGraph& gcs);
-    [[nodiscard]] const GcsSolvingStrategy& getStrategy() const { return *m_strategy; }
-    [[nodiscard]] GcsSolvingStrategy& getStrategy() { return *m_strategy; }
 
-private:
-    std::unique_ptr<GcsSolvingStrategy> m_strategy;
+    // check -> (resolve) -> decompose -> solve.  Throws std::runtime_error("Gcs is not
+    // well-constrained, ...") when the check fails and resolve() cannot repair the sketch, and
+    // whatever the strategy throws (no CUDA device: std::runtime_error; malformed leaf:
+    // std::bad_expected_access).  Results land in the Element objects of `gcs`.
+    void solveGeometricConstraintSystem(ConstraintGraph& gcs);
+
+    [[nodiscard]] GcsSolvingStrategy& getStrategy() { return *m_strategy; }
+    [[nodiscard]] const GcsSolvingStrategy& getStrategy() const { return *m_strategy; }
 };
 
 }  // namespace Gcs

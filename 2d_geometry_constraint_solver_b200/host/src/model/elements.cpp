@@ -1,69 +1,90 @@
-// Element value types: constructors, position updates, line helpers (reference:
-// src/constraint_solver/src/model/elements.cpp:1-145).  Line::length() / unitDirection() /
-// midpoint() are read by the packer (point_line_solvers.cpp:506, :636-673;
-// line_angle_solvers.cpp:551), so their operation order is Eigen's: norm = sqrt(x*x + y*y),
-// normalized = v / norm when the squared norm is positive, midpoint = (p1 + p2) / 2.0.
+// Members of the element value types (reference: src/constraint_solver/src/model/elements.cpp).
+// The packer reads Line::length() / unitDirection() / midpoint() (point_line_solvers.cpp:506,
+// :636-673; line_angle_solvers.cpp:551), so those keep Eigen's operation order: norm =
+// sqrt(x*x + y*y), normalized = v / norm when the squared norm is positive, midpoint =
+// (p1 + p2) / 2.0.  The text forms are the reference's, character for character.
 #include <format>
 
 #include <gcs/model/elements.hpp>
 
 namespace Gcs {
 
-Point::Point() : canvasPosition { Eigen::Vector2d::Zero() }, position { Eigen::Vector2d::Zero() } {}
-Point::Point(const Eigen::Vector2d& canvasPos) : canvasPosition { canvasPos }, position { Eigen::Vector2d::Zero() } {}
-std::string Point::getTypeName() const { return "Point"; }
-std::string Point::toString() const
-{
-    return std::format("CanvasCoords({},{}), Calculated({},{})", canvasPosition.x(), canvasPosition.y(), position.x(),
-        position.y());
-}
-void Point::updateElementPosition(const Eigen::Vector2d& newPosition) { position = newPosition; }
+namespace {
 
-FixedRadiusCircle::FixedRadiusCircle() : position { Eigen::Vector2d::Zero() }, fixedRadius { 0.0 } {}
-FixedRadiusCircle::FixedRadiusCircle(const Eigen::Vector2d& centerPos, double r) : position { centerPos }, fixedRadius { r } {}
+using Vec = Eigen::Vector2d;
+
+Vec origin() { return Vec::Zero(); }
+
+// "x,y" as std::format prints two doubles
+std::string xy(const Vec& v) { return std::format("{},{}", v.x(), v.y()); }
+
+}  // namespace
+
+// ---- Point: a canvas position and, once solved, a solver-space position ----
+Point::Point() : Point(origin()) {}
+
+Point::Point(const Vec& canvasPos) : canvasPosition(canvasPos), position(origin()) {}
+
+void Point::updateElementPosition(const Vec& newPosition) { position = newPosition; }
+
+std::string Point::getTypeName() const { return "Point"; }
+
+std::string Point::toString() const { return "CanvasCoords(" + xy(canvasPosition) + "), Calculated(" + xy(position) + ")"; }
+
+// ---- FixedRadiusCircle: kept for the variant's shape; no solver handles it ----
+FixedRadiusCircle::FixedRadiusCircle() : FixedRadiusCircle(origin(), 0.0) {}
+
+FixedRadiusCircle::FixedRadiusCircle(const Vec& centerPos, double r) : position(centerPos), fixedRadius(r) {}
+
+void FixedRadiusCircle::updateElementPosition(const Vec& newPosition) { position = newPosition; }
+
 std::string FixedRadiusCircle::getTypeName() const { return "FixedRadiusCircle"; }
+
 std::string FixedRadiusCircle::toString() const
 {
     return std::format("FixedRadiusCircle(x: {}, y: {}, radius: {})", position.x(), position.y(), fixedRadius);
 }
-void FixedRadiusCircle::updateElementPosition(const Eigen::Vector2d& newPosition) { position = newPosition; }
 
-Line::Line()
-    : canvasP1 { Eigen::Vector2d::Zero() }, canvasP2 { Eigen::Vector2d::Zero() }, p1 { Eigen::Vector2d::Zero() }, p2 { Eigen::Vector2d::Zero() }
+// ---- Line: two canvas endpoints and, once solved, two solver-space endpoints ----
+Line::Line() : Line(origin(), origin()) {}
+
+Line::Line(const Vec& canvasEndpoint1, const Vec& canvasEndpoint2)
+    : canvasP1(canvasEndpoint1), canvasP2(canvasEndpoint2), p1(origin()), p2(origin())
 {
 }
-Line::Line(const Eigen::Vector2d& canvasEndpoint1, const Eigen::Vector2d& canvasEndpoint2)
-    : canvasP1 { canvasEndpoint1 }, canvasP2 { canvasEndpoint2 }, p1 { Eigen::Vector2d::Zero() }, p2 { Eigen::Vector2d::Zero() }
-{
-}
+
+void Line::updateElementPosition(const Vec& newP1, const Vec& newP2) { p1 = newP1, p2 = newP2; }
+
 std::string Line::getTypeName() const { return "Line"; }
+
 std::string Line::toString() const
 {
-    return std::format("Line(CanvasP1:({},{}), CanvasP2:({},{}), CalcP1:({},{}), CalcP2:({},{}))", canvasP1.x(),
-        canvasP1.y(), canvasP2.x(), canvasP2.y(), p1.x(), p1.y(), p2.x(), p2.y());
+    return "Line(CanvasP1:(" + xy(canvasP1) + "), CanvasP2:(" + xy(canvasP2) + "), CalcP1:(" + xy(p1) + "), CalcP2:(" + xy(p2) + "))";
 }
-void Line::updateElementPosition(const Eigen::Vector2d& newP1, const Eigen::Vector2d& newP2)
-{
-    p1 = newP1;
-    p2 = newP2;
-}
-Eigen::Vector2d Line::direction() const { return p2 - p1; }
-Eigen::Vector2d Line::unitDirection() const { return (p2 - p1).normalized(); }
-Eigen::Vector2d Line::normal() const
-{
-    const Eigen::Vector2d dir = direction();
-    return Eigen::Vector2d(-dir.y(), dir.x());
-}
-double Line::length() const { return (p2 - p1).norm(); }
-Eigen::Vector2d Line::midpoint() const { return (p1 + p2) / 2.0; }
 
+Vec Line::direction() const { return p2 - p1; }
+
+double Line::length() const { return direction().norm(); }
+
+Vec Line::unitDirection() const { return direction().normalized(); }
+
+Vec Line::normal() const
+{
+    const Vec d = direction();
+    return { -d.y(), d.x() };
+}
+
+Vec Line::midpoint() const { return (p1 + p2) / 2.0; }
+
+// ---- Element: forwards to the active alternative ----
 std::string Element::getElementName() const
 {
-    return std::visit([](const auto& elem) { return elem.getTypeName(); }, m_element);
+    return std::visit([](const auto& shape) { return shape.getTypeName(); }, m_element);
 }
+
 std::string Element::toString() const
 {
-    return std::visit([](const auto& elem) { return elem.toString(); }, m_element);
+    return std::visit([](const auto& shape) { return shape.toString(); }, m_element);
 }
 
 }  // namespace Gcs
