@@ -226,8 +226,16 @@ __device__ __forceinline__ int predict_remaining(double d2, double d3)
 #ifndef GCS_SORTED_THREADS
 #define GCS_SORTED_THREADS 128
 #endif
-#ifndef GCS_SORTED_MINB
-#define GCS_SORTED_MINB 6
+// CTAs per SM the register allocation is held to: 6 (80 registers) for the point kinds, 7 (72)
+// for the line kinds K2/K5, whose runs are short (mean 5-6 updates) so that a larger share of a
+// CTA's life is spent at barriers and in the load / selection phases, where more resident CTAs
+// help (measured: K5 68.6 vs 71.7 us, K2 72.7 vs 75.2 us; K1 and K3 lose 2 % at 7).
+#ifdef GCS_SORTED_MINB
+template <int KIND>
+constexpr int kSortedMinBlocks = GCS_SORTED_MINB;
+#else
+template <int KIND>
+constexpr int kSortedMinBlocks = (KIND == GCS_KIND_SDD || KIND == GCS_KIND_ANG) ? 7 : 6;
 #endif
 
 // One CTA of THREADS lanes owns a tile of TILE sub-systems = RUNS = TILE*NS = 2*THREADS runs: two
@@ -239,7 +247,7 @@ __device__ __forceinline__ int predict_remaining(double d2, double d3)
 // of 32, longest first; warp w takes blocks w and 2W-1-w (a long one and a short one), so the
 // warps of the CTA reach the last barrier at about the same time.
 template <int KIND, int NS, int TILE, int THREADS>
-__global__ void __launch_bounds__(THREADS, GCS_SORTED_MINB) newton_sorted_kernel(const BatchDev p)
+__global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted_kernel(const BatchDev p)
 {
     using S = Sys<KIND>;
     constexpr int RUNS = TILE * NS;
@@ -249,7 +257,8 @@ __global__ void __launch_bounds__(THREADS, GCS_SORTED_MINB) newton_sorted_kernel
     __shared__ short s_it[RUNS];
     __shared__ unsigned short s_order[RUNS];
     __shared__ unsigned char s_cv[RUNS];
-    __shared__ int s_bin[kSortBins + 1];  // counts, then offsets; [kSortBins] = live runs
+    __shared__ int s_bin[kSortBins];   // live runs per sort key
+    __shared__ int s_fill[kSortBins];  // slots handed out per sort key during the scatter
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(THREADS, GCS_SORTED_MINB) newton_sorted_kernel
     const int cnt = (int)((p.n - base < TILE) ? (p.n - base) : TILE);
     FastConsts fc;
     fc.init((double)(p.n >> 62));  // 0.0 for every valid n, opaque to the compiler
-    if (tid <= kSortBins) s_bin[tid] = 0;
+    if (tid < kSortBins) s_bin[tid] = 0, s_fill[tid] = 0;
     __syncthreads();
 
     // ---- (A) iteration-0 test, three updates, prediction; this lane's runs: tid and tid + THREADS,
@@ -310,8 +319,11 @@ __global__ void __launch_bounds__(THREADS, GCS_SORTED_MINB) newton_sorted_kernel
         }
     }
     __syncthreads();
-    // ---- (B) counting sort of the live runs, longest predicted first ----
-    if (tid < 32) {
+    // ---- (B) counting sort of the live runs, longest predicted first.  Every warp scans the 32
+    //      bin counts for itself (lane k ends up with the first slot of key k), so no barrier is
+    //      needed between the scan and the scatter; slots inside a key come from s_fill ----
+    int n_live;
+    {
         const int c = s_bin[lane];
         int incl = c;
 #pragma unroll
@@ -319,28 +331,27 @@ __global__ void __launch_bounds__(THREADS, GCS_SORTED_MINB) newton_sorted_kernel
             const int v = __shfl_up_sync(kFull, incl, o);
             if (lane >= o) incl += v;
         }
-        s_bin[lane] = incl - c;
-        if (lane == 31) s_bin[kSortBins] = incl;
-    }
-    __syncthreads();
+        n_live = __shfl_sync(kFull, incl, 31);
+        const int first = incl - c;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int kk = key[q];
-        const unsigned live = __ballot_sync(kFull, kk >= 0);
-        if (kk >= 0) {
-            const unsigned peers = __match_any_sync(live, kk);
-            const int leader = __ffs(peers) - 1;
-            int o = 0;
-            if (lane == leader) o = atomicAdd(&s_bin[kk], __popc(peers));
-            o = __shfl_sync(peers, o, leader);
-            s_order[o + __popc(peers & lanemask_lt())] = (unsigned short)(tid + q * THREADS);
+        for (int q = 0; q < 2; ++q) {
+            const int kk = key[q];
+            const int slot0 = __shfl_sync(kFull, first, kk & 31);
+            const unsigned live = __ballot_sync(kFull, kk >= 0);
+            if (kk >= 0) {
+                const unsigned peers = __match_any_sync(live, kk);
+                const int leader = __ffs(peers) - 1;
+                int o = 0;
+                if (lane == leader) o = atomicAdd(&s_fill[kk], __popc(peers));
+                o = __shfl_sync(peers, o, leader);
+                s_order[slot0 + o + __popc(peers & lanemask_lt())] = (unsigned short)(tid + q * THREADS);
+            }
         }
     }
     __syncthreads();
 
     // ---- (C) the rest of every live run: warp w takes sorted blocks w and 2W-1-w ----
     {
-        const int n_live = s_bin[kSortBins];
         const int w = tid >> 5;
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {

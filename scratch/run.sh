@@ -1,3 +1,3 @@
-GCS_B200_TRACE=1 python scratch/trace.py 2> gpurun_out/trace_e2e.log; tail -40 gpurun_out/trace_e2e.log
-python scratch/e2e_probe.py
-for p in 3 6 8; do echo parts $p; GCS_B200_PARTS=$p python scratch/e2e_probe.py | grep both; done
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py -m gpu -x -q 2>&1 | tail -2
+python scratch/kbench.py 3 1,2,3,5
+python scratch/kbench.py 3 1 524288 8
