@@ -428,7 +428,13 @@ int gcs_b200_solve(const gcs_b200_batch* b, int device, void* cuda_stream)
 //
 // (Recording the same calls as a CUDA graph and replaying it was measured too: 1.80 ms per bench
 // step against 1.77 ms for plain stream calls - the enqueue cost, ~0.1 ms, already hides behind
-// the transfers - so the plain form stayed.)
+// the transfers - so the plain form stayed.  Also measured and dropped: splitting the rows of a
+// slab copy over two upload streams, 1.95 ms - the engines contend for the link; letting the
+// kernel read and write the pinned buffers itself (zero copy, static kernel, no arena), 1.80 ms -
+// SM loads pull ~45 GB/s over PCIe against ~47 GB/s for the copy engine on these row sizes; ranges
+// that halve (n/2, n/4, n/8, n/8), 1.73 ms - the same as equal ranges.  What keeps the call at
+// 1.71 ms instead of the 1.46 ms of one contiguous 80.7 MB copy is the strided copy itself: the
+// engine spends ~4.6 us per row of a 2-D copy on top of the bytes.)
 namespace {
 
 // GCS_B200_TRACE=1: timing events at the stage boundaries of the (non-graph) pipeline, printed at drain
@@ -593,6 +599,9 @@ int record_pipeline(DeviceState* d, const gcs_b200_batch* b, size_t off)
     }
     int rc = ensure_events(d, 2 * ranges.size());
     if (rc != GCS_OK) return rc;
+    // the one-byte code column goes up whole, ahead of the first range: one copy instead of one
+    // per range (every copy costs a few microseconds of engine time whatever its size)
+    CUDA_TRY(cudaMemcpyAsync(dcode, b->code, n, cudaMemcpyHostToDevice, d->h2d));
     for (const auto& range : ranges) {
         const int64_t lo = range.first, len = range.second;
         const size_t m = (size_t)len;
@@ -609,7 +618,6 @@ int record_pipeline(DeviceState* d, const gcs_b200_batch* b, size_t off)
             }
             c += run;
         }
-        CUDA_TRY(cudaMemcpyAsync(dcode + lo, b->code + lo, m, cudaMemcpyHostToDevice, d->h2d));
         if (b->guesses)
             CUDA_TRY(cudaMemcpy2DAsync(dguess + lo, n * 8, b->guesses + lo, n * 8, m * 8, (size_t)(2 * ns),
                 cudaMemcpyHostToDevice, d->h2d));
