@@ -114,6 +114,7 @@ GCS_API SolveResult solveSingle(SolverId id, ConstraintGraph& component, int dev
 
 struct BatchReport {
     std::size_t leaves = 0, solved = 0, unsupported = 0, waves = 0, launches = 0;
+    double planSeconds = 0, packSeconds = 0, deviceSeconds = 0, applySeconds = 0;  // where solveLeaves spent its time
     std::vector<SolveResult> results;  // per leaf, in input order
     std::vector<int> level;            // wave of each leaf (-1 = unsupported)
     std::vector<SolverId> solver;      // solver chosen per leaf

@@ -14,6 +14,7 @@
 // Numerics on this side are plain IEEE doubles evaluated in the reference's order (one rounding
 // per operation; the host build uses -ffp-contract=off like the reference's baseline x86-64 build).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <exception>
 #include <stdexcept>
@@ -521,11 +522,11 @@ int kindOf(SolverId id)
     return 0;
 }
 
-bool matches(SolverId id, const ConstraintGraph& g, const SetQuery& q)
+namespace {
+
+// the eight matches() predicates on the counts of one leaf
+bool matchesCounts(SolverId id, const ConstraintGraph& g, const Census& c, const ConstraintCensus& k)
 {
-    if (g.nodeCount() != 3) return false;
-    const Census c = census(g, q);
-    const ConstraintCensus k = constraintCensus(g);
     const bool allDistance = k.distance == k.total;
     switch (id) {
     case SolverId::ZeroFixedPointsTriangle:
@@ -551,14 +552,25 @@ bool matches(SolverId id, const ConstraintGraph& g, const SetQuery& q)
     return false;
 }
 
+}  // namespace
+
+bool matches(SolverId id, const ConstraintGraph& g, const SetQuery& q)
+{
+    if (g.nodeCount() != 3) return false;
+    return matchesCounts(id, g, census(g, q), constraintCensus(g));
+}
+
 SolverId classify(const ConstraintGraph& g, const SetQuery& q)
 {
     // component_solver.hpp:35-60: fully unsolved shapes first, then the partially solved ones
     static constexpr SolverId order[] = { SolverId::ZeroFixedPointsTriangle, SolverId::ZeroFixedPPLTriangle,
         SolverId::ZeroFixedLLPAngleTriangle, SolverId::TwoFixedPointsDistance, SolverId::TwoFixedPointsLine,
         SolverId::FixedPointAndLineFreePoint, SolverId::TwoFixedLinesFreePoint, SolverId::FixedLineAndPointFreeLine };
+    if (g.nodeCount() != 3) return SolverId::None;
+    const Census c = census(g, q);  // counted once: the predicates differ only in what they ask of the counts
+    const ConstraintCensus k = constraintCensus(g);
     for (SolverId id : order)
-        if (matches(id, g, q)) return id;
+        if (matchesCounts(id, g, c, k)) return id;
     return SolverId::None;
 }
 
@@ -638,26 +650,47 @@ SolveResult solveSingle(SolverId id, ConstraintGraph& component, int device)
     return SolveResult::success();  // every reference solver returns success() (e.g. point_point_solvers.cpp:163)
 }
 
-BatchReport planLeaves(const std::vector<ConstraintGraph>& leaves) { return makePlan(leaves).report; }
+BatchReport planLeaves(const std::vector<ConstraintGraph>& leaves)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    BatchReport rep = makePlan(leaves).report;
+    rep.planSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rep;
+}
 
 BatchReport solveLeaves(std::vector<ConstraintGraph>& leaves, int device)
 {
+    using Clock = std::chrono::steady_clock;
+    auto since = [](Clock::time_point t) { return std::chrono::duration<double>(Clock::now() - t).count(); };
+    auto t0 = Clock::now();
     Plan plan = makePlan(leaves);
     BatchReport& rep = plan.report;
+    rep.planSeconds = since(t0);
     // leaves of a wave, in input order
     std::vector<std::vector<std::size_t>> byWave(rep.waves);
     for (std::size_t i = 0; i < plan.stop; ++i)
         if (rep.level[i] >= 0) byWave[static_cast<std::size_t>(rep.level[i])].push_back(i);
     KindBatch batches[GCS_KIND_COUNT + 1];
     for (const auto& wave : byWave) {
+        t0 = Clock::now();
         for (int k = 1; k <= GCS_KIND_COUNT; ++k) batches[k] = KindBatch(k);
         for (std::size_t i : wave) {
             const PackedLeaf row = packNumeric(plan.roles[i]);
             batches[row.kind].push(row);
         }
+        rep.packSeconds += since(t0);
         for (int k = 1; k <= GCS_KIND_COUNT; ++k) {
             if (batches[k].size() == 0) continue;
-            solveBatchOnDevice(batches[k], device);
+            t0 = Clock::now();
+            gcs_b200_batch d = batches[k].descriptor();
+            const int rc = gcs_b200_solve_host(&d, device);
+            if (rc != GCS_OK)
+                throw std::runtime_error(std::string("gcs_b200_solve_host failed (") + std::to_string(rc) + "): "
+                    + gcs_b200_last_error() + " - the sub-problem solvers run on the CUDA path only");
+            rep.deviceSeconds += since(t0);
+            t0 = Clock::now();
+            batches[k].applyAll();
+            rep.applySeconds += since(t0);
             ++rep.launches;
         }
     }

@@ -176,7 +176,7 @@ GCS_API int gcs_host_component_pack(int n_el, gcs_host_element* el, int n_edges,
 //   mode 0: the reference's loop, one classifyAndSolve per leaf (a launch per leaf)
 //        1: DeficitStreeBasedTopDownStrategy::solveGcs (dependency waves, a launch per kind per wave)
 //        2: plan only (no device): solver + wave per leaf
-//   status/level/solver [n_leaves] (may be NULL); stats[0] = waves, stats[1] = launches, stats[2] = solved
+//   status/level/solver [n_leaves] (may be NULL); stats[0] = waves, stats[1] = launches, stats[2] = solved, stats[3] = microseconds spent planning
 // Returns 0, or -1 after an exception (elements solved before it are still written back).
 GCS_API int gcs_host_leaves_solve(int n_el, gcs_host_element* el, int n_leaves, const int32_t* leaf_elems,
     const int32_t* edge_offsets, const gcs_host_edge* edges, int mode, int32_t* status, int32_t* level, int32_t* solver,
@@ -189,7 +189,7 @@ GCS_API int gcs_host_leaves_solve(int n_el, gcs_host_element* el, int n_leaves, 
         std::vector<Gcs::ConstraintGraph> leaves;
         for (int l = 0; l < n_leaves; ++l)
             leaves.push_back(makeLeaf(elems, leaf_elems + 3 * l, 3, edges + edge_offsets[l], edge_offsets[l + 1] - edge_offsets[l]));
-        if (stats) stats[0] = stats[1] = stats[2] = 0;
+        if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
         if (mode == 0) {
             for (int l = 0; l < n_leaves; ++l) {
                 const Gcs::B200::SolverId id = Gcs::B200::classify(leaves[static_cast<std::size_t>(l)]);
@@ -219,7 +219,7 @@ GCS_API int gcs_host_leaves_solve(int n_el, gcs_host_element* el, int n_leaves, 
                 if (level) level[l] = rep.level[i];
                 if (solver) solver[l] = static_cast<int32_t>(rep.solver[i]);
             }
-            if (stats) stats[0] = static_cast<int64_t>(rep.waves), stats[1] = static_cast<int64_t>(rep.launches), stats[2] = static_cast<int64_t>(rep.solved);
+            if (stats) stats[0] = static_cast<int64_t>(rep.waves), stats[1] = static_cast<int64_t>(rep.launches), stats[2] = static_cast<int64_t>(rep.solved), stats[3] = static_cast<int64_t>(rep.planSeconds * 1e6);
         }
     } catch (const std::exception& ex) {
         rc = fail(ex);
@@ -265,7 +265,8 @@ GCS_API int gcs_host_solve2d(int pair, const double* p, const double* guesses, d
 // decomposition (a 3-element sketch is its own leaf - BASELINE config 1; larger Henneberg-style
 // sketches go through the degree-2 peeling of gcs/b200/peel_decomposition.hpp - config 4), then
 // the batched solveGcs.  stats (may be NULL): [0] leaves, [1] waves, [2] launches, [3] solved,
-// [4] microseconds in check + decomposition, [5] microseconds in solveGcs.
+// [4] microseconds in check + decomposition, [5] microseconds in solveGcs, of which [6] planning
+// (symbolic classification + wave levels), [7] packing, [8] device calls, [9] write-back.
 GCS_API int gcs_host_system_solve_ex(int n_el, gcs_host_element* el, int n_edges, const gcs_host_edge* edges, int64_t* stats)
 {
     try {
@@ -307,6 +308,8 @@ GCS_API int gcs_host_system_solve_ex(int n_el, gcs_host_element* el, int n_edges
             stats[2] = static_cast<int64_t>(rep.launches), stats[3] = static_cast<int64_t>(rep.solved);
             stats[4] = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
             stats[5] = std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
+            stats[6] = static_cast<int64_t>(rep.planSeconds * 1e6), stats[7] = static_cast<int64_t>(rep.packSeconds * 1e6);
+            stats[8] = static_cast<int64_t>(rep.deviceSeconds * 1e6), stats[9] = static_cast<int64_t>(rep.applySeconds * 1e6);
         }
         for (int i = 0; i < n_el; ++i) readBack(*elems[static_cast<std::size_t>(i)], el[i]);
         return 0;

@@ -98,9 +98,9 @@ def system_solve(elements, edges):
 def system_solve_ex(elements, edges):
     """Whole sketch through check -> decompose -> batched solveGcs.  Returns (rc, elements, stats dict)."""
     els, eds = to_c(elements, edges)
-    stats = (C.c_int64 * 6)()
+    stats = (C.c_int64 * 10)()
     rc = load().gcs_host_system_solve_ex(len(elements), els, len(edges), eds, stats)
-    keys = ("leaves", "waves", "launches", "solved", "decompose_us", "solve_us")
+    keys = ("leaves", "waves", "launches", "solved", "decompose_us", "solve_us", "plan_us", "pack_us", "device_us", "apply_us")
     return rc, from_c(elements, els), dict(zip(keys, list(stats)))
 
 
@@ -142,10 +142,10 @@ def leaves_solve(elements, leaves, mode):
     status = (C.c_int32 * max(n, 1))()
     level = (C.c_int32 * max(n, 1))()
     solver = (C.c_int32 * max(n, 1))()
-    stats = (C.c_int64 * 3)()
+    stats = (C.c_int64 * 4)()
     rc = load().gcs_host_leaves_solve(len(elements), els, n, le, eo, eds, mode, status, level, solver, stats)
     return {"rc": rc, "status": list(status)[:n], "level": list(level)[:n], "solver": list(solver)[:n],
-            "waves": stats[0], "launches": stats[1], "solved": stats[2], "elements": from_c(elements, els)}
+            "waves": stats[0], "launches": stats[1], "solved": stats[2], "plan_us": stats[3], "elements": from_c(elements, els)}
 
 
 def solve2d(pair, params, guesses=None):
