@@ -432,9 +432,9 @@ int gcs_b200_solve(const gcs_b200_batch* b, int device, void* cuda_stream)
 // slab copy over two upload streams, 1.95 ms - the engines contend for the link; letting the
 // kernel read and write the pinned buffers itself (zero copy, static kernel, no arena), 1.80 ms -
 // SM loads pull ~45 GB/s over PCIe against ~47 GB/s for the copy engine on these row sizes; ranges
-// that halve (n/2, n/4, n/8, n/8), 1.73 ms - the same as equal ranges.  What keeps the call at
-// 1.71 ms instead of the 1.46 ms of one contiguous 80.7 MB copy is the strided copy itself: the
-// engine spends ~4.6 us per row of a 2-D copy on top of the bytes.)
+// that halve (n/2, n/4, n/8, n/8), 1.73 ms - the same as equal ranges; packed sub-batches of
+// 131072 rows uploaded with one 1-D copy each, 1.70 ms - the same again.  Copies of pipeline-stage
+// size (7-14 MB) reach ~48 GB/s on the box, the 55 GB/s of its PCIe link need 64 MB and more.)
 namespace {
 
 // GCS_B200_TRACE=1: timing events at the stage boundaries of the (non-graph) pipeline, printed at drain

@@ -1,2 +1,6 @@
-python -m pytest tests/test_gpu_host.py tests/test_merge3.py tests/test_sketch_io.py -m gpu -x -q 2>&1 | tail -2
-python profiles/sketch_bench.py 100000 2>/dev/null | tail -1 > gpurun_out/sketch_bench_r1i.json; cut -c1-420 gpurun_out/sketch_bench_r1i.json
+python scratch/e2e_probe.py | grep both
+python scratch/e2e_sub.py 131072 131072
+python scratch/e2e_sub.py 131072 65536
+python scratch/e2e_sub.py 65536 65536
+GCS_B200_TRACE=1 python scratch/e2e_sub.py 131072 65536 2>&1 | grep trace | tail -42 | grep -E "up-begin|flags-end" | head -30
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
