@@ -130,7 +130,9 @@ extern "C" {
 #define GCS_MEM_HOST 0
 #define GCS_MEM_DEVICE 1
 
-/* kernel selection (0 = library default). Both produce bit-identical results. */
+/* kernel selection.  Every variant produces bit-identical results (same device functions, same
+ * operation order per Newton run); they differ in how runs are mapped to lanes.
+ * DEFAULT = SORTED for launches of at least 2^18 runs (n * n_seeds), STATIC below. */
 #define GCS_VARIANT_DEFAULT 0
 #define GCS_VARIANT_STATIC 1 /* one lane per (sub-system, seed), static mapping */
 #define GCS_VARIANT_REFILL 2 /* persistent CTAs, TMA-staged tiles, warp-level lane refill */
