@@ -1,12 +1,11 @@
 // MathUtils::PropertyMap: id -> value, iterated in ascending id order (reference:
-// src/structures/include/structures/property_map.hpp:33-180, a std::flat_map there; an ordered
-// std::map here - g++ 13 has no <flat_map>, the iteration order is what matters).
+// src/structures/include/structures/property_map.hpp:33-180, a std::flat_map there; the sorted
+// vector of simple_graph.hpp here - g++ 13 has no <flat_map>).
 #pragma once
 
 #include <cstddef>
 #include <expected>
 #include <functional>
-#include <map>
 #include <utility>
 
 #include <structures/simple_graph.hpp>
@@ -21,10 +20,14 @@ public:
     using KeyType = KeyId;
     using ValueType = Value;
 
-    Value& operator[](const KeyId& id) { return m_data[id]; }
-    std::expected<std::reference_wrapper<const Value>, PropertyMapError> get(const KeyId& id) const
+    Value& operator[](const KeyId& id)
     {
         auto it = m_data.find(id);
+        return it != m_data.end() ? it->second : m_data.put(id, Value {}).second;
+    }
+    std::expected<std::reference_wrapper<const Value>, PropertyMapError> get(const KeyId& id) const
+    {
+        const auto it = m_data.find(id);
         if (it == m_data.end()) return std::unexpected(PropertyMapError::KeyNotFound);
         return std::cref(it->second);
     }
@@ -34,14 +37,14 @@ public:
         if (it == m_data.end()) return std::unexpected(PropertyMapError::KeyNotFound);
         return std::ref(it->second);
     }
-    void set(const KeyId& id, Value value) { m_data.insert_or_assign(id, std::move(value)); }
+    void set(const KeyId& id, Value value) { m_data.put(id, std::move(value)); }
     std::expected<void, PropertyMapError> erase(const KeyId& id)
     {
-        if (m_data.erase(id) == 0) return std::unexpected(PropertyMapError::KeyNotFound);
+        if (!m_data.erase(id)) return std::unexpected(PropertyMapError::KeyNotFound);
         return {};
     }
     void clear() { m_data.clear(); }
-    bool contains(const KeyId& id) const { return m_data.count(id) != 0; }
+    bool contains(const KeyId& id) const { return m_data.contains(id); }
     std::size_t size() const { return m_data.size(); }
     bool empty() const { return m_data.empty(); }
     auto begin() { return m_data.begin(); }
@@ -50,7 +53,7 @@ public:
     auto end() const { return m_data.end(); }
 
 private:
-    std::map<KeyId, Value> m_data;
+    detail::FlatTable<KeyId, Value> m_data;  // sorted by id, like the reference's std::flat_map
 };
 
 template <typename Value>

@@ -1,16 +1,21 @@
 // MathUtils::NodeId / EdgeId / SimpleGraph with the interface the constraint graph relies on
 // (reference: src/structures/include/structures/simple_graph.hpp:23-188).  Only what the solver
 // path needs is provided: id-stable node/edge insertion and removal, endpoint and incidence
-// queries.  Storage is ordered (std::map) - ids iterate ascending, which is the order the
-// reference's flat_map property maps expose and its role assignment depends on.
+// queries.
+//
+// Storage is flat: sorted vectors keyed by id (ids are handed out ascending, so insertion is an
+// append).  A leaf component is a 3-node graph and a decomposition creates one per element of the
+// sketch; node-based containers cost ~20 heap allocations per leaf there, sorted vectors three.
+// Ids iterate ascending, the order the reference's flat_map property maps expose and its role
+// assignment depends on.
 #pragma once
 
+#include <algorithm>
 #include <compare>
 #include <cstddef>
 #include <expected>
 #include <functional>
-#include <map>
-#include <set>
+#include <stdexcept>
 #include <utility>
 #include <vector>
 
@@ -30,15 +35,75 @@ struct EdgeId {
     auto operator<=>(const EdgeId&) const = default;
 };
 
+namespace detail {
+
+// id -> value in a vector sorted by id.  find() is a linear scan while the table is tiny (the
+// leaf case) and a binary search beyond; keys at or past the end append.
+template <typename Key, typename Value>
+class FlatTable {
+public:
+    using Entry = std::pair<Key, Value>;
+    using iterator = typename std::vector<Entry>::iterator;
+    using const_iterator = typename std::vector<Entry>::const_iterator;
+
+    iterator begin() { return m_rows.begin(); }
+    iterator end() { return m_rows.end(); }
+    const_iterator begin() const { return m_rows.begin(); }
+    const_iterator end() const { return m_rows.end(); }
+    std::size_t size() const { return m_rows.size(); }
+    bool empty() const { return m_rows.empty(); }
+    void clear() { m_rows.clear(); }
+
+    const_iterator find(const Key& k) const { return locate(m_rows.begin(), m_rows.end(), k); }
+    iterator find(const Key& k) { return locate(m_rows.begin(), m_rows.end(), k); }
+    bool contains(const Key& k) const { return find(k) != m_rows.end(); }
+
+    // insert or overwrite; returns the entry
+    Entry& put(const Key& k, Value v)
+    {
+        if (m_rows.empty() || m_rows.back().first < k) return m_rows.emplace_back(k, std::move(v));
+        auto it = std::lower_bound(m_rows.begin(), m_rows.end(), k, [](const Entry& e, const Key& key) { return e.first < key; });
+        if (it != m_rows.end() && it->first == k) {
+            it->second = std::move(v);
+            return *it;
+        }
+        return *m_rows.insert(it, Entry(k, std::move(v)));
+    }
+    bool erase(const Key& k)
+    {
+        auto it = find(k);
+        if (it == m_rows.end()) return false;
+        m_rows.erase(it);
+        return true;
+    }
+
+private:
+    template <typename It>
+    static It locate(It first, It last, const Key& k)
+    {
+        if (last - first <= 8) {
+            for (It it = first; it != last; ++it)
+                if (it->first == k) return it;
+            return last;
+        }
+        It it = std::lower_bound(first, last, k, [](const Entry& e, const Key& key) { return e.first < key; });
+        return (it != last && it->first == k) ? it : last;
+    }
+    std::vector<Entry> m_rows;
+};
+
+}  // namespace detail
+
 class SimpleGraph {
 public:
     using NodeIdType = NodeId;
     using EdgeIdType = EdgeId;
+    using EdgeList = std::vector<EdgeId>;  // ascending
 
     NodeId addNode()
     {
         const NodeId id { m_nextNode++ };
-        m_incident.emplace(id, std::set<EdgeId> {});
+        m_incident.put(id, EdgeList {});
         return id;
     }
 
@@ -47,9 +112,9 @@ public:
         auto is = m_incident.find(s), it = m_incident.find(t);
         if (is == m_incident.end() || it == m_incident.end()) return std::unexpected(GraphError::NodeNotFound);
         const EdgeId id { m_nextEdge++ };
-        m_ends.emplace(id, std::make_pair(s, t));
-        is->second.insert(id);
-        it->second.insert(id);
+        m_ends.put(id, std::make_pair(s, t));
+        is->second.push_back(id);  // the newest id is the largest: lists stay ascending
+        if (it != is) it->second.push_back(id);
         return id;
     }
 
@@ -57,9 +122,11 @@ public:
     {
         auto f = m_ends.find(e);
         if (f == m_ends.end()) return std::unexpected(GraphError::EdgeNotFound);
-        m_incident[f->second.first].erase(e);
-        m_incident[f->second.second].erase(e);
-        m_ends.erase(f);
+        for (NodeId n : { f->second.first, f->second.second }) {
+            auto in = m_incident.find(n);
+            if (in != m_incident.end()) std::erase(in->second, e);
+        }
+        m_ends.erase(e);
         return {};
     }
 
@@ -67,7 +134,7 @@ public:
     {
         auto f = m_incident.find(n);
         if (f == m_incident.end()) return std::unexpected(GraphError::NodeNotFound);
-        const std::vector<EdgeId> gone(f->second.begin(), f->second.end());
+        const EdgeList gone = f->second;
         for (EdgeId e : gone) removeEdge(e);
         m_incident.erase(n);
         return {};
@@ -76,17 +143,29 @@ public:
     std::vector<NodeId> getNodes() const
     {
         std::vector<NodeId> v;
+        v.reserve(m_incident.size());
         for (const auto& kv : m_incident) v.push_back(kv.first);
         return v;
     }
     std::vector<EdgeId> getEdges() const
     {
         std::vector<EdgeId> v;
+        v.reserve(m_ends.size());
         for (const auto& kv : m_ends) v.push_back(kv.first);
         return v;
     }
-    const std::set<EdgeId>& getEdges(NodeId n) const { return m_incident.at(n); }
-    std::pair<NodeId, NodeId> getEndpoints(EdgeId e) const { return m_ends.at(e); }
+    const EdgeList& getEdges(NodeId n) const
+    {
+        const auto it = m_incident.find(n);
+        if (it == m_incident.end()) throw std::out_of_range("SimpleGraph::getEdges: unknown node");
+        return it->second;
+    }
+    std::pair<NodeId, NodeId> getEndpoints(EdgeId e) const
+    {
+        const auto it = m_ends.find(e);
+        if (it == m_ends.end()) throw std::out_of_range("SimpleGraph::getEndpoints: unknown edge");
+        return it->second;
+    }
     std::vector<NodeId> getNeighbors(NodeId n) const
     {
         std::vector<NodeId> v;
@@ -99,15 +178,15 @@ public:
 
     std::size_t nodeCount() const { return m_incident.size(); }
     std::size_t edgeCount() const { return m_ends.size(); }
-    bool hasNode(NodeId n) const { return m_incident.count(n) != 0; }
-    bool hasEdge(EdgeId e) const { return m_ends.count(e) != 0; }
+    bool hasNode(NodeId n) const { return m_incident.contains(n); }
+    bool hasEdge(EdgeId e) const { return m_ends.contains(e); }
 
     std::expected<EdgeId, GraphError> getEdgeBetween(NodeId s, NodeId t) const
     {
-        auto is = m_incident.find(s);
+        const auto is = m_incident.find(s);
         if (is == m_incident.end() || !hasNode(t)) return std::unexpected(GraphError::EdgeNotFound);
         for (EdgeId e : is->second) {
-            const auto& ends = m_ends.at(e);
+            const auto ends = m_ends.find(e)->second;
             if ((ends.first == s && ends.second == t) || (ends.first == t && ends.second == s)) return e;
         }
         return std::unexpected(GraphError::EdgeNotFound);
@@ -117,8 +196,8 @@ public:
 private:
     int m_nextNode { 0 };
     int m_nextEdge { 0 };
-    std::map<NodeId, std::set<EdgeId>> m_incident;
-    std::map<EdgeId, std::pair<NodeId, NodeId>> m_ends;
+    detail::FlatTable<NodeId, EdgeList> m_incident;
+    detail::FlatTable<EdgeId, std::pair<NodeId, NodeId>> m_ends;
 };
 
 }  // namespace MathUtils

@@ -441,15 +441,36 @@ Plan makePlan(const std::vector<ConstraintGraph>& leaves)
     plan.roles.resize(n);
     plan.stop = n;
 
-    std::unordered_set<const Element*> predicted;  // solved once the leaves so far have run
-    std::unordered_map<const Element*, int> lastWrite, lastRead;
-    const SetQuery q = [&](const Element* e) { return e->isElementSet() || predicted.count(e) != 0; };
-    auto levelOf = [](const std::unordered_map<const Element*, int>& m, const Element* e) {
-        const auto it = m.find(e);
-        return it == m.end() ? -1 : it->second;
+    // Every element gets a dense index on first sight; what the symbolic pass knows about it
+    // (solved once the leaves so far have run; wave of its last write / last read) lives in flat
+    // arrays.  One hash lookup per element of a leaf - the predicates and the role assignment then
+    // ask a three-entry table.
+    std::unordered_map<const Element*, int> indexOf;
+    indexOf.reserve(2 * n + 16);
+    std::vector<char> predicted;
+    std::vector<int> lastWrite, lastRead;
+    const Element* leafEl[3] = { nullptr, nullptr, nullptr };
+    int leafIx[3] = { -1, -1, -1 };
+    int leafCount = 0;
+    auto slotOf = [&](const Element* e) {
+        for (int k = 0; k < leafCount; ++k)
+            if (leafEl[k] == e) return leafIx[k];
+        const auto it = indexOf.find(e);  // not an element of the current leaf: cannot happen for 3-node leaves
+        return it == indexOf.end() ? -1 : it->second;
+    };
+    const SetQuery q = [&](const Element* e) {
+        if (e->isElementSet()) return true;
+        const int ix = slotOf(e);
+        return ix >= 0 && predicted[static_cast<std::size_t>(ix)] != 0;
     };
     int top = -1;
     for (std::size_t i = 0; i < n; ++i) {
+        leafCount = 0;
+        for (const auto& [node, e] : leaves[i].getElementMap()) {
+            const auto [it, fresh] = indexOf.try_emplace(e.get(), static_cast<int>(predicted.size()));
+            if (fresh) predicted.push_back(0), lastWrite.push_back(-1), lastRead.push_back(-1);
+            if (leafCount < 3) leafEl[leafCount] = e.get(), leafIx[leafCount] = it->second, ++leafCount;
+        }
         const SolverId id = classify(leaves[i], q);
         plan.report.solver[i] = id;
         if (id == SolverId::None) {
@@ -466,16 +487,22 @@ Plan makePlan(const std::vector<ConstraintGraph>& leaves)
         }
         const Footprint f = footprintOf(plan.roles[i]);
         int lvl = -1;
-        for (int k = 0; k < f.nReads; ++k) lvl = std::max(lvl, levelOf(lastWrite, f.reads[k]));
-        for (int k = 0; k < f.nWrites; ++k)
-            lvl = std::max({ lvl, levelOf(lastWrite, f.writes[k]), levelOf(lastRead, f.writes[k]) });
+        for (int k = 0; k < f.nReads; ++k) lvl = std::max(lvl, lastWrite[static_cast<std::size_t>(slotOf(f.reads[k]))]);
+        for (int k = 0; k < f.nWrites; ++k) {
+            const auto w = static_cast<std::size_t>(slotOf(f.writes[k]));
+            lvl = std::max({ lvl, lastWrite[w], lastRead[w] });
+        }
         ++lvl;
         plan.report.level[i] = lvl;
         top = std::max(top, lvl);
-        for (int k = 0; k < f.nReads; ++k) lastRead[f.reads[k]] = std::max(levelOf(lastRead, f.reads[k]), lvl);
+        for (int k = 0; k < f.nReads; ++k) {
+            int& r = lastRead[static_cast<std::size_t>(slotOf(f.reads[k]))];
+            r = std::max(r, lvl);
+        }
         for (int k = 0; k < f.nWrites; ++k) {
-            lastWrite[f.writes[k]] = lvl;
-            predicted.insert(f.writes[k]);
+            const auto w = static_cast<std::size_t>(slotOf(f.writes[k]));
+            lastWrite[w] = lvl;
+            predicted[w] = 1;
         }
         plan.report.results[i] = SolveResult::success();
         ++plan.report.solved;

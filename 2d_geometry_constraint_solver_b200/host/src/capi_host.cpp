@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <limits>
@@ -369,7 +370,11 @@ GCS_API int gcs_host_decompose(int n_el, const gcs_host_element* el, int n_edges
                 g.addConstraint(eid, std::make_shared<Gcs::Constraint>(Gcs::AngleConstraint(ed.value, ed.flip != 0)));
         }
         Gcs::DeficitStreeBasedTopDownStrategy st;
+        const auto t0 = std::chrono::steady_clock::now();
         const auto leaves = st.decomposeConstraintGraph(g);
+        if (std::getenv("GCS_HOST_TRACE"))
+            std::fprintf(stderr, "[host] decomposeConstraintGraph: %.1f ms for %zu leaves\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), leaves.size());
         int l = 0;
         for (const auto& leaf : leaves) {
             if (l >= capacity) break;

@@ -59,7 +59,10 @@ std::vector<ConstraintGraph> decomposeByPeeling(const ConstraintGraph& gcs, Peel
 
     // live adjacency: node -> incident live edges
     std::map<NodeId, std::set<EdgeId>> incident;
-    for (NodeId n : graph.getNodes()) incident.emplace(n, graph.getEdges(n));
+    for (NodeId n : graph.getNodes()) {
+        const auto& es = graph.getEdges(n);
+        incident.emplace(n, std::set<EdgeId>(es.begin(), es.end()));
+    }
     auto other = [&](EdgeId e, NodeId n) {
         const auto [s, t] = graph.getEndpoints(e);
         return s == n ? t : s;
