@@ -337,6 +337,22 @@ int gcs_b200_kind_out_cols(int kind)
     return (kind >= 1 && kind <= GCS_KIND_COUNT) ? t[kind] : 0;
 }
 
+void* gcs_b200_host_alloc(size_t bytes)
+{
+    if (bytes == 0 || ensure_init() != GCS_OK || g_devs.empty()) return nullptr;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void gcs_b200_host_free(void* p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
+}
+
 int gcs_b200_device_count(void)
 {
     int n = 0;

@@ -15,6 +15,8 @@
 // per operation; the host build uses -ffp-contract=off like the reference's baseline x86-64 build).
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <exception>
 #include <stdexcept>
@@ -714,7 +716,10 @@ BatchReport solveLeaves(std::vector<ConstraintGraph>& leaves, int device)
             if (rc != GCS_OK)
                 throw std::runtime_error(std::string("gcs_b200_solve_host failed (") + std::to_string(rc) + "): "
                     + gcs_b200_last_error() + " - the sub-problem solvers run on the CUDA path only");
-            rep.deviceSeconds += since(t0);
+            const double call = since(t0);
+            rep.deviceSeconds += call;
+            if (std::getenv("GCS_HOST_TRACE"))
+                std::fprintf(stderr, "[host] wave launch kind %d rows %zu: %.1f us\n", k, batches[k].size(), call * 1e6);
             t0 = Clock::now();
             batches[k].applyAll();
             rep.applySeconds += since(t0);

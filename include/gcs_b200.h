@@ -200,6 +200,14 @@ GCS_B200_API int gcs_b200_default_variant(int64_t n, int n_seeds);
  * Returns a negative GCS_E_* code as a double on failure. */
 GCS_B200_API double gcs_b200_fp64_probe(int device, int what);
 
+/* Page-locked host memory for batch columns: the host-buffer entry points move pinned buffers at
+ * PCIe rate and asynchronously, pageable ones through the driver's staging copies.  Returns NULL
+ * when no CUDA device is available (callers may then fall back to ordinary memory: only the
+ * transfer gets slower).  Free with gcs_b200_host_free.  (A C++ host such as the reference has no
+ * other way to get pinned memory without linking the CUDA runtime itself.) */
+GCS_B200_API void* gcs_b200_host_alloc(size_t bytes);
+GCS_B200_API void gcs_b200_host_free(void* p);
+
 /* On-device synthetic instance generator for the parametric sweep (BASELINE config 5) and the
  * 1M-cluster configs: fills K1 columns for indices [first, first+n) with the counter-based
  * splitmix64 stream documented in DESIGN.md.  All pointers are device pointers. */

@@ -55,6 +55,9 @@ def test_no_cpu_fallback_without_a_device(gcs, built):
     with pytest.raises(capi.GcsError):
         capi.solve_host(hb, 0)
     assert lib.gcs_b200_fp64_probe(0, 0) < 0
+    lib.gcs_b200_host_alloc.restype = C.c_void_p
+    lib.gcs_b200_host_alloc.argtypes = [C.c_size_t]
+    assert lib.gcs_b200_host_alloc(4096) is None  # no device: the caller falls back to ordinary memory
 
 
 def test_product_does_not_reference_the_oracle():

@@ -361,3 +361,29 @@ def test_sharded_solve_over_all_devices_matches_single_device(gpu, gcs):
         b.want_cand = False
         capi.solve_host(b.alloc_outputs(), 0)
         assert_batches_identical(a, b, f"sharded kind {kind} over {ndev} devices")
+
+
+def test_page_locked_columns_from_the_abi_allocator(gpu, gcs):
+    """gcs_b200_host_alloc / gcs_b200_host_free: pinned memory for hosts that do not link the CUDA
+    runtime (the C++ mirror).  Same results as pageable columns."""
+    import ctypes as C
+    capi, synth = gcs.capi, gcs.synth
+    lib = capi.load()
+    lib.gcs_b200_host_alloc.restype = C.c_void_p
+    lib.gcs_b200_host_alloc.argtypes = [C.c_size_t]
+    lib.gcs_b200_host_free.argtypes = [C.c_void_p]
+    n = 5000
+    ref = capi.solve_host(synth.make_pp(n).alloc_outputs(), 0)
+    h = synth.make_pp(n)
+    nbytes = 6 * n * 8
+    p = lib.gcs_b200_host_alloc(nbytes)
+    assert p, "pinned allocation failed on a GPU box"
+    try:
+        slab = np.ctypeslib.as_array((C.c_double * (6 * n)).from_address(p)).reshape(6, n)
+        slab[...] = np.stack(h.cols)
+        hb = capi.HostBatch(1, 2, [slab[c] for c in range(6)], h.code)
+        capi.solve_host(hb.alloc_outputs(), 0)
+        assert_batches_identical(hb, ref, "pinned columns")
+    finally:
+        lib.gcs_b200_host_free(p)
+    assert lib.gcs_b200_host_alloc(0) is None
