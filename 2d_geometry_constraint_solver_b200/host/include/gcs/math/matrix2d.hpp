@@ -7,7 +7,7 @@
 
 #include <gcs/math/vector2d.hpp>
 
-#if !(__has_include(<Eigen/Core>) && !defined(GCS_B200_NO_EIGEN))
+#if !(__has_include(<Eigen/src/Core/Matrix.h>) && !defined(GCS_B200_NO_EIGEN))
 namespace Eigen {
 
 class Matrix2d {

@@ -5,7 +5,7 @@
 // normalized: z = squaredNorm, z > 0 ? v / sqrt(z) : v; v / s is a true division).
 #pragma once
 
-#if __has_include(<Eigen/Core>) && !defined(GCS_B200_NO_EIGEN)
+#if __has_include(<Eigen/src/Core/Matrix.h>) && !defined(GCS_B200_NO_EIGEN)
 #include <Eigen/Core>
 #else
 #include <cmath>
@@ -42,6 +42,13 @@ public:
     Vector2d operator-() const { return Vector2d(-m_x, -m_y); }
     Vector2d& operator+=(const Vector2d& o) { m_x += o.m_x; m_y += o.m_y; return *this; }
     Vector2d& operator-=(const Vector2d& o) { m_x -= o.m_x; m_y -= o.m_y; return *this; }
+    Vector2d& operator/=(double s) { m_x /= s; m_y /= s; return *this; }
+    Vector2d& operator*=(double s) { m_x *= s; m_y *= s; return *this; }
+    // v.transpose(): a row view, only ever the right operand of an outer product u * v.transpose()
+    struct Row {
+        double a, b;
+    };
+    Row transpose() const { return { m_x, m_y }; }
     friend Vector2d operator+(const Vector2d& a, const Vector2d& b) { return Vector2d(a.m_x + b.m_x, a.m_y + b.m_y); }
     friend Vector2d operator-(const Vector2d& a, const Vector2d& b) { return Vector2d(a.m_x - b.m_x, a.m_y - b.m_y); }
     friend Vector2d operator*(double s, const Vector2d& a) { return Vector2d(s * a.m_x, s * a.m_y); }
