@@ -32,6 +32,8 @@ IN_COL_NAMES = {
 
 MEM_HOST, MEM_DEVICE = 0, 1
 VARIANT_DEFAULT, VARIANT_STATIC, VARIANT_REFILL, VARIANT_SORTED, VARIANT_PAIR = 0, 1, 2, 3, 4
+# tolerance-class arithmetic (discrete outputs identical, coordinates to 1e-9): auto / static / sorted
+VARIANT_CONTRACTED, VARIANT_CONTRACTED_STATIC, VARIANT_CONTRACTED_SORTED, VARIANT_CONTRACTED_PAIR = 5, 6, 7, 8
 
 CODE_COLLINEAR = 0x10
 CODE_CANVAS_PARALLEL = 0x20
@@ -77,6 +79,7 @@ EXPORTS = [
     "gcs_b200_shutdown", "gcs_b200_last_error", "gcs_b200_version", "gcs_b200_solve",
     "gcs_b200_solve_host", "gcs_b200_solve_host_async", "gcs_b200_wait", "gcs_b200_solve_sharded", "gcs_b200_launch_count", "gcs_b200_kernel_name", "gcs_b200_default_variant",
     "gcs_b200_fp64_probe", "gcs_b200_synth_pp", "gcs_b200_selftest", "gcs_b200_host_alloc", "gcs_b200_host_free",
+    "gcs_b200_contracted_stats",
 ]
 
 
@@ -104,6 +107,7 @@ def load():
     lib.gcs_b200_kernel_name.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.gcs_b200_kernel_name.restype = C.c_char_p
     lib.gcs_b200_default_variant.argtypes = [C.c_int64, C.c_int]
+    lib.gcs_b200_contracted_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.c_int]
     lib.gcs_b200_fp64_probe.argtypes = [C.c_int, C.c_int]
     lib.gcs_b200_fp64_probe.restype = C.c_double
     lib.gcs_b200_selftest.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.POINTER(C.c_uint64)]

@@ -47,6 +47,8 @@ int fail(int code, const char* fmt, ...)
 constexpr long long kSortedMinRuns = 1ll << 18;
 inline int resolve_variant(int variant, long long n, int n_seeds)
 {
+    if (variant == GCS_VARIANT_CONTRACTED)
+        return n * n_seeds >= kSortedMinRuns ? GCS_VARIANT_CONTRACTED_SORTED : GCS_VARIANT_CONTRACTED_STATIC;
     if (variant != GCS_VARIANT_DEFAULT) return variant;
     return n * n_seeds >= kSortedMinRuns ? GCS_VARIANT_SORTED : GCS_VARIANT_STATIC;
 }
@@ -156,14 +158,14 @@ BatchDev to_dev(const gcs_b200_batch* b)
     return p;
 }
 
-template <int KIND, int NS>
+template <int KIND, int NS, bool RLX = false>
 int launch_static(const BatchDev& p, cudaStream_t st)
 {
     const long long threads = p.n * NS;
     static const int block = getenv("GCS_STATIC_BLOCK") ? atoi(getenv("GCS_STATIC_BLOCK")) : 128;  // tuning knob (multiple of 32)
     const long long grid = (threads + block - 1) / block;
     if (grid > 0x7fffffffLL) return fail(GCS_E_INVALID, "batch too large for one launch");
-    newton_static_kernel<KIND, NS><<<(unsigned)grid, block, 0, st>>>(p);
+    newton_static_kernel<KIND, NS, RLX><<<(unsigned)grid, block, 0, st>>>(p);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return GCS_OK;
@@ -181,12 +183,23 @@ int launch_pair(const BatchDev& p, cudaStream_t st)
 }
 
 template <int KIND, int NS>
+int launch_pair_relaxed(const BatchDev& p, cudaStream_t st)
+{
+    const long long grid = (p.n + 127) / 128;
+    if (grid > 0x7fffffffLL) return fail(GCS_E_INVALID, "batch too large for one launch");
+    newton_pair_relaxed_kernel<KIND, NS><<<(unsigned)grid, 128, 0, st>>>(p);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCS_OK;
+}
+
+template <int KIND, int NS, bool RLX = false>
 int launch_sorted(const BatchDev& p, cudaStream_t st)
 {
     constexpr int T = GCS_SORTED_THREADS, TILE = 2 * T / NS;  // two runs per lane
     const long long grid = (p.n + TILE - 1) / TILE;
     if (grid > 0x7fffffffLL) return fail(GCS_E_INVALID, "batch too large for one launch");
-    newton_sorted_kernel<KIND, NS, TILE, T><<<(unsigned)grid, T, 0, st>>>(p);
+    newton_sorted_kernel<KIND, NS, TILE, T, RLX><<<(unsigned)grid, T, 0, st>>>(p);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return GCS_OK;
@@ -229,11 +242,17 @@ int launch_kind(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cuda
     const int variant = resolve_variant(b->variant, p.n, b->n_seeds);
     constexpr bool column_guess = (KIND == GCS_KIND_SDD || KIND == GCS_KIND_ANG);
     if (b->n_seeds == 2) {
+        if (variant == GCS_VARIANT_CONTRACTED_PAIR) return launch_pair_relaxed<KIND, 2>(p, st);
+        if (variant == GCS_VARIANT_CONTRACTED_SORTED) return launch_sorted<KIND, 2, true>(p, st);
+        if (variant == GCS_VARIANT_CONTRACTED_STATIC) return launch_static<KIND, 2, true>(p, st);
         if (variant == GCS_VARIANT_SORTED) return launch_sorted<KIND, 2>(p, st);
         if (variant == GCS_VARIANT_PAIR) return launch_pair<KIND>(p, st);
         return variant == GCS_VARIANT_REFILL ? launch_refill<KIND, 2>(d, p, st) : launch_static<KIND, 2>(p, st);
     }
     if constexpr (!column_guess) {
+        if (variant == GCS_VARIANT_CONTRACTED_PAIR) return launch_pair_relaxed<KIND, 8>(p, st);
+        if (variant == GCS_VARIANT_CONTRACTED_SORTED) return launch_sorted<KIND, 8, true>(p, st);
+        if (variant == GCS_VARIANT_CONTRACTED_STATIC) return launch_static<KIND, 8, true>(p, st);
         if (variant == GCS_VARIANT_SORTED) return launch_sorted<KIND, 8>(p, st);
         return variant == GCS_VARIANT_REFILL ? launch_refill<KIND, 8>(d, p, st) : launch_static<KIND, 8>(p, st);
     }
@@ -409,6 +428,9 @@ const char* gcs_b200_kernel_name(int kind, int n_seeds, int variant)
     static thread_local char name[96];
     variant = resolve_variant(variant, kSortedMinRuns, 1);  // default: named for a launch that fills the device
     const char* base = variant == GCS_VARIANT_REFILL ? "newton_refill_kernel"
+        : variant == GCS_VARIANT_CONTRACTED_PAIR     ? "newton_pair_relaxed_kernel"
+        : variant == GCS_VARIANT_CONTRACTED_SORTED   ? "newton_sorted_kernel[contracted]"
+        : variant == GCS_VARIANT_CONTRACTED_STATIC   ? "newton_static_kernel[contracted]"
         : variant == GCS_VARIANT_SORTED              ? "newton_sorted_kernel"
         : (variant == GCS_VARIANT_PAIR && n_seeds == 2) ? "newton_pair_kernel"
                                                      : "newton_static_kernel";
@@ -791,6 +813,27 @@ int gcs_b200_solve_sharded(const gcs_b200_batch* b, int n_dev)
     for (auto& t : th) t.join();
     for (int g = 0; g < n_dev; ++g)
         if (rcs[g] != GCS_OK) return fail(rcs[g], "shard %d: %s", g, msgs[g].c_str());
+    return GCS_OK;
+}
+
+int gcs_b200_contracted_stats(int device, uint64_t out[2], int reset)
+{
+    int rc = ensure_init();
+    if (rc != GCS_OK) return rc;
+    DeviceState* d = find_dev(device);
+    if (!d) return fail(GCS_E_NO_DEVICE, "device %d not present", device);
+    int cur = -1;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != device) CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned long long v[2] = { 0, 0 };
+    CUDA_TRY(cudaMemcpyFromSymbol(v, gcsk::g_relax_reruns, sizeof(v)));
+    if (reset) {
+        const unsigned long long z[2] = { 0, 0 };
+        CUDA_TRY(cudaMemcpyToSymbol(gcsk::g_relax_reruns, z, sizeof(z)));
+    }
+    if (out) out[0] = v[0], out[1] = v[1];
+    if (cur != device && cur >= 0) cudaSetDevice(cur);
     return GCS_OK;
 }
 

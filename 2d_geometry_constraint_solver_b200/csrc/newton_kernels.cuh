@@ -27,6 +27,7 @@
 #include <cstring>
 
 #include "newton_core.cuh"
+#include "newton_relaxed.cuh"
 
 namespace gcsk {
 
@@ -58,7 +59,9 @@ __device__ __forceinline__ unsigned lanemask_lt()
 #ifndef GCS_STATIC_MINB
 #define GCS_STATIC_MINB 1
 #endif
-template <int KIND, int NS>
+// RLX: closed-form updates with guards (newton_relaxed.cuh); a run or a selection the guards do
+// not vouch for is redone with the literal device functions.
+template <int KIND, int NS, bool RLX = false>
 __global__ void __launch_bounds__(128, GCS_STATIC_MINB) newton_static_kernel(const BatchDev p)
 {
     using S = Sys<KIND>;
@@ -84,10 +87,30 @@ __global__ void __launch_bounds__(128, GCS_STATIC_MINB) newton_static_kernel(con
     } else {
         default_seed(seed, x, y);
     }
-    FastConsts fc;
-    fc.init((double)(p.n >> 62));  // 0.0 for every valid n, opaque to the compiler
+    const double runtime_zero = (double)(p.n >> 62);  // 0.0 for every valid n, opaque to the compiler
     int it, conv;
-    newton_run<KIND>(sys, fc, x, y, it, conv);
+    bool literal = !RLX;
+    if constexpr (RLX) {
+        Rsys<KIND> rs;
+        RelaxGuard g;
+        rs.load(k, g);
+        it = 0;
+        int state = kRlxConverged;
+        // iteration 0 compares the guess with prev = (0, 0)
+        if (!(fabs(0.0 - x) < kTol && fabs(0.0 - y) < kTol)) {
+            double u0, u1;
+            state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1);
+        }
+        conv = 1;
+        if (state != kRlxConverged) {
+            literal_rerun<KIND>(p.guesses, p.stride, i, k, seed, runtime_zero, x, y, it, conv);
+            literal = true;
+        }
+    } else {
+        FastConsts fc;
+        fc.init(runtime_zero);
+        newton_run<KIND>(sys, fc, x, y, it, conv);
+    }
 
     // exchange candidates inside the NS-lane group
     const int lane = threadIdx.x & 31;
@@ -97,6 +120,19 @@ __global__ void __launch_bounds__(128, GCS_STATIC_MINB) newton_static_kernel(con
     for (int s = 0; s < NS; ++s) {
         cx[s] = __shfl_sync(kFull, x, lead + s);
         cy[s] = __shfl_sync(kFull, y, lead + s);
+    }
+    if constexpr (RLX) {
+        // (G5) a selection the margins do not vouch for: the whole group goes literal
+        int redo = (seed == 0 && !selection_is_robust<KIND, NS>(k, code, cx, cy)) ? 1 : 0;
+        redo = __shfl_sync(kFull, redo, lead);
+        if (__any_sync(kFull, redo)) {
+            if (redo && !literal) literal_rerun<KIND>(p.guesses, p.stride, i, k, seed, runtime_zero, x, y, it, conv, 1);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                cx[s] = __shfl_sync(kFull, x, lead + s);
+                cy[s] = __shfl_sync(kFull, y, lead + s);
+            }
+        }
     }
     if (valid) {
         if (p.iters) p.iters[(long long)seed * p.stride + sub] = (int16_t)it;
@@ -168,6 +204,74 @@ __global__ void __launch_bounds__(128, GCS_PAIR_MINB) newton_pair_kernel(const B
 #pragma unroll
     for (int c = 0; c < S::kOut; ++c) p.out[c][i] = out[c];
     if (p.root) p.root[i] = (uint8_t)root;
+}
+
+// ------------------------------------------------------------------------------------------
+// contracted pair variant: one lane per sub-system; its seeds are iterated two at a time in
+// lockstep with the closed-form update (relaxed_updates2), the lane then selects in registers.
+// No shuffles, no shared memory, no barriers; per-sub-system work (loads, guard constants,
+// selection, stores) is paid once per sub-system instead of once per run.
+// ------------------------------------------------------------------------------------------
+#ifndef GCS_RPAIR_MINB
+#define GCS_RPAIR_MINB 6
+#endif
+template <int KIND, int NS>
+__global__ void __launch_bounds__(128, GCS_RPAIR_MINB) newton_pair_relaxed_kernel(const BatchDev p)
+{
+    using S = Sys<KIND>;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    double k[S::kCols];
+#pragma unroll
+    for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + i);
+    const uint8_t code = p.code ? __ldg(p.code + i) : (uint8_t)GCS_MAKE_CODE(0, 0, 0);
+    const double runtime_zero = (double)(p.n >> 62);
+    Rsys<KIND> rs;
+    RelaxGuard g;
+    rs.load(k, g);
+    double cx[NS], cy[NS];
+    int its[NS], cvs[NS];
+    unsigned literal = 0;  // bit s: seed s came out of the literal code
+#pragma unroll
+    for (int s = 0; s < NS; s += 2) {
+        run_seed<KIND>(p.guesses, p.stride, i, k, s, cx[s], cy[s]);
+        run_seed<KIND>(p.guesses, p.stride, i, k, s + 1, cx[s + 1], cy[s + 1]);
+        its[s] = its[s + 1] = 0;
+        // iteration 0 compares the guess with prev = (0,0) (newton_raphson.hpp:58, :83-88)
+        int sa = (fabs(0.0 - cx[s]) < kTol && fabs(0.0 - cy[s]) < kTol) ? kRlxConverged : kRlxRunning;
+        int sb = (fabs(0.0 - cx[s + 1]) < kTol && fabs(0.0 - cy[s + 1]) < kTol) ? kRlxConverged : kRlxRunning;
+        relaxed_updates2<KIND>(rs, g, cx[s], cy[s], its[s], sa, cx[s + 1], cy[s + 1], its[s + 1], sb);
+        cvs[s] = cvs[s + 1] = 1;
+        if (sa != kRlxConverged) {
+            literal_rerun<KIND>(p.guesses, p.stride, i, k, s, runtime_zero, cx[s], cy[s], its[s], cvs[s]);
+            literal |= 1u << s;
+        }
+        if (sb != kRlxConverged) {
+            literal_rerun<KIND>(p.guesses, p.stride, i, k, s + 1, runtime_zero, cx[s + 1], cy[s + 1], its[s + 1], cvs[s + 1]);
+            literal |= 2u << s;
+        }
+    }
+    // (G5) a selection the margins do not vouch for: every seed of the sub-system goes literal
+    if (!selection_is_robust<KIND, NS>(k, code, cx, cy)) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if (!((literal >> s) & 1u)) literal_rerun<KIND>(p.guesses, p.stride, i, k, s, runtime_zero, cx[s], cy[s], its[s], cvs[s], 1);
+    }
+    double out[4];
+    const int root = select_and_finish<KIND, NS>(k, code, cx, cy, out);
+#pragma unroll
+    for (int c = 0; c < S::kOut; ++c) p.out[c][i] = out[c];
+    if (p.root) p.root[i] = (uint8_t)root;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const long long pi = (long long)s * p.stride + i;
+        if (p.iters) p.iters[pi] = (int16_t)its[s];
+        if (p.converged) p.converged[pi] = (uint8_t)cvs[s];
+        if (p.cand) {
+            p.cand[((long long)s * 2 + 0) * p.stride + i] = cx[s];
+            p.cand[((long long)s * 2 + 1) * p.stride + i] = cy[s];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -246,7 +350,9 @@ constexpr int kSortedMinBlocks = (KIND == GCS_KIND_SDD || KIND == GCS_KIND_ANG) 
 // and the occupancy where the register file puts it.  In phase C the sorted runs form 2*W blocks
 // of 32, longest first; warp w takes blocks w and 2W-1-w (a long one and a short one), so the
 // warps of the CTA reach the last barrier at about the same time.
-template <int KIND, int NS, int TILE, int THREADS>
+// (RLX: 8 CTAs per SM at 64 registers measured the same as 6-7 at 72-80 - the contracted kernels
+// are bound by instruction issue, not by latency - so the allocation of the literal kernels is kept.)
+template <int KIND, int NS, int TILE, int THREADS, bool RLX = false>
 __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted_kernel(const BatchDev p)
 {
     using S = Sys<KIND>;
@@ -279,6 +385,28 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
             double k[S::kCols];
 #pragma unroll
             for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + gi);
+            if constexpr (RLX) {
+                Rsys<KIND> rs;
+                RelaxGuard g;
+                rs.load(k, g);
+#pragma unroll 1
+                for (int q = 0; q < 2; ++q) {
+                    const int r = tid + q * THREADS;
+                    double x, y;
+                    run_seed<KIND>(p.guesses, p.stride, gi, k, r / TILE, x, y);
+                    int it = 0, state = kRlxConverged;
+                    double d2 = 0.0, d3 = 0.0;
+                    if (!(fabs(0.0 - x) < kTol && fabs(0.0 - y) < kTol))
+                        state = relaxed_updates<KIND, true>(rs, g, x, y, it, 3, d2, d3);
+                    s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
+                    s_cv[r] = (unsigned char)state;  // kRlxUncertain (2): phase C redoes the run literally
+                    if (state != kRlxConverged) {
+                        const int kk = (state == kRlxUncertain) ? 0 : kSortBins - 1 - predict_remaining(d2, d3);
+                        atomicAdd(&s_bin[kk], 1);
+                        if (q == 0) key[0] = kk; else key[1] = kk;
+                    }
+                }
+            } else {
             S sys;
             sys.load(k);
 #pragma unroll 1
@@ -315,6 +443,7 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                     atomicAdd(&s_bin[kk], 1);
                     if (q == 0) key[0] = kk; else key[1] = kk;
                 }
+            }
             }
         }
     }
@@ -362,6 +491,22 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                 double k[S::kCols];
 #pragma unroll
                 for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + base + sub);  // only what load() reads survives
+                if constexpr (RLX) {
+                    double x = s_x[r], y = s_y[r];
+                    int it = s_it[r], conv = 1;
+                    int state = s_cv[r];
+                    if (state != kRlxUncertain) {
+                        Rsys<KIND> rs;
+                        RelaxGuard g;
+                        rs.load(k, g);
+                        double u0, u1;
+                        state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1);
+                    }
+                    if (state != kRlxConverged)
+                        literal_rerun<KIND>(p.guesses, p.stride, base + sub, k, r / TILE, (double)(p.n >> 62), x, y, it, conv);
+                    s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
+                    s_cv[r] = (unsigned char)conv;
+                } else {
                 S sys;
                 sys.load(k);
                 double x = s_x[r], y = s_y[r];
@@ -376,24 +521,53 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                 }
                 s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
                 s_cv[r] = (conv && it < kMaxIt) ? 1 : 0;
+                }
             }
         }
+    }
+    // the columns of this lane's phase-D sub-system are requested before the barrier, so that
+    // their latency overlaps the wait for the slower warps of the CTA (TILE <= THREADS: one
+    // sub-system per lane)
+    static_assert(TILE <= THREADS, "phase D handles one sub-system per lane");
+    double kd[S::kCols];
+    uint8_t coded = (uint8_t)GCS_MAKE_CODE(0, 0, 0);
+    if (tid < cnt) {
+#pragma unroll
+        for (int c = 0; c < S::kCols; ++c) kd[c] = __ldg(p.in[c] + base + tid);
+        if (p.code) coded = __ldg(p.code + base + tid);
     }
     __syncthreads();
 
     // ---- (D) selection + write-back, coalesced, every lane busy ----
-#pragma unroll 1
-    for (int sub = tid; sub < cnt; sub += THREADS) {
+    if (tid < cnt) {
+        const int sub = tid;
         const long long gi = base + sub;
-        double k[S::kCols];
-#pragma unroll
-        for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + gi);
-        const uint8_t code = p.code ? __ldg(p.code + gi) : (uint8_t)GCS_MAKE_CODE(0, 0, 0);
+        double* k = kd;
+        const uint8_t code = coded;
         double cx[NS], cy[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             cx[s] = s_x[s * TILE + sub];
             cy[s] = s_y[s * TILE + sub];
+        }
+        if constexpr (RLX) {
+            // (G5) a selection the margins do not vouch for: every seed of the sub-system goes literal
+            if (!selection_is_robust<KIND, NS>(k, code, cx, cy)) {
+#pragma unroll 1
+                for (int s = 0; s < NS; ++s) {
+                    int it, conv;
+                    double x, y;
+                    literal_rerun<KIND>(p.guesses, p.stride, gi, k, s, (double)(p.n >> 62), x, y, it, conv, 1);
+                    s_x[s * TILE + sub] = x, s_y[s * TILE + sub] = y;
+                    s_it[s * TILE + sub] = (short)it;
+                    s_cv[s * TILE + sub] = (unsigned char)conv;
+                }
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    cx[s] = s_x[s * TILE + sub];
+                    cy[s] = s_y[s * TILE + sub];
+                }
+            }
         }
         double out[4];
         const int root = select_and_finish<KIND, NS>(k, code, cx, cy, out);

@@ -1,0 +1,432 @@
+// newton_relaxed.cuh — the tolerance-class arithmetic of GCS_VARIANT_CONTRACTED (sm_100a).
+//
+// The bit-identical kernels spend 35 of their 72 FP64 instructions per update on the four IEEE
+// divisions and the square root of Eigen's Householder QR, and may not contract a*b+c.  The
+// correctness contract of the path (BASELINE.json north_star) is narrower than bit identity:
+//     iteration count, convergence flag, chosen root   identical to the reference,
+//     solved coordinates                               within 1e-9 relative.
+// This file solves the same 2x2 Newton system in closed form (Cramer's rule on fused
+// multiply-adds, one reciprocal refined to ~2^-60) - about 21 FP64 instructions per update - and
+// keeps the discrete outputs identical by construction:
+//
+//   * every decision that could come out differently under a perturbation of the iterate is
+//     detected and the run is redone with the literal device functions of newton_core.cuh
+//     (newton_run, the same code the bit-identical kernels execute).  Detected means:
+//       (G1) |det J| has fallen under 2^-10 of its size at a well-conditioned root of this system
+//            (per-system constant): the step is sensitive to rounding, deviations between the
+//            two arithmetics could be amplified;
+//       (G3) the length of an update lies inside a band around the convergence threshold
+//            (newton_raphson.hpp:83-88), band = 2^-16 tol + 2^-36 S with S the magnitude of the
+//            system's coordinates: the two arithmetics could disagree on `< tol`;
+//       (G4) no convergence after kRelaxCap updates (slow or chaotic runs: no real root, tangent
+//            circles), or a non-finite / huge update;
+//       (G5) in the root selection, an orientation (or a distance difference) within 2^-24
+//            relative of zero: the sign (or the comparison) could flip.
+//   * why that suffices: both arithmetics are backward stable on a 2x2 system, so from the same
+//     iterate their updates differ by O(cond(J) eps |step|) plus O(cond(J) ulp(S)) from the
+//     residuals.  Every equation pair of the path is a circle and a line (newton_kernels.cuh,
+//     "Prediction"): once on the line, Newton's map along it is w <- (w^2 + h^2)/(2w) whose
+//     derivative (1 - h^2/w^2)/2 has magnitude <= 1/2 for |w| >= h, which holds from the second
+//     update on when the roots are real - deviations are halved per update, then squared.  The
+//     one update that can amplify (the landing point close to the foot of the line, |w| << h) is
+//     bounded by (G1): net amplification h/w <= 2^11.  A deviation of 2^-40 relative therefore
+//     stays below 2^-29 S, the band of (G3) is 2^-36 S wide only where the conditioning (G1) has
+//     been established at that same iterate (cond <= 2^11, deviation there <= 2^-39 S from the
+//     residuals, the contracted history is smaller still).
+//   * tests/test_gpu_relaxed.py and the soak (profiles/) compare iteration counts, flags and root
+//     indices for equality and coordinates to 1e-9 against the CPU checker on every parity case.
+#pragma once
+
+#include "newton_core.cuh"
+
+namespace gcsk {
+
+constexpr int kRelaxCap = 64;  // updates a run may take on the closed-form path (G4)
+
+// How often the guards hand work to the literal code (read by gcs_b200_contracted_stats):
+// [0] runs redone because a run-level guard fired, [1] runs redone because the selection guard fired.
+// Touched on the rare path only.
+__device__ unsigned long long g_relax_reruns[2];
+
+// 1/b to ~2^-60 relative: MUFU.RCP64H seed (>= 20 bits) and one cubic refinement
+__device__ __forceinline__ double rcp_relaxed(double b)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = __fma_rn(-b, r, 1.0);
+    e = __fma_rn(e, e, e);
+    return __fma_rn(r, e, r);
+}
+
+__device__ __forceinline__ int abs_hi(double v) { return __double2hiint(v) & 0x7fffffff; }
+
+// high word of a non-negative double, rounded outwards (thresholds of integer comparisons)
+__device__ __forceinline__ int hi_floor(double v) { return v > 0.0 ? __double2hiint(v) : 0; }
+
+// Per-run constants of the guards, derived once per run from the system's scale.
+struct RelaxGuard {
+    int lo_h, hi_h;  // hi(|s|) < lo_h: converged for certain; >= hi_h: not converged for certain
+    int det_h;       // hi(|det|) must reach this (G1)
+    double cs, dr;   // coordinate scale S and |det| at a well-conditioned root (second-level test)
+    static constexpr int kBigH = 0x5F300000;  // 2^500: anything from here on is "non-finite / huge" (G4)
+    // step_scale: the closed-form solve returns step / step_scale (K1 works on J/2)
+    __device__ __forceinline__ void init(double coord_scale, double det_root, double step_scale)
+    {
+        cs = coord_scale, dr = det_root;
+        const double band = __fma_rn(0x1p-36, coord_scale, 0x1p-16 * kTol);
+        const double inv = 1.0 / step_scale;  // 1 or 2: exact
+        lo_h = hi_floor((kTol - band) * inv) - 1;
+        hi_h = hi_floor((kTol + band) * inv) + 1;
+        if (!(band < kTol)) lo_h = 0;          // also catches a NaN scale: never "certain"
+        if (lo_h < 0) lo_h = 0;
+        if (!(hi_h > 0 && hi_h < kBigH)) hi_h = kBigH;
+        det_h = hi_floor(0x1p-10 * det_root) + 1;
+        if (!(det_root > 0.0 && det_root < 0x1p900)) det_h = 0x7ff00000;  // degenerate / NaN / inf scale: always uncertain
+    }
+    // Second level of (G3), reached only by an update whose length fell between lo_h and hi_h (the
+    // first-level band, integer tests on high words, is 2^-36 S wide; about one run in a thousand
+    // gets here).  From the same iterate the two arithmetics' updates differ by at most
+    // ~8 (dr/|det|) 2^-52 S: the residuals carry O(ulp(S)) rounding, the solve divides by det
+    // (newton_relaxed.cuh header; dr/|det| <= 2^10 by G1).  With 32x margin:
+    //     | m - tol | > 2^-44 S dr/|det| + 2^-40 tol   ->   `m < tol` is the literal code's decision too.
+    // Returns +1 converged for certain, -1 not converged for certain, 0 undecided.
+    __device__ __forceinline__ int precise(double m, double det) const
+    {
+        const double margin = __fma_rn(0x1p-44 * cs, dr * rcp_relaxed(fabs(det)), 0x1p-40 * kTol);
+        const double gap = m - kTol;
+        if (gap > margin) return -1;
+        if (-gap > margin) return 1;
+        return 0;  // NaN margins land here
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// The five equation pairs with fused multiply-adds: J = [[a b],[c d]], right-hand side (-f, -g).
+// load() takes the same input columns as Sys<KIND>::load.
+// ------------------------------------------------------------------------------------------
+template <int KIND>
+struct Rsys;
+
+// K1: two circles.  Works on J/2 = [[dxa dya],[dxb dyb]]: the solve returns twice the step.
+template <>
+struct Rsys<GCS_KIND_PP> {
+    static constexpr double kStepScale = 0.5;
+    double ax, ay, qa, bx, by, qb;
+    __device__ __forceinline__ void load(const double* k, RelaxGuard& g)
+    {
+        ax = k[0], ay = k[1], qa = k[2] * k[2];
+        bx = k[3], by = k[4], qb = k[5] * k[5];
+        // at a root det(J/2) = (P-A) x (P-B) = ra rb sin(angle at P)
+        g.init(fabs(ax) + fabs(ay) + fabs(bx) + fabs(by) + fabs(k[2]) + fabs(k[5]), fabs(k[2] * k[5]), kStepScale);
+    }
+    __device__ __forceinline__ void eval(
+        double x, double y, double& a, double& b, double& c, double& d, double& r0, double& r1) const
+    {
+        a = x - ax, b = y - ay, c = x - bx, d = y - by;
+        r0 = __fma_rn(-b, b, __fma_rn(-a, a, qa));
+        r1 = __fma_rn(-d, d, __fma_rn(-c, c, qb));
+    }
+};
+
+// K2: signed-distance difference (linear) + unit normal
+template <>
+struct Rsys<GCS_KIND_SDD> {
+    static constexpr double kStepScale = 1.0;
+    double dX, dY, c0;
+    __device__ __forceinline__ void load(const double* k, RelaxGuard& g)
+    {
+        dX = k[2] - k[0], dY = k[3] - k[1];
+        c0 = k[4] - k[5];
+        const double l1 = fabs(dX) + fabs(dY);
+        // iterates are unit normals; the linear residual carries the offsets in units of |delta|
+        g.init(1.0 + (fabs(k[4]) + fabs(k[5])) * rcp_relaxed(l1), 2.0 * l1 * 0.70710678118654746, kStepScale);
+    }
+    __device__ __forceinline__ void eval(
+        double x, double y, double& a, double& b, double& c, double& d, double& r0, double& r1) const
+    {
+        a = dX, b = dY, c = x + x, d = y + y;
+        r0 = -__fma_rn(dX, x, __fma_rn(dY, y, c0));
+        r1 = __fma_rn(-x, x, __fma_rn(-y, y, 1.0));
+    }
+};
+
+struct RP2L {
+    double xa, ya, ex, ey, ld, len;
+    __device__ __forceinline__ void set(double xa_, double ya_, double xb_, double yb_, double s_)
+    {
+        xa = xa_, ya = ya_;
+        ex = xb_ - xa_, ey = yb_ - ya_;
+        len = sqrt(__fma_rn(ex, ex, ey * ey));
+        ld = len * s_;
+    }
+    // -f of pointToLineDistance: ld - uy ex + ux ey
+    __device__ __forceinline__ double neg_f(double x, double y) const
+    {
+        return __fma_rn(x - xa, ey, __fma_rn(-(y - ya), ex, ld));
+    }
+};
+
+// K3: circle + point-to-line (linear)
+template <>
+struct Rsys<GCS_KIND_PPL> {
+    static constexpr double kStepScale = 1.0;
+    double px, py, q;
+    RP2L l;
+    __device__ __forceinline__ void load(const double* k, RelaxGuard& g)
+    {
+        px = k[0], py = k[1], q = k[2] * k[2];
+        l.set(k[3], k[4], k[5], k[6], k[7]);
+        // at a root det J = 2 (P - C) . e = 2 r L cos(.)
+        g.init(fabs(px) + fabs(py) + fabs(k[2]) + fabs(k[3]) + fabs(k[4]) + fabs(k[7]), 2.0 * fabs(k[2]) * l.len, kStepScale);
+    }
+    __device__ __forceinline__ void eval(
+        double x, double y, double& a, double& b, double& c, double& d, double& r0, double& r1) const
+    {
+        const double dx = x - px, dy = y - py;
+        a = dx + dx, b = dy + dy, c = -l.ey, d = l.ex;
+        r0 = __fma_rn(-dy, dy, __fma_rn(-dx, dx, q));
+        r1 = l.neg_f(x, y);
+    }
+};
+
+// K4: two point-to-line equations (linear system, constant Jacobian)
+template <>
+struct Rsys<GCS_KIND_PLL> {
+    static constexpr double kStepScale = 1.0;
+    RP2L l1, l2;
+    __device__ __forceinline__ void load(const double* k, RelaxGuard& g)
+    {
+        l1.set(k[0], k[1], k[2], k[3], k[4]);
+        l2.set(k[5], k[6], k[7], k[8], k[9]);
+        g.init(fabs(k[0]) + fabs(k[1]) + fabs(k[5]) + fabs(k[6]) + fabs(k[4]) + fabs(k[9]), l1.len * l2.len, kStepScale);
+    }
+    __device__ __forceinline__ void eval(
+        double x, double y, double& a, double& b, double& c, double& d, double& r0, double& r1) const
+    {
+        a = -l1.ey, b = l1.ex, c = -l2.ey, d = l2.ex;
+        r0 = l1.neg_f(x, y);
+        r1 = l2.neg_f(x, y);
+    }
+};
+
+// K5: normal-angle (linear) + unit normal
+template <>
+struct Rsys<GCS_KIND_ANG> {
+    static constexpr double kStepScale = 1.0;
+    double fdx, fdy, cl;
+    __device__ __forceinline__ void load(const double* k, RelaxGuard& g)
+    {
+        fdx = k[0], fdy = k[1];
+        const double len = sqrt(__fma_rn(fdx, fdx, fdy * fdy));
+        cl = k[2] * len;
+        // unit normals; the linear residual is L (cos(phi) - cosA): scale 2; det J = 2 L sin(.)
+        g.init(2.0, 2.0 * len, kStepScale);
+    }
+    __device__ __forceinline__ void eval(
+        double x, double y, double& a, double& b, double& c, double& d, double& r0, double& r1) const
+    {
+        a = fdy, b = -fdx, c = x + x, d = y + y;
+        r0 = __fma_rn(fdx, y, __fma_rn(-fdy, x, cl));
+        r1 = __fma_rn(-x, x, __fma_rn(-y, y, 1.0));
+    }
+};
+
+// Outcome of a stretch of closed-form updates
+enum : int { kRlxRunning = 0, kRlxConverged = 1, kRlxUncertain = 2 };
+
+// Up to `limit` closed-form updates from (x, y), `it` updates applied so far.  Returns
+//   kRlxConverged : the last update was shorter than the threshold for certain (and no guard fired)
+//   kRlxUncertain : a guard fired - the caller redoes the run from its seed with newton_run
+//   kRlxRunning   : `limit` reached, every update so far longer than the threshold for certain.
+// d2 / d3 (optional): squared lengths of the last two updates, for the sort key of the sorted kernel.
+template <int KIND, bool kTrack>
+__device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, const RelaxGuard& g, double& x, double& y, int& it,
+    int limit, double& d2, double& d3)
+{
+    bool bad = false;
+    const unsigned span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
+    int state = kRlxRunning;
+#pragma unroll 1
+    while (it < limit) {
+        double a, b, c, d, r0, r1;
+        rs.eval(x, y, a, b, c, d, r0, r1);
+        const double det = __fma_rn(a, d, -(b * c));
+        const double r = rcp_relaxed(det);
+        const double n0 = __fma_rn(r0, d, -(r1 * b));
+        const double n1 = __fma_rn(a, r1, -(c * r0));
+        const double s0 = n0 * r, s1 = n1 * r;
+        if constexpr (Rsys<KIND>::kStepScale == 1.0) {
+            x += s0, y += s1;
+        } else {
+            x = __fma_rn(s0, Rsys<KIND>::kStepScale, x);
+            y = __fma_rn(s1, Rsys<KIND>::kStepScale, y);
+        }
+        ++it;
+        if constexpr (kTrack) {
+            d2 = d3;
+            d3 = __fma_rn(s0, s0, s1 * s1) * (Rsys<KIND>::kStepScale * Rsys<KIND>::kStepScale);
+        }
+        bad |= abs_hi(det) < g.det_h;  // (G1); a NaN determinant shows up in mh below
+        const int mh = max(abs_hi(s0), abs_hi(s1));
+        if ((unsigned)(mh - g.hi_h) < span) continue;  // longer than the threshold for certain
+        // ---- rare from here: the run ends, or the update sits in the first-level band ----
+        if (mh >= RelaxGuard::kBigH || bad) {  // non-finite / huge (G4), or ill-conditioned on the way (G1)
+            state = kRlxUncertain;
+            break;
+        }
+        if (mh < g.lo_h) {
+            state = kRlxConverged;
+            break;
+        }
+        const int verdict = g.precise(fmax(fabs(s0), fabs(s1)) * Rsys<KIND>::kStepScale, det);
+        if (verdict < 0) continue;
+        state = verdict > 0 ? kRlxConverged : kRlxUncertain;
+        break;
+    }
+    if (state == kRlxRunning && (bad || limit >= kRelaxCap)) state = kRlxUncertain;  // (G1) / cap reached (G4)
+    return state;
+}
+
+// Two runs of one sub-system in lockstep in one lane (two independent dependency chains: the
+// closed-form update is a chain of ~10 dependent FP64 operations and only ~60 issue cycles long, so
+// a second chain per lane fills the pipe where the literal kernels could not use one).  A finished
+// run rides along with its position update predicated off.  sa / sb: kRlxRunning on entry for a
+// run that iterates; on return kRlxConverged or kRlxUncertain for those.
+template <int KIND>
+__device__ __forceinline__ void relaxed_updates2(const Rsys<KIND>& rs, const RelaxGuard& g, double& xa, double& ya, int& ita,
+    int& sa, double& xb, double& yb, int& itb, int& sb)
+{
+    const unsigned span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
+    bool la = sa == kRlxRunning, lb = sb == kRlxRunning;
+    bool bada = false, badb = false;
+    // end of a run, or an update inside the first-level band: decide this run's state
+    auto settle = [&](bool& live, int& state, bool bad, int mh, double s0, double s1, double det, int it) {
+        if (mh < g.lo_h && !bad) {
+            state = kRlxConverged, live = false;
+        } else if (mh >= RelaxGuard::kBigH || bad) {
+            state = kRlxUncertain, live = false;
+        } else if (mh < g.lo_h) {
+            state = kRlxUncertain, live = false;
+        } else {
+            const int verdict = g.precise(fmax(fabs(s0), fabs(s1)) * Rsys<KIND>::kStepScale, det);
+            if (verdict >= 0) state = verdict > 0 ? kRlxConverged : kRlxUncertain, live = false;
+        }
+        if (live && it >= kRelaxCap) state = kRlxUncertain, live = false;
+    };
+#pragma unroll 1
+    while (la | lb) {
+        double a0, b0, c0, d0, p0, q0, a1, b1, c1, d1, p1, q1;
+        rs.eval(xa, ya, a0, b0, c0, d0, p0, q0);
+        rs.eval(xb, yb, a1, b1, c1, d1, p1, q1);
+        const double det0 = __fma_rn(a0, d0, -(b0 * c0));
+        const double det1 = __fma_rn(a1, d1, -(b1 * c1));
+        const double r0 = rcp_relaxed(det0);
+        const double r1 = rcp_relaxed(det1);
+        const double s00 = __fma_rn(p0, d0, -(q0 * b0)) * r0, s01 = __fma_rn(a0, q0, -(c0 * p0)) * r0;
+        const double s10 = __fma_rn(p1, d1, -(q1 * b1)) * r1, s11 = __fma_rn(a1, q1, -(c1 * p1)) * r1;
+        if (la) {
+            xa = __fma_rn(s00, Rsys<KIND>::kStepScale, xa), ya = __fma_rn(s01, Rsys<KIND>::kStepScale, ya);
+            ++ita;
+        }
+        if (lb) {
+            xb = __fma_rn(s10, Rsys<KIND>::kStepScale, xb), yb = __fma_rn(s11, Rsys<KIND>::kStepScale, yb);
+            ++itb;
+        }
+        bada |= abs_hi(det0) < g.det_h;
+        badb |= abs_hi(det1) < g.det_h;
+        const int mha = max(abs_hi(s00), abs_hi(s01));
+        const int mhb = max(abs_hi(s10), abs_hi(s11));
+        const bool fara = (unsigned)(mha - g.hi_h) < span && ita < kRelaxCap;
+        const bool farb = (unsigned)(mhb - g.hi_h) < span && itb < kRelaxCap;
+        if (la && !fara) settle(la, sa, bada, mha, s00, s01, det0, ita);
+        if (lb && !farb) settle(lb, sb, badb, mhb, s10, s11, det1, itb);
+    }
+}
+
+// seed `seed` of sub-system `gi` as the kernels take it
+template <int KIND>
+__device__ __forceinline__ void run_seed(
+    const double* guesses, long long stride, long long gi, const double* k, int seed, double& x, double& y)
+{
+    if (guesses) {
+        x = __ldg(guesses + ((long long)seed * 2 + 0) * stride + gi);
+        y = __ldg(guesses + ((long long)seed * 2 + 1) * stride + gi);
+    } else if constexpr (Sys<KIND>::kGuessFromCols) {
+        column_seed<KIND>(k, seed, x, y);
+    } else {
+        default_seed(seed, x, y);
+    }
+}
+
+// The literal run of one seed (what an uncertain closed-form run is replaced by).  Inlined: the
+// columns are in registers at every call site, and the kernels' register budgets are those of the
+// literal kernels anyway.
+template <int KIND>
+__device__ __forceinline__ void literal_rerun(const double* guesses, long long stride, long long gi, const double* k,
+    int seed, double runtime_zero, double& x, double& y, int& it, int& conv, int why = 0)
+{
+    Sys<KIND> sys;
+    sys.load(k);
+    FastConsts fc;
+    fc.init(runtime_zero);
+    run_seed<KIND>(guesses, stride, gi, k, seed, x, y);
+    newton_run<KIND>(sys, fc, x, y, it, conv);
+    atomicAdd(&g_relax_reruns[why], 1ull);
+}
+
+// (G5) is the root selection safe against a perturbation of the candidates by 2^-36 of the
+// coordinate scale?  Mirrors the tests of select_and_finish with a margin of 2^-24 relative.
+template <int KIND, int NS>
+__device__ __forceinline__ bool selection_is_robust(const double* k, uint8_t code, const double* cx, const double* cy)
+{
+    constexpr double kMargin = 0x1p-24;
+    bool ok = true;
+    if constexpr (KIND == GCS_KIND_PP || KIND == GCS_KIND_PPL || KIND == GCS_KIND_PLL) {
+        bool nearest = false;
+        double ax = 0, ay = 0, bx = 0, by = 0;
+        if constexpr (KIND != GCS_KIND_PP) {
+            nearest = (code & GCS_CODE_COLLINEAR) != 0;
+            if constexpr (KIND == GCS_KIND_PLL) nearest = nearest || (code & GCS_CODE_CANVAS_PARALLEL);
+        }
+        if (!nearest) nearest = !orientation_frame<KIND>(k, ax, ay, bx, by);
+        if (nearest) {
+            constexpr int cf = (KIND == GCS_KIND_PPL) ? 8 : 10;
+            const double fx = (KIND == GCS_KIND_PP) ? 0.0 : k[cf];
+            const double fy = (KIND == GCS_KIND_PP) ? 0.0 : k[cf + 1];
+            double dd[NS], sc = fabs(fx) + fabs(fy);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const double dx = cx[s] - fx, dy = cy[s] - fy;
+                dd[s] = dx * dx + dy * dy;
+                sc = fmax(sc, fabs(cx[s]) + fabs(cy[s]));
+            }
+            const double floor_ = 0x1p-44 * sc * sc;
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int t = s + 1; t < NS; ++t)
+                    ok = ok && (fabs(dd[s] - dd[t]) > 0x1p-22 * (dd[s] + dd[t]) + floor_);
+        } else {
+            const double ab = fabs(bx - ax) + fabs(by - ay);
+            const double sa = fabs(ax) + fabs(ay) + fabs(bx) + fabs(by);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const double ori = triangle_orientation(ax, ay, bx, by, cx[s], cy[s]);
+                ok = ok && (fabs(ori) > kMargin * ab * (sa + fabs(cx[s]) + fabs(cy[s])));
+            }
+        }
+    } else if constexpr (KIND == GCS_KIND_SDD) {
+        const double dot0 = cx[0] * k[0] + cy[0] * k[1];
+        const double p0 = dot0 - k[4];
+        const double d1 = dot0 - p0;
+        const double d2 = (cx[0] * k[2] + cy[0] * k[3]) - p0;
+        const double sc = kMargin * (fabs(k[0]) + fabs(k[1]) + fabs(k[2]) + fabs(k[3]) + fabs(k[4]));
+        ok = (fabs(d1) > sc) && (fabs(d2) > sc);
+    } else {
+        const double cross0 = (k[5] * cx[0]) + (k[6] * cy[0]);
+        ok = fabs(cross0) > kMargin * (fabs(k[5]) + fabs(k[6]));
+    }
+    return ok;
+}
+
+}  // namespace gcsk

@@ -130,7 +130,7 @@ extern "C" {
 #define GCS_MEM_HOST 0
 #define GCS_MEM_DEVICE 1
 
-/* kernel selection.  Every variant produces bit-identical results (same device functions, same
+/* kernel selection.  Variants 0-4 produce bit-identical results (same device functions, same
  * operation order per Newton run); they differ in how runs are mapped to lanes.
  * DEFAULT = SORTED for launches of at least 2^18 runs (n * n_seeds), STATIC below. */
 #define GCS_VARIANT_DEFAULT 0
@@ -138,6 +138,16 @@ extern "C" {
 #define GCS_VARIANT_REFILL 2 /* persistent CTAs, TMA-staged tiles, warp-level lane refill */
 #define GCS_VARIANT_SORTED 3 /* CTA tiles; runs sorted by predicted update count, one lane finishes one run */
 #define GCS_VARIANT_PAIR 4 /* one lane per sub-system, its two seeds iterated in lockstep (2 seeds only; else static) */
+/* Tolerance-class arithmetic (csrc/newton_relaxed.cuh): closed-form 2x2 solve on fused
+ * multiply-adds.  Iteration counts, convergence flags and root indices are IDENTICAL to every other
+ * variant (runs and selections whose decisions could depend on the arithmetic are detected by
+ * guards and redone with the literal device functions); coordinates agree to 1e-9 relative (the
+ * north star's tolerance) instead of bit for bit.  Opt-in: DEFAULT never resolves to it.
+ * CONTRACTED = the sorted kernel from 2^18 runs per launch, the static kernel below. */
+#define GCS_VARIANT_CONTRACTED 5
+#define GCS_VARIANT_CONTRACTED_STATIC 6
+#define GCS_VARIANT_CONTRACTED_SORTED 7
+#define GCS_VARIANT_CONTRACTED_PAIR 8 /* one lane per sub-system, seeds two at a time in lockstep */
 
 typedef struct gcs_b200_batch {
     int32_t kind;    /* GCS_KIND_* */
@@ -192,6 +202,11 @@ GCS_B200_API int64_t gcs_b200_launch_count(void);
 GCS_B200_API const char* gcs_b200_kernel_name(int kind, int n_seeds, int variant);
 /* the variant GCS_VARIANT_DEFAULT resolves to for a launch of n sub-systems x n_seeds seeds */
 GCS_B200_API int gcs_b200_default_variant(int64_t n, int n_seeds);
+
+/* GCS_VARIANT_CONTRACTED*: cumulative number of Newton runs on `device` that the guards handed to
+ * the literal code since the last call with reset != 0: out[0] run-level guards (conditioning,
+ * convergence band, update cap), out[1] root-selection guard.  Diagnostic; synchronises the device. */
+GCS_B200_API int gcs_b200_contracted_stats(int device, uint64_t out[2], int reset);
 
 /* FP64 pipe micro-benchmarks used as roofline denominators (seconds-scale, device `device`):
  *   what = 0: dependent-free DFMA throughput, returns TFLOP/s counting FMA = 2 flops

@@ -24,5 +24,13 @@ for kind in kinds:
         e0.record(st); db.solve(); e1.record(st); e1.synchronize()
         ts.append(e0.elapsed_time(e1))
     it = db.iters.cpu().numpy()
+    extra = ""
+    if variant >= 5:
+        import ctypes as C
+        st2 = (C.c_uint64 * 2)()
+        capi.load().gcs_b200_contracted_stats(0, st2, 1)
+        db.solve()
+        capi.load().gcs_b200_contracted_stats(0, st2, 1)
+        extra = f"  literal re-runs per launch: {st2[0]} (run guards) + {st2[1]} (selection guard) of {n * ns} runs"
     chk = int(db.out[0].view(torch.int64).sum().item()) ^ int(db.out[1].view(torch.int64).sum().item()) ^ int(it.astype(np.int64).sum()) ^ (int(db.root_index.sum().item()) << 20)
-    print(f"K{kind} n {n} seeds {ns} variant {variant}: median {np.median(ts)*1e3:.1f} us  min {np.min(ts)*1e3:.1f} us  checksum {chk & 0xffffffffffff:012x}")
+    print(f"K{kind} n {n} seeds {ns} variant {variant}: median {np.median(ts)*1e3:.1f} us  min {np.min(ts)*1e3:.1f} us  checksum {chk & 0xffffffffffff:012x}{extra}")

@@ -1,0 +1,127 @@
+"""GPU parity of the tolerance-class variants (GCS_VARIANT_CONTRACTED*, csrc/newton_relaxed.cuh)
+against the CPU oracle, through the C ABI.
+
+Bar (BASELINE.json north_star, spelled out in util.assert_batches_within_contract): iteration
+counts, convergence flags and the chosen root IDENTICAL; coordinates within 1e-9 relative.  The
+cases are those of test_gpu_parity.py, including the ones built to sit on decision boundaries
+(flat triangles, extreme scales, NaN / inf / degenerate inputs, never-converging rows, explicit
+guesses inside the iteration-0 box), because those are where a different arithmetic could change a
+discrete output and the guards must hand the run to the literal code."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from util import assert_batches_identical, assert_batches_within_contract, bits
+
+pytestmark = pytest.mark.gpu
+
+KINDS = [1, 2, 3, 4, 5]
+VARIANTS = [6, 7, 8]  # contracted static, sorted, pair
+
+
+def _solve_pair(gpu, synth, kind, n, variant, **kw):
+    hb = synth.make(kind, n, **kw)
+    hb.variant = variant
+    gpu.solve_host(hb.alloc_outputs(), 0)
+    ref = O.solve(synth.make(kind, n, **kw).alloc_outputs())
+    return hb, ref
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n", [1, 2, 31, 64, 65, 127, 4099])
+def test_contract_small_and_ragged(gpu, gcs, kind, n, variant):
+    hb, ref = _solve_pair(gpu, gcs.synth, kind, n, variant)
+    assert_batches_within_contract(hb, ref, f"kind {kind} n {n} variant {variant}")
+
+
+@pytest.mark.parametrize("variant", VARIANTS + [5])
+@pytest.mark.parametrize("kind", KINDS)
+def test_contract_512k(gpu, gcs, kind, variant):
+    hb, ref = _solve_pair(gpu, gcs.synth, kind, 1 << 19, variant)
+    worst = assert_batches_within_contract(hb, ref, f"kind {kind} variant {variant}")
+    assert worst <= 1e-9
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("kind", [1, 3, 4])
+def test_contract_multistart_8_seeds(gpu, gcs, kind, variant):
+    hb, ref = _solve_pair(gpu, gcs.synth, kind, 20001, variant, n_seeds=8)
+    assert_batches_within_contract(hb, ref, f"8 seeds kind {kind}")
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_contract_explicit_guesses_and_early_exit(gpu, gcs, variant):
+    synth = gcs.synth
+    n = 5000
+    rng = np.random.default_rng(7)
+    g = rng.uniform(-3000, 3000, size=(2, 2, n))
+    g[:, :, ::7] = rng.uniform(-9e-6, 9e-6, size=g[:, :, ::7].shape)  # |guess| < 1e-5: exits at i = 0
+    g = np.ascontiguousarray(g)
+    hb = synth.make_pp(n)
+    hb.guesses, hb.variant = g, variant
+    gpu.solve_host(hb.alloc_outputs(), 0)
+    ref = synth.make_pp(n)
+    ref.guesses = g
+    O.solve(ref.alloc_outputs())
+    assert_batches_within_contract(hb, ref, "explicit guesses")
+    assert (hb.iters[:, ::7] == 0).all() and (hb.converged[:, ::7] == 1).all()
+    assert np.array_equal(bits(hb.cand[:, :, ::7]), bits(g[:, :, ::7]))
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_contract_nan_inf_and_degenerate_inputs(gpu, gcs, variant):
+    """Inputs on which no arithmetic can be trusted: every such run must come out of the literal
+    code, i.e. bit-identical to the oracle."""
+    synth = gcs.synth
+    n = 256
+    hb = synth.make_pp(n)
+    ref = synth.make_pp(n)
+    for b in (hb, ref):
+        c = b.cols
+        c[2][0::16] = np.nan
+        c[0][1::16] = np.inf
+        c[3][2::16] = c[0][2::16]
+        c[4][2::16] = c[1][2::16]          # B == A: singular Jacobian for ever
+        c[2][3::16] = 0.0
+        c[5][3::16] = 0.0                  # zero radii
+        c[2][4::16] = 1e-3
+        c[5][4::16] = 1e-3                 # circles that do not meet
+        c[0][5::16] = 1e300                # overflow in the residual
+    hb.variant = variant
+    gpu.solve_host(hb.alloc_outputs(), 0)
+    O.solve(ref.alloc_outputs())
+    assert_batches_within_contract(hb, ref, "degenerate")
+    bad = np.zeros(n, bool)
+    for o in range(6):
+        bad[o::16] = True
+    a, b = hb.cand[..., bad], ref.cand[..., bad]
+    assert ((bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))).all()
+    assert (hb.iters[:, 0::16] == 1000).all() and (hb.converged[:, 0::16] == 0).all()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("scale,flat", [(1e-6, None), (1e6, None), (1.0, 1e-7), (1.0, 1e-12), (1e3, 1e-4), (1e-150, None), (1e140, None)])
+def test_contract_flat_triangles_and_extreme_scales(gpu, gcs, variant, scale, flat):
+    """Flat triangles (ill-conditioned at the root: guard G1), tiny and huge scales (the band of
+    guard G3 against an absolute threshold of 1e-5)."""
+    n = 2000 if scale > 1e100 else 20000
+    hb, ref = _solve_pair(gpu, gcs.synth, 1, n, variant, scale=scale, flat=flat)
+    assert_batches_within_contract(hb, ref, f"scale {scale} flat {flat}")
+
+
+def test_contract_device_resident_batch_and_default_is_still_bit_identical(gpu, gcs):
+    import torch
+    synth, capi = gcs.synth, gcs.capi
+    hb = synth.make_ang(70001)
+    db = capi.DeviceBatch(hb, "cuda:0", want_cand=True)
+    ref = O.solve(synth.make_ang(70001).alloc_outputs())
+    for variant in (5, 6, 7, 8):
+        db.set_variant(variant)
+        db.solve()
+        torch.cuda.synchronize()
+        assert_batches_within_contract(db.to_host(synth.make_ang(70001)), ref, f"device batch variant {variant}")
+    db.set_variant(0)
+    db.solve()
+    torch.cuda.synchronize()
+    assert_batches_identical(db.to_host(synth.make_ang(70001)), ref, "default variant")
