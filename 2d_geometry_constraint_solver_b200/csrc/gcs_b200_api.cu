@@ -47,8 +47,9 @@ int fail(int code, const char* fmt, ...)
 constexpr long long kSortedMinRuns = 1ll << 18;
 inline int resolve_variant(int variant, long long n, int n_seeds)
 {
-    if (variant == GCS_VARIANT_CONTRACTED)
-        return n * n_seeds >= kSortedMinRuns ? GCS_VARIANT_CONTRACTED_SORTED : GCS_VARIANT_CONTRACTED_STATIC;
+    // contracted arithmetic: the static kernel at every size (with a 55-cycle update the sort's
+    // bookkeeping costs more than the idle lanes it removes: K1 51 vs 57 us, K3 68 vs 84 us per 2^19)
+    if (variant == GCS_VARIANT_CONTRACTED) return GCS_VARIANT_CONTRACTED_STATIC;
     if (variant != GCS_VARIANT_DEFAULT) return variant;
     return n * n_seeds >= kSortedMinRuns ? GCS_VARIANT_SORTED : GCS_VARIANT_STATIC;
 }

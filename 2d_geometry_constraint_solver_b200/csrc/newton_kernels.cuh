@@ -61,8 +61,15 @@ __device__ __forceinline__ unsigned lanemask_lt()
 #endif
 // RLX: closed-form updates with guards (newton_relaxed.cuh); a run or a selection the guards do
 // not vouch for is redone with the literal device functions.
+// RLX: held to 64 registers (8 CTAs of 128 lanes per SM).  The closed-form loop needs ~45; what is
+// spilled belongs to the inlined literal re-run, which one run in a thousand takes.  Measured per
+// 2^19 sub-systems, 5 / 6 / 8 / 10 / 12 CTAs per SM: K1 53.2 / 51.2 / 51.2 / 51.2 / 53.3 us,
+// K5 51.2 / 45.1 / 44.0 / 43.0 / 45.0 us, K3 75.8 / 69.6 / 67.6 / 69.6 / 73.7 us.
+#ifndef GCS_STATIC_RLX_MINB
+#define GCS_STATIC_RLX_MINB 8
+#endif
 template <int KIND, int NS, bool RLX = false>
-__global__ void __launch_bounds__(128, GCS_STATIC_MINB) newton_static_kernel(const BatchDev p)
+__global__ void __launch_bounds__(128, RLX ? GCS_STATIC_RLX_MINB : GCS_STATIC_MINB) newton_static_kernel(const BatchDev p)
 {
     using S = Sys<KIND>;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -363,6 +370,9 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
     __shared__ short s_it[RUNS];
     __shared__ unsigned short s_order[RUNS];
     __shared__ unsigned char s_cv[RUNS];
+    // RLX: the guard constants of each sub-system, computed once in phase A and read back in phase C
+    __shared__ int s_glo[RLX ? TILE : 1], s_ghi[RLX ? TILE : 1], s_gdt[RLX ? TILE : 1];
+    __shared__ double s_gpm[RLX ? TILE : 1];
     __shared__ int s_bin[kSortBins];   // live runs per sort key
     __shared__ int s_fill[kSortBins];  // slots handed out per sort key during the scatter
 
@@ -389,6 +399,7 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                 Rsys<KIND> rs;
                 RelaxGuard g;
                 rs.load(k, g);
+                s_glo[sub] = g.lo_h, s_ghi[sub] = g.hi_h, s_gdt[sub] = g.det_h, s_gpm[sub] = g.pm;
 #pragma unroll 1
                 for (int q = 0; q < 2; ++q) {
                     const int r = tid + q * THREADS;
@@ -498,7 +509,8 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                     if (state != kRlxUncertain) {
                         Rsys<KIND> rs;
                         RelaxGuard g;
-                        rs.load(k, g);
+                        rs.template load<false>(k, g);
+                        g.lo_h = s_glo[sub], g.hi_h = s_ghi[sub], g.det_h = s_gdt[sub], g.pm = s_gpm[sub];
                         double u0, u1;
                         state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1);
                     }

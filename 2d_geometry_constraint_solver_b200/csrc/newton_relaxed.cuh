@@ -67,12 +67,12 @@ __device__ __forceinline__ int hi_floor(double v) { return v > 0.0 ? __double2hi
 struct RelaxGuard {
     int lo_h, hi_h;  // hi(|s|) < lo_h: converged for certain; >= hi_h: not converged for certain
     int det_h;       // hi(|det|) must reach this (G1)
-    double cs, dr;   // coordinate scale S and |det| at a well-conditioned root (second-level test)
+    double pm;       // 2^-44 S dr: numerator of the second-level margin (S coordinate scale, dr = |det| at a well-conditioned root)
     static constexpr int kBigH = 0x5F300000;  // 2^500: anything from here on is "non-finite / huge" (G4)
     // step_scale: the closed-form solve returns step / step_scale (K1 works on J/2)
     __device__ __forceinline__ void init(double coord_scale, double det_root, double step_scale)
     {
-        cs = coord_scale, dr = det_root;
+        pm = 0x1p-44 * coord_scale * det_root;
         const double band = __fma_rn(0x1p-36, coord_scale, 0x1p-16 * kTol);
         const double inv = 1.0 / step_scale;  // 1 or 2: exact
         lo_h = hi_floor((kTol - band) * inv) - 1;
@@ -92,7 +92,7 @@ struct RelaxGuard {
     // Returns +1 converged for certain, -1 not converged for certain, 0 undecided.
     __device__ __forceinline__ int precise(double m, double det) const
     {
-        const double margin = __fma_rn(0x1p-44 * cs, dr * rcp_relaxed(fabs(det)), 0x1p-40 * kTol);
+        const double margin = __fma_rn(pm, rcp_relaxed(fabs(det)), 0x1p-40 * kTol);
         const double gap = m - kTol;
         if (gap > margin) return -1;
         if (-gap > margin) return 1;
@@ -112,12 +112,14 @@ template <>
 struct Rsys<GCS_KIND_PP> {
     static constexpr double kStepScale = 0.5;
     double ax, ay, qa, bx, by, qb;
+    // kGuard = false: only the system's constants (the guard comes from where it was stashed)
+    template <bool kGuard = true>
     __device__ __forceinline__ void load(const double* k, RelaxGuard& g)
     {
         ax = k[0], ay = k[1], qa = k[2] * k[2];
         bx = k[3], by = k[4], qb = k[5] * k[5];
         // at a root det(J/2) = (P-A) x (P-B) = ra rb sin(angle at P)
-        g.init(fabs(ax) + fabs(ay) + fabs(bx) + fabs(by) + fabs(k[2]) + fabs(k[5]), fabs(k[2] * k[5]), kStepScale);
+        if constexpr (kGuard) g.init(fabs(ax) + fabs(ay) + fabs(bx) + fabs(by) + fabs(k[2]) + fabs(k[5]), fabs(k[2] * k[5]), kStepScale);
     }
     __device__ __forceinline__ void eval(
         double x, double y, double& a, double& b, double& c, double& d, double& r0, double& r1) const
@@ -133,13 +135,15 @@ template <>
 struct Rsys<GCS_KIND_SDD> {
     static constexpr double kStepScale = 1.0;
     double dX, dY, c0;
+    // kGuard = false: only the system's constants (the guard comes from where it was stashed)
+    template <bool kGuard = true>
     __device__ __forceinline__ void load(const double* k, RelaxGuard& g)
     {
         dX = k[2] - k[0], dY = k[3] - k[1];
         c0 = k[4] - k[5];
         const double l1 = fabs(dX) + fabs(dY);
         // iterates are unit normals; the linear residual carries the offsets in units of |delta|
-        g.init(1.0 + (fabs(k[4]) + fabs(k[5])) * rcp_relaxed(l1), 2.0 * l1 * 0.70710678118654746, kStepScale);
+        if constexpr (kGuard) g.init(1.0 + (fabs(k[4]) + fabs(k[5])) * rcp_relaxed(l1), 2.0 * l1 * 0.70710678118654746, kStepScale);
     }
     __device__ __forceinline__ void eval(
         double x, double y, double& a, double& b, double& c, double& d, double& r0, double& r1) const
@@ -172,12 +176,14 @@ struct Rsys<GCS_KIND_PPL> {
     static constexpr double kStepScale = 1.0;
     double px, py, q;
     RP2L l;
+    // kGuard = false: only the system's constants (the guard comes from where it was stashed)
+    template <bool kGuard = true>
     __device__ __forceinline__ void load(const double* k, RelaxGuard& g)
     {
         px = k[0], py = k[1], q = k[2] * k[2];
         l.set(k[3], k[4], k[5], k[6], k[7]);
         // at a root det J = 2 (P - C) . e = 2 r L cos(.)
-        g.init(fabs(px) + fabs(py) + fabs(k[2]) + fabs(k[3]) + fabs(k[4]) + fabs(k[7]), 2.0 * fabs(k[2]) * l.len, kStepScale);
+        if constexpr (kGuard) g.init(fabs(px) + fabs(py) + fabs(k[2]) + fabs(k[3]) + fabs(k[4]) + fabs(k[7]), 2.0 * fabs(k[2]) * l.len, kStepScale);
     }
     __device__ __forceinline__ void eval(
         double x, double y, double& a, double& b, double& c, double& d, double& r0, double& r1) const
@@ -194,11 +200,13 @@ template <>
 struct Rsys<GCS_KIND_PLL> {
     static constexpr double kStepScale = 1.0;
     RP2L l1, l2;
+    // kGuard = false: only the system's constants (the guard comes from where it was stashed)
+    template <bool kGuard = true>
     __device__ __forceinline__ void load(const double* k, RelaxGuard& g)
     {
         l1.set(k[0], k[1], k[2], k[3], k[4]);
         l2.set(k[5], k[6], k[7], k[8], k[9]);
-        g.init(fabs(k[0]) + fabs(k[1]) + fabs(k[5]) + fabs(k[6]) + fabs(k[4]) + fabs(k[9]), l1.len * l2.len, kStepScale);
+        if constexpr (kGuard) g.init(fabs(k[0]) + fabs(k[1]) + fabs(k[5]) + fabs(k[6]) + fabs(k[4]) + fabs(k[9]), l1.len * l2.len, kStepScale);
     }
     __device__ __forceinline__ void eval(
         double x, double y, double& a, double& b, double& c, double& d, double& r0, double& r1) const
@@ -214,13 +222,15 @@ template <>
 struct Rsys<GCS_KIND_ANG> {
     static constexpr double kStepScale = 1.0;
     double fdx, fdy, cl;
+    // kGuard = false: only the system's constants (the guard comes from where it was stashed)
+    template <bool kGuard = true>
     __device__ __forceinline__ void load(const double* k, RelaxGuard& g)
     {
         fdx = k[0], fdy = k[1];
         const double len = sqrt(__fma_rn(fdx, fdx, fdy * fdy));
         cl = k[2] * len;
         // unit normals; the linear residual is L (cos(phi) - cosA): scale 2; det J = 2 L sin(.)
-        g.init(2.0, 2.0 * len, kStepScale);
+        if constexpr (kGuard) g.init(2.0, 2.0 * len, kStepScale);
     }
     __device__ __forceinline__ void eval(
         double x, double y, double& a, double& b, double& c, double& d, double& r0, double& r1) const
@@ -243,34 +253,42 @@ template <int KIND, bool kTrack>
 __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, const RelaxGuard& g, double& x, double& y, int& it,
     int limit, double& d2, double& d3)
 {
-    bool bad = false;
     const unsigned span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
+    int dmin = 0x7fffffff;  // smallest hi(|det|) seen: (G1) is evaluated when the run leaves the hot loop
     int state = kRlxRunning;
+    if (it >= limit) return (limit >= kRelaxCap) ? kRlxUncertain : kRlxRunning;
 #pragma unroll 1
-    while (it < limit) {
-        double a, b, c, d, r0, r1;
-        rs.eval(x, y, a, b, c, d, r0, r1);
-        const double det = __fma_rn(a, d, -(b * c));
-        const double r = rcp_relaxed(det);
-        const double n0 = __fma_rn(r0, d, -(r1 * b));
-        const double n1 = __fma_rn(a, r1, -(c * r0));
-        const double s0 = n0 * r, s1 = n1 * r;
-        if constexpr (Rsys<KIND>::kStepScale == 1.0) {
-            x += s0, y += s1;
-        } else {
-            x = __fma_rn(s0, Rsys<KIND>::kStepScale, x);
-            y = __fma_rn(s1, Rsys<KIND>::kStepScale, y);
-        }
-        ++it;
-        if constexpr (kTrack) {
-            d2 = d3;
-            d3 = __fma_rn(s0, s0, s1 * s1) * (Rsys<KIND>::kStepScale * Rsys<KIND>::kStepScale);
-        }
-        bad |= abs_hi(det) < g.det_h;  // (G1); a NaN determinant shows up in mh below
-        const int mh = max(abs_hi(s0), abs_hi(s1));
-        if ((unsigned)(mh - g.hi_h) < span) continue;  // longer than the threshold for certain
-        // ---- rare from here: the run ends, or the update sits in the first-level band ----
-        if (mh >= RelaxGuard::kBigH || bad) {  // non-finite / huge (G4), or ill-conditioned on the way (G1)
+    for (;;) {
+        int mh;
+        double s0, s1, det;
+        // hot loop: one closed-form update per trip, left when the update is no longer longer than
+        // the threshold for certain (or is non-finite / huge), or at the limit
+#pragma unroll 1
+        do {
+            double a, b, c, d, r0, r1;
+            rs.eval(x, y, a, b, c, d, r0, r1);
+            det = __fma_rn(a, d, -(b * c));
+            const double r = rcp_relaxed(det);
+            const double n0 = __fma_rn(r0, d, -(r1 * b));
+            const double n1 = __fma_rn(a, r1, -(c * r0));
+            s0 = n0 * r, s1 = n1 * r;
+            if constexpr (Rsys<KIND>::kStepScale == 1.0) {
+                x += s0, y += s1;
+            } else {
+                x = __fma_rn(s0, Rsys<KIND>::kStepScale, x);
+                y = __fma_rn(s1, Rsys<KIND>::kStepScale, y);
+            }
+            ++it;
+            if constexpr (kTrack) {
+                d2 = d3;
+                d3 = __fma_rn(s0, s0, s1 * s1) * (Rsys<KIND>::kStepScale * Rsys<KIND>::kStepScale);
+            }
+            dmin = min(dmin, abs_hi(det));  // a NaN determinant shows up in mh
+            mh = max(abs_hi(s0), abs_hi(s1));
+        } while ((unsigned)(mh - g.hi_h) < span && it < limit);
+        // ---- rare from here ----
+        if ((unsigned)(mh - g.hi_h) < span) break;  // limit reached, every update longer than the threshold
+        if (mh >= RelaxGuard::kBigH || dmin < g.det_h) {  // non-finite / huge (G4), ill-conditioned on the way (G1)
             state = kRlxUncertain;
             break;
         }
@@ -279,11 +297,13 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, const Relax
             break;
         }
         const int verdict = g.precise(fmax(fabs(s0), fabs(s1)) * Rsys<KIND>::kStepScale, det);
-        if (verdict < 0) continue;
-        state = verdict > 0 ? kRlxConverged : kRlxUncertain;
-        break;
+        if (verdict >= 0) {
+            state = verdict > 0 ? kRlxConverged : kRlxUncertain;
+            break;
+        }
+        if (it >= limit) break;  // not converged for certain, and out of updates
     }
-    if (state == kRlxRunning && (bad || limit >= kRelaxCap)) state = kRlxUncertain;  // (G1) / cap reached (G4)
+    if (state == kRlxRunning && (dmin < g.det_h || limit >= kRelaxCap)) state = kRlxUncertain;  // (G1) / cap reached (G4)
     return state;
 }
 

@@ -143,7 +143,8 @@ extern "C" {
  * variant (runs and selections whose decisions could depend on the arithmetic are detected by
  * guards and redone with the literal device functions); coordinates agree to 1e-9 relative (the
  * north star's tolerance) instead of bit for bit.  Opt-in: DEFAULT never resolves to it.
- * CONTRACTED = the sorted kernel from 2^18 runs per launch, the static kernel below. */
+ * CONTRACTED = CONTRACTED_STATIC (measured fastest at every size); SORTED and PAIR map the same
+ * arithmetic onto the sorted tiles / onto one lane per sub-system. */
 #define GCS_VARIANT_CONTRACTED 5
 #define GCS_VARIANT_CONTRACTED_STATIC 6
 #define GCS_VARIANT_CONTRACTED_SORTED 7

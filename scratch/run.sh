@@ -1,3 +1,4 @@
 set -x
-for v in 3 7; do python scratch/kbench.py $v 1,2,3,5 2>&1 | grep variant; done
-python -m pytest tests/test_gpu_relaxed.py tests/test_gpu_parity.py -x -q 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_r1n.json 2> gpurun_out/bench_r1n.err; tail -c 300 gpurun_out/bench_r1n.err
+python scratch/soak_relaxed.py 2097152 > gpurun_out/soak_relaxed.log 2>&1; tail -3 gpurun_out/soak_relaxed.log
