@@ -126,4 +126,13 @@ GCS_API BatchReport planLeaves(const std::vector<ConstraintGraph>& leaves);
 // Batched solve with the reference's sequential semantics; one launch per kind per wave.
 GCS_API BatchReport solveLeaves(std::vector<ConstraintGraph>& leaves, int device = 0);
 
+// Kernel class of every batch the host mirror launches: GCS_VARIANT_DEFAULT (bit-identical to the
+// reference arithmetic; the default) or GCS_VARIANT_CONTRACTED (iteration counts, flags and roots
+// of each solve identical for identical inputs, coordinates to 1e-9 relative - in a sketch the
+// coordinates of one wave are the inputs of the next, so results then agree with the reference's
+// loop to that tolerance, not bit for bit).  The environment variable GCS_B200_HOST_VARIANT sets
+// the initial value.  Returns the previous setting.
+GCS_API int setKernelVariant(int variant);
+GCS_API int kernelVariant();
+
 }  // namespace Gcs::B200

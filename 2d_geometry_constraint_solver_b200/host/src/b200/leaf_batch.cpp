@@ -635,6 +635,25 @@ void KindBatch::push(const PackedLeaf& leaf)
     m_leaves.push_back(leaf);
 }
 
+namespace {
+int& variantSetting()
+{
+    static int v = [] {
+        const char* e = std::getenv("GCS_B200_HOST_VARIANT");
+        return e ? std::atoi(e) : GCS_VARIANT_DEFAULT;
+    }();
+    return v;
+}
+}  // namespace
+
+int kernelVariant() { return variantSetting(); }
+int setKernelVariant(int variant)
+{
+    const int old = variantSetting();
+    variantSetting() = variant;
+    return old;
+}
+
 gcs_b200_batch KindBatch::descriptor()
 {
     gcs_b200_batch d {};
@@ -643,7 +662,7 @@ gcs_b200_batch KindBatch::descriptor()
     d.n_seeds = 2;  // Equations::solve2D runs exactly two guesses (newton_raphson.hpp:42-53)
     d.n = static_cast<std::int64_t>(n);
     d.mem = GCS_MEM_HOST;
-    d.variant = GCS_VARIANT_DEFAULT;
+    d.variant = variantSetting();
     const int nin = gcs_b200_kind_in_cols(m_kind), nout = gcs_b200_kind_out_cols(m_kind);
     for (int c = 0; c < nin; ++c) d.in[c] = m_in[static_cast<std::size_t>(c)].data();
     d.code = m_code.data();

@@ -120,6 +120,9 @@ extern "C" {
 
 GCS_API const char* gcs_host_last_error(void) { return g_msg; }
 
+// Kernel class of the host mirror's launches (Gcs::B200::setKernelVariant); returns the previous one.
+GCS_API int gcs_host_set_variant(int variant) { return Gcs::B200::setKernelVariant(variant); }
+
 // A 3-element leaf through classifyAndSolve (batch of one on the device).
 // Returns SolveStatus (0 Success, 1 Unsupported, 2 Failed) or -1 on an exception.
 GCS_API int gcs_host_component_solve(int n_el, gcs_host_element* el, int n_edges, const gcs_host_edge* edges)

@@ -368,8 +368,18 @@ def run_extra(args, rank, local_rank, world):
 
 
 # --------------------------------------------------------------------------------------------
+def _quiet_stdout():
+    """Library chatter on file descriptor 1 (NCCL prints its version there on some boxes) goes to
+    stderr; the JSON line is the only thing written to the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 def main():
     args = parse()
+    _quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -107,6 +107,27 @@ def test_solve_gcs_batched_equals_the_reference_loop_on_golden_sketches(host):
                 assert r["launches"] <= 5 * r["waves"] and r["waves"] < len(sk["leaves"])
 
 
+def test_solve_gcs_with_the_contracted_kernels_agrees_to_the_tolerance(host):
+    """Gcs::B200::setKernelVariant(GCS_VARIANT_CONTRACTED): each wave's coordinates feed the next
+    wave, so a whole sketch agrees with the bit-identical run to the north star's 1e-9 relative
+    (the solved flags and statuses are identical)."""
+    lib = H.load()
+    el, lv = S.make_sketch(5000, seed=11, first_shape=2)
+    base = H.leaves_solve(el, lv, 1)
+    old = lib.gcs_host_set_variant(5)
+    try:
+        fast = H.leaves_solve(el, lv, 1)
+    finally:
+        lib.gcs_host_set_variant(old)
+    assert old == 0 and base["rc"] == 0 and fast["rc"] == 0 and base["status"] == fast["status"]
+    scale = max(max(abs(v) for v in e["pos"]) for e in base["elements"])
+    worst = 0.0
+    for x, y in zip(base["elements"], fast["elements"]):
+        assert x["is_set"] == y["is_set"]
+        worst = max(worst, max(abs(a - b) for a, b in zip(x["pos"], y["pos"])) / max(1.0, scale))
+    assert worst <= 1e-9, worst
+
+
 def test_solve_gcs_batched_equals_sequential_at_scale(host):
     """20k leaves: one launch per kind per wave (a few hundred launches) against one launch per
     leaf; the final element state must be bit-identical."""
