@@ -13,28 +13,42 @@
 //     detected and the run is redone with the literal device functions of newton_core.cuh
 //     (newton_run, the same code the bit-identical kernels execute).  Detected means:
 //       (G1) |det J| has fallen under 2^-10 of its size at a well-conditioned root of this system
-//            (per-system constant): the step is sensitive to rounding, deviations between the
-//            two arithmetics could be amplified;
+//            (per-system constant): the step is sensitive to rounding;
+//       (G2) |det J| has grown 16x over its smallest value so far: the iterate has been thrown
+//            back out from near the line where J is singular - the one event that amplifies a
+//            deviation between the two arithmetics (and the signature of a run without real roots);
 //       (G3) the length of an update lies inside a band around the convergence threshold
-//            (newton_raphson.hpp:83-88), band = 2^-16 tol + 2^-36 S with S the magnitude of the
-//            system's coordinates: the two arithmetics could disagree on `< tol`;
+//            (newton_raphson.hpp:83-88).  First level, integer tests: band = 2^-16 tol + 2^-36 S with
+//            S the magnitude of the system's coordinates.  Second level, for the update that falls
+//            into that band: | m - tol | <= 2^-44 S dr/|det| + 2^-40 tol, 32x the bound on how far
+//            the two arithmetics' updates can be apart from the same iterate;
 //       (G4) no convergence after kRelaxCap updates (slow or chaotic runs: no real root, tangent
 //            circles), or a non-finite / huge update;
 //       (G5) in the root selection, an orientation (or a distance difference) within 2^-24
 //            relative of zero: the sign (or the comparison) could flip.
-//   * why that suffices: both arithmetics are backward stable on a 2x2 system, so from the same
-//     iterate their updates differ by O(cond(J) eps |step|) plus O(cond(J) ulp(S)) from the
-//     residuals.  Every equation pair of the path is a circle and a line (newton_kernels.cuh,
-//     "Prediction"): once on the line, Newton's map along it is w <- (w^2 + h^2)/(2w) whose
-//     derivative (1 - h^2/w^2)/2 has magnitude <= 1/2 for |w| >= h, which holds from the second
-//     update on when the roots are real - deviations are halved per update, then squared.  The
-//     one update that can amplify (the landing point close to the foot of the line, |w| << h) is
-//     bounded by (G1): net amplification h/w <= 2^11.  A deviation of 2^-40 relative therefore
-//     stays below 2^-29 S, the band of (G3) is 2^-36 S wide only where the conditioning (G1) has
-//     been established at that same iterate (cond <= 2^11, deviation there <= 2^-39 S from the
-//     residuals, the contracted history is smaller still).
+//   * why that suffices - an argument, backed by the tests, not a machine-checked proof.  Both
+//     arithmetics are backward stable on a 2x2 system, so from the same iterate their updates
+//     differ by O(cond(J) (eps |step| + ulp(S))).  Every equation pair of the path is a circle and
+//     a line (newton_kernels.cuh, "Prediction"): the first update lands on the line, and along it
+//     Newton's map is w <- (w^2 + h^2)/(2w), +-h the roots, with derivative (1 - h^2/w^2)/2.
+//       - Landing from a far seed (|seed| = G) is itself ill conditioned (cond ~ G/d): the two
+//         arithmetics land a RELATIVE eps G/d apart.  While |w| >> h the map halves w and the
+//         deviation alike: the relative deviation is carried, not grown.
+//       - Once |w| ~ h the map contracts quadratically: the deviation is multiplied by
+//         (w - h)/h per update, so at the deciding update (the first one shorter than tol) what is
+//         left of the history is below eps (G/d) sqrt(2 h tol) times further factors < 0.4 - orders
+//         of magnitude under the band at every scale the soak covers (1e-6 .. 1e6).
+//       - The only amplifying event is a landing (or a seed) with |w| << h, which throws the
+//         iterate out to h^2/(2w): |det| grows by (h/w)^2/2.  (G2) sends those runs to the
+//         literal code, so nothing is amplified by more than 4x on the closed-form path.
+//       - At the deciding update the fresh difference between the two arithmetics is
+//         ~8 (dr/|det|) 2^-52 S with dr/|det| <= 2^10 by (G1): 2^-39 S against a first-level band
+//         of 2^-36 S, and the second level scales its margin with the actual dr/|det|.
+//       - Runs without real roots never meet the threshold and leave by (G2) / (G4); non-finite
+//         values by (G4).
 //   * tests/test_gpu_relaxed.py and the soak (profiles/) compare iteration counts, flags and root
-//     indices for equality and coordinates to 1e-9 against the CPU checker on every parity case.
+//     indices for equality and coordinates to 1e-9 against the CPU checker on every parity case;
+//     bench.py re-checks its whole batch against the bit-identical kernels in every run.
 #pragma once
 
 #include "newton_core.cuh"
@@ -42,6 +56,7 @@
 namespace gcsk {
 
 constexpr int kRelaxCap = 64;  // updates a run may take on the closed-form path (G4)
+constexpr int kBounce = 4 << 20;  // (G2) four binades of growth of |det| over its running minimum
 
 // How often the guards hand work to the literal code (read by gcs_b200_contracted_stats):
 // [0] runs redone because a run-level guard fired, [1] runs redone because the selection guard fired.
@@ -254,41 +269,61 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, const Relax
     int limit, double& d2, double& d3)
 {
     const unsigned span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
-    int dmin = 0x7fffffff;  // smallest hi(|det|) seen: (G1) is evaluated when the run leaves the hot loop
+    // smallest hi(|det|) at the iterates after the seed, and its largest growth over that running
+    // minimum; the determinant AT THE SEED (d1) counts for (G1) only: both arithmetics start from
+    // the same seed, so a badly conditioned first update creates a deviation (eps cond, carried
+    // and then contracted) but has none to amplify, and |det| growing from the seed to the
+    // landing point is routine (a seed that happens to lie near the singular line).
+    int dmin = 0x7fffffff, grow = 0, d1 = 0x7fffffff;
     int state = kRlxRunning;
     if (it >= limit) return (limit >= kRelaxCap) ? kRlxUncertain : kRlxRunning;
+    int mh, dh;
+    double s0, s1, det;
+    // one closed-form update; leaves mh = larger high word of the update's components, dh = hi(|det|)
+    auto update = [&]() {
+        double a, b, c, d, r0, r1;
+        rs.eval(x, y, a, b, c, d, r0, r1);
+        det = __fma_rn(a, d, -(b * c));
+        const double r = rcp_relaxed(det);
+        const double n0 = __fma_rn(r0, d, -(r1 * b));
+        const double n1 = __fma_rn(a, r1, -(c * r0));
+        s0 = n0 * r, s1 = n1 * r;
+        if constexpr (Rsys<KIND>::kStepScale == 1.0) {
+            x += s0, y += s1;
+        } else {
+            x = __fma_rn(s0, Rsys<KIND>::kStepScale, x);
+            y = __fma_rn(s1, Rsys<KIND>::kStepScale, y);
+        }
+        ++it;
+        if constexpr (kTrack) {
+            d2 = d3;
+            d3 = __fma_rn(s0, s0, s1 * s1) * (Rsys<KIND>::kStepScale * Rsys<KIND>::kStepScale);
+        }
+        dh = abs_hi(det);  // a NaN determinant shows up in mh
+        mh = max(abs_hi(s0), abs_hi(s1));
+    };
+    bool in_loop = true;
+    if (it == 0) {  // the update from the seed, peeled (see above)
+        update();
+        d1 = dh;
+        in_loop = (unsigned)(mh - g.hi_h) < span && it < limit;
+    }
 #pragma unroll 1
     for (;;) {
-        int mh;
-        double s0, s1, det;
-        // hot loop: one closed-form update per trip, left when the update is no longer longer than
-        // the threshold for certain (or is non-finite / huge), or at the limit
+        // hot loop: one update per trip, left when the update is no longer longer than the
+        // threshold for certain (or is non-finite / huge), or at the limit
+        if (in_loop) {
 #pragma unroll 1
-        do {
-            double a, b, c, d, r0, r1;
-            rs.eval(x, y, a, b, c, d, r0, r1);
-            det = __fma_rn(a, d, -(b * c));
-            const double r = rcp_relaxed(det);
-            const double n0 = __fma_rn(r0, d, -(r1 * b));
-            const double n1 = __fma_rn(a, r1, -(c * r0));
-            s0 = n0 * r, s1 = n1 * r;
-            if constexpr (Rsys<KIND>::kStepScale == 1.0) {
-                x += s0, y += s1;
-            } else {
-                x = __fma_rn(s0, Rsys<KIND>::kStepScale, x);
-                y = __fma_rn(s1, Rsys<KIND>::kStepScale, y);
-            }
-            ++it;
-            if constexpr (kTrack) {
-                d2 = d3;
-                d3 = __fma_rn(s0, s0, s1 * s1) * (Rsys<KIND>::kStepScale * Rsys<KIND>::kStepScale);
-            }
-            dmin = min(dmin, abs_hi(det));  // a NaN determinant shows up in mh
-            mh = max(abs_hi(s0), abs_hi(s1));
-        } while ((unsigned)(mh - g.hi_h) < span && it < limit);
+            do {
+                update();
+                grow = max(grow, dh - dmin);  // (G2), in high-word units (2^20 per binade)
+                dmin = min(dmin, dh);
+            } while ((unsigned)(mh - g.hi_h) < span && it < limit);
+        }
+        in_loop = true;
         // ---- rare from here ----
         if ((unsigned)(mh - g.hi_h) < span) break;  // limit reached, every update longer than the threshold
-        if (mh >= RelaxGuard::kBigH || dmin < g.det_h) {  // non-finite / huge (G4), ill-conditioned on the way (G1)
+        if (mh >= RelaxGuard::kBigH || min(dmin, d1) < g.det_h || grow > kBounce) {  // (G4) / (G1) / (G2)
             state = kRlxUncertain;
             break;
         }
@@ -303,7 +338,7 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, const Relax
         }
         if (it >= limit) break;  // not converged for certain, and out of updates
     }
-    if (state == kRlxRunning && (dmin < g.det_h || limit >= kRelaxCap)) state = kRlxUncertain;  // (G1) / cap reached (G4)
+    if (state == kRlxRunning && (min(dmin, d1) < g.det_h || grow > kBounce || limit >= kRelaxCap)) state = kRlxUncertain;
     return state;
 }
 
@@ -319,6 +354,7 @@ __device__ __forceinline__ void relaxed_updates2(const Rsys<KIND>& rs, const Rel
     const unsigned span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
     bool la = sa == kRlxRunning, lb = sb == kRlxRunning;
     bool bada = false, badb = false;
+    int dmina = 0x7fffffff - kBounce, dminb = 0x7fffffff - kBounce;
     // end of a run, or an update inside the first-level band: decide this run's state
     auto settle = [&](bool& live, int& state, bool bad, int mh, double s0, double s1, double det, int it) {
         if (mh < g.lo_h && !bad) {
@@ -352,8 +388,12 @@ __device__ __forceinline__ void relaxed_updates2(const Rsys<KIND>& rs, const Rel
             xb = __fma_rn(s10, Rsys<KIND>::kStepScale, xb), yb = __fma_rn(s11, Rsys<KIND>::kStepScale, yb);
             ++itb;
         }
-        bada |= abs_hi(det0) < g.det_h;
-        badb |= abs_hi(det1) < g.det_h;
+        const int dha = abs_hi(det0), dhb = abs_hi(det1);
+        bada |= dha < g.det_h || dha > dmina + kBounce;
+        badb |= dhb < g.det_h || dhb > dminb + kBounce;
+        // the determinant at the seed (the run's first update) does not enter the running minimum
+        if (ita > 1) dmina = min(dmina, dha);
+        if (itb > 1) dminb = min(dminb, dhb);
         const int mha = max(abs_hi(s00), abs_hi(s01));
         const int mhb = max(abs_hi(s10), abs_hi(s11));
         const bool fara = (unsigned)(mha - g.hi_h) < span && ita < kRelaxCap;

@@ -70,6 +70,32 @@ def test_contract_explicit_guesses_and_early_exit(gpu, gcs, variant):
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
+def test_contract_guesses_next_to_the_singular_line(gpu, gcs, variant):
+    """Seeds a hair off the line through the two centres, where the distance-distance Jacobian is
+    singular: the first update throws the iterate far out (the one event that amplifies a
+    deviation between two arithmetics, guard G2) - iteration counts must still be the oracle's."""
+    synth = gcs.synth
+    n = 20000
+    rng = np.random.default_rng(11)
+    hb = synth.make_pp(n)
+    ax, ay, _, bx, by, _ = hb.cols
+    t = rng.uniform(-0.5, 1.5, size=(2, n))
+    off = np.exp(rng.uniform(np.log(1e-9), np.log(1e-1), size=(2, n))) * rng.choice([-1.0, 1.0], size=(2, n))
+    ux, uy = bx - ax, by - ay
+    g = np.empty((2, 2, n))
+    g[:, 0, :] = ax + t * ux - off * uy
+    g[:, 1, :] = ay + t * uy + off * ux
+    g = np.ascontiguousarray(g)
+    hb.guesses, hb.variant = g, variant
+    gpu.solve_host(hb.alloc_outputs(), 0)
+    ref = synth.make_pp(n)
+    ref.guesses = g
+    O.solve(ref.alloc_outputs())
+    assert_batches_within_contract(hb, ref, "guesses next to the singular line")
+    assert ref.converged.mean() > 0.9  # the case is about runs that do converge, after a detour
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_contract_nan_inf_and_degenerate_inputs(gpu, gcs, variant):
     """Inputs on which no arithmetic can be trusted: every such run must come out of the literal
     code, i.e. bit-identical to the oracle."""
