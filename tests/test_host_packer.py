@@ -173,3 +173,11 @@ def test_wave_plan_reproduces_the_reference_loop_on_golden_sketches(gcs, host):
         for got, exp in zip(els, sk["expected"]):
             assert got.get("is_set") == exp["is_set"]
             assert same_pos(got["pos"], exp["pos"])
+
+
+def test_kernel_variant_setting_of_the_host_mirror(host):
+    """Gcs::B200::setKernelVariant: the default is the bit-identical class; the setter returns the
+    previous value (what KindBatch::descriptor() puts into gcs_b200_batch.variant)."""
+    assert host.gcs_host_set_variant(5) == 0
+    assert host.gcs_host_set_variant(0) == 5
+    assert host.gcs_host_set_variant(0) == 0
