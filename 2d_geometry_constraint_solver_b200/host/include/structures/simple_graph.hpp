@@ -86,6 +86,8 @@ private:
                 if (it->first == k) return it;
             return last;
         }
+        // ids handed out in sequence and never erased sit at their own index: one probe
+        if (k.value >= 0 && k.value < last - first && (first + k.value)->first == k) return first + k.value;
         It it = std::lower_bound(first, last, k, [](const Entry& e, const Key& key) { return e.first < key; });
         return (it != last && it->first == k) ? it : last;
     }

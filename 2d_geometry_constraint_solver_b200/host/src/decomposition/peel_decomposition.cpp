@@ -1,6 +1,7 @@
 // Degree-2 peeling decomposition (see gcs/b200/peel_decomposition.hpp).
 #include <algorithm>
 #include <array>
+#include <functional>
 #include <map>
 #include <set>
 #include <stdexcept>
@@ -57,59 +58,86 @@ std::vector<ConstraintGraph> decomposeByPeeling(const ConstraintGraph& gcs, Peel
     const auto& graph = gcs.getGraph();
     if (graph.nodeCount() < 3) throw std::runtime_error("decomposeByPeeling: fewer than three elements");
 
-    // live adjacency: node -> incident live edges
-    std::map<NodeId, std::set<EdgeId>> incident;
-    for (NodeId n : graph.getNodes()) {
-        const auto& es = graph.getEdges(n);
-        incident.emplace(n, std::set<EdgeId>(es.begin(), es.end()));
+    // live adjacency in flat arrays over the dense positions of the nodes in ascending id order:
+    // the live incident edges of node slot i are inc[i] (ascending, as SimpleGraph keeps them; a
+    // node of degree <= 2 is all the peel ever looks into, higher degrees only lose edges)
+    const auto nodeList = graph.getNodes();
+    const std::size_t nn = nodeList.size();
+    std::vector<NodeId> ids(nodeList.begin(), nodeList.end());
+    std::sort(ids.begin(), ids.end());
+    auto slotOf = [&](NodeId n) -> std::size_t {
+        if (n.value >= 0 && static_cast<std::size_t>(n.value) < nn && ids[static_cast<std::size_t>(n.value)] == n)
+            return static_cast<std::size_t>(n.value);
+        return static_cast<std::size_t>(std::lower_bound(ids.begin(), ids.end(), n) - ids.begin());
+    };
+    std::vector<std::vector<EdgeId>> inc(nn);
+    std::vector<char> alive(nn, 1);
+    for (std::size_t i = 0; i < nn; ++i) {
+        const auto& es = graph.getEdges(ids[i]);
+        inc[i].assign(es.begin(), es.end());
+        std::sort(inc[i].begin(), inc[i].end());
     }
     auto other = [&](EdgeId e, NodeId n) {
         const auto [s, t] = graph.getEndpoints(e);
         return s == n ? t : s;
     };
-    std::set<NodeId> degreeTwo;
-    for (const auto& [n, es] : incident)
-        if (es.size() == 2) degreeTwo.insert(n);
+    auto dropEdge = [&](std::size_t slot, EdgeId e) {
+        auto& v = inc[slot];
+        v.erase(std::find(v.begin(), v.end(), e));
+    };
+    // candidates in ascending id order: a min-heap of slots with lazy deletion (a slot is looked
+    // at again whenever its degree becomes two)
+    std::vector<std::size_t> heap;
+    auto push = [&](std::size_t slot) {
+        heap.push_back(slot);
+        std::push_heap(heap.begin(), heap.end(), std::greater<>());
+    };
+    for (std::size_t i = 0; i < nn; ++i)
+        if (inc[i].size() == 2) push(i);
+    std::vector<std::size_t> parked;  // degree-2 slots whose two edges form a double edge (skipped, kept)
 
     std::vector<Peel> peels;
-    peels.reserve(graph.nodeCount());
-    while (incident.size() > 3) {
+    peels.reserve(nn);
+    std::size_t remaining = nn;
+    while (remaining > 3) {
         // smallest-id degree-2 node whose two edges lead to two different neighbours
-        NodeId v {};
         bool found = false;
-        for (auto it = degreeTwo.begin(); it != degreeTwo.end();) {
-            const auto& es = incident.at(*it);
-            if (es.size() != 2) {
-                it = degreeTwo.erase(it);
+        std::size_t vs = 0;
+        while (!heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end(), std::greater<>());
+            const std::size_t c = heap.back();
+            heap.pop_back();
+            if (!alive[c] || inc[c].size() != 2) continue;  // stale entry
+            if (other(inc[c][0], ids[c]) == other(inc[c][1], ids[c])) {  // a double edge, not a separation pair
+                parked.push_back(c);
                 continue;
             }
-            const EdgeId e0 = *es.begin(), e1 = *std::next(es.begin());
-            if (other(e0, *it) == other(e1, *it)) {  // a double edge, not a separation pair
-                ++it;
-                continue;
-            }
-            v = *it;
+            vs = c;
             found = true;
             break;
         }
+        for (std::size_t c : parked) push(c);  // they stay candidates for later rounds, in id order
+        parked.clear();
         if (!found)
-            throw std::runtime_error("decomposeByPeeling: no degree-2 element left with " + std::to_string(incident.size())
+            throw std::runtime_error("decomposeByPeeling: no degree-2 element left with " + std::to_string(remaining)
                 + " elements remaining; general separation pairs need the OGDF-based decomposition of the reference");
-        const auto es = incident.at(v);
-        const EdgeId e0 = *es.begin(), e1 = *std::next(es.begin());
+        const NodeId v = ids[vs];
+        const EdgeId e0 = inc[vs][0], e1 = inc[vs][1];
         const NodeId a = other(e0, v), b = other(e1, v);
         peels.push_back({ v, a, b, e0, e1 });
-        incident.at(a).erase(e0);
-        incident.at(b).erase(e1);
-        incident.erase(v);
-        degreeTwo.erase(v);
-        for (NodeId n : { a, b }) {
-            if (incident.at(n).size() == 2)
-                degreeTwo.insert(n);
-            else
-                degreeTwo.erase(n);
-        }
+        const std::size_t sa = slotOf(a), sb = slotOf(b);
+        dropEdge(sa, e0);
+        dropEdge(sb, e1);
+        alive[vs] = 0;
+        inc[vs].clear();
+        --remaining;
+        for (std::size_t sl : { sa, sb })
+            if (inc[sl].size() == 2) push(sl);
     }
+    // what the base-leaf code below iterates: the three remaining nodes with their live edges
+    std::map<NodeId, std::set<EdgeId>> incident;
+    for (std::size_t i = 0; i < nn; ++i)
+        if (alive[i]) incident.emplace(ids[i], std::set<EdgeId>(inc[i].begin(), inc[i].end()));
 
     std::vector<ConstraintGraph> leaves;
     leaves.reserve(peels.size() + 1);

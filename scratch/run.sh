@@ -1,3 +1,2 @@
-python scratch/kbench.py 8 1,2,3,5 2>&1 | grep variant | cut -c1-80
-GCS_B200_LIB=build/libgcs_rpair8.so python scratch/kbench.py 8 1,2,3,5 2>&1 | grep variant | cut -c1-80
-GCS_B200_LIB=build/libgcs_rpair10.so python scratch/kbench.py 8 1,2,3,5 2>&1 | grep variant | cut -c1-80
+python -m pytest tests/test_gpu_host.py tests/test_dropin_client.py tests/test_decomposition.py -m gpu -x -q 2>&1 | tail -3
+python profiles/sketch_bench.py 100000 2>&1 | tail -2
