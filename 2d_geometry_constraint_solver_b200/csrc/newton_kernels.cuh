@@ -20,6 +20,11 @@
 //      lane finishes one run, so the lanes of a warp stop (almost) together.  See the kernel.
 //
 // All produce bit-identical results (same device functions, same operation order per run).
+//
+//  The static and sorted kernels also exist in a contracted instantiation (template flag RLX), and
+//  newton_pair_relaxed_kernel maps the same arithmetic onto one lane per sub-system: closed-form
+//  updates on fused multiply-adds with guards (newton_relaxed.cuh) - iteration counts, flags and
+//  root indices identical to the kernels above, coordinates within 1e-9 relative.
 #pragma once
 
 #include <cuda_runtime.h>
