@@ -1,3 +1,1 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-python -c "import __graft_entry__ as e; e.smoke()" 2>&1 | tail -1
-python bench.py --steps 20 --warmup 3 2>/dev/null | head -c 400
+python -m pytest tests/test_gpu_golden.py -x -q 2>&1 | tail -8
