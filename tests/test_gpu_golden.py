@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from test_golden import check_against_golden, load_numeric
+from test_golden import check_against_golden, check_against_golden_contract, load_numeric
 
 pytestmark = pytest.mark.gpu
 
@@ -25,30 +25,4 @@ def test_contracted_cuda_matches_reference_golden_to_the_contract(gpu, gcs, kind
     hb, z = load_numeric(gcs.capi, kind)
     hb.variant = variant
     gpu.solve_host(hb.alloc_outputs(), 0)
-    what = f"cuda kind {kind} variant {variant}"
-    git, gcv = z["iters"], z["converged"]
-    capped = git >= 999  # the reference's count cannot tell i=999 from the cap (see ref_driver.cpp)
-    assert np.array_equal(hb.iters[~capped], git[~capped]), f"{what}: iteration counts differ"
-    assert (hb.iters[capped] >= 999).all()
-    assert np.array_equal(hb.converged[~capped], gcv[~capped])
-    seen = z["root"] != 2  # 2 = both candidates identical, root unobservable in the reference
-    assert np.array_equal(hb.root_index[seen], z["root"][seen]), f"{what}: chosen root differs"
-    with np.errstate(invalid="ignore", over="ignore"):
-        scale = np.maximum(1.0, np.max(np.stack([np.where(np.isfinite(c), np.abs(c), 0.0) for c in hb.cols]), axis=0))
-
-        def close(a, b):
-            assert np.array_equal(np.isnan(a), np.isnan(b)), f"{what}: NaN pattern differs"
-            fin = np.isfinite(b)
-            sc = np.broadcast_to(scale, b.shape)
-            err = np.abs(a[fin] - b[fin]) / np.maximum(sc[fin], np.abs(b[fin]))
-            assert err.size == 0 or err.max() <= 1e-9, f"{what}: max relative error {err.max():.3e}"
-
-        close(hb.cand, z["cand"])
-        if kind in (1, 3, 4):
-            for c in range(2):
-                close(hb.out[c], z["out"][c])
-        else:
-            r = hb.root_index.astype(int)
-            idx = np.arange(hb.n)
-            close(hb.cand[r, 0, idx], z["out"][0])
-            close(hb.cand[r, 1, idx], z["out"][1])
+    check_against_golden_contract(hb, z, kind, f"cuda kind {kind} variant {variant}")
