@@ -423,43 +423,43 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                     }
                 }
             } else {
-            S sys;
-            sys.load(k);
+                S sys;
+                sys.load(k);
 #pragma unroll 1
-            for (int q = 0; q < 2; ++q) {
-                const int r = tid + q * THREADS;
-                const int seed = r / TILE;
-                double x, y;
-                if (p.guesses) {
-                    x = __ldg(p.guesses + ((long long)seed * 2 + 0) * p.stride + gi);
-                    y = __ldg(p.guesses + ((long long)seed * 2 + 1) * p.stride + gi);
-                } else if constexpr (S::kGuessFromCols) {
-                    column_seed<KIND>(k, seed, x, y);
-                } else {
-                    default_seed(seed, x, y);
-                }
-                // iteration 0 compares the guess with prev = (0,0) (newton_raphson.hpp:58, :83-88)
-                bool conv = fabs(0.0 - x) < fc.tol && fabs(0.0 - y) < fc.tol;
-                int it = 0;
-                double d2 = 0.0, d3 = 0.0;
+                for (int q = 0; q < 2; ++q) {
+                    const int r = tid + q * THREADS;
+                    const int seed = r / TILE;
+                    double x, y;
+                    if (p.guesses) {
+                        x = __ldg(p.guesses + ((long long)seed * 2 + 0) * p.stride + gi);
+                        y = __ldg(p.guesses + ((long long)seed * 2 + 1) * p.stride + gi);
+                    } else if constexpr (S::kGuessFromCols) {
+                        column_seed<KIND>(k, seed, x, y);
+                    } else {
+                        default_seed(seed, x, y);
+                    }
+                    // iteration 0 compares the guess with prev = (0,0) (newton_raphson.hpp:58, :83-88)
+                    bool conv = fabs(0.0 - x) < fc.tol && fabs(0.0 - y) < fc.tol;
+                    int it = 0;
+                    double d2 = 0.0, d3 = 0.0;
 #pragma unroll 1
-                for (int j = 0; j < 3 && !conv && it < kMaxIt; ++j) {
-                    double nx, ny;
-                    newton_update<KIND>(sys, fc, x, y, nx, ny, it);
-                    const double ex = x - nx, ey = y - ny;
-                    conv = fabs(ex) < fc.tol && fabs(ey) < fc.tol;
-                    d2 = d3;
-                    d3 = ex * ex + ey * ey;
-                    x = nx, y = ny;
+                    for (int j = 0; j < 3 && !conv && it < kMaxIt; ++j) {
+                        double nx, ny;
+                        newton_update<KIND>(sys, fc, x, y, nx, ny, it);
+                        const double ex = x - nx, ey = y - ny;
+                        conv = fabs(ex) < fc.tol && fabs(ey) < fc.tol;
+                        d2 = d3;
+                        d3 = ex * ex + ey * ey;
+                        x = nx, y = ny;
+                    }
+                    s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
+                    s_cv[r] = (conv && it < kMaxIt) ? 1 : 0;
+                    if (!conv && it < kMaxIt) {
+                        const int kk = kSortBins - 1 - predict_remaining(d2, d3);
+                        atomicAdd(&s_bin[kk], 1);
+                        if (q == 0) key[0] = kk; else key[1] = kk;
+                    }
                 }
-                s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
-                s_cv[r] = (conv && it < kMaxIt) ? 1 : 0;
-                if (!conv && it < kMaxIt) {
-                    const int kk = kSortBins - 1 - predict_remaining(d2, d3);
-                    atomicAdd(&s_bin[kk], 1);
-                    if (q == 0) key[0] = kk; else key[1] = kk;
-                }
-            }
             }
         }
     }
@@ -524,20 +524,20 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                     s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
                     s_cv[r] = (unsigned char)conv;
                 } else {
-                S sys;
-                sys.load(k);
-                double x = s_x[r], y = s_y[r];
-                int it = s_it[r];
-                bool conv = false;
+                    S sys;
+                    sys.load(k);
+                    double x = s_x[r], y = s_y[r];
+                    int it = s_it[r];
+                    bool conv = false;
 #pragma unroll 1
-                while (!conv && it < kMaxIt) {
-                    double nx, ny;
-                    newton_update<KIND>(sys, fc, x, y, nx, ny, it);
-                    conv = fabs(x - nx) < fc.tol && fabs(y - ny) < fc.tol;
-                    x = nx, y = ny;
-                }
-                s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
-                s_cv[r] = (conv && it < kMaxIt) ? 1 : 0;
+                    while (!conv && it < kMaxIt) {
+                        double nx, ny;
+                        newton_update<KIND>(sys, fc, x, y, nx, ny, it);
+                        conv = fabs(x - nx) < fc.tol && fabs(y - ny) < fc.tol;
+                        x = nx, y = ny;
+                    }
+                    s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
+                    s_cv[r] = (conv && it < kMaxIt) ? 1 : 0;
                 }
             }
         }
