@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
     // RLX: the guard constants of each sub-system, computed once in phase A and read back in phase C
     __shared__ int s_glo[RLX ? TILE : 1], s_ghi[RLX ? TILE : 1], s_gdt[RLX ? TILE : 1];
     __shared__ double s_gpm[RLX ? TILE : 1];
+    __shared__ int s_dmin[RLX ? RUNS : 1];  // running minimum of hi(|det|) of each run at the hand-off (guard G2)
     __shared__ int s_bin[kSortBins];   // live runs per sort key
     __shared__ int s_fill[kSortBins];  // slots handed out per sort key during the scatter
 
@@ -412,8 +413,10 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                     run_seed<KIND>(p.guesses, p.stride, gi, k, r / TILE, x, y);
                     int it = 0, state = kRlxConverged;
                     double d2 = 0.0, d3 = 0.0;
+                    int dmin = 0x7fffffff;
                     if (!(fabs(0.0 - x) < kTol && fabs(0.0 - y) < kTol))
-                        state = relaxed_updates<KIND, true>(rs, g, x, y, it, 3, d2, d3);
+                        state = relaxed_updates<KIND, true>(rs, g, x, y, it, 3, d2, d3, &dmin);
+                    s_dmin[r] = dmin;
                     s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
                     s_cv[r] = (unsigned char)state;  // kRlxUncertain (2): phase C redoes the run literally
                     if (state != kRlxConverged) {
@@ -517,7 +520,8 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                         rs.template load<false>(k, g);
                         g.lo_h = s_glo[sub], g.hi_h = s_ghi[sub], g.det_h = s_gdt[sub], g.pm = s_gpm[sub];
                         double u0, u1;
-                        state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1);
+                        int dmin = s_dmin[r];
+                        state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1, &dmin);
                     }
                     if (state != kRlxConverged)
                         literal_rerun<KIND>(p.guesses, p.stride, base + sub, k, r / TILE, (double)(p.n >> 62), x, y, it, conv);

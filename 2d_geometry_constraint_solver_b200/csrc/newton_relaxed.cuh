@@ -264,9 +264,11 @@ enum : int { kRlxRunning = 0, kRlxConverged = 1, kRlxUncertain = 2 };
 //   kRlxUncertain : a guard fired - the caller redoes the run from its seed with newton_run
 //   kRlxRunning   : `limit` reached, every update so far longer than the threshold for certain.
 // d2 / d3 (optional): squared lengths of the last two updates, for the sort key of the sorted kernel.
+// dmin_io (optional): the running minimum of hi(|det|) after the seed, carried from one stretch of a
+// run to the next so that (G2) sees growth across the hand-off.
 template <int KIND, bool kTrack>
 __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, const RelaxGuard& g, double& x, double& y, int& it,
-    int limit, double& d2, double& d3)
+    int limit, double& d2, double& d3, int* dmin_io = nullptr)
 {
     const unsigned span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
     // smallest hi(|det|) at the iterates after the seed, and its largest growth over that running
@@ -275,6 +277,7 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, const Relax
     // and then contracted) but has none to amplify, and |det| growing from the seed to the
     // landing point is routine (a seed that happens to lie near the singular line).
     int dmin = 0x7fffffff, grow = 0, d1 = 0x7fffffff;
+    if (dmin_io && it > 0) dmin = *dmin_io;  // a run continued from an earlier stretch (sorted kernel)
     int state = kRlxRunning;
     if (it >= limit) return (limit >= kRelaxCap) ? kRlxUncertain : kRlxRunning;
     int mh, dh;
@@ -339,6 +342,7 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, const Relax
         if (it >= limit) break;  // not converged for certain, and out of updates
     }
     if (state == kRlxRunning && (min(dmin, d1) < g.det_h || grow > kBounce || limit >= kRelaxCap)) state = kRlxUncertain;
+    if (dmin_io) *dmin_io = dmin;
     return state;
 }
 
