@@ -33,7 +33,7 @@ IN_COL_NAMES = {
 MEM_HOST, MEM_DEVICE = 0, 1
 VARIANT_DEFAULT, VARIANT_STATIC, VARIANT_REFILL, VARIANT_SORTED, VARIANT_PAIR = 0, 1, 2, 3, 4
 # tolerance-class arithmetic (discrete outputs identical, coordinates to 1e-9): auto / static / sorted
-VARIANT_CONTRACTED, VARIANT_CONTRACTED_STATIC, VARIANT_CONTRACTED_SORTED, VARIANT_CONTRACTED_PAIR = 5, 6, 7, 8
+VARIANT_CONTRACTED, VARIANT_CONTRACTED_STATIC, VARIANT_CONTRACTED_SORTED = 5, 6, 7
 
 CODE_COLLINEAR = 0x10
 CODE_CANVAS_PARALLEL = 0x20

@@ -183,17 +183,6 @@ int launch_pair(const BatchDev& p, cudaStream_t st)
     return GCS_OK;
 }
 
-template <int KIND, int NS>
-int launch_pair_relaxed(const BatchDev& p, cudaStream_t st)
-{
-    const long long grid = (p.n + 127) / 128;
-    if (grid > 0x7fffffffLL) return fail(GCS_E_INVALID, "batch too large for one launch");
-    newton_pair_relaxed_kernel<KIND, NS><<<(unsigned)grid, 128, 0, st>>>(p);
-    g_launches.fetch_add(1);
-    CUDA_TRY(cudaGetLastError());
-    return GCS_OK;
-}
-
 template <int KIND, int NS, bool RLX = false>
 int launch_sorted(const BatchDev& p, cudaStream_t st)
 {
@@ -243,7 +232,6 @@ int launch_kind(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cuda
     const int variant = resolve_variant(b->variant, p.n, b->n_seeds);
     constexpr bool column_guess = (KIND == GCS_KIND_SDD || KIND == GCS_KIND_ANG);
     if (b->n_seeds == 2) {
-        if (variant == GCS_VARIANT_CONTRACTED_PAIR) return launch_pair_relaxed<KIND, 2>(p, st);
         if (variant == GCS_VARIANT_CONTRACTED_SORTED) return launch_sorted<KIND, 2, true>(p, st);
         if (variant == GCS_VARIANT_CONTRACTED_STATIC) return launch_static<KIND, 2, true>(p, st);
         if (variant == GCS_VARIANT_SORTED) return launch_sorted<KIND, 2>(p, st);
@@ -251,7 +239,6 @@ int launch_kind(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cuda
         return variant == GCS_VARIANT_REFILL ? launch_refill<KIND, 2>(d, p, st) : launch_static<KIND, 2>(p, st);
     }
     if constexpr (!column_guess) {
-        if (variant == GCS_VARIANT_CONTRACTED_PAIR) return launch_pair_relaxed<KIND, 8>(p, st);
         if (variant == GCS_VARIANT_CONTRACTED_SORTED) return launch_sorted<KIND, 8, true>(p, st);
         if (variant == GCS_VARIANT_CONTRACTED_STATIC) return launch_static<KIND, 8, true>(p, st);
         if (variant == GCS_VARIANT_SORTED) return launch_sorted<KIND, 8>(p, st);
@@ -429,7 +416,6 @@ const char* gcs_b200_kernel_name(int kind, int n_seeds, int variant)
     static thread_local char name[96];
     variant = resolve_variant(variant, kSortedMinRuns, 1);  // default: named for a launch that fills the device
     const char* base = variant == GCS_VARIANT_REFILL ? "newton_refill_kernel"
-        : variant == GCS_VARIANT_CONTRACTED_PAIR     ? "newton_pair_relaxed_kernel"
         : variant == GCS_VARIANT_CONTRACTED_SORTED   ? "newton_sorted_kernel[contracted]"
         : variant == GCS_VARIANT_CONTRACTED_STATIC   ? "newton_static_kernel[contracted]"
         : variant == GCS_VARIANT_SORTED              ? "newton_sorted_kernel"

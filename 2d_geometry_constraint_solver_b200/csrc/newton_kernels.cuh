@@ -21,10 +21,9 @@
 //
 // All produce bit-identical results (same device functions, same operation order per run).
 //
-//  The static and sorted kernels also exist in a contracted instantiation (template flag RLX), and
-//  newton_pair_relaxed_kernel maps the same arithmetic onto one lane per sub-system: closed-form
-//  updates on fused multiply-adds with guards (newton_relaxed.cuh) - iteration counts, flags and
-//  root indices identical to the kernels above, coordinates within 1e-9 relative.
+//  The static and sorted kernels also exist in a contracted instantiation (template flag RLX):
+//  closed-form updates on fused multiply-adds with guards (newton_relaxed.cuh) - iteration counts,
+//  flags and root indices identical to the kernels above, coordinates within 1e-9 relative.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -219,74 +218,6 @@ __global__ void __launch_bounds__(128, GCS_PAIR_MINB) newton_pair_kernel(const B
 }
 
 // ------------------------------------------------------------------------------------------
-// contracted pair variant: one lane per sub-system; its seeds are iterated two at a time in
-// lockstep with the closed-form update (relaxed_updates2), the lane then selects in registers.
-// No shuffles, no shared memory, no barriers; per-sub-system work (loads, guard constants,
-// selection, stores) is paid once per sub-system instead of once per run.
-// ------------------------------------------------------------------------------------------
-#ifndef GCS_RPAIR_MINB
-#define GCS_RPAIR_MINB 6
-#endif
-template <int KIND, int NS>
-__global__ void __launch_bounds__(128, GCS_RPAIR_MINB) newton_pair_relaxed_kernel(const BatchDev p)
-{
-    using S = Sys<KIND>;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n) return;
-    double k[S::kCols];
-#pragma unroll
-    for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + i);
-    const uint8_t code = p.code ? __ldg(p.code + i) : (uint8_t)GCS_MAKE_CODE(0, 0, 0);
-    const double runtime_zero = (double)(p.n >> 62);
-    Rsys<KIND> rs;
-    RelaxGuard g;
-    rs.load(k, g);
-    double cx[NS], cy[NS];
-    int its[NS], cvs[NS];
-    unsigned literal = 0;  // bit s: seed s came out of the literal code
-#pragma unroll
-    for (int s = 0; s < NS; s += 2) {
-        run_seed<KIND>(p.guesses, p.stride, i, k, s, cx[s], cy[s]);
-        run_seed<KIND>(p.guesses, p.stride, i, k, s + 1, cx[s + 1], cy[s + 1]);
-        its[s] = its[s + 1] = 0;
-        // iteration 0 compares the guess with prev = (0,0) (newton_raphson.hpp:58, :83-88)
-        int sa = (fabs(0.0 - cx[s]) < kTol && fabs(0.0 - cy[s]) < kTol) ? kRlxConverged : kRlxRunning;
-        int sb = (fabs(0.0 - cx[s + 1]) < kTol && fabs(0.0 - cy[s + 1]) < kTol) ? kRlxConverged : kRlxRunning;
-        relaxed_updates2<KIND>(rs, g, cx[s], cy[s], its[s], sa, cx[s + 1], cy[s + 1], its[s + 1], sb);
-        cvs[s] = cvs[s + 1] = 1;
-        if (sa != kRlxConverged) {
-            literal_rerun<KIND>(p.guesses, p.stride, i, k, s, runtime_zero, cx[s], cy[s], its[s], cvs[s]);
-            literal |= 1u << s;
-        }
-        if (sb != kRlxConverged) {
-            literal_rerun<KIND>(p.guesses, p.stride, i, k, s + 1, runtime_zero, cx[s + 1], cy[s + 1], its[s + 1], cvs[s + 1]);
-            literal |= 2u << s;
-        }
-    }
-    // (G5) a selection the margins do not vouch for: every seed of the sub-system goes literal
-    if (!selection_is_robust<KIND, NS>(k, code, cx, cy)) {
-#pragma unroll
-        for (int s = 0; s < NS; ++s)
-            if (!((literal >> s) & 1u)) literal_rerun<KIND>(p.guesses, p.stride, i, k, s, runtime_zero, cx[s], cy[s], its[s], cvs[s], 1);
-    }
-    double out[4];
-    const int root = select_and_finish<KIND, NS>(k, code, cx, cy, out);
-#pragma unroll
-    for (int c = 0; c < S::kOut; ++c) p.out[c][i] = out[c];
-    if (p.root) p.root[i] = (uint8_t)root;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        const long long pi = (long long)s * p.stride + i;
-        if (p.iters) p.iters[pi] = (int16_t)its[s];
-        if (p.converged) p.converged[pi] = (uint8_t)cvs[s];
-        if (p.cand) {
-            p.cand[((long long)s * 2 + 0) * p.stride + i] = cx[s];
-            p.cand[((long long)s * 2 + 1) * p.stride + i] = cy[s];
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // sorted variant
 //
 // The static kernel loses lanes to the spread of iteration counts: a warp lasts as long as its
@@ -375,9 +306,7 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
     __shared__ short s_it[RUNS];
     __shared__ unsigned short s_order[RUNS];
     __shared__ unsigned char s_cv[RUNS];
-    // RLX: the guard constants of each sub-system, computed once in phase A and read back in phase C
-    __shared__ int s_glo[RLX ? TILE : 1], s_ghi[RLX ? TILE : 1], s_gdt[RLX ? TILE : 1];
-    __shared__ double s_gpm[RLX ? TILE : 1];
+    __shared__ double s_carry[RLX ? RUNS : 1];  // RLX: each run's carry term (RelaxGuard::add_carry) at the hand-off
     __shared__ int s_dmin[RLX ? RUNS : 1];  // running minimum of hi(|det|) of each run at the hand-off (guard G2)
     __shared__ int s_bin[kSortBins];   // live runs per sort key
     __shared__ int s_fill[kSortBins];  // slots handed out per sort key during the scatter
@@ -405,18 +334,19 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                 Rsys<KIND> rs;
                 RelaxGuard g;
                 rs.load(k, g);
-                s_glo[sub] = g.lo_h, s_ghi[sub] = g.hi_h, s_gdt[sub] = g.det_h, s_gpm[sub] = g.pm;
 #pragma unroll 1
                 for (int q = 0; q < 2; ++q) {
                     const int r = tid + q * THREADS;
+                    RelaxGuard gr = g;  // the run's own copy: its first update adds the carry term
                     double x, y;
                     run_seed<KIND>(p.guesses, p.stride, gi, k, r / TILE, x, y);
                     int it = 0, state = kRlxConverged;
                     double d2 = 0.0, d3 = 0.0;
                     int dmin = 0x7fffffff;
                     if (!(fabs(0.0 - x) < kTol && fabs(0.0 - y) < kTol))
-                        state = relaxed_updates<KIND, true>(rs, g, x, y, it, 3, d2, d3, &dmin);
+                        state = relaxed_updates<KIND, true>(rs, gr, x, y, it, 3, d2, d3, &dmin);
                     s_dmin[r] = dmin;
+                    s_carry[r] = gr.carry;
                     s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
                     s_cv[r] = (unsigned char)state;  // kRlxUncertain (2): phase C redoes the run literally
                     if (state != kRlxConverged) {
@@ -517,8 +447,8 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                     if (state != kRlxUncertain) {
                         Rsys<KIND> rs;
                         RelaxGuard g;
-                        rs.template load<false>(k, g);
-                        g.lo_h = s_glo[sub], g.hi_h = s_ghi[sub], g.det_h = s_gdt[sub], g.pm = s_gpm[sub];
+                        rs.load(k, g);
+                        g.add_carry(s_carry[r], Rsys<KIND>::kStepScale);
                         double u0, u1;
                         int dmin = s_dmin[r];
                         state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1, &dmin);

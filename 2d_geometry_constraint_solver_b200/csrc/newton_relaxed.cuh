@@ -33,7 +33,11 @@
 //     Newton's map is w <- (w^2 + h^2)/(2w), +-h the roots, with derivative (1 - h^2/w^2)/2.
 //       - Landing from a far seed (|seed| = G) is itself ill conditioned (cond ~ G/d): the two
 //         arithmetics land a RELATIVE eps G/d apart.  While |w| >> h the map halves w and the
-//         deviation alike: the relative deviation is carried, not grown.
+//         deviation alike: the relative deviation is carried, not grown.  A system smaller than
+//         the tolerance (h <~ 1e-5) meets `< tol` while still in that phase, so the carried
+//         deviation eps cond(J_seed) * |update| is part of both levels of (G3)
+//         (RelaxGuard::add_carry; found by a 1.1e8-system soak: one run in 4.2e6 at scale 1e-6
+//         had decided differently before this term existed).
 //       - Once |w| ~ h the map contracts quadratically: the deviation is multiplied by
 //         (w - h)/h per update, so at the deciding update (the first one shorter than tol) what is
 //         left of the history is below eps (G/d) sqrt(2 h tol) times further factors < 0.4 - orders
@@ -50,6 +54,8 @@
 //     indices for equality and coordinates to 1e-9 against the CPU checker on every parity case;
 //     bench.py re-checks its whole batch against the bit-identical kernels in every run.
 #pragma once
+
+#include <type_traits>
 
 #include "newton_core.cuh"
 
@@ -83,20 +89,42 @@ struct RelaxGuard {
     int lo_h, hi_h;  // hi(|s|) < lo_h: converged for certain; >= hi_h: not converged for certain
     int det_h;       // hi(|det|) must reach this (G1)
     double pm;       // 2^-44 S dr: numerator of the second-level margin (S coordinate scale, dr = |det| at a well-conditioned root)
+    double band;     // first-level band of this system before the run's own carry term
+    double carry;    // 2^-48 cond(J at the seed): relative deviation the run carries from its first update (x4 margin)
     static constexpr int kBigH = 0x5F300000;  // 2^500: anything from here on is "non-finite / huge" (G4)
-    // step_scale: the closed-form solve returns step / step_scale (K1 works on J/2)
+    // thresholds of the integer tests for a first-level band of `b` around tol; step_scale: the
+    // closed-form solve returns step / step_scale (K1 works on J/2)
+    __device__ __forceinline__ void set_band(double b, double step_scale)
+    {
+        const double inv = 1.0 / step_scale;  // 1 or 2: exact
+        lo_h = hi_floor((kTol - b) * inv) - 1;
+        hi_h = hi_floor((kTol + b) * inv) + 1;
+        if (!(b < kTol)) lo_h = 0;  // also catches a NaN band: never "certain"
+        if (lo_h < 0) lo_h = 0;
+        if (!(hi_h > 0 && hi_h < kBigH)) hi_h = kBigH;
+    }
     __device__ __forceinline__ void init(double coord_scale, double det_root, double step_scale)
     {
         pm = 0x1p-44 * coord_scale * det_root;
-        const double band = __fma_rn(0x1p-36, coord_scale, 0x1p-16 * kTol);
-        const double inv = 1.0 / step_scale;  // 1 or 2: exact
-        lo_h = hi_floor((kTol - band) * inv) - 1;
-        hi_h = hi_floor((kTol + band) * inv) + 1;
-        if (!(band < kTol)) lo_h = 0;          // also catches a NaN scale: never "certain"
-        if (lo_h < 0) lo_h = 0;
-        if (!(hi_h > 0 && hi_h < kBigH)) hi_h = kBigH;
+        band = __fma_rn(0x1p-36, coord_scale, 0x1p-16 * kTol);
+        carry = 0.0;
+        set_band(band, step_scale);
         det_h = hi_floor(0x1p-10 * det_root) + 1;
         if (!(det_root > 0.0 && det_root < 0x1p900)) det_h = 0x7ff00000;  // degenerate / NaN / inf scale: always uncertain
+    }
+    // The update from the seed is as ill conditioned as the seed is far (cond ~ |seed| / d for the
+    // default seeds): the two arithmetics land a RELATIVE 2^-53 cond(J_seed) apart, and that relative
+    // deviation rides along while the iteration halves its way in.  Where the roots are closer
+    // together than the tolerance (small systems: h <~ 1e-5) the deciding update happens in that
+    // phase, before the quadratic contraction has wiped the history out, and the update length then
+    // differs by ~2^-53 cond * 2 |update|.  With c = cond(J_seed) = |J|_F^2 / |det|:
+    //     carry = 2^-48 c   (2^-53 c, x2 for |w| ~ 2 |update|, x4 for the halving-phase updates'
+    //                        own contributions, x4 margin),
+    // added as carry * tol to the first-level band and as carry * m to the second-level margin.
+    __device__ __forceinline__ void add_carry(double c, double step_scale)
+    {
+        carry = c;
+        set_band(__fma_rn(c, kTol, band), step_scale);
     }
     // Second level of (G3), reached only by an update whose length fell between lo_h and hi_h (the
     // first-level band, integer tests on high words, is 2^-36 S wide; about one run in a thousand
@@ -107,7 +135,7 @@ struct RelaxGuard {
     // Returns +1 converged for certain, -1 not converged for certain, 0 undecided.
     __device__ __forceinline__ int precise(double m, double det) const
     {
-        const double margin = __fma_rn(pm, rcp_relaxed(fabs(det)), 0x1p-40 * kTol);
+        const double margin = __fma_rn(carry, m, __fma_rn(pm, rcp_relaxed(fabs(det)), 0x1p-40 * kTol));
         const double gap = m - kTol;
         if (gap > margin) return -1;
         if (-gap > margin) return 1;
@@ -267,10 +295,10 @@ enum : int { kRlxRunning = 0, kRlxConverged = 1, kRlxUncertain = 2 };
 // dmin_io (optional): the running minimum of hi(|det|) after the seed, carried from one stretch of a
 // run to the next so that (G2) sees growth across the hand-off.
 template <int KIND, bool kTrack>
-__device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, const RelaxGuard& g, double& x, double& y, int& it,
+__device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard& g, double& x, double& y, int& it,
     int limit, double& d2, double& d3, int* dmin_io = nullptr)
 {
-    const unsigned span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
+    unsigned span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
     // smallest hi(|det|) at the iterates after the seed, and its largest growth over that running
     // minimum; the determinant AT THE SEED (d1) counts for (G1) only: both arithmetics start from
     // the same seed, so a badly conditioned first update creates a deviation (eps cond, carried
@@ -283,11 +311,17 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, const Relax
     int mh, dh;
     double s0, s1, det;
     // one closed-form update; leaves mh = larger high word of the update's components, dh = hi(|det|)
-    auto update = [&]() {
+    auto update = [&](auto from_seed) {
         double a, b, c, d, r0, r1;
         rs.eval(x, y, a, b, c, d, r0, r1);
         det = __fma_rn(a, d, -(b * c));
         const double r = rcp_relaxed(det);
+        if constexpr (decltype(from_seed)::value) {
+            // the carry term of this run (RelaxGuard::add_carry): cond(J_seed) = |J|_F^2 / |det|
+            const double q = __fma_rn(a, a, __fma_rn(b, b, __fma_rn(c, c, d * d)));
+            g.add_carry(0x1p-48 * q * fabs(r), Rsys<KIND>::kStepScale);
+            span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
+        }
         const double n0 = __fma_rn(r0, d, -(r1 * b));
         const double n1 = __fma_rn(a, r1, -(c * r0));
         s0 = n0 * r, s1 = n1 * r;
@@ -307,7 +341,7 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, const Relax
     };
     bool in_loop = true;
     if (it == 0) {  // the update from the seed, peeled (see above)
-        update();
+        update(std::true_type {});
         d1 = dh;
         in_loop = (unsigned)(mh - g.hi_h) < span && it < limit;
     }
@@ -318,7 +352,7 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, const Relax
         if (in_loop) {
 #pragma unroll 1
             do {
-                update();
+                update(std::false_type {});
                 grow = max(grow, dh - dmin);  // (G2), in high-word units (2^20 per binade)
                 dmin = min(dmin, dh);
             } while ((unsigned)(mh - g.hi_h) < span && it < limit);
@@ -344,67 +378,6 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, const Relax
     if (state == kRlxRunning && (min(dmin, d1) < g.det_h || grow > kBounce || limit >= kRelaxCap)) state = kRlxUncertain;
     if (dmin_io) *dmin_io = dmin;
     return state;
-}
-
-// Two runs of one sub-system in lockstep in one lane (two independent dependency chains: the
-// closed-form update is a chain of ~10 dependent FP64 operations and only ~60 issue cycles long, so
-// a second chain per lane fills the pipe where the literal kernels could not use one).  A finished
-// run rides along with its position update predicated off.  sa / sb: kRlxRunning on entry for a
-// run that iterates; on return kRlxConverged or kRlxUncertain for those.
-template <int KIND>
-__device__ __forceinline__ void relaxed_updates2(const Rsys<KIND>& rs, const RelaxGuard& g, double& xa, double& ya, int& ita,
-    int& sa, double& xb, double& yb, int& itb, int& sb)
-{
-    const unsigned span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
-    bool la = sa == kRlxRunning, lb = sb == kRlxRunning;
-    bool bada = false, badb = false;
-    int dmina = 0x7fffffff - kBounce, dminb = 0x7fffffff - kBounce;
-    // end of a run, or an update inside the first-level band: decide this run's state
-    auto settle = [&](bool& live, int& state, bool bad, int mh, double s0, double s1, double det, int it) {
-        if (mh < g.lo_h && !bad) {
-            state = kRlxConverged, live = false;
-        } else if (mh >= RelaxGuard::kBigH || bad) {
-            state = kRlxUncertain, live = false;
-        } else if (mh < g.lo_h) {
-            state = kRlxUncertain, live = false;
-        } else {
-            const int verdict = g.precise(fmax(fabs(s0), fabs(s1)) * Rsys<KIND>::kStepScale, det);
-            if (verdict >= 0) state = verdict > 0 ? kRlxConverged : kRlxUncertain, live = false;
-        }
-        if (live && it >= kRelaxCap) state = kRlxUncertain, live = false;
-    };
-#pragma unroll 1
-    while (la | lb) {
-        double a0, b0, c0, d0, p0, q0, a1, b1, c1, d1, p1, q1;
-        rs.eval(xa, ya, a0, b0, c0, d0, p0, q0);
-        rs.eval(xb, yb, a1, b1, c1, d1, p1, q1);
-        const double det0 = __fma_rn(a0, d0, -(b0 * c0));
-        const double det1 = __fma_rn(a1, d1, -(b1 * c1));
-        const double r0 = rcp_relaxed(det0);
-        const double r1 = rcp_relaxed(det1);
-        const double s00 = __fma_rn(p0, d0, -(q0 * b0)) * r0, s01 = __fma_rn(a0, q0, -(c0 * p0)) * r0;
-        const double s10 = __fma_rn(p1, d1, -(q1 * b1)) * r1, s11 = __fma_rn(a1, q1, -(c1 * p1)) * r1;
-        if (la) {
-            xa = __fma_rn(s00, Rsys<KIND>::kStepScale, xa), ya = __fma_rn(s01, Rsys<KIND>::kStepScale, ya);
-            ++ita;
-        }
-        if (lb) {
-            xb = __fma_rn(s10, Rsys<KIND>::kStepScale, xb), yb = __fma_rn(s11, Rsys<KIND>::kStepScale, yb);
-            ++itb;
-        }
-        const int dha = abs_hi(det0), dhb = abs_hi(det1);
-        bada |= dha < g.det_h || dha > dmina + kBounce;
-        badb |= dhb < g.det_h || dhb > dminb + kBounce;
-        // the determinant at the seed (the run's first update) does not enter the running minimum
-        if (ita > 1) dmina = min(dmina, dha);
-        if (itb > 1) dminb = min(dminb, dhb);
-        const int mha = max(abs_hi(s00), abs_hi(s01));
-        const int mhb = max(abs_hi(s10), abs_hi(s11));
-        const bool fara = (unsigned)(mha - g.hi_h) < span && ita < kRelaxCap;
-        const bool farb = (unsigned)(mhb - g.hi_h) < span && itb < kRelaxCap;
-        if (la && !fara) settle(la, sa, bada, mha, s00, s01, det0, ita);
-        if (lb && !farb) settle(lb, sb, badb, mhb, s10, s11, det1, itb);
-    }
 }
 
 // seed `seed` of sub-system `gi` as the kernels take it

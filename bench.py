@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", type=int, default=5,
                     help="5 (default) contracted arithmetic: discrete outputs identical to the reference, coordinates to 1e-9 "
-                         "(6 static / 7 sorted / 8 pair); 0 the library default = bit-identical kernels (1 static, 2 refill, "
+                         "(6 static / 7 sorted); 0 the library default = bit-identical kernels (1 static, 2 refill, "
                          "3 sorted, 4 pair).  With a contracted variant the bit-identical default is timed beside it.")
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="solves per GPU (default 2^20)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time of the cpu_baseline sample")
@@ -606,7 +606,7 @@ def main():
     ach_tf = w_k1 / (k1_ms * 1e-3) / 1e12
     traffic = load_traffic()
     vname = {0: "default", 1: "static", 2: "refill", 3: "sorted", 4: "pair", 5: "contracted", 6: "contracted-static",
-             7: "contracted-sorted", 8: "contracted-pair"}[args.variant]
+             7: "contracted-sorted"}[args.variant]
     rerun_stats = None
     if args.variant >= 5:
         import ctypes as C

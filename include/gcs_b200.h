@@ -143,12 +143,11 @@ extern "C" {
  * variant (runs and selections whose decisions could depend on the arithmetic are detected by
  * guards and redone with the literal device functions); coordinates agree to 1e-9 relative (the
  * north star's tolerance) instead of bit for bit.  Opt-in: DEFAULT never resolves to it.
- * CONTRACTED = CONTRACTED_STATIC (measured fastest at every size); SORTED and PAIR map the same
- * arithmetic onto the sorted tiles / onto one lane per sub-system. */
+ * CONTRACTED = CONTRACTED_STATIC (measured fastest at every size); CONTRACTED_SORTED maps the same
+ * arithmetic onto the sorted tiles. */
 #define GCS_VARIANT_CONTRACTED 5
 #define GCS_VARIANT_CONTRACTED_STATIC 6
 #define GCS_VARIANT_CONTRACTED_SORTED 7
-#define GCS_VARIANT_CONTRACTED_PAIR 8 /* one lane per sub-system, seeds two at a time in lockstep */
 
 typedef struct gcs_b200_batch {
     int32_t kind;    /* GCS_KIND_* */

@@ -16,7 +16,7 @@ from util import assert_batches_identical, assert_batches_within_contract, bits
 pytestmark = pytest.mark.gpu
 
 KINDS = [1, 2, 3, 4, 5]
-VARIANTS = [6, 7, 8]  # contracted static, sorted, pair
+VARIANTS = [6, 7]  # contracted static, contracted sorted
 
 
 def _solve_pair(gpu, synth, kind, n, variant, **kw):
@@ -136,13 +136,26 @@ def test_contract_flat_triangles_and_extreme_scales(gpu, gcs, variant, scale, fl
     assert_batches_within_contract(hb, ref, f"scale {scale} flat {flat}")
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("scale", [1e-6, 1e-7, 3e-5])
+def test_contract_systems_smaller_than_the_tolerance_at_4m(gpu, gcs, variant, scale):
+    """Systems whose roots lie closer together than the absolute 1e-5 threshold meet `< tol` while
+    the iteration is still halving its way in from the far seed, carrying the relative deviation of
+    the ill-conditioned first update (cond ~ 20000 / d, up to 2e9 here).  A soak of 1.1e8
+    sub-systems found one run in 4.2e6 deciding differently before that deviation entered the
+    guard band (RelaxGuard::add_carry); 2^22 sub-systems per case make such a run likely."""
+    n = 1 << 22
+    hb, ref = _solve_pair(gpu, gcs.synth, 1, n, variant, seed=4242, scale=scale)
+    assert_batches_within_contract(hb, ref, f"scale {scale} variant {variant}")
+
+
 def test_contract_device_resident_batch_and_default_is_still_bit_identical(gpu, gcs):
     import torch
     synth, capi = gcs.synth, gcs.capi
     hb = synth.make_ang(70001)
     db = capi.DeviceBatch(hb, "cuda:0", want_cand=True)
     ref = O.solve(synth.make_ang(70001).alloc_outputs())
-    for variant in (5, 6, 7, 8):
+    for variant in (5, 6, 7):
         db.set_variant(variant)
         db.solve()
         torch.cuda.synchronize()
