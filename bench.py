@@ -306,6 +306,28 @@ def run_extra(args, rank, local_rank, world):
     w = float((it.to(torch.int64) + 1).sum().item()) * synth.F_EVAL[1] + n * synth.F_SELECT[1]
     ach = w / (float(ms.mean()) * 1e-3) / 1e12
     conv = float(db.converged.to(torch.float32).mean().item())
+    # contracted variants: the same batch through the bit-identical kernels, and the contract between
+    # the two checked on this rank's whole batch (device-side comparison)
+    contract = None
+    if args.variant >= 5:
+        if gen is None:
+            db0 = capi.DeviceBatch(hb, dev, want_cand=False, variant=0)
+        else:
+            db0 = capi.DeviceBatch.empty(capi.KIND_PP, 2, n, dev, variant=0)
+            for dst, src in zip(db0.cols, db.cols):
+                dst.copy_(src)
+            db0.code.copy_(db.code)
+        db.solve()
+        db0.solve()
+        torch.cuda.synchronize(dev)
+        same = bool(torch.equal(db.iters, db0.iters)) and bool(torch.equal(db.converged, db0.converged)) \
+            and bool(torch.equal(db.root_index, db0.root_index))
+        scale = torch.clamp(torch.stack([c.abs() for c in db.cols]).max(dim=0).values, min=1.0)
+        worst = max(float(((x - y).abs() / torch.maximum(scale, y.abs())).max().item()) for x, y in zip(db.out, db0.out))
+        if not same or not worst <= 1e-9:
+            raise SystemExit(f"contract violated on the bench batch: discrete outputs equal = {same}, max relative error = {worst:.3e}")
+        contract = {"iters_flags_roots_equal": same, "max_rel_coordinate_error": worst, "tolerance": 1e-9, "solves_compared": int(n)}
+        del db0, scale
     # end to end: generation (sweep) or pinned H2D (multi-start), solve, results back to pinned host memory
     e2e_steps = max(3, min(args.steps, 10))
     if gen is None:
@@ -354,7 +376,8 @@ def run_extra(args, rank, local_rank, world):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "solves_total": n_total, "solves_rank0": n, "l2": "256 MiB flush write between timed steps",
-                       "converged_fraction_rank0": conv, "mean_iters_per_seed_rank0": float(it.to(torch.float32).mean().item())},
+                       "converged_fraction_rank0": conv, "mean_iters_per_seed_rank0": float(it.to(torch.float32).mean().item()),
+                       "variant": args.variant, "contract_check_rank0": contract},
             "e2e": {"value": n_total * e2e_steps / float(et.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "gcs_b200_solve_host (pinned)" if gen is None else "gcs_b200_synth_pp + gcs_b200_solve + D2H of (x, y, root) to pinned memory"},
             "gpu_launches": int(launches),

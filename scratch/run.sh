@@ -1,1 +1,2 @@
-timeout 1000 python scratch/soak_relaxed_scaled.py 2097152 > gpurun_out/soak_relaxed_scaled.log 2>&1; tail -26 gpurun_out/soak_relaxed_scaled.log
+python bench.py --workload sweep64m --steps 5 --warmup 3 2>&1 | tail -1 | cut -c1-900
+python bench.py --workload multistart8 --steps 5 --warmup 3 2>&1 | tail -1 | cut -c1-700
