@@ -324,8 +324,18 @@ def run_extra(args, rank, local_rank, world):
             and bool(torch.equal(db.root_index, db0.root_index))
         scale = torch.clamp(torch.stack([c.abs() for c in db.cols]).max(dim=0).values, min=1.0)
         worst = max(float(((x - y).abs() / torch.maximum(scale, y.abs())).max().item()) for x, y in zip(db.out, db0.out))
-        if not same or not worst <= 1e-9:
-            raise SystemExit(f"contract violated on the bench batch: discrete outputs equal = {same}, max relative error = {worst:.3e}")
+        ok = torch.tensor([1 if (same and worst <= 1e-9) else 0], device=dev, dtype=torch.int32)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            # never report a number from results that failed their check: rerun this workload on the
+            # bit-identical kernels (every rank takes this branch together)
+            print(f"[bench] CONTRACT VIOLATED by variant {args.variant} (discrete outputs equal = {same}, max relative error = "
+                  f"{worst:.3e}); rerunning on the bit-identical kernels", file=sys.stderr, flush=True)
+            if world > 1:
+                dist.destroy_process_group()
+            args.variant = 0
+            return run_extra(args, rank, local_rank, world)
         contract = {"iters_flags_roots_equal": same, "max_rel_coordinate_error": worst, "tolerance": 1e-9, "solves_compared": int(n)}
         del db0, scale
     # end to end: generation (sweep) or pinned H2D (multi-start), solve, results back to pinned host memory
@@ -519,6 +529,7 @@ def main():
     # ---- the bit-identical kernels on the same batches, timed the same way, and the contract
     #      between the two checked on the full batch (contracted variants only) ----
     bit_identical = None
+    violation = None
     if args.variant >= 5:
         devb0 = [capi.DeviceBatch(h, dev, want_cand=False, variant=0) for h in host]
         for _ in range(warmup):
@@ -547,8 +558,24 @@ def main():
             scale = torch.clamp(torch.stack([c.abs() for c in a.cols]).max(dim=0).values, min=1.0)
             for x, y in zip(a.out, b.out):
                 worst = max(worst, float(((x - y).abs() / torch.maximum(scale, y.abs())).max().item()))
-        if not same or not worst <= 1e-9:
-            raise SystemExit(f"contract violated on the bench batch: discrete outputs equal = {same}, max relative error = {worst:.3e}")
+        if os.environ.get("GCS_BENCH_TEST_VIOLATION"):  # exercises the fallback below
+            same = False
+        ok = torch.tensor([1 if (same and worst <= 1e-9) else 0], device=dev, dtype=torch.int32)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            # Never report a number from results that failed their check: the line falls back to the
+            # bit-identical kernels (timed above, on the same batches) and says so.
+            print(f"[bench] CONTRACT VIOLATED by variant {args.variant} on rank {rank}'s view (discrete outputs equal = {same}, "
+                  f"max relative error = {worst:.3e}); reporting the bit-identical kernels instead", file=sys.stderr, flush=True)
+            violation = {"variant": args.variant, "iters_flags_roots_equal_rank": same, "max_rel_coordinate_error_rank": worst}
+            args.variant = 0
+            two_stream = None
+            devb, ms_k1, ms_k5 = devb0, ms0_k1, ms0_k5
+            total_ms = float(t0_sum.item())
+            value = (n * world * args.steps) / (total_ms * 1e-3)
+            for h in host:
+                h.variant = 0
         bit_identical = {
             "variant": "default (newton_sorted_kernel, literal Householder QR, no contraction)",
             "value": (n * world * args.steps) / (float(t0_sum.item()) * 1e-3), "unit": UNIT,
@@ -557,7 +584,8 @@ def main():
             "contract_check_rank0": {"iters_flags_roots_equal": same, "max_rel_coordinate_error": worst, "tolerance": 1e-9,
                                      "solves_compared": int(sum(d.n for d in devb))},
         }
-        del devb0
+        if violation is None:
+            del devb0
 
     # ---- iteration histogram -> algorithmic work of the dominant kernel ----
     it1 = devb[0].iters.cpu().numpy()
@@ -686,6 +714,7 @@ def main():
                                         "coordinates within 1e-9 relative (checked in this run against the bit-identical kernels)"
                                         if args.variant >= 5 else "bit-identical to the reference arithmetic"),
                        "literal_reruns": rerun_stats,
+                       "contract_violation": violation,
                        "timing": "per-launch CUDA events on the launching stream, sum over steps, max over ranks",
                        "wall_s_timed_region_incl_flush": t_wall},
             "clocks": clocks,
