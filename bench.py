@@ -17,7 +17,8 @@ space; no data-path collective (NCCL only carries the barrier and the max-over-r
           + gcs_b200_wait): pinned HOST inputs and outputs, H2D + kernels + D2H inside the region.
 `bit_identical` (contracted variants, the default) the same step with the library-default kernels
           (bit-identical to the reference arithmetic), timed the same way in the same run, and the
-          contract between the two checked on the whole batch.
+          contract between the two checked on the whole batch (a failed check makes the line report
+          the bit-identical kernels and name the violation: no number from unverified results).
 `roofline` the dominant kernel (K1): algorithmic FP64 flops (work model of DESIGN.md section 3,
           from the MEASURED iteration counts) / its event-timed duration, against the DFMA peak
           measured live by gcs_b200_fp64_probe (MEASURED_PEAKS.json has no FP64 figure); the HBM
