@@ -125,6 +125,8 @@ int validate(const gcs_b200_batch* b)
     if (!b) return fail(GCS_E_INVALID, "null batch");
     if (b->kind < 1 || b->kind > GCS_KIND_COUNT) return fail(GCS_E_INVALID, "unknown kind %d", b->kind);
     if (b->n < 0) return fail(GCS_E_INVALID, "negative n");
+    if (b->variant < GCS_VARIANT_DEFAULT || b->variant > GCS_VARIANT_CONTRACTED_SORTED)
+        return fail(GCS_E_INVALID, "unknown variant %d", b->variant);
     const bool column_guess = (b->kind == GCS_KIND_SDD || b->kind == GCS_KIND_ANG);
     if (column_guess) {
         if (b->n_seeds != 2) return fail(GCS_E_INVALID, "kind %d takes exactly 2 seeds", b->kind);

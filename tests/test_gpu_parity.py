@@ -212,6 +212,10 @@ def test_error_paths(gpu, gcs):
     cb.kind = 9
     assert lib.gcs_b200_solve_host(C.byref(cb), 0) == capi.GCS_E_INVALID
     cb = hb.cbatch()
+    cb.variant = 8
+    assert lib.gcs_b200_solve_host(C.byref(cb), 0) == capi.GCS_E_INVALID
+    assert b"unknown variant" in lib.gcs_b200_last_error()
+    cb = hb.cbatch()
     assert lib.gcs_b200_solve(C.byref(cb), 0, None) == capi.GCS_E_INVALID  # host pointers to the device entry
     empty = synth.make_pp(0).alloc_outputs()
     gpu.solve_host(empty, 0)
