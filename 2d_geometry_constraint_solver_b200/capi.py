@@ -79,7 +79,8 @@ EXPORTS = [
     "gcs_b200_shutdown", "gcs_b200_last_error", "gcs_b200_version", "gcs_b200_solve",
     "gcs_b200_solve_host", "gcs_b200_solve_host_async", "gcs_b200_wait", "gcs_b200_solve_sharded", "gcs_b200_launch_count", "gcs_b200_kernel_name", "gcs_b200_default_variant",
     "gcs_b200_fp64_probe", "gcs_b200_synth_pp", "gcs_b200_selftest", "gcs_b200_host_alloc", "gcs_b200_host_free",
-    "gcs_b200_contracted_stats",
+    "gcs_b200_contracted_stats", "gcs_b200_contracted_stats_ex", "gcs_b200_column_may_be_null", "gcs_b200_host_alloc_ex",
+    "gcs_b200_solve_host_range_async", "gcs_b200_pcie_probe",
 ]
 
 
@@ -103,11 +104,20 @@ def load():
     lib.gcs_b200_solve_sharded.argtypes = [C.POINTER(CBatch), C.c_int]
     lib.gcs_b200_solve_host_async.argtypes = [C.POINTER(CBatch), C.c_int]
     lib.gcs_b200_wait.argtypes = [C.c_int]
+    lib.gcs_b200_solve_host_range_async.argtypes = [C.POINTER(CBatch), C.c_int, C.c_int64, C.c_int64]
     lib.gcs_b200_launch_count.restype = C.c_int64
     lib.gcs_b200_kernel_name.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.gcs_b200_kernel_name.restype = C.c_char_p
     lib.gcs_b200_default_variant.argtypes = [C.c_int64, C.c_int]
     lib.gcs_b200_contracted_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.c_int]
+    lib.gcs_b200_contracted_stats_ex.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.c_int]
+    lib.gcs_b200_column_may_be_null.argtypes = [C.c_int, C.c_int]
+    lib.gcs_b200_host_alloc.argtypes = [C.c_size_t]
+    lib.gcs_b200_host_alloc.restype = C.c_void_p
+    lib.gcs_b200_host_alloc_ex.argtypes = [C.c_size_t, C.c_int]
+    lib.gcs_b200_host_alloc_ex.restype = C.c_void_p
+    lib.gcs_b200_host_free.argtypes = [C.c_void_p]
+    lib.gcs_b200_pcie_probe.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     lib.gcs_b200_fp64_probe.argtypes = [C.c_int, C.c_int]
     lib.gcs_b200_fp64_probe.restype = C.c_double
     lib.gcs_b200_selftest.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.POINTER(C.c_uint64)]
@@ -115,6 +125,34 @@ def load():
                                       C.c_int, C.POINTER(C.c_void_p), C.c_void_p]
     _lib = lib
     return lib
+
+
+def pcie_probe(device, bytes_up, bytes_down, pieces=1, write_combined=False, reps=5):
+    """gcs_b200_pcie_probe -> dict(h2d_gbs, d2h_gbs, both_ms_best, both_ms_median)."""
+    out = (C.c_double * 4)()
+    check(load().gcs_b200_pcie_probe(device, bytes_up, bytes_down, pieces, 1 if write_combined else 0, reps, out), "gcs_b200_pcie_probe")
+    return {"h2d_gbs": out[0], "d2h_gbs": out[1], "both_ms_best": out[2], "both_ms_median": out[3]}
+
+
+class PinnedArray:
+    """numpy view of page-locked memory from gcs_b200_host_alloc[_ex] (freed with the object)."""
+
+    def __init__(self, shape, dtype=np.float64, write_combined=False):
+        self.shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.nbytes = int(np.prod(self.shape)) * np.dtype(dtype).itemsize
+        self.ptr = load().gcs_b200_host_alloc_ex(max(self.nbytes, 1), 1 if write_combined else 0)
+        if not self.ptr:
+            raise GcsError("gcs_b200_host_alloc_ex failed (no CUDA device?)")
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                load().gcs_b200_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
 
 
 class GcsError(RuntimeError):
@@ -141,7 +179,7 @@ class HostBatch:
     """A batch whose columns are numpy arrays (GCS_MEM_HOST).  Keeps the arrays alive."""
     kind: int
     n_seeds: int
-    cols: list                      # kind-specific input columns, float64[n]
+    cols: list                      # kind-specific input columns, float64[n]; None = an anchor column of zeros (passed as NULL)
     code: np.ndarray                # uint8[n]
     guesses: np.ndarray | None = None   # float64[n_seeds, 2, n]
     variant: int = VARIANT_DEFAULT
@@ -168,15 +206,48 @@ class HostBatch:
     def slice(self, lo, hi):
         """Contiguous index range [lo, hi) as a new HostBatch (inputs are views)."""
         g = None if self.guesses is None else np.ascontiguousarray(self.guesses[:, :, lo:hi])
-        return HostBatch(self.kind, self.n_seeds, [c[lo:hi] for c in self.cols], self.code[lo:hi],
+        return HostBatch(self.kind, self.n_seeds, [None if c is None else c[lo:hi] for c in self.cols], self.code[lo:hi],
                          g, self.variant, self.want_cand)
 
-    def cbatch(self) -> CBatch:
+    def take(self, index):
+        """The rows `index` (bool mask or index array) as a new HostBatch (inputs are copies)."""
+        g = None if self.guesses is None else np.ascontiguousarray(self.guesses[:, :, index])
+        return HostBatch(self.kind, self.n_seeds, [None if c is None else np.ascontiguousarray(c[index]) for c in self.cols],
+                         np.ascontiguousarray(self.code[index]), g, self.variant, self.want_cand)
+
+    def anchored(self):
+        """The same batch with every anchor column that is identically +0.0 replaced by None (NULL at
+        the ABI: not stored, not copied).  Raises if a column the shape needs to be zero is not."""
+        cols = list(self.cols)
+        lib = load()
+        for c, col in enumerate(cols):
+            if col is not None and lib.gcs_b200_column_may_be_null(self.kind, c) and not col.view(np.uint64).any():
+                cols[c] = None
+        return HostBatch(self.kind, self.n_seeds, cols, self.code, self.guesses, self.variant, self.want_cand)
+
+    def dense_cols(self):
+        """Input columns with the NULL ones materialised as zeros (for checkers that take no NULLs)."""
+        n = self.n
+        return [np.zeros(n) if c is None else c for c in self.cols]
+
+    def input_bytes(self):
+        """Bytes of input a host-buffer call uploads: present columns + the code column (+ guesses)."""
+        n = self.n
+        b = sum(8 * n for c in self.cols if c is not None) + n
+        return b + (0 if self.guesses is None else self.guesses.nbytes)
+
+    def cbatch(self, dense=False) -> CBatch:
         assert len(self.cols) == IN_COLS[self.kind], (len(self.cols), self.kind)
         b = CBatch()
         b.kind, b.n_seeds, b.n, b.mem, b.variant = self.kind, self.n_seeds, self.n, MEM_HOST, self.variant
         n = self.n
-        for i, c in enumerate(self.cols):
+        cols = self.cols
+        if dense:
+            cols = self._dense = self.dense_cols()  # kept alive with the batch
+        for i, c in enumerate(cols):
+            if c is None:
+                b.in_[i] = None
+                continue
             assert c.dtype == np.float64 and c.flags["C_CONTIGUOUS"] and c.shape == (n,)
             b.in_[i] = c.ctypes.data
         assert self.code.dtype == np.uint8 and self.code.flags["C_CONTIGUOUS"]
@@ -212,6 +283,15 @@ def solve_host_async(batch: HostBatch, device: int = 0) -> HostBatch:
     return batch
 
 
+def solve_host_range_async(batch: HostBatch, device: int, first: int, count: int) -> HostBatch:
+    """gcs_b200_solve_host_range_async: rows [first, first+count) only; valid after wait(device)."""
+    if not batch.out:
+        batch.alloc_outputs()
+    cb = batch.cbatch()
+    check(load().gcs_b200_solve_host_range_async(C.byref(cb), device, first, count), "gcs_b200_solve_host_range_async")
+    return batch
+
+
 def wait(device: int = 0):
     check(load().gcs_b200_wait(device), "gcs_b200_wait")
 
@@ -235,7 +315,7 @@ class DeviceBatch:
         self.variant = host.variant if variant is None else variant
         self.n = host.n
         dev = self.device
-        self.cols = [torch.from_numpy(c).to(dev) for c in host.cols]
+        self.cols = [None if c is None else torch.from_numpy(c).to(dev) for c in host.cols]
         self.code = torch.from_numpy(host.code).to(dev)
         self.guesses = None if host.guesses is None else torch.from_numpy(host.guesses).to(dev)
         n = self.n
@@ -270,7 +350,7 @@ class DeviceBatch:
         b = CBatch()
         b.kind, b.n_seeds, b.n, b.mem, b.variant = self.kind, self.n_seeds, self.n, MEM_DEVICE, self.variant
         for i, c in enumerate(self.cols):
-            b.in_[i] = c.data_ptr()
+            b.in_[i] = None if c is None else c.data_ptr()
         b.code = self.code.data_ptr()
         b.guesses = self.guesses.data_ptr() if self.guesses is not None else None
         for i, o in enumerate(self.out):
@@ -303,7 +383,7 @@ class DeviceBatch:
     def algorithmic_bytes(self):
         """Minimum HBM traffic of one launch: inputs + code + outputs + per-seed flags."""
         n, ns = self.n, self.n_seeds
-        b = IN_COLS[self.kind] * 8 + 1 + OUT_COLS[self.kind] * 8 + ns * 3 + 1
+        b = sum(8 for c in self.cols if c is not None) + 1 + OUT_COLS[self.kind] * 8 + ns * 3 + 1
         if self.cand is not None:
             b += ns * 16
         if self.guesses is not None:

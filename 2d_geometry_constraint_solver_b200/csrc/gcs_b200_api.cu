@@ -4,6 +4,7 @@
 // needs a CUDA device and reports GCS_E_NO_DEVICE otherwise.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -76,7 +77,8 @@ struct DeviceState {
 };
 
 std::mutex g_mu;
-std::vector<DeviceState*> g_devs;  // indexed by position in the init list
+std::vector<DeviceState*> g_devs;  // one per CUDA device, indexed by ordinal
+std::vector<int> g_init_list;      // the devices of the last gcs_b200_init, in its order (what solve_sharded shards over)
 std::atomic<long long> g_launches { 0 };
 
 DeviceState* find_dev(int device)
@@ -107,6 +109,7 @@ int ensure_init()
 
 int prepare_device(DeviceState* d)
 {
+    std::lock_guard<std::mutex> lk(g_mu);  // two first-time callers on one device must not both allocate
     if (d->tickets) return GCS_OK;
     CUDA_TRY(cudaSetDevice(d->device));
     cudaDeviceProp prop;
@@ -119,6 +122,23 @@ int prepare_device(DeviceState* d)
     CUDA_TRY(cudaStreamCreateWithFlags(&d->d2h, cudaStreamNonBlocking));
     return GCS_OK;
 }
+
+}  // namespace
+
+extern "C" int gcs_b200_column_may_be_null(int kind, int c)
+{
+    // columns that are identically zero in the anchored shapes of the zero-fixed solvers:
+    // K1 ax, ay, by (point_point_solvers.cpp:48-50); K2 p1x, p1y, p2y (point_line_solvers.cpp:179-181);
+    // K5 fdy, px, r2x, r2y (line_angle_solvers.cpp:249-274, :355-361)
+    switch (kind) {
+    case GCS_KIND_PP: return c == 0 || c == 1 || c == 4;
+    case GCS_KIND_SDD: return c == 0 || c == 1 || c == 3;
+    case GCS_KIND_ANG: return c == 1 || c == 7 || c == 10 || c == 11;
+    }
+    return 0;
+}
+
+namespace {
 
 int validate(const gcs_b200_batch* b)
 {
@@ -136,7 +156,8 @@ int validate(const gcs_b200_batch* b)
     if (b->n == 0) return GCS_OK;
     const int nin = gcs_b200_kind_in_cols(b->kind);
     for (int c = 0; c < nin; ++c)
-        if (!b->in[c]) return fail(GCS_E_INVALID, "input column %d is null", c);
+        if (!b->in[c] && !gcs_b200_column_may_be_null(b->kind, c))
+            return fail(GCS_E_INVALID, "input column %d of kind %d is null (only the anchor columns may be)", c, b->kind);
     if (!b->code) return fail(GCS_E_INVALID, "code column is null");
     const int nout = gcs_b200_kind_out_cols(b->kind);
     for (int c = 0; c < nout; ++c)
@@ -161,11 +182,20 @@ BatchDev to_dev(const gcs_b200_batch* b)
     return p;
 }
 
+// GCS_STATIC_BLOCK (tuning knob): lanes per CTA of the static kernel; anything but 32 / 64 / 96 / 128
+// (whole warps within __launch_bounds__(128)) is ignored
+inline int static_block_size()
+{
+    const char* e = getenv("GCS_STATIC_BLOCK");
+    const int v = e ? atoi(e) : 128;
+    return (v == 32 || v == 64 || v == 96 || v == 128) ? v : 128;
+}
+
 template <int KIND, int NS, bool RLX = false>
 int launch_static(const BatchDev& p, cudaStream_t st)
 {
     const long long threads = p.n * NS;
-    static const int block = getenv("GCS_STATIC_BLOCK") ? atoi(getenv("GCS_STATIC_BLOCK")) : 128;  // tuning knob (multiple of 32)
+    static const int block = static_block_size();
     const long long grid = (threads + block - 1) / block;
     if (grid > 0x7fffffffLL) return fail(GCS_E_INVALID, "batch too large for one launch");
     newton_static_kernel<KIND, NS, RLX><<<(unsigned)grid, block, 0, st>>>(p);
@@ -346,11 +376,14 @@ int gcs_b200_kind_out_cols(int kind)
     return (kind >= 1 && kind <= GCS_KIND_COUNT) ? t[kind] : 0;
 }
 
-void* gcs_b200_host_alloc(size_t bytes)
+void* gcs_b200_host_alloc(size_t bytes) { return gcs_b200_host_alloc_ex(bytes, 0); }
+
+void* gcs_b200_host_alloc_ex(size_t bytes, int flags)
 {
     if (bytes == 0 || ensure_init() != GCS_OK || g_devs.empty()) return nullptr;
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    const unsigned f = cudaHostAllocPortable | ((flags & GCS_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : 0u);
+    if (cudaHostAlloc(&p, bytes, f) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
@@ -378,12 +411,18 @@ int gcs_b200_init(int device_count, const int* devices)
     if (rc != GCS_OK) return rc;
     const int avail = (int)g_devs.size();
     if (device_count <= 0) device_count = avail;
+    std::vector<int> list;
     for (int i = 0; i < device_count; ++i) {
         const int dev = devices ? devices[i] : i;
         if (dev < 0 || dev >= avail) return fail(GCS_E_NO_DEVICE, "device %d out of range (%d present)", dev, avail);
+        for (int seen : list)
+            if (seen == dev) return fail(GCS_E_INVALID, "device %d listed twice", dev);
         rc = prepare_device(g_devs[dev]);
         if (rc != GCS_OK) return rc;
+        list.push_back(dev);
     }
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_init_list = list;
     return GCS_OK;
 }
 
@@ -403,11 +442,17 @@ void gcs_b200_shutdown(void)
         delete d;
     }
     g_devs.clear();
+    g_init_list.clear();
 }
 
 const char* gcs_b200_last_error(void) { return g_err; }
 
-const char* gcs_b200_version(void) { return "gcs_b200 0.1.0 (sm_100a, fp64, fmad=false)"; }
+#ifndef GCS_SRC_HASH
+#define GCS_SRC_HASH "unstamped"
+#endif
+// "src <hash>": sha256 prefix of csrc/*, the public header and the compiler flags this binary was
+// built from (__graft_entry__.cuda_source_hash), so that a stale library is detectable
+const char* gcs_b200_version(void) { return "gcs_b200 0.2.0 (sm_100a, fp64, fmad=false; src " GCS_SRC_HASH ")"; }
 
 int64_t gcs_b200_launch_count(void) { return g_launches.load(); }
 
@@ -498,12 +543,15 @@ void trace_dump()
     g_trace.clear();
 }
 
-size_t arena_need(const gcs_b200_batch* b)
+// Device bytes one index range of `count` sub-systems of batch `b` needs in the staging arena.
+size_t arena_need(const gcs_b200_batch* b, int64_t count)
 {
-    const size_t n = (size_t)b->n;
+    const size_t n = (size_t)count;
     const int ns = b->n_seeds;
     const int nin = gcs_b200_kind_in_cols(b->kind), nout = gcs_b200_kind_out_cols(b->kind);
-    size_t need = align_up(n * 8, 256) * (size_t)(nin + nout) + align_up(n, 256) * 2;  // columns, code, root
+    int present = 0;
+    for (int c = 0; c < nin; ++c) present += b->in[c] != nullptr;
+    size_t need = align_up(n * 8, 256) * (size_t)(present + nout) + align_up(n, 256) * 2;  // columns, code, root
     if (b->guesses) need += align_up(n * 8 * 2 * ns, 256);
     if (b->cand) need += align_up(n * 8 * 2 * ns, 256);
     need += align_up(n * 2 * ns, 256) + align_up(n * ns, 256);  // iters + converged
@@ -563,20 +611,44 @@ int64_t chunk_len(int64_t n, bool slabs)
     // Ranges per batch: 4 when every range moves with a handful of strided copies, 3 when each
     // column needs its own call; never below 32 Ki sub-systems nor above 256 Ki (pipeline ramp);
     // multiples of 128 keep every slice 16-byte aligned
-    static const int forced = getenv("GCS_B200_PARTS") ? atoi(getenv("GCS_B200_PARTS")) : 0;  // tuning knob
-    const int parts = forced > 0 ? forced : (slabs ? 4 : 3);
+    static const int forced = getenv("GCS_B200_PARTS") ? atoi(getenv("GCS_B200_PARTS")) : 0;  // tuning knob, 1..64
+    const int parts = (forced > 0 && forced <= 64) ? forced : (slabs ? 4 : 3);
     int64_t c = (n + parts - 1) / parts;
     if (c < 32768) c = 32768;
     if (c > 262144) c = 262144;
     return (c + 127) / 128 * 128;
 }
 
-// Issues the whole pipeline of one batch on (h2d, stream, d2h), device buffers at arena + off.
+// Maximal runs of host columns at one constant positive spacing: such a run moves with ONE strided
+// copy per index range.  runs[j] = length of the run starting at present-column j (0 inside a run).
+void find_runs(const char* const* cols, int count, size_t row_bytes, int* runs, size_t* pitch)
+{
+    const bool off = getenv("GCS_B200_NOSLAB") != nullptr;
+    for (int j = 0; j < count;) {
+        int run = 1;
+        size_t sp = 0;
+        if (!off && j + 1 < count && cols[j + 1] > cols[j]) {
+            sp = (size_t)(cols[j + 1] - cols[j]);
+            if (sp >= row_bytes && sp <= 0x7fffffffull) {
+                run = 2;
+                while (j + run < count && cols[j + run] > cols[j + run - 1] && (size_t)(cols[j + run] - cols[j + run - 1]) == sp) ++run;
+            }
+        }
+        runs[j] = run;
+        pitch[j] = sp;
+        for (int q = 1; q < run; ++q) runs[j + q] = 0;
+        j += run;
+    }
+}
+
+// Issues the whole pipeline of the index range [first, first + count) of host batch `b` on
+// (h2d, stream, d2h), device buffers at arena + off.  The per-seed planes of the host batch keep
+// the full batch's pitch (b->n), so several devices can fill disjoint ranges of the same arrays.
 // Nothing joins the streams here: the next batch's upload may start at once (its buffers are a
 // different arena region); gcs_b200_wait / drain synchronises all three.
-int record_pipeline(DeviceState* d, const gcs_b200_batch* b, size_t off)
+int record_pipeline(DeviceState* d, const gcs_b200_batch* b, size_t off, int64_t first, int64_t count)
 {
-    const size_t n = (size_t)b->n;
+    const size_t n = (size_t)count, host_n = (size_t)b->n;
     const int ns = b->n_seeds;
     const int nin = gcs_b200_kind_in_cols(b->kind), nout = gcs_b200_kind_out_cols(b->kind);
     const size_t colb = align_up(n * 8, 256);
@@ -586,38 +658,42 @@ int record_pipeline(DeviceState* d, const gcs_b200_batch* b, size_t off)
         cur_p += align_up(bytes, 256);
         return r;
     };
+    // NULL input columns (all zeros, gcs_b200.h) have no device buffer and no copy
     double* din[GCS_MAX_IN_COLS] = {};
     double* dout[GCS_MAX_OUT_COLS] = {};
-    for (int c = 0; c < nin; ++c) din[c] = reinterpret_cast<double*>(take(n * 8));
+    int pres[GCS_MAX_IN_COLS], npres = 0;
+    const char* hin[GCS_MAX_IN_COLS];
+    for (int c = 0; c < nin; ++c) {
+        if (!b->in[c]) continue;
+        din[c] = reinterpret_cast<double*>(take(n * 8));
+        hin[npres] = reinterpret_cast<const char*>(b->in[c] + first);
+        pres[npres++] = c;
+    }
     uint8_t* dcode = take(n);
     double* dguess = b->guesses ? reinterpret_cast<double*>(take(n * 8 * 2 * ns)) : nullptr;
-    for (int c = 0; c < nout; ++c) dout[c] = reinterpret_cast<double*>(take(n * 8));
+    const char* hout[GCS_MAX_OUT_COLS];
+    for (int c = 0; c < nout; ++c) {
+        dout[c] = reinterpret_cast<double*>(take(n * 8));
+        hout[c] = reinterpret_cast<const char*>(b->out[c] + first);
+    }
     double* dcand = b->cand ? reinterpret_cast<double*>(take(n * 8 * 2 * ns)) : nullptr;
     int16_t* diters = reinterpret_cast<int16_t*>(take(n * 2 * ns));
     uint8_t* dconv = take(n * ns);
     uint8_t* droot = take(n);
 
-    // runs of columns at one constant positive spacing (bytes) in host memory
     int in_runs[GCS_MAX_IN_COLS] = {}, out_runs[GCS_MAX_OUT_COLS] = {};
-    size_t in_pitch = 0, out_pitch = 0;
-    auto find_runs = [&](auto* const* cols, int count, int* runs, size_t* pitch) {
-        for (int c = 0; c < count; ++c) runs[c] = 1;
-        if (count < 2 || getenv("GCS_B200_NOSLAB")) return;
-        const ptrdiff_t sp = reinterpret_cast<const char*>(cols[1]) - reinterpret_cast<const char*>(cols[0]);
-        if (sp < (ptrdiff_t)(n * 8)) return;
-        for (int c = 2; c < count; ++c)
-            if (reinterpret_cast<const char*>(cols[c]) - reinterpret_cast<const char*>(cols[c - 1]) != sp) return;
-        runs[0] = count;
-        *pitch = (size_t)sp;
-    };
-    find_runs(b->in, nin, in_runs, &in_pitch);
-    find_runs(b->out, nout, out_runs, &out_pitch);
-    const bool slabs = in_runs[0] == nin && out_runs[0] == nout;
+    size_t in_pitch[GCS_MAX_IN_COLS] = {}, out_pitch[GCS_MAX_OUT_COLS] = {};
+    find_runs(hin, npres, n * 8, in_runs, in_pitch);
+    find_runs(hout, nout, n * 8, out_runs, out_pitch);
+    int in_calls = 0, out_calls = 0;
+    for (int j = 0; j < npres; ++j) in_calls += in_runs[j] > 0;
+    for (int j = 0; j < nout; ++j) out_calls += out_runs[j] > 0;
+    const bool slabs = in_calls <= 2 && out_calls <= 2;
 
     // index ranges: equal steps, the last one halved so that less work trails the final upload
-    const int64_t step = chunk_len(b->n, slabs);
+    const int64_t step = chunk_len(count, slabs);
     std::vector<std::pair<int64_t, int64_t>> ranges;
-    for (int64_t lo = 0; lo < b->n; lo += step) ranges.push_back({ lo, (b->n - lo < step) ? (b->n - lo) : step });
+    for (int64_t lo = 0; lo < count; lo += step) ranges.push_back({ lo, (count - lo < step) ? (count - lo) : step });
     if (ranges.size() >= 2 && ranges.back().second >= 65536) {
         const auto last = ranges.back();
         const int64_t half = (last.second / 2 + 127) / 128 * 128;
@@ -628,25 +704,27 @@ int record_pipeline(DeviceState* d, const gcs_b200_batch* b, size_t off)
     if (rc != GCS_OK) return rc;
     // the one-byte code column goes up whole, ahead of the first range: one copy instead of one
     // per range (every copy costs a few microseconds of engine time whatever its size)
-    CUDA_TRY(cudaMemcpyAsync(dcode, b->code, n, cudaMemcpyHostToDevice, d->h2d));
+    CUDA_TRY(cudaMemcpyAsync(dcode, b->code + first, n, cudaMemcpyHostToDevice, d->h2d));
     for (const auto& range : ranges) {
         const int64_t lo = range.first, len = range.second;
         const size_t m = (size_t)len;
         trace_mark(d->h2d, "up-begin", b->kind, lo);
         // up: columns that sit at a constant spacing in host memory (one [cols][n] slab) go up as
-        // one strided copy, anything else column by column
-        for (int c = 0; c < nin;) {
-            const int run = in_runs[c];
+        // one strided copy (their device buffers are consecutive, pitch colb), anything else
+        // column by column
+        for (int j = 0; j < npres;) {
+            const int run = in_runs[j];
+            double* dst = din[pres[j]] + lo;
+            const char* src = hin[j] + (size_t)lo * 8;
             if (run > 1) {
-                CUDA_TRY(cudaMemcpy2DAsync(din[c] + lo, colb, b->in[c] + lo, in_pitch, m * 8, (size_t)run,
-                    cudaMemcpyHostToDevice, d->h2d));
+                CUDA_TRY(cudaMemcpy2DAsync(dst, colb, src, in_pitch[j], m * 8, (size_t)run, cudaMemcpyHostToDevice, d->h2d));
             } else {
-                CUDA_TRY(cudaMemcpyAsync(din[c] + lo, b->in[c] + lo, m * 8, cudaMemcpyHostToDevice, d->h2d));
+                CUDA_TRY(cudaMemcpyAsync(dst, src, m * 8, cudaMemcpyHostToDevice, d->h2d));
             }
-            c += run;
+            j += run;
         }
         if (b->guesses)
-            CUDA_TRY(cudaMemcpy2DAsync(dguess + lo, n * 8, b->guesses + lo, n * 8, m * 8, (size_t)(2 * ns),
+            CUDA_TRY(cudaMemcpy2DAsync(dguess + lo, n * 8, b->guesses + first + lo, host_n * 8, m * 8, (size_t)(2 * ns),
                 cudaMemcpyHostToDevice, d->h2d));
         cudaEvent_t up = d->events[d->ev_next++], done = d->events[d->ev_next++];
         CUDA_TRY(cudaEventRecord(up, d->h2d));
@@ -655,7 +733,7 @@ int record_pipeline(DeviceState* d, const gcs_b200_batch* b, size_t off)
         CUDA_TRY(cudaStreamWaitEvent(d->stream, up, 0));
         BatchDev p;
         memset(&p, 0, sizeof(p));
-        for (int c = 0; c < nin; ++c) p.in[c] = din[c] + lo;
+        for (int c = 0; c < nin; ++c) p.in[c] = din[c] ? din[c] + lo : nullptr;
         p.code = dcode + lo;
         p.guesses = dguess ? dguess + lo : nullptr;
         for (int c = 0; c < nout; ++c) p.out[c] = dout[c] + lo;
@@ -664,55 +742,53 @@ int record_pipeline(DeviceState* d, const gcs_b200_batch* b, size_t off)
         p.converged = dconv + lo;
         p.root = droot + lo;
         p.n = len;
-        p.stride = b->n;
+        p.stride = count;
         rc = solve_dev(d, b, p, d->stream);
         if (rc != GCS_OK) return rc;
         CUDA_TRY(cudaEventRecord(done, d->stream));
         trace_mark(d->stream, "solved", b->kind, lo);
         // down
         CUDA_TRY(cudaStreamWaitEvent(d->d2h, done, 0));
-        for (int c = 0; c < nout;) {
-            const int run = out_runs[c];
+        for (int j = 0; j < nout;) {
+            const int run = out_runs[j];
+            char* dst = const_cast<char*>(hout[j]) + (size_t)lo * 8;
             if (run > 1) {
-                CUDA_TRY(cudaMemcpy2DAsync(b->out[c] + lo, out_pitch, dout[c] + lo, colb, m * 8, (size_t)run,
-                    cudaMemcpyDeviceToHost, d->d2h));
+                CUDA_TRY(cudaMemcpy2DAsync(dst, out_pitch[j], dout[j] + lo, colb, m * 8, (size_t)run, cudaMemcpyDeviceToHost, d->d2h));
             } else {
-                CUDA_TRY(cudaMemcpyAsync(b->out[c] + lo, dout[c] + lo, m * 8, cudaMemcpyDeviceToHost, d->d2h));
+                CUDA_TRY(cudaMemcpyAsync(dst, dout[j] + lo, m * 8, cudaMemcpyDeviceToHost, d->d2h));
             }
-            c += run;
+            j += run;
         }
         if (b->cand)
-            CUDA_TRY(cudaMemcpy2DAsync(b->cand + lo, n * 8, dcand + lo, n * 8, m * 8, (size_t)(2 * ns),
+            CUDA_TRY(cudaMemcpy2DAsync(b->cand + first + lo, host_n * 8, dcand + lo, n * 8, m * 8, (size_t)(2 * ns),
                 cudaMemcpyDeviceToHost, d->d2h));
         if (b->iters)
-            CUDA_TRY(cudaMemcpy2DAsync(b->iters + lo, n * 2, diters + lo, n * 2, m * 2, (size_t)ns, cudaMemcpyDeviceToHost, d->d2h));
+            CUDA_TRY(cudaMemcpy2DAsync(b->iters + first + lo, host_n * 2, diters + lo, n * 2, m * 2, (size_t)ns, cudaMemcpyDeviceToHost, d->d2h));
         if (b->converged)
-            CUDA_TRY(cudaMemcpy2DAsync(b->converged + lo, n, dconv + lo, n, m, (size_t)ns, cudaMemcpyDeviceToHost, d->d2h));
-        if (b->root_index) CUDA_TRY(cudaMemcpyAsync(b->root_index + lo, droot + lo, m, cudaMemcpyDeviceToHost, d->d2h));
+            CUDA_TRY(cudaMemcpy2DAsync(b->converged + first + lo, host_n, dconv + lo, n, m, (size_t)ns, cudaMemcpyDeviceToHost, d->d2h));
+        if (b->root_index) CUDA_TRY(cudaMemcpyAsync(b->root_index + first + lo, droot + lo, m, cudaMemcpyDeviceToHost, d->d2h));
     }
     trace_mark(d->d2h, "flags-end", b->kind, -1);
     return GCS_OK;
 }
 
 // arena_mu held, device current
-int enqueue_host(DeviceState* d, const gcs_b200_batch* b)
+int enqueue_host(DeviceState* d, const gcs_b200_batch* b, int64_t first, int64_t count)
 {
-    const size_t need = arena_need(b);
+    const size_t need = arena_need(b, count);
     int rc = reserve_arena(d, need);
     if (rc != GCS_OK) return rc;
     const size_t off = d->arena_used;
-    rc = record_pipeline(d, b, off);
+    rc = record_pipeline(d, b, off, first, count);
     d->arena_used = off + need;
     d->in_flight = true;
     return rc;
 }
 
-int host_entry(const gcs_b200_batch* b, int device, bool wait)
+// index range [first, first + count) of a validated host batch on `device`
+int host_range_entry(const gcs_b200_batch* b, int device, int64_t first, int64_t count, bool wait)
 {
-    int rc = validate(b);
-    if (rc != GCS_OK) return rc;
-    if (b->mem != GCS_MEM_HOST) return fail(GCS_E_INVALID, "this entry point needs host pointers (mem=GCS_MEM_HOST)");
-    rc = ensure_init();
+    int rc = ensure_init();
     if (rc != GCS_OK) return rc;
     DeviceState* d = find_dev(device);
     if (!d) return fail(GCS_E_NO_DEVICE, "device %d not present", device);
@@ -722,7 +798,7 @@ int host_entry(const gcs_b200_batch* b, int device, bool wait)
     int cur = -1;
     CUDA_TRY(cudaGetDevice(&cur));
     if (cur != device) CUDA_TRY(cudaSetDevice(device));
-    if (b->n > 0) rc = enqueue_host(d, b);
+    if (count > 0) rc = enqueue_host(d, b, first, count);
     if (rc != GCS_OK) {
         drain(d);  // leave nothing behind a failed call
     } else if (wait && d->in_flight) {
@@ -732,11 +808,30 @@ int host_entry(const gcs_b200_batch* b, int device, bool wait)
     return rc;
 }
 
+int host_entry(const gcs_b200_batch* b, int device, bool wait)
+{
+    int rc = validate(b);
+    if (rc != GCS_OK) return rc;
+    if (b->mem != GCS_MEM_HOST) return fail(GCS_E_INVALID, "this entry point needs host pointers (mem=GCS_MEM_HOST)");
+    return host_range_entry(b, device, 0, b->n, wait);
+}
+
 }  // namespace
 
 int gcs_b200_solve_host(const gcs_b200_batch* b, int device) { return host_entry(b, device, true); }
 
 int gcs_b200_solve_host_async(const gcs_b200_batch* b, int device) { return host_entry(b, device, false); }
+
+int gcs_b200_solve_host_range_async(const gcs_b200_batch* b, int device, int64_t first, int64_t count)
+{
+    int rc = validate(b);
+    if (rc != GCS_OK) return rc;
+    if (b->mem != GCS_MEM_HOST) return fail(GCS_E_INVALID, "this entry point needs host pointers (mem=GCS_MEM_HOST)");
+    if (first < 0 || count < 0 || first > b->n || count > b->n - first)
+        return fail(GCS_E_INVALID, "index range [%lld, %lld) outside the batch of %lld", (long long)first,
+            (long long)(first + count), (long long)b->n);
+    return host_range_entry(b, device, first, count, false);
+}
 
 int gcs_b200_wait(int device)
 {
@@ -761,51 +856,55 @@ int gcs_b200_solve_sharded(const gcs_b200_batch* b, int n_dev)
     if (b->mem != GCS_MEM_HOST) return fail(GCS_E_INVALID, "gcs_b200_solve_sharded needs host pointers");
     rc = ensure_init();
     if (rc != GCS_OK) return rc;
-    const int avail = (int)g_devs.size();
+    // the devices of the last gcs_b200_init, in its order; without one, ordinals 0..count-1
+    std::vector<int> list;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        list = g_init_list;
+    }
+    if (list.empty())
+        for (int i = 0; i < (int)g_devs.size(); ++i) list.push_back(i);
+    const int avail = (int)list.size();
     if (n_dev <= 0) n_dev = avail;
-    if (n_dev > avail) return fail(GCS_E_NO_DEVICE, "%d devices requested, %d present", n_dev, avail);
-    if (n_dev == 1) return gcs_b200_solve_host(b, 0);
-    if (b->guesses || b->cand) {
-        // [seed][2][n] planes are not contiguous per shard
-        return fail(GCS_E_INVALID, "sharded solve does not take explicit guesses / cand planes");
-    }
-    std::vector<int> rcs(n_dev, GCS_OK);
-    std::vector<std::string> msgs(n_dev);
-    std::vector<std::thread> th;
+    if (n_dev > avail) return fail(GCS_E_NO_DEVICE, "%d devices requested, %d initialised", n_dev, avail);
+    // One pipeline per device, all enqueued from this thread before any is waited for; every
+    // device fills its own index range of the caller's arrays (the per-seed planes keep the
+    // full batch's pitch), so nothing is gathered afterwards and nothing crosses between devices.
     const int64_t n = b->n;
-    for (int g = 0; g < n_dev; ++g) {
-        th.emplace_back([&, g]() {
-            const int64_t lo = n * g / n_dev, hi = n * (g + 1) / n_dev;
-            gcs_b200_batch s = *b;
-            s.n = hi - lo;
-            const int nin = gcs_b200_kind_in_cols(b->kind), nout = gcs_b200_kind_out_cols(b->kind);
-            for (int c = 0; c < nin; ++c) s.in[c] = b->in[c] + lo;
-            s.code = b->code + lo;
-            for (int c = 0; c < nout; ++c) s.out[c] = b->out[c] + lo;
-            if (b->root_index) s.root_index = b->root_index + lo;
-            // per-seed planes [seed][n]: solve into shard-local temporaries, then scatter
-            std::vector<int16_t> its;
-            std::vector<uint8_t> cvs;
-            if (b->iters) its.resize((size_t)s.n * b->n_seeds), s.iters = its.data();
-            if (b->converged) cvs.resize((size_t)s.n * b->n_seeds), s.converged = cvs.data();
-            rcs[g] = gcs_b200_solve_host(&s, g);
-            if (rcs[g] != GCS_OK) {
-                msgs[g] = g_err;
-                return;
-            }
-            for (int k = 0; k < b->n_seeds; ++k) {
-                if (b->iters) memcpy(b->iters + (size_t)k * n + lo, its.data() + (size_t)k * s.n, (size_t)s.n * 2);
-                if (b->converged) memcpy(b->converged + (size_t)k * n + lo, cvs.data() + (size_t)k * s.n, (size_t)s.n);
-            }
-        });
+    int first_rc = GCS_OK;
+    std::string first_msg;
+    int enqueued = 0;
+    for (int g = 0; g < n_dev && first_rc == GCS_OK; ++g) {
+        const int64_t lo = n * g / n_dev, hi = n * (g + 1) / n_dev;
+        rc = host_range_entry(b, list[g], lo, hi - lo, false);
+        if (rc != GCS_OK) first_rc = rc, first_msg = "shard " + std::to_string(g) + " (device " + std::to_string(list[g]) + "): " + g_err;
+        ++enqueued;
     }
-    for (auto& t : th) t.join();
-    for (int g = 0; g < n_dev; ++g)
-        if (rcs[g] != GCS_OK) return fail(rcs[g], "shard %d: %s", g, msgs[g].c_str());
+    for (int g = 0; g < enqueued; ++g) {
+        rc = gcs_b200_wait(list[g]);
+        if (rc != GCS_OK && first_rc == GCS_OK) first_rc = rc, first_msg = "shard " + std::to_string(g) + ": " + g_err;
+    }
+    if (first_rc != GCS_OK) return fail(first_rc, "%s", first_msg.c_str());
     return GCS_OK;
 }
 
+int gcs_b200_contracted_stats_ex(int device, uint64_t out[8], int reset);
+
 int gcs_b200_contracted_stats(int device, uint64_t out[2], int reset)
+{
+    uint64_t v[8] = {};
+    const int rc = gcs_b200_contracted_stats_ex(device, v, reset);
+    if (rc != GCS_OK) return rc;
+    if (out) {
+        out[1] = v[gcsk::kWhySelection];
+        out[0] = 0;
+        for (int k = 0; k < gcsk::kWhyCount; ++k)
+            if (k != gcsk::kWhySelection) out[0] += v[k];
+    }
+    return GCS_OK;
+}
+
+int gcs_b200_contracted_stats_ex(int device, uint64_t out[8], int reset)
 {
     int rc = ensure_init();
     if (rc != GCS_OK) return rc;
@@ -815,13 +914,14 @@ int gcs_b200_contracted_stats(int device, uint64_t out[2], int reset)
     CUDA_TRY(cudaGetDevice(&cur));
     if (cur != device) CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaDeviceSynchronize());
-    unsigned long long v[2] = { 0, 0 };
+    unsigned long long v[gcsk::kWhyCount] = {};
     CUDA_TRY(cudaMemcpyFromSymbol(v, gcsk::g_relax_reruns, sizeof(v)));
     if (reset) {
-        const unsigned long long z[2] = { 0, 0 };
+        const unsigned long long z[gcsk::kWhyCount] = {};
         CUDA_TRY(cudaMemcpyToSymbol(gcsk::g_relax_reruns, z, sizeof(z)));
     }
-    if (out) out[0] = v[0], out[1] = v[1];
+    if (out)
+        for (int k = 0; k < gcsk::kWhyCount; ++k) out[k] = v[k];
     if (cur != device && cur >= 0) cudaSetDevice(cur);
     return GCS_OK;
 }
@@ -896,6 +996,87 @@ double gcs_b200_fp64_probe(int device, int what)
     cudaFree(out);
     if (e != cudaSuccess) return (double)fail(GCS_E_CUDA, "fp64 probe: %s", cudaGetErrorString(e));
     return result;
+}
+
+// Copy-only probe of the host link: what the host-buffer entry points could reach at best with the
+// same byte counts.  Pinned (optionally write-combined) host buffers, `pieces` equal copies per
+// direction (1 = one contiguous copy; the pipeline moves stage-sized pieces), the two directions on
+// the library's two copy streams.  out[0] = H2D alone GB/s, out[1] = D2H alone GB/s, out[2] =
+// milliseconds for both directions issued together (best of `reps`), out[3] = the same, median.
+int gcs_b200_pcie_probe(int device, size_t bytes_up, size_t bytes_down, int pieces, int write_combined, int reps, double out[4])
+{
+    if (!out || pieces < 1 || reps < 1 || bytes_up == 0 || bytes_down == 0) return fail(GCS_E_INVALID, "bad probe arguments");
+    int rc = ensure_init();
+    if (rc != GCS_OK) return rc;
+    DeviceState* d = find_dev(device);
+    if (!d) return fail(GCS_E_NO_DEVICE, "device %d not present", device);
+    rc = prepare_device(d);
+    if (rc != GCS_OK) return rc;
+    int cur = -1;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != device) CUDA_TRY(cudaSetDevice(device));
+    void *hu = nullptr, *hd = nullptr, *du = nullptr, *dd = nullptr;
+    cudaEvent_t e[4] = {};
+    auto cleanup = [&]() {
+        if (hu) cudaFreeHost(hu);
+        if (hd) cudaFreeHost(hd);
+        if (du) cudaFree(du);
+        if (dd) cudaFree(dd);
+        for (auto ev : e)
+            if (ev) cudaEventDestroy(ev);
+        if (cur != device && cur >= 0) cudaSetDevice(cur);
+    };
+    cudaError_t ce = cudaHostAlloc(&hu, bytes_up, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u));
+    if (ce == cudaSuccess) ce = cudaHostAlloc(&hd, bytes_down, cudaHostAllocPortable);
+    if (ce == cudaSuccess) ce = cudaMalloc(&du, bytes_up);
+    if (ce == cudaSuccess) ce = cudaMalloc(&dd, bytes_down);
+    for (int k = 0; k < 4 && ce == cudaSuccess; ++k) ce = cudaEventCreate(&e[k]);
+    if (ce != cudaSuccess) {
+        cleanup();
+        return fail(GCS_E_NOMEM, "pcie probe: %s", cudaGetErrorString(ce));
+    }
+    memset(hu, 1, bytes_up);
+    auto up = [&]() {
+        const size_t piece = (bytes_up / pieces + 255) / 256 * 256;
+        for (size_t o = 0; o < bytes_up; o += piece)
+            cudaMemcpyAsync((char*)du + o, (char*)hu + o, bytes_up - o < piece ? bytes_up - o : piece, cudaMemcpyHostToDevice, d->h2d);
+    };
+    auto down = [&]() {
+        const size_t piece = (bytes_down / pieces + 255) / 256 * 256;
+        for (size_t o = 0; o < bytes_down; o += piece)
+            cudaMemcpyAsync((char*)hd + o, (char*)dd + o, bytes_down - o < piece ? bytes_down - o : piece, cudaMemcpyDeviceToHost, d->d2h);
+    };
+    std::vector<double> both;
+    double best_up = 1e30, best_down = 1e30;
+    for (int r = 0; r < reps + 1; ++r) {
+        float ms = 0;
+        cudaEventRecord(e[0], d->h2d), up(), cudaEventRecord(e[1], d->h2d);
+        cudaEventSynchronize(e[1]);
+        cudaEventElapsedTime(&ms, e[0], e[1]);
+        if (r > 0 && ms < best_up) best_up = ms;
+        cudaEventRecord(e[2], d->d2h), down(), cudaEventRecord(e[3], d->d2h);
+        cudaEventSynchronize(e[3]);
+        cudaEventElapsedTime(&ms, e[2], e[3]);
+        if (r > 0 && ms < best_down) best_down = ms;
+        // both directions at once: from the common start to the later of the two ends
+        cudaEventRecord(e[0], d->h2d);
+        cudaStreamWaitEvent(d->d2h, e[0], 0);
+        up(), down();
+        cudaEventRecord(e[1], d->h2d), cudaEventRecord(e[3], d->d2h);
+        cudaEventSynchronize(e[1]), cudaEventSynchronize(e[3]);
+        float a = 0, b2 = 0;
+        cudaEventElapsedTime(&a, e[0], e[1]), cudaEventElapsedTime(&b2, e[0], e[3]);
+        if (r > 0) both.push_back(a > b2 ? a : b2);
+    }
+    ce = cudaGetLastError();
+    std::sort(both.begin(), both.end());
+    out[0] = (double)bytes_up / (best_up * 1e-3) / 1e9;
+    out[1] = (double)bytes_down / (best_down * 1e-3) / 1e9;
+    out[2] = both.front();
+    out[3] = both[both.size() / 2];
+    cleanup();
+    if (ce != cudaSuccess) return fail(GCS_E_CUDA, "pcie probe: %s", cudaGetErrorString(ce));
+    return GCS_OK;
 }
 
 int gcs_b200_selftest_launch(uint64_t seed, long long n, unsigned long long* dev_counts, int sm_count);  // selftest.cu

@@ -50,6 +50,15 @@ struct BatchDev {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+// Input column c of sub-system i.  A NULL column is a column of zeros (gcs_b200.h: the anchored
+// shapes of the zero-fixed solvers place elements at the origin / on the x axis, so those columns
+// need not exist, let alone cross PCIe); the test is uniform over the launch.
+__device__ __forceinline__ double ldcol(const BatchDev& p, int c, long long i)
+{
+    const double* q = p.in[c];
+    return q ? __ldg(q + i) : 0.0;
+}
+
 __device__ __forceinline__ unsigned lanemask_lt()
 {
     unsigned m;
@@ -84,7 +93,7 @@ __global__ void __launch_bounds__(128, RLX ? GCS_STATIC_RLX_MINB : GCS_STATIC_MI
 
     double k[S::kCols];
 #pragma unroll
-    for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + i);
+    for (int c = 0; c < S::kCols; ++c) k[c] = ldcol(p, c, i);
     const uint8_t code = p.code ? __ldg(p.code + i) : (uint8_t)GCS_MAKE_CODE(0, 0, 0);
 
     S sys;
@@ -114,7 +123,7 @@ __global__ void __launch_bounds__(128, RLX ? GCS_STATIC_RLX_MINB : GCS_STATIC_MI
         }
         conv = 1;
         if (state != kRlxConverged) {
-            literal_rerun<KIND>(p.guesses, p.stride, i, k, seed, runtime_zero, x, y, it, conv);
+            literal_rerun<KIND>(p.guesses, p.stride, i, k, seed, runtime_zero, x, y, it, conv, state - kRlxUncertain);
             literal = true;
         }
     } else {
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(128, RLX ? GCS_STATIC_RLX_MINB : GCS_STATIC_MI
         int redo = (seed == 0 && !selection_is_robust<KIND, NS>(k, code, cx, cy)) ? 1 : 0;
         redo = __shfl_sync(kFull, redo, lead);
         if (__any_sync(kFull, redo)) {
-            if (redo && !literal) literal_rerun<KIND>(p.guesses, p.stride, i, k, seed, runtime_zero, x, y, it, conv, 1);
+            if (redo && !literal) literal_rerun<KIND>(p.guesses, p.stride, i, k, seed, runtime_zero, x, y, it, conv, kWhySelection);
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 cx[s] = __shfl_sync(kFull, x, lead + s);
@@ -176,7 +185,7 @@ __global__ void __launch_bounds__(128, GCS_PAIR_MINB) newton_pair_kernel(const B
     if (i >= p.n) return;
     double k[S::kCols];
 #pragma unroll
-    for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + i);
+    for (int c = 0; c < S::kCols; ++c) k[c] = ldcol(p, c, i);
     const uint8_t code = p.code ? __ldg(p.code + i) : (uint8_t)GCS_MAKE_CODE(0, 0, 0);
     S sys;
     sys.load(k);
@@ -329,7 +338,7 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
             const long long gi = base + sub;
             double k[S::kCols];
 #pragma unroll
-            for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + gi);
+            for (int c = 0; c < S::kCols; ++c) k[c] = ldcol(p, c, gi);
             if constexpr (RLX) {
                 Rsys<KIND> rs;
                 RelaxGuard g;
@@ -348,9 +357,9 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                     s_dmin[r] = dmin;
                     s_carry[r] = gr.carry;
                     s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
-                    s_cv[r] = (unsigned char)state;  // kRlxUncertain (2): phase C redoes the run literally
+                    s_cv[r] = (unsigned char)state;  // >= kRlxUncertain: phase C redoes the run literally
                     if (state != kRlxConverged) {
-                        const int kk = (state == kRlxUncertain) ? 0 : kSortBins - 1 - predict_remaining(d2, d3);
+                        const int kk = rlx_uncertain(state) ? 0 : kSortBins - 1 - predict_remaining(d2, d3);
                         atomicAdd(&s_bin[kk], 1);
                         if (q == 0) key[0] = kk; else key[1] = kk;
                     }
@@ -439,12 +448,12 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                 const int sub = r & (TILE - 1);
                 double k[S::kCols];
 #pragma unroll
-                for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + base + sub);  // only what load() reads survives
+                for (int c = 0; c < S::kCols; ++c) k[c] = ldcol(p, c, base + sub);  // only what load() reads survives
                 if constexpr (RLX) {
                     double x = s_x[r], y = s_y[r];
                     int it = s_it[r], conv = 1;
                     int state = s_cv[r];
-                    if (state != kRlxUncertain) {
+                    if (!rlx_uncertain(state)) {
                         Rsys<KIND> rs;
                         RelaxGuard g;
                         rs.load(k, g);
@@ -454,7 +463,7 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                         state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1, &dmin);
                     }
                     if (state != kRlxConverged)
-                        literal_rerun<KIND>(p.guesses, p.stride, base + sub, k, r / TILE, (double)(p.n >> 62), x, y, it, conv);
+                        literal_rerun<KIND>(p.guesses, p.stride, base + sub, k, r / TILE, (double)(p.n >> 62), x, y, it, conv, state - kRlxUncertain);
                     s_x[r] = x, s_y[r] = y, s_it[r] = (short)it;
                     s_cv[r] = (unsigned char)conv;
                 } else {
@@ -484,7 +493,7 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
     uint8_t coded = (uint8_t)GCS_MAKE_CODE(0, 0, 0);
     if (tid < cnt) {
 #pragma unroll
-        for (int c = 0; c < S::kCols; ++c) kd[c] = __ldg(p.in[c] + base + tid);
+        for (int c = 0; c < S::kCols; ++c) kd[c] = ldcol(p, c, base + tid);
         if (p.code) coded = __ldg(p.code + base + tid);
     }
     __syncthreads();
@@ -508,7 +517,7 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                 for (int s = 0; s < NS; ++s) {
                     int it, conv;
                     double x, y;
-                    literal_rerun<KIND>(p.guesses, p.stride, gi, k, s, (double)(p.n >> 62), x, y, it, conv, 1);
+                    literal_rerun<KIND>(p.guesses, p.stride, gi, k, s, (double)(p.n >> 62), x, y, it, conv, kWhySelection);
                     s_x[s * TILE + sub] = x, s_y[s * TILE + sub] = y;
                     s_it[s * TILE + sub] = (short)it;
                     s_cv[s * TILE + sub] = (unsigned char)conv;
@@ -621,6 +630,16 @@ __global__ void __launch_bounds__(WARPS * 32)
         mbar_init(&sl.bar[0], 1);
         mbar_init(&sl.bar[1], 1);
     }
+    // NULL columns (all zeros) never arrive by TMA: their slab rows are zeroed once, here
+    int present_cols = 0;
+#pragma unroll
+    for (int c = 0; c < S::kCols; ++c) {
+        if (p.in[c]) {
+            ++present_cols;
+        } else {
+            for (int j = lane; j < CH; j += 32) sl.in[0][c][j] = 0.0, sl.in[1][c][j] = 0.0;
+        }
+    }
     // make the barrier initialisation visible to the async proxy
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
@@ -633,16 +652,16 @@ __global__ void __launch_bounds__(WARPS * 32)
         if (bulk) {
             if (lane == 0) {
                 fence_proxy_async();  // earlier generic reads of this buffer precede the async writes
-                mbar_expect_tx(&sl.bar[buf], (uint32_t)(S::kCols * CH * 8 + CH));
+                mbar_expect_tx(&sl.bar[buf], (uint32_t)(present_cols * CH * 8 + CH));
 #pragma unroll
                 for (int c = 0; c < S::kCols; ++c)
-                    tma_bulk_g2s(&sl.in[buf][c][0], p.in[c] + base, CH * 8, &sl.bar[buf]);
+                    if (p.in[c]) tma_bulk_g2s(&sl.in[buf][c][0], p.in[c] + base, CH * 8, &sl.bar[buf]);
                 tma_bulk_g2s(&sl.code[buf][0], p.code + base, CH, &sl.bar[buf]);
             }
         } else {
             for (int j = lane; j < cnt; j += 32) {
 #pragma unroll
-                for (int c = 0; c < S::kCols; ++c) sl.in[buf][c][j] = __ldg(p.in[c] + base + j);
+                for (int c = 0; c < S::kCols; ++c) sl.in[buf][c][j] = ldcol(p, c, base + j);
                 sl.code[buf][j] = p.code ? __ldg(p.code + base + j) : (uint8_t)GCS_MAKE_CODE(0, 0, 0);
             }
         }

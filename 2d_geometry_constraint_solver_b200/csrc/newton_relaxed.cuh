@@ -64,10 +64,18 @@ namespace gcsk {
 constexpr int kRelaxCap = 64;  // updates a run may take on the closed-form path (G4)
 constexpr int kBounce = 4 << 20;  // (G2) four binades of growth of |det| over its running minimum
 
-// How often the guards hand work to the literal code (read by gcs_b200_contracted_stats):
-// [0] runs redone because a run-level guard fired, [1] runs redone because the selection guard fired.
-// Touched on the rare path only.
-__device__ unsigned long long g_relax_reruns[2];
+// How often the guards hand work to the literal code (read by gcs_b200_contracted_stats[_ex]), by
+// reason (kWhy*): touched on the rare path only.
+enum : int {
+    kWhyCond = 0,       // (G1) |det J| under its floor: conditioning past what the margins cover
+    kWhySelection = 1,  // (G5) root selection within its margin
+    kWhyBounce = 2,     // (G2) |det J| grew 16x over its running minimum
+    kWhyBand = 3,       // (G3) update length inside the second-level margin around the threshold
+    kWhyCap = 4,        // (G4) kRelaxCap updates without convergence
+    kWhyHuge = 5,       // (G4) non-finite / huge update
+    kWhyCount = 8
+};
+__device__ unsigned long long g_relax_reruns[kWhyCount];
 
 // 1/b to ~2^-60 relative: MUFU.RCP64H seed (>= 20 bits) and one cubic refinement
 __device__ __forceinline__ double rcp_relaxed(double b)
@@ -284,8 +292,10 @@ struct Rsys<GCS_KIND_ANG> {
     }
 };
 
-// Outcome of a stretch of closed-form updates
+// Outcome of a stretch of closed-form updates.  Uncertain outcomes carry the reason:
+// state = kRlxUncertain + kWhy*.
 enum : int { kRlxRunning = 0, kRlxConverged = 1, kRlxUncertain = 2 };
+__device__ __forceinline__ bool rlx_uncertain(int state) { return state >= kRlxUncertain; }
 
 // Up to `limit` closed-form updates from (x, y), `it` updates applied so far.  Returns
 //   kRlxConverged : the last update was shorter than the threshold for certain (and no guard fired)
@@ -307,7 +317,7 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
     int dmin = 0x7fffffff, grow = 0, d1 = 0x7fffffff;
     if (dmin_io && it > 0) dmin = *dmin_io;  // a run continued from an earlier stretch (sorted kernel)
     int state = kRlxRunning;
-    if (it >= limit) return (limit >= kRelaxCap) ? kRlxUncertain : kRlxRunning;
+    if (it >= limit) return (limit >= kRelaxCap) ? kRlxUncertain + kWhyCap : kRlxRunning;
     int mh, dh;
     double s0, s1, det;
     // one closed-form update; leaves mh = larger high word of the update's components, dh = hi(|det|)
@@ -361,7 +371,7 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
         // ---- rare from here ----
         if ((unsigned)(mh - g.hi_h) < span) break;  // limit reached, every update longer than the threshold
         if (mh >= RelaxGuard::kBigH || min(dmin, d1) < g.det_h || grow > kBounce) {  // (G4) / (G1) / (G2)
-            state = kRlxUncertain;
+            state = kRlxUncertain + (mh >= RelaxGuard::kBigH ? kWhyHuge : min(dmin, d1) < g.det_h ? kWhyCond : kWhyBounce);
             break;
         }
         if (mh < g.lo_h) {
@@ -370,12 +380,13 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
         }
         const int verdict = g.precise(fmax(fabs(s0), fabs(s1)) * Rsys<KIND>::kStepScale, det);
         if (verdict >= 0) {
-            state = verdict > 0 ? kRlxConverged : kRlxUncertain;
+            state = verdict > 0 ? kRlxConverged : kRlxUncertain + kWhyBand;
             break;
         }
         if (it >= limit) break;  // not converged for certain, and out of updates
     }
-    if (state == kRlxRunning && (min(dmin, d1) < g.det_h || grow > kBounce || limit >= kRelaxCap)) state = kRlxUncertain;
+    if (state == kRlxRunning && (min(dmin, d1) < g.det_h || grow > kBounce || limit >= kRelaxCap))
+        state = kRlxUncertain + (min(dmin, d1) < g.det_h ? kWhyCond : grow > kBounce ? kWhyBounce : kWhyCap);
     if (dmin_io) *dmin_io = dmin;
     return state;
 }

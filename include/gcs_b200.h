@@ -25,8 +25,11 @@
  *     the internal per-device staging arena used by the host-buffer entry points.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     GCS_E_NO_DEVICE.
- *   - arithmetic is IEEE-754 binary64 without contraction; constants below equal the reference's
- *     (newton_raphson.hpp:17, :20, :105-107; heuristics.hpp:173, :209).
+ *   - arithmetic is IEEE-754 binary64; the default kernels (GCS_VARIANT_DEFAULT .. GCS_VARIANT_PAIR)
+ *     use no contraction and reproduce the reference's roundings, the opt-in GCS_VARIANT_CONTRACTED*
+ *     kernels use fused multiply-adds under the tolerance contract stated at their definition;
+ *     constants below equal the reference's (newton_raphson.hpp:17, :20, :105-107;
+ *     heuristics.hpp:173, :209).
  */
 #ifndef GCS_B200_H
 #define GCS_B200_H
@@ -102,6 +105,14 @@ extern "C" {
  *     fixed line direction (solver space), cos(angle), canvas unit normal of the free line,
  *     canvas direction of the fixed line, the constraining point (solver space) and its signed
  *     distance to the free line, second reference point for reconstruction, canvas length.
+ *
+ * Anchored shapes.  The zero-fixed solvers place their first elements at the origin / on the x
+ * axis (point_point_solvers.cpp:48-50, point_line_solvers.cpp:179-181,
+ * line_angle_solvers.cpp:249-274), which makes some columns identically zero.  Such a column may
+ * be passed as NULL: it is read as all zeros (same arithmetic, same results), needs no buffer and
+ * is never copied to the device.  Allowed (gcs_b200_column_may_be_null): K1 ax, ay, by (0, 1, 4);
+ * K2 p1x, p1y, p2y (0, 1, 3); K5 fdy, px, r2x, r2y (1, 7, 10, 11).  Any other NULL input column is
+ * GCS_E_INVALID.
  */
 #define GCS_MAX_IN_COLS 13
 #define GCS_MAX_OUT_COLS 4
@@ -139,10 +150,14 @@ extern "C" {
 #define GCS_VARIANT_SORTED 3 /* CTA tiles; runs sorted by predicted update count, one lane finishes one run */
 #define GCS_VARIANT_PAIR 4 /* one lane per sub-system, its two seeds iterated in lockstep (2 seeds only; else static) */
 /* Tolerance-class arithmetic (csrc/newton_relaxed.cuh): closed-form 2x2 solve on fused
- * multiply-adds.  Iteration counts, convergence flags and root indices are IDENTICAL to every other
- * variant (runs and selections whose decisions could depend on the arithmetic are detected by
- * guards and redone with the literal device functions); coordinates agree to 1e-9 relative (the
- * north star's tolerance) instead of bit for bit.  Opt-in: DEFAULT never resolves to it.
+ * multiply-adds.  Contract: iteration counts, convergence flags and root indices equal to every
+ * other variant's; coordinates within 1e-9 relative (the north star's tolerance) instead of bit
+ * for bit.  The discrete half of the contract rests on guards (runs and selections whose decisions
+ * could depend on the arithmetic are detected and redone with the literal device functions) whose
+ * sufficiency is an error-analysis argument plus evidence - tests/test_gpu_relaxed.py,
+ * tests/test_gpu_soak.py and the soaks of profiles/ (> 1e8 sub-systems without a difference; an
+ * earlier soak did find one, which is why the carry term exists) - NOT a machine-checked proof.
+ * Opt-in: DEFAULT never resolves to it, and the host mirror stays on the bit-identical kernels.
  * CONTRACTED = CONTRACTED_STATIC (measured fastest at every size); CONTRACTED_SORTED maps the same
  * arithmetic onto the sorted tiles. */
 #define GCS_VARIANT_CONTRACTED 5
@@ -168,6 +183,8 @@ typedef struct gcs_b200_batch {
 /* number of input / output columns of a kind (0 for an unknown kind) */
 GCS_B200_API int gcs_b200_kind_in_cols(int kind);
 GCS_B200_API int gcs_b200_kind_out_cols(int kind);
+/* 1 if input column `col` of `kind` may be NULL (an anchor column, read as zeros), else 0 */
+GCS_B200_API int gcs_b200_column_may_be_null(int kind, int col);
 
 /* library / device management */
 GCS_B200_API int gcs_b200_device_count(void);
@@ -191,9 +208,17 @@ GCS_B200_API int gcs_b200_solve_host(const gcs_b200_batch* batch, int device);
  * valid and outputs are undefined until gcs_b200_wait(device) returns. */
 GCS_B200_API int gcs_b200_solve_host_async(const gcs_b200_batch* batch, int device);
 GCS_B200_API int gcs_b200_wait(int device);
+/* Only the sub-systems [first, first + count) of the batch, on `device`, asynchronously: the
+ * unit gcs_b200_solve_sharded is made of (a caller can place index ranges on devices its own way).
+ * The range's results land in rows first .. first+count-1 of the batch's arrays; the per-seed
+ * planes keep the full batch's pitch n. */
+GCS_B200_API int gcs_b200_solve_host_range_async(const gcs_b200_batch* batch, int device, int64_t first, int64_t count);
 
-/* Host buffers, sharded by batch index over the first n_dev initialised devices
- * (contiguous ranges [g*n/G, (g+1)*n/G)); no collective, per-device D2H into disjoint slices. */
+/* Host buffers, sharded by batch index over the first n_dev devices of the last gcs_b200_init
+ * call, in the order given there (without an init call: ordinals 0..n_dev-1; n_dev <= 0: all of
+ * them): device g takes the contiguous range [g*n/G, (g+1)*n/G).  No collective: every device
+ * runs its own upload / solve / download pipeline and writes its range of the caller's arrays
+ * (explicit guesses and cand planes included).  Synchronous. */
 GCS_B200_API int gcs_b200_solve_sharded(const gcs_b200_batch* batch, int n_dev);
 
 /* number of kernel launches issued by this process so far (bench bookkeeping) */
@@ -207,6 +232,10 @@ GCS_B200_API int gcs_b200_default_variant(int64_t n, int n_seeds);
  * the literal code since the last call with reset != 0: out[0] run-level guards (conditioning,
  * convergence band, update cap), out[1] root-selection guard.  Diagnostic; synchronises the device. */
 GCS_B200_API int gcs_b200_contracted_stats(int device, uint64_t out[2], int reset);
+/* the same by reason: out[0] conditioning floor (G1), [1] root selection (G5), [2] |det| bounce (G2),
+ * [3] convergence band undecided (G3), [4] update cap (G4), [5] non-finite / huge update (G4),
+ * [6], [7] reserved (0) */
+GCS_B200_API int gcs_b200_contracted_stats_ex(int device, uint64_t out[8], int reset);
 
 /* FP64 pipe micro-benchmarks used as roofline denominators (seconds-scale, device `device`):
  *   what = 0: dependent-free DFMA throughput, returns TFLOP/s counting FMA = 2 flops
@@ -215,12 +244,24 @@ GCS_B200_API int gcs_b200_contracted_stats(int device, uint64_t out[2], int rese
  * Returns a negative GCS_E_* code as a double on failure. */
 GCS_B200_API double gcs_b200_fp64_probe(int device, int what);
 
+/* Copy-only probe of the host link on `device` (the ceiling of the host-buffer entry points for
+ * the same byte counts): `bytes_up` host->device and `bytes_down` device->host, each as `pieces`
+ * equal copies from / to pinned (write_combined != 0: write-combined) host memory, on the
+ * library's two copy streams.  out[0] = H2D alone GB/s, out[1] = D2H alone GB/s, out[2] / out[3] =
+ * best / median milliseconds over `reps` for both directions issued together. */
+GCS_B200_API int gcs_b200_pcie_probe(int device, size_t bytes_up, size_t bytes_down, int pieces, int write_combined,
+    int reps, double out[4]);
+
 /* Page-locked host memory for batch columns: the host-buffer entry points move pinned buffers at
  * PCIe rate and asynchronously, pageable ones through the driver's staging copies.  Returns NULL
  * when no CUDA device is available (callers may then fall back to ordinary memory: only the
  * transfer gets slower).  Free with gcs_b200_host_free.  (A C++ host such as the reference has no
  * other way to get pinned memory without linking the CUDA runtime itself.) */
 GCS_B200_API void* gcs_b200_host_alloc(size_t bytes);
+/* flags: GCS_HOST_WRITE_COMBINED = write-combined pinned memory for INPUT columns the host only
+ * ever writes front to back (uncached for host reads; no cache snooping on the way to the device) */
+#define GCS_HOST_WRITE_COMBINED 1
+GCS_B200_API void* gcs_b200_host_alloc_ex(size_t bytes, int flags);
 GCS_B200_API void gcs_b200_host_free(void* p);
 
 /* On-device synthetic instance generator for the parametric sweep (BASELINE config 5) and the

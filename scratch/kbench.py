@@ -27,10 +27,11 @@ for kind in kinds:
     extra = ""
     if variant >= 5:
         import ctypes as C
-        st2 = (C.c_uint64 * 2)()
-        capi.load().gcs_b200_contracted_stats(0, st2, 1)
+        st2 = (C.c_uint64 * 8)()
+        capi.load().gcs_b200_contracted_stats_ex(0, st2, 1)
         db.solve()
-        capi.load().gcs_b200_contracted_stats(0, st2, 1)
-        extra = f"  literal re-runs per launch: {st2[0]} (run guards) + {st2[1]} (selection guard) of {n * ns} runs"
+        capi.load().gcs_b200_contracted_stats_ex(0, st2, 1)
+        extra = (f"  literal re-runs per launch of {n * ns} runs: cond {st2[0]} selection {st2[1]} bounce {st2[2]} band {st2[3]} "
+                 f"cap {st2[4]} huge {st2[5]}")
     chk = int(db.out[0].view(torch.int64).sum().item()) ^ int(db.out[1].view(torch.int64).sum().item()) ^ int(it.astype(np.int64).sum()) ^ (int(db.root_index.sum().item()) << 20)
     print(f"K{kind} n {n} seeds {ns} variant {variant}: median {np.median(ts)*1e3:.1f} us  min {np.min(ts)*1e3:.1f} us  checksum {chk & 0xffffffffffff:012x}{extra}")

@@ -36,7 +36,7 @@ def solve(batch, threads=0):
     """Run the oracle on a capi.HostBatch (allocates outputs if needed)."""
     if not batch.out:
         batch.alloc_outputs()
-    cb = batch.cbatch()
+    cb = batch.cbatch(dense=True)
     rc = load().gcs_oracle_solve(C.byref(cb), threads)
     if rc != 0:
         raise RuntimeError(f"gcs_oracle_solve -> {rc}")

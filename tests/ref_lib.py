@@ -55,7 +55,7 @@ def load():
 def solve_batch(batch, count_iters=True, threads=0):
     if not batch.out:
         batch.alloc_outputs()
-    cb = batch.cbatch()
+    cb = batch.cbatch(dense=True)
     rc = load().gcs_ref_solve_batch(C.byref(cb), 1 if count_iters else 0, threads)
     if rc != 0:
         raise RuntimeError(f"gcs_ref_solve_batch -> {rc}")

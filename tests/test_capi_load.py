@@ -60,6 +60,33 @@ def test_no_cpu_fallback_without_a_device(gcs, built):
     assert lib.gcs_b200_host_alloc(4096) is None  # no device: the caller falls back to ordinary memory
 
 
+def test_null_columns_only_where_the_shape_is_anchored(gcs, built):
+    """A NULL input column is a column of zeros, allowed only for the anchor columns of the
+    zero-fixed solvers (gcs_b200.h); anything else is GCS_E_INVALID - checked before any device is
+    touched, so it runs here."""
+    capi, synth = gcs.capi, gcs.synth
+    lib = capi.load()
+    allowed = {1: [0, 1, 4], 2: [0, 1, 3], 3: [], 4: [], 5: [1, 7, 10, 11]}
+    for kind, cols in allowed.items():
+        assert [c for c in range(capi.IN_COLS[kind]) if lib.gcs_b200_column_may_be_null(kind, c)] == cols
+        for c in range(capi.IN_COLS[kind]):
+            hb = synth.make(kind, 4).alloc_outputs()
+            hb.cols[c] = None
+            cb = hb.cbatch()
+            rc = lib.gcs_b200_solve_host(C.byref(cb), 0)
+            if c in cols:
+                assert rc != capi.GCS_E_INVALID  # accepted by validation (then: no device here, or solved)
+            else:
+                assert rc == capi.GCS_E_INVALID and b"anchor" in lib.gcs_b200_last_error()
+
+
+def test_library_is_built_from_the_sources_in_the_tree(gcs, built):
+    """gcs_b200_version() carries the hash of csrc/*, the header and the flags it was compiled
+    from: a stale libgcs_b200.so (the .so is not in git but travels to the GPU box) fails here."""
+    import __graft_entry__ as g
+    assert g.cuda_source_hash().encode() in gcs.capi.load().gcs_b200_version()
+
+
 def test_product_does_not_reference_the_oracle():
     """The oracle is test infrastructure: nothing under the package or include/ may name it."""
     pkg = os.path.join(ROOT, "2d_geometry_constraint_solver_b200")

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from util import assert_batches_identical, bits, rel_err
+from util import assert_batches_identical, assert_batches_within_contract, bits, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -391,3 +391,72 @@ def test_page_locked_columns_from_the_abi_allocator(gpu, gcs):
     finally:
         lib.gcs_b200_host_free(p)
     assert lib.gcs_b200_host_alloc(0) is None
+
+
+def test_null_anchor_columns_are_columns_of_zeros(gpu, gcs):
+    """Anchored shapes (ZeroFixedPoints point_point_solvers.cpp:48-50, ZeroFixedPPL
+    point_line_solvers.cpp:179-181, ZeroFixedLLPAngle line_angle_solvers.cpp:249-274): the columns
+    that are identically zero may be NULL at the ABI - not stored, not copied - and every kernel
+    variant returns what it returns for explicit zero columns, bit for bit."""
+    synth, capi = gcs.synth, gcs.capi
+    for kind, nulls in ((1, [0, 1, 4]), (2, [0, 1, 3]), (5, [1, 7, 10, 11])):
+        full = synth.make(kind, 40000)
+        even = np.arange(0, full.n, 2)  # the generators put the anchored shape on even indices
+        dense = full.take(even)
+        sparse = dense.anchored()
+        assert [c for c, col in enumerate(sparse.cols) if col is None] == nulls, kind
+        ref = O.solve(full.take(even).alloc_outputs())
+        for variant in (capi.VARIANT_STATIC, capi.VARIANT_SORTED, capi.VARIANT_REFILL, capi.VARIANT_PAIR):
+            sparse.variant = variant
+            capi.solve_host(sparse.alloc_outputs(), 0)
+            assert_batches_identical(sparse, ref, f"NULL anchor columns, kind {kind} variant {variant}")
+        for variant in (capi.VARIANT_CONTRACTED_STATIC, capi.VARIANT_CONTRACTED_SORTED):
+            sparse.variant = variant
+            capi.solve_host(sparse.alloc_outputs(), 0)
+            assert_batches_within_contract(sparse, ref, f"NULL anchor columns, kind {kind} variant {variant}")
+        # device-resident form
+        sparse.variant = capi.VARIANT_DEFAULT
+        db = capi.DeviceBatch(sparse, "cuda:0", want_cand=True)
+        db.solve()
+        got = db.to_host(full.take(even))
+        assert_batches_identical(got, ref, f"NULL anchor columns, device-resident, kind {kind}")
+    # a NULL column that is not an anchor column is refused
+    bad = synth.make(3, 16)
+    bad.cols[0] = None
+    with pytest.raises(capi.GcsError):
+        capi.solve_host(bad.alloc_outputs(), 0)
+
+
+def test_host_index_ranges_fill_their_rows_of_the_full_arrays(gpu, gcs):
+    """gcs_b200_solve_host_range_async (what gcs_b200_solve_sharded places on each device): ragged
+    index ranges of one batch, each with its own pipeline, write their rows of the caller's
+    arrays - outputs, explicit guesses, cand / iters / converged planes at the FULL batch's pitch."""
+    synth, capi = gcs.synth, gcs.capi
+    rng = np.random.default_rng(11)
+    for kind, n, ns in ((1, 70001, 2), (3, 33333, 8), (5, 50000, 2)):
+        a = synth.make(kind, n, n_seeds=ns) if ns != 2 else synth.make(kind, n)
+        if kind != 5:
+            a.guesses = np.ascontiguousarray(rng.uniform(-3e4, 3e4, size=(ns, 2, n)))
+        ref = O.solve(capi.HostBatch(a.kind, ns, a.cols, a.code, a.guesses).alloc_outputs())
+        a.alloc_outputs()
+        cuts = [0, 1, 4097, n // 2 + 3, n - 1, n]
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            capi.solve_host_range_async(a, 0, lo, hi - lo)
+        capi.wait(0)
+        assert_batches_identical(a, ref, f"index ranges, kind {kind}")
+        with pytest.raises(capi.GcsError):
+            capi.solve_host_range_async(a, 0, n - 5, 6)
+
+
+def test_sharded_solve_takes_guesses_and_candidate_planes(gpu, gcs):
+    synth, capi = gcs.synth, gcs.capi
+    ndev = capi.load().gcs_b200_device_count()
+    capi.init(list(range(ndev)))
+    rng = np.random.default_rng(12)
+    n = 60001
+    a = synth.make_pp(n)
+    a.guesses = np.ascontiguousarray(rng.uniform(-3e4, 3e4, size=(2, 2, n)))
+    capi.solve_sharded(a.alloc_outputs(), ndev)
+    ref = O.solve(capi.HostBatch(a.kind, 2, a.cols, a.code, a.guesses).alloc_outputs())
+    assert_batches_identical(a, ref, f"sharded with guesses over {ndev} devices")
+    capi.init([0])

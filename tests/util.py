@@ -33,7 +33,7 @@ def assert_batches_within_contract(got, ref, what="", rel=1e-9):
     assert np.array_equal(got.converged, ref.converged), f"{what}: converged flags differ"
     assert np.array_equal(got.root_index, ref.root_index), f"{what}: root index differs at {np.nonzero(got.root_index != ref.root_index)[0][:8]}"
     with np.errstate(invalid="ignore", over="ignore"):
-        finite_cols = [np.where(np.isfinite(c), np.abs(c), 0.0) for c in ref.cols]
+        finite_cols = [np.where(np.isfinite(c), np.abs(c), 0.0) for c in ref.dense_cols()]
         scale = np.max(np.stack(finite_cols), axis=0)
 
         def close(a, b, sc):
