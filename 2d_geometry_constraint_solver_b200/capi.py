@@ -80,7 +80,7 @@ EXPORTS = [
     "gcs_b200_solve_host", "gcs_b200_solve_host_async", "gcs_b200_wait", "gcs_b200_solve_sharded", "gcs_b200_launch_count", "gcs_b200_kernel_name", "gcs_b200_default_variant",
     "gcs_b200_fp64_probe", "gcs_b200_synth_pp", "gcs_b200_selftest", "gcs_b200_host_alloc", "gcs_b200_host_free",
     "gcs_b200_contracted_stats", "gcs_b200_contracted_stats_ex", "gcs_b200_column_may_be_null", "gcs_b200_host_alloc_ex",
-    "gcs_b200_solve_host_range_async", "gcs_b200_pcie_probe",
+    "gcs_b200_solve_host_range_async", "gcs_b200_pcie_probe", "gcs_b200_solve_many",
 ]
 
 
@@ -100,6 +100,7 @@ def load():
     lib.gcs_b200_last_error.restype = C.c_char_p
     lib.gcs_b200_version.restype = C.c_char_p
     lib.gcs_b200_solve.argtypes = [C.POINTER(CBatch), C.c_int, C.c_void_p]
+    lib.gcs_b200_solve_many.argtypes = [C.POINTER(C.POINTER(CBatch)), C.c_int, C.c_int, C.c_void_p]
     lib.gcs_b200_solve_host.argtypes = [C.POINTER(CBatch), C.c_int]
     lib.gcs_b200_solve_sharded.argtypes = [C.POINTER(CBatch), C.c_int]
     lib.gcs_b200_solve_host_async.argtypes = [C.POINTER(CBatch), C.c_int]
@@ -302,6 +303,16 @@ def solve_sharded(batch: HostBatch, n_dev: int) -> HostBatch:
     cb = batch.cbatch()
     check(load().gcs_b200_solve_sharded(C.byref(cb), n_dev), "gcs_b200_solve_sharded")
     return batch
+
+
+def solve_many(device_batches, stream=None):
+    """gcs_b200_solve_many over DeviceBatch objects of one device, on `stream` (default: torch's current)."""
+    first = device_batches[0]
+    torch = first.torch
+    s = torch.cuda.current_stream(first.device) if stream is None else stream
+    idx = first.device.index if first.device.index is not None else torch.cuda.current_device()
+    arr = (C.POINTER(CBatch) * len(device_batches))(*[C.pointer(b._cb) for b in device_batches])
+    check(load().gcs_b200_solve_many(arr, len(device_batches), idx, C.c_void_p(s.cuda_stream)), "gcs_b200_solve_many")
 
 
 class DeviceBatch:

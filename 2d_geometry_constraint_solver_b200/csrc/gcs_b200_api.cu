@@ -62,13 +62,23 @@ struct DeviceState {
     int device = -1;
     int sm_count = 0;
     unsigned* tickets = nullptr;  // kTicketSlots x 2 counters, zero between launches
+    // a column of zeros the kernels read in place of the ABI's NULL anchor columns (grown on demand,
+    // read-only afterwards: a few MB that stay in L2 and are shared by every NULL column of a batch)
+    double* zeros = nullptr;
+    size_t zeros_n = 0;
     std::atomic<unsigned> ticket_rr { 0 };
     // staging arena for the host-buffer entry points
-    std::mutex arena_mu;
+    std::mutex arena_mu, zeros_mu;
     unsigned char* arena = nullptr;
     size_t arena_bytes = 0;
     size_t arena_used = 0;        // bump pointer; reset when the device is drained
     bool in_flight = false;       // host-buffer work enqueued and not yet waited for
+    // gcs_b200_solve_many: launches beyond the first of a job go to these, forked from / joined
+    // back into the caller's stream
+    static constexpr int kSide = 3;
+    std::mutex side_mu;
+    cudaStream_t side[kSide] = {};
+    cudaEvent_t side_fork = nullptr, side_join[kSide] = {};
     cudaStream_t stream = nullptr;  // kernels
     cudaStream_t h2d = nullptr;     // input copies  (own copy engine)
     cudaStream_t d2h = nullptr;     // output copies (the other copy engine)
@@ -120,6 +130,11 @@ int prepare_device(DeviceState* d)
     CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&d->h2d, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&d->d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < DeviceState::kSide; ++k) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&d->side[k], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&d->side_join[k], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&d->side_fork, cudaEventDisableTiming));
     return GCS_OK;
 }
 
@@ -139,6 +154,36 @@ extern "C" int gcs_b200_column_may_be_null(int kind, int c)
 }
 
 namespace {
+
+// device `d` current.  The zero column covers at least n sub-systems.
+int ensure_zeros(DeviceState* d, size_t n)
+{
+    std::lock_guard<std::mutex> lk(d->zeros_mu);
+    if (n <= d->zeros_n) return GCS_OK;
+    size_t want = (size_t)1 << 16;
+    while (want < n) want <<= 1;
+    if (d->zeros) {
+        CUDA_TRY(cudaDeviceSynchronize());  // launches in flight may still read the old one
+        CUDA_TRY(cudaFree(d->zeros));
+        d->zeros = nullptr, d->zeros_n = 0;
+    }
+    if (cudaMalloc(&d->zeros, want * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(GCS_E_NOMEM, "cudaMalloc(%zu) for the zero column failed", want * sizeof(double));
+    }
+    CUDA_TRY(cudaMemsetAsync(d->zeros, 0, want * sizeof(double), d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    d->zeros_n = want;
+    return GCS_OK;
+}
+
+bool has_null_column(const gcs_b200_batch* b)
+{
+    const int nin = gcs_b200_kind_in_cols(b->kind);
+    for (int c = 0; c < nin; ++c)
+        if (!b->in[c]) return true;
+    return false;
+}
 
 int validate(const gcs_b200_batch* b)
 {
@@ -295,7 +340,14 @@ int solve_dev(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cudaSt
 int solve_on(DeviceState* d, const gcs_b200_batch* b, cudaStream_t st)
 {
     if (b->n == 0) return GCS_OK;
-    return solve_dev(d, b, to_dev(b), st);
+    BatchDev p = to_dev(b);
+    if (has_null_column(b)) {
+        const int rc = ensure_zeros(d, (size_t)b->n);
+        if (rc != GCS_OK) return rc;
+        for (int c = 0; c < gcs_b200_kind_in_cols(b->kind); ++c)
+            if (!p.in[c]) p.in[c] = d->zeros;
+    }
+    return solve_dev(d, b, p, st);
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -435,8 +487,14 @@ void gcs_b200_shutdown(void)
             if (d->stream) cudaStreamSynchronize(d->stream), cudaStreamDestroy(d->stream);
             if (d->h2d) cudaStreamSynchronize(d->h2d), cudaStreamDestroy(d->h2d);
             if (d->d2h) cudaStreamSynchronize(d->d2h), cudaStreamDestroy(d->d2h);
+            for (int k = 0; k < DeviceState::kSide; ++k) {
+                if (d->side[k]) cudaStreamSynchronize(d->side[k]), cudaStreamDestroy(d->side[k]);
+                if (d->side_join[k]) cudaEventDestroy(d->side_join[k]);
+            }
+            if (d->side_fork) cudaEventDestroy(d->side_fork);
             for (cudaEvent_t e : d->events) cudaEventDestroy(e);
             if (d->tickets) cudaFree(d->tickets);
+            if (d->zeros) cudaFree(d->zeros);
             if (d->arena) cudaFree(d->arena);
         }
         delete d;
@@ -487,6 +545,56 @@ int gcs_b200_solve(const gcs_b200_batch* b, int device, void* cuda_stream)
     CUDA_TRY(cudaGetDevice(&cur));
     if (cur != device) CUDA_TRY(cudaSetDevice(device));
     rc = solve_on(d, b, static_cast<cudaStream_t>(cuda_stream));
+    if (cur != device && cur >= 0) cudaSetDevice(cur);
+    return rc;
+}
+
+int gcs_b200_solve_many(const gcs_b200_batch* const* batches, int count, int device, void* cuda_stream)
+{
+    if (count < 0 || (count > 0 && !batches)) return fail(GCS_E_INVALID, "bad batch list");
+    for (int i = 0; i < count; ++i) {
+        const int rc = validate(batches[i]);
+        if (rc != GCS_OK) return rc;
+        if (batches[i]->mem != GCS_MEM_DEVICE) return fail(GCS_E_INVALID, "gcs_b200_solve_many needs device pointers (batch %d)", i);
+    }
+    if (count == 0) return GCS_OK;
+    if (count == 1) return gcs_b200_solve(batches[0], device, cuda_stream);
+    int rc = ensure_init();
+    if (rc != GCS_OK) return rc;
+    DeviceState* d = find_dev(device);
+    if (!d) return fail(GCS_E_NO_DEVICE, "device %d not present", device);
+    rc = prepare_device(d);
+    if (rc != GCS_OK) return rc;
+    int cur = -1;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != device) CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t user = static_cast<cudaStream_t>(cuda_stream);
+    {
+        // The batches are independent jobs: the first stays on the caller's stream, the others go
+        // round-robin to side streams that start where the caller's stream stands now and are
+        // joined back into it, so the call is stream-ordered as a whole while one kernel's ramp-up,
+        // drain and literal re-runs are covered by its neighbours' throughput work.
+        std::lock_guard<std::mutex> lk(d->side_mu);
+        bool used[DeviceState::kSide] = {};
+        rc = cudaEventRecord(d->side_fork, user) == cudaSuccess ? GCS_OK : fail(GCS_E_CUDA, "event record failed");
+        for (int i = 0; i < count && rc == GCS_OK; ++i) {
+            cudaStream_t st = user;
+            if (i > 0) {
+                const int k = (i - 1) % DeviceState::kSide;
+                st = d->side[k];
+                if (!used[k]) {
+                    if (cudaStreamWaitEvent(st, d->side_fork, 0) != cudaSuccess) rc = fail(GCS_E_CUDA, "stream wait failed");
+                    used[k] = true;
+                }
+            }
+            if (rc == GCS_OK) rc = solve_on(d, batches[i], st);
+        }
+        for (int k = 0; k < DeviceState::kSide; ++k) {
+            if (!used[k]) continue;  // joined even after a failure: nothing may be left running unordered
+            if (cudaEventRecord(d->side_join[k], d->side[k]) != cudaSuccess || cudaStreamWaitEvent(user, d->side_join[k], 0) != cudaSuccess)
+                if (rc == GCS_OK) rc = fail(GCS_E_CUDA, "joining the side streams failed");
+        }
+    }
     if (cur != device && cur >= 0) cudaSetDevice(cur);
     return rc;
 }
@@ -702,6 +810,10 @@ int record_pipeline(DeviceState* d, const gcs_b200_batch* b, size_t off, int64_t
     }
     int rc = ensure_events(d, 2 * ranges.size());
     if (rc != GCS_OK) return rc;
+    if (npres < nin) {
+        rc = ensure_zeros(d, (size_t)step + 65536);
+        if (rc != GCS_OK) return rc;
+    }
     // the one-byte code column goes up whole, ahead of the first range: one copy instead of one
     // per range (every copy costs a few microseconds of engine time whatever its size)
     CUDA_TRY(cudaMemcpyAsync(dcode, b->code + first, n, cudaMemcpyHostToDevice, d->h2d));
@@ -733,7 +845,7 @@ int record_pipeline(DeviceState* d, const gcs_b200_batch* b, size_t off, int64_t
         CUDA_TRY(cudaStreamWaitEvent(d->stream, up, 0));
         BatchDev p;
         memset(&p, 0, sizeof(p));
-        for (int c = 0; c < nin; ++c) p.in[c] = din[c] ? din[c] + lo : nullptr;
+        for (int c = 0; c < nin; ++c) p.in[c] = din[c] ? din[c] + lo : d->zeros;
         p.code = dcode + lo;
         p.guesses = dguess ? dguess + lo : nullptr;
         for (int c = 0; c < nout; ++c) p.out[c] = dout[c] + lo;

@@ -36,7 +36,7 @@
 namespace gcsk {
 
 struct BatchDev {
-    const double* in[GCS_MAX_IN_COLS];
+    const double* in[GCS_MAX_IN_COLS];  // never null here: the ABI's NULL anchor columns arrive as the device's zero column
     const uint8_t* code;
     const double* guesses;  // [NS][2][n] or null
     double* out[GCS_MAX_OUT_COLS];
@@ -49,15 +49,6 @@ struct BatchDev {
 };
 
 constexpr unsigned kFull = 0xffffffffu;
-
-// Input column c of sub-system i.  A NULL column is a column of zeros (gcs_b200.h: the anchored
-// shapes of the zero-fixed solvers place elements at the origin / on the x axis, so those columns
-// need not exist, let alone cross PCIe); the test is uniform over the launch.
-__device__ __forceinline__ double ldcol(const BatchDev& p, int c, long long i)
-{
-    const double* q = p.in[c];
-    return q ? __ldg(q + i) : 0.0;
-}
 
 __device__ __forceinline__ unsigned lanemask_lt()
 {
@@ -93,7 +84,7 @@ __global__ void __launch_bounds__(128, RLX ? GCS_STATIC_RLX_MINB : GCS_STATIC_MI
 
     double k[S::kCols];
 #pragma unroll
-    for (int c = 0; c < S::kCols; ++c) k[c] = ldcol(p, c, i);
+    for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + i);
     const uint8_t code = p.code ? __ldg(p.code + i) : (uint8_t)GCS_MAKE_CODE(0, 0, 0);
 
     S sys;
@@ -185,7 +176,7 @@ __global__ void __launch_bounds__(128, GCS_PAIR_MINB) newton_pair_kernel(const B
     if (i >= p.n) return;
     double k[S::kCols];
 #pragma unroll
-    for (int c = 0; c < S::kCols; ++c) k[c] = ldcol(p, c, i);
+    for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + i);
     const uint8_t code = p.code ? __ldg(p.code + i) : (uint8_t)GCS_MAKE_CODE(0, 0, 0);
     S sys;
     sys.load(k);
@@ -338,7 +329,7 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
             const long long gi = base + sub;
             double k[S::kCols];
 #pragma unroll
-            for (int c = 0; c < S::kCols; ++c) k[c] = ldcol(p, c, gi);
+            for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + gi);
             if constexpr (RLX) {
                 Rsys<KIND> rs;
                 RelaxGuard g;
@@ -448,7 +439,7 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                 const int sub = r & (TILE - 1);
                 double k[S::kCols];
 #pragma unroll
-                for (int c = 0; c < S::kCols; ++c) k[c] = ldcol(p, c, base + sub);  // only what load() reads survives
+                for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + base + sub);  // only what load() reads survives
                 if constexpr (RLX) {
                     double x = s_x[r], y = s_y[r];
                     int it = s_it[r], conv = 1;
@@ -493,7 +484,7 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
     uint8_t coded = (uint8_t)GCS_MAKE_CODE(0, 0, 0);
     if (tid < cnt) {
 #pragma unroll
-        for (int c = 0; c < S::kCols; ++c) kd[c] = ldcol(p, c, base + tid);
+        for (int c = 0; c < S::kCols; ++c) kd[c] = __ldg(p.in[c] + base + tid);
         if (p.code) coded = __ldg(p.code + base + tid);
     }
     __syncthreads();
@@ -630,16 +621,6 @@ __global__ void __launch_bounds__(WARPS * 32)
         mbar_init(&sl.bar[0], 1);
         mbar_init(&sl.bar[1], 1);
     }
-    // NULL columns (all zeros) never arrive by TMA: their slab rows are zeroed once, here
-    int present_cols = 0;
-#pragma unroll
-    for (int c = 0; c < S::kCols; ++c) {
-        if (p.in[c]) {
-            ++present_cols;
-        } else {
-            for (int j = lane; j < CH; j += 32) sl.in[0][c][j] = 0.0, sl.in[1][c][j] = 0.0;
-        }
-    }
     // make the barrier initialisation visible to the async proxy
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
@@ -652,16 +633,16 @@ __global__ void __launch_bounds__(WARPS * 32)
         if (bulk) {
             if (lane == 0) {
                 fence_proxy_async();  // earlier generic reads of this buffer precede the async writes
-                mbar_expect_tx(&sl.bar[buf], (uint32_t)(present_cols * CH * 8 + CH));
+                mbar_expect_tx(&sl.bar[buf], (uint32_t)(S::kCols * CH * 8 + CH));
 #pragma unroll
                 for (int c = 0; c < S::kCols; ++c)
-                    if (p.in[c]) tma_bulk_g2s(&sl.in[buf][c][0], p.in[c] + base, CH * 8, &sl.bar[buf]);
+                    tma_bulk_g2s(&sl.in[buf][c][0], p.in[c] + base, CH * 8, &sl.bar[buf]);
                 tma_bulk_g2s(&sl.code[buf][0], p.code + base, CH, &sl.bar[buf]);
             }
         } else {
             for (int j = lane; j < cnt; j += 32) {
 #pragma unroll
-                for (int c = 0; c < S::kCols; ++c) sl.in[buf][c][j] = ldcol(p, c, base + j);
+                for (int c = 0; c < S::kCols; ++c) sl.in[buf][c][j] = __ldg(p.in[c] + base + j);
                 sl.code[buf][j] = p.code ? __ldg(p.code + base + j) : (uint8_t)GCS_MAKE_CODE(0, 0, 0);
             }
         }

@@ -63,6 +63,10 @@ namespace gcsk {
 
 constexpr int kRelaxCap = 64;  // updates a run may take on the closed-form path (G4)
 constexpr int kBounce = 4 << 20;  // (G2) four binades of growth of |det| over its running minimum
+#ifndef GCS_CAREFUL_BINADES
+#define GCS_CAREFUL_BINADES 4
+#endif
+constexpr int kCarefulBinades = GCS_CAREFUL_BINADES;  // careful mode reaches this many binades under the (G1) line 2^-10 dr (0: off)
 
 // How often the guards hand work to the literal code (read by gcs_b200_contracted_stats[_ex]), by
 // reason (kWhy*): touched on the rare path only.
@@ -315,10 +319,14 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
     // and then contracted) but has none to amplify, and |det| growing from the seed to the
     // landing point is routine (a seed that happens to lie near the singular line).
     int dmin = 0x7fffffff, grow = 0, d1 = 0x7fffffff;
-    if (dmin_io && it > 0) dmin = *dmin_io;  // a run continued from an earlier stretch (sorted kernel)
+    // smallest length (high word) of the updates BEFORE the latest one: what lets a run whose
+    // conditioning falls under the (G1) line late be certified after the fact (careful mode below)
+    // instead of being redone.  Unknown (0) for a run continued from an earlier stretch.
+    int mmin = 0x7fffffff;
+    if (dmin_io && it > 0) dmin = *dmin_io, mmin = 0;  // a run continued from an earlier stretch (sorted kernel)
     int state = kRlxRunning;
     if (it >= limit) return (limit >= kRelaxCap) ? kRlxUncertain + kWhyCap : kRlxRunning;
-    int mh, dh;
+    int mh = 0x7fffffff, dh;
     double s0, s1, det;
     // one closed-form update; leaves mh = larger high word of the update's components, dh = hi(|det|)
     auto update = [&](auto from_seed) {
@@ -355,26 +363,62 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
         d1 = dh;
         in_loop = (unsigned)(mh - g.hi_h) < span && it < limit;
     }
+    // Careful mode (the static kernels only: whole runs, every update's length on record).  A run
+    // whose |det J| falls under the (G1) line 2^-10 dr - flat triangles, lines that nearly touch
+    // their circle - used to be redone literally: one long chain of dependent FP64 operations that
+    // outlived its launch (the re-run tail).  Its decisions are still certifiable: the
+    // second-level margin of (G3) already scales with the actual conditioning, 2^-44 S dr/|det|.
+    // So down to |det| >= 2^-14 dr (the coordinates differ by ~8 (dr/|det|) 2^-52 S between the two
+    // arithmetics: 2^-35 S there, a factor 30 inside the 1e-9 tolerance; past it: literal) the run continues with EVERY update decided by that margin test, provided
+    // no earlier update - decided by the first-level band, which is only wide enough for
+    // dr/|det| <= 2^10 - was shorter than tol + the margin at the floor (mmin).
+    constexpr bool kCareful = !kTrack;
+    bool careful = false;
 #pragma unroll 1
     for (;;) {
-        // hot loop: one update per trip, left when the update is no longer longer than the
-        // threshold for certain (or is non-finite / huge), or at the limit
-        if (in_loop) {
+        if (!careful) {
+            // hot loop: one update per trip, left when the update is no longer longer than the
+            // threshold for certain (or is non-finite / huge), or at the limit
+            if (in_loop) {
 #pragma unroll 1
-            do {
-                update(std::false_type {});
-                grow = max(grow, dh - dmin);  // (G2), in high-word units (2^20 per binade)
-                dmin = min(dmin, dh);
-            } while ((unsigned)(mh - g.hi_h) < span && it < limit);
+                do {
+                    if constexpr (kCareful) mmin = min(mmin, mh);
+                    update(std::false_type {});
+                    grow = max(grow, dh - dmin);  // (G2), in high-word units (2^20 per binade)
+                    dmin = min(dmin, dh);
+                } while ((unsigned)(mh - g.hi_h) < span && it < limit);
+            }
+            in_loop = true;
+            // ---- rare from here ----
+            if ((unsigned)(mh - g.hi_h) < span) break;  // limit reached, every update longer than the threshold
+        } else {
+            if (it >= limit) break;
+            mmin = min(mmin, mh);
+            update(std::false_type {});
+            grow = max(grow, dh - dmin);
+            dmin = min(dmin, dh);
         }
-        in_loop = true;
-        // ---- rare from here ----
-        if ((unsigned)(mh - g.hi_h) < span) break;  // limit reached, every update longer than the threshold
-        if (mh >= RelaxGuard::kBigH || min(dmin, d1) < g.det_h || grow > kBounce) {  // (G4) / (G1) / (G2)
-            state = kRlxUncertain + (mh >= RelaxGuard::kBigH ? kWhyHuge : min(dmin, d1) < g.det_h ? kWhyCond : kWhyBounce);
+        const int dlow = min(dmin, d1);
+        if (mh >= RelaxGuard::kBigH || grow > kBounce) {  // (G4) / (G2)
+            state = kRlxUncertain + (mh >= RelaxGuard::kBigH ? kWhyHuge : kWhyBounce);
             break;
         }
-        if (mh < g.lo_h) {
+        if (dlow < g.det_h) {  // (G1)
+            bool ok = kCareful && kCarefulBinades > 0 && limit >= kRelaxCap && dlow >= g.det_h - (kCarefulBinades << 20);  // |det| >= 2^-14 dr
+            if (ok && !careful) {
+                // every earlier update longer, for certain, than tol + the widest margin careful mode admits
+                const double wide = g.carry < 0.5
+                    ? (kTol * (1.0 + 0x1p-39) + (double)(1 << (kCarefulBinades + 2)) * (g.band - 0x1p-16 * kTol)) / (1.0 - g.carry)
+                    : 0x1p900;
+                ok = mmin > hi_floor(wide * (1.0 / Rsys<KIND>::kStepScale)) + 1;
+            }
+            if (!ok) {
+                state = kRlxUncertain + kWhyCond;
+                break;
+            }
+            careful = true;
+        }
+        if (!careful && mh < g.lo_h) {
             state = kRlxConverged;
             break;
         }
@@ -385,8 +429,11 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
         }
         if (it >= limit) break;  // not converged for certain, and out of updates
     }
-    if (state == kRlxRunning && (min(dmin, d1) < g.det_h || grow > kBounce || limit >= kRelaxCap))
-        state = kRlxUncertain + (min(dmin, d1) < g.det_h ? kWhyCond : grow > kBounce ? kWhyBounce : kWhyCap);
+    if (state == kRlxRunning) {
+        const int dlow = min(dmin, d1);
+        if ((dlow < g.det_h && !careful) || grow > kBounce || limit >= kRelaxCap)
+            state = kRlxUncertain + ((dlow < g.det_h && !careful) ? kWhyCond : grow > kBounce ? kWhyBounce : kWhyCap);
+    }
     if (dmin_io) *dmin_io = dmin;
     return state;
 }

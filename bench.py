@@ -4,32 +4,40 @@
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, host cores
 
-Workload (config.workload): BASELINE.json configs[1] — 2^20 independent synthetic triangle
-clusters per GPU, half K1 (distance+distance: ZeroFixedPoints / TwoFixedPointsDistance shapes),
-half K5 (angle + unit normal), one solve2D-equivalent each (2 seeds, reference defaults) + root
-selection (+ line reconstruction for K5).  A step = one pass over that batch = one K1 launch +
+Workload of the line (config.workload): BASELINE.json configs[1] — 2^20 independent synthetic
+triangle clusters per GPU, half K1 (distance+distance: ZeroFixedPoints / TwoFixedPointsDistance
+shapes), half K5 (angle + unit normal), one solve2D-equivalent each (2 seeds, reference defaults) +
+root selection (+ line reconstruction for K5).  A step = one pass over that batch = one K1 launch +
 one K5 launch.  Weak scaling: rank r owns instances [r*2^19, (r+1)*2^19) of each kind's index
 space; no data-path collective (NCCL only carries the barrier and the max-over-ranks of the time).
 
-`value`   whole-job solves/s with the batch resident in HBM; per-launch CUDA events on the
-          launching stream, summed over the steps, max over ranks; L2 flushed between steps.
-`e2e`     the same metric through the host-buffer C-ABI calls (gcs_b200_solve_host_async per kind
-          + gcs_b200_wait): pinned HOST inputs and outputs, H2D + kernels + D2H inside the region.
-`bit_identical` (contracted variants, the default) the same step with the library-default kernels
-          (bit-identical to the reference arithmetic), timed the same way in the same run, and the
-          contract between the two checked on the whole batch (a failed check makes the line report
-          the bit-identical kernels and name the violation: no number from unverified results).
+`value`   whole-job solves/s with the batch resident in HBM; a step is one gcs_b200_solve_many call
+          (both launches as one job), CUDA events around it on the launching stream, summed over
+          the steps, max over ranks; L2 flushed between steps.  `sequential_launches` = the two
+          launches one after the other, each between its own events (what `roofline` is quoted on).
+          Kernel class: config.variant (the opt-in contracted kernels by default; the library
+          default = bit-identical kernels is timed beside it under `bit_identical`).
+`e2e`     the same metric through the host-buffer C-ABI calls (gcs_b200_solve_host_async per batch
+          + gcs_b200_wait): pinned HOST inputs and outputs, H2D + kernels + D2H inside the region;
+          batches in the shape the packer emits them (anchor columns of the zero-fixed solvers
+          NULL); `e2e.pcie` = copy-only ceiling of the same byte counts, probed in the same run.
 `roofline` the dominant kernel (K1): algorithmic FP64 flops (work model of DESIGN.md section 3,
           from the MEASURED iteration counts) / its event-timed duration, against the DFMA peak
           measured live by gcs_b200_fp64_probe (MEASURED_PEAKS.json has no FP64 figure); the HBM
           side is reported beside it against MEASURED_PEAKS.json.
+`configs` the other BASELINE configs, each measured in this run: multistart8 (configs[2]),
+          sweep64m (configs[4]: 2^26 instances sharded over the N ranks, strong scaling), kinds
+          (K2 / K3 / K4 kernel lines; K4 is the HBM-bound kind), sketch100k (configs[3] through
+          GeometricConstraintSystem), sharded (N > 1: gcs_b200_solve_sharded in ONE process over
+          the N devices, checked against one device).
 `cpu_baseline` / `--impl reference`  the reference's own solve2D + primitives + heuristics sources
           (oracle/_ref, built from /root/reference against stand-in Eigen/autodiff headers) where
-          that library is present, else the restated C oracle; all host threads, bounded sample.
+          that library is present, else the restated C oracle; all host threads.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import importlib
 import json
 import os
@@ -47,6 +55,8 @@ METRIC = "subsystem Newton solves/sec"
 UNIT = "solves/s"
 WORKLOAD = ("configs[1]: 2^20 synthetic triangle clusters per GPU (2^19 K1 distance-distance + 2^19 K5 "
             "angle-normal), 2 seeds each, FP64")
+VARIANT_NAMES = {0: "default", 1: "static", 2: "refill", 3: "sorted", 4: "pair", 5: "contracted", 6: "contracted-static",
+                 7: "contracted-sorted"}
 
 
 def parse():
@@ -60,12 +70,12 @@ def parse():
                          "(6 static / 7 sorted); 0 the library default = bit-identical kernels (1 static, 2 refill, "
                          "3 sorted, 4 pair).  With a contracted variant the bit-identical default is timed beside it.")
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="solves per GPU (default 2^20)")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only the configs[1] line (skip the `configs` key)")
     ap.add_argument("--workload", default="configs1", choices=["configs1", "multistart8", "sweep64m"],
-                    help="configs1 = the bench line (BASELINE configs[1]); multistart8 = configs[2] (2^20 K1 x 8 seeds per "
-                         "GPU, weak); sweep64m = configs[4] (2^26 perturbed K1 instances generated on the device, sharded "
-                         "over the ranks, strong)")
+                    help="configs1 = the bench line (BASELINE configs[1], with the other configs under `configs`); "
+                         "multistart8 / sweep64m: that config alone as the line")
     return ap.parse_args()
 
 
@@ -79,14 +89,20 @@ def load_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic():
-    """dram bytes per launch of the dominant kernel from the last committed `ncu --set full`
-    capture (profiles/traffic.json), or None."""
+def load_traffic(lib):
+    """Per-launch DRAM bytes / executed flops of the dominant kernel from the last committed
+    `ncu --set full` capture (profiles/traffic.json).  The capture names the source hash of the
+    library it was taken from; `stale` says whether the library running now is another build."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p))
+        t = json.load(open(p))
     except Exception:
-        return {}
+        return {}, None
+    now = lib.gcs_b200_version().decode()
+    stale = None
+    if t.get("_src_hash"):
+        stale = t["_src_hash"] not in now
+    return t, stale
 
 
 class ClockSampler:
@@ -162,6 +178,18 @@ def make_batches(synth, n, rank):
     return [synth.make_pp(half, first=first), synth.make_ang(half, first=first)]
 
 
+def base_config(args):
+    """`config` is built from the command line alone, so both arms print the same dict (the driver
+    compares them); what a run found out about itself goes under `run`."""
+    v = args.variant
+    return {"workload": WORKLOAD, "solves_per_gpu": args.n, "kinds": "K1 x n/2 + K5 x n/2", "seeds": 2, "dtype": "f64",
+            "l2": "GPU arm: 256 MiB flush write between timed steps; CPU arm: a step's 113 MB of columns exceed the host caches",
+            "gpu_kernel_class": (f"{VARIANT_NAMES.get(v, v)}: the opt-in GCS_VARIANT_CONTRACTED kernels (iteration counts, flags, roots "
+                                 "identical to the reference, coordinates to 1e-9) - NOT the library default; the default bit-identical "
+                                 "kernels are timed in the same run under `bit_identical`" if v >= 5 else
+                                 f"{VARIANT_NAMES.get(v, v)}: bit-identical to the reference arithmetic")}
+
+
 # --------------------------------------------------------------------------------------------
 # CPU leg: the reference's own sources where oracle/_ref exists, else the restated oracle
 # --------------------------------------------------------------------------------------------
@@ -183,15 +211,19 @@ def cpu_backend():
             "restated C oracle (oracle/gcs_oracle.c): oracle/_ref is not present on this box")
 
 
+def host_threads():
+    # every core this process may run on (torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant
+    # to use the whole host)
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 def cpu_rate(gcs, seconds, threads=0):
     """Solves/s of the CPU path on a bounded sample of the same workload (same generators, same
     K1/K5 mix), repeated until about `seconds` of wall time have been spent."""
     synth = gcs.synth
     kind, solve, cores, what = cpu_backend()
     if threads < 1:
-        # every core this process may run on (torchrun exports OMP_NUM_THREADS=1; the CPU arm is
-        # meant to use the whole host)
-        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        threads = host_threads()
     cores = threads
     m = 1 << 15
     bs = [synth.make_pp(m).alloc_outputs(), synth.make_ang(m).alloc_outputs()]
@@ -209,25 +241,108 @@ def cpu_rate(gcs, seconds, threads=0):
     return done / t_total, cores, kind, sample
 
 
+def faithful_rate(n_leaves=8192):
+    """The reference's REAL per-leaf path: classifyAndSolve on ConstraintGraphs of shared_ptr
+    elements (matches() probes, role assignment, solve2D through autodiff, heuristics, write-back,
+    the two std::cerr prints per leaf, here sent to /dev/null), one thread as in the reference.
+    n_leaves zero-fixed triangles (K1) + n_leaves zero-fixed line-line-point angle leaves (K5);
+    the timed call also builds each leaf's 3-node graph.  None where oracle/_ref is absent."""
+    try:
+        import ref_lib as R
+        if not R.available():
+            return None
+        import math
+        rng = np.random.default_rng(5)
+        el, lv = [], []
+        for i in range(n_leaves):
+            d = rng.uniform(10, 500)
+            px, py = rng.uniform(-300, 800), rng.uniform(5, 500) * (1 if rng.random() < 0.5 else -1)
+            pts = [(0.0, 0.0), (d, 0.0), (px, py)]
+            b = len(el)
+            el += [{"type": 0, "canvas": [float(x + 500), float(y + 500)]} for x, y in pts]
+            lv.append({"elems": [b, b + 1, b + 2], "edges": [
+                {"a": b, "b": b + 1, "type": 0, "value": float(d)},
+                {"a": b, "b": b + 2, "type": 0, "value": float(math.hypot(px, py))},
+                {"a": b + 1, "b": b + 2, "type": 0, "value": float(math.hypot(px - d, py))}]})
+        for i in range(n_leaves):
+            l1 = rng.uniform(50, 500)
+            ang = rng.uniform(math.radians(5), math.radians(175))
+            l2 = rng.uniform(50, 500)
+            ox, oy = rng.uniform(-100, 100), rng.uniform(-100, 100)
+            line1 = [0.0, 0.0, l1, 0.0]
+            line2 = [ox, oy, ox + l2 * math.cos(ang), oy + l2 * math.sin(ang)]
+            p = (rng.uniform(-200, 200), rng.uniform(20, 300))
+            ex, ey = line2[2] - line2[0], line2[3] - line2[1]
+            d2 = abs(ex * (p[1] - line2[1]) - ey * (p[0] - line2[0])) / math.hypot(ex, ey)
+            b = len(el)
+            el += [{"type": 1, "canvas": [float(v + 500) for v in line1]}, {"type": 1, "canvas": [float(v + 500) for v in line2]},
+                   {"type": 0, "canvas": [float(p[0] + 500), float(p[1] + 500)]}]
+            lv.append({"elems": [b, b + 1, b + 2], "edges": [
+                {"a": b, "b": b + 1, "type": 1, "value": float(ang), "flip": False},
+                {"a": b + 2, "b": b, "type": 0, "value": float(abs(p[1]))},
+                {"a": b + 2, "b": b + 1, "type": 0, "value": float(d2)}]})
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(2)
+        sys.stderr.flush()
+        os.dup2(devnull, 2)
+        try:
+            R.leaves_solve(el[:30], lv[:10])  # warm
+            t0 = time.perf_counter()
+            rc, status, _ = R.leaves_solve(el, lv)
+            dt = time.perf_counter() - t0
+        finally:
+            os.dup2(saved, 2)
+            os.close(devnull)
+            os.close(saved)
+        # the ctypes marshalling of the element / edge arrays happens inside leaves_solve too: time it alone and subtract
+        t1 = time.perf_counter()
+        import host_lib as H
+        H.to_c(el, [], R.RefElement, R.RefEdge)
+        H.to_c([], [e for lf in lv for e in lf["edges"]], R.RefElement, R.RefEdge)
+        H.from_c(el, H.to_c(el, [], R.RefElement, R.RefEdge)[0])
+        marshal = time.perf_counter() - t1
+        solve_s = max(dt - marshal, 1e-9)
+        ok = int(sum(1 for s in status if s == 0))
+        return {"value": 2 * n_leaves / solve_s, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": f"{n_leaves} ZeroFixedPointsTriangle + {n_leaves} ZeroFixedLLPAngleTriangle leaves through the reference's own "
+                          f"classifyAndSolve on ConstraintGraphs (its per-leaf std::cerr prints to /dev/null), single thread as the "
+                          f"reference runs; {solve_s:.2f} s after subtracting {marshal:.2f} s of Python marshalling; {ok} of "
+                          f"{2 * n_leaves} leaves returned Success; includes building each leaf's 3-node graph"}
+    except Exception as ex:  # pragma: no cover - diagnostic leg only
+        return {"error": repr(ex)[:200]}
+
+
 def run_reference(args, rank):
+    """--impl reference: the CPU path on the box's host cores, rank 0 only.  A step = the FULL
+    configs[1] batch (n/2 K1 + n/2 K5 solves) on all host threads; ms_per_step is measured."""
     if rank != 0:
         return
     gcs = importlib.import_module("2d_geometry_constraint_solver_b200")
-    n_steps = max(args.steps, 1)
-    per_step = min(max(args.cpu_seconds / (n_steps + args.warmup), 0.25), 20.0)
-    rates = []
-    desc = cores = kind = None
-    for i in range(args.warmup + n_steps):
-        r, cores, kind, desc = cpu_rate(gcs, per_step)
+    kind, solve, _, what = cpu_backend()
+    threads = host_threads()
+    n = args.n
+    bs = [b.alloc_outputs() for b in make_batches(gcs.synth, n, 0)]
+    for b in bs:
+        b.want_cand = False
+    ts = []
+    for i in range(args.warmup + max(args.steps, 1)):
+        t0 = time.perf_counter()
+        for b in bs:
+            solve(b, threads)
+        dt = time.perf_counter() - t0
         if i >= args.warmup:
-            rates.append(r)
-    v = float(np.mean(rates))
+            ts.append(dt)
+    total = float(np.sum(ts))
+    v = n * len(ts) / total
+    sample = f"{len(ts)} steps x ({n // 2} K1 + {n // 2} K5) solves = the full configs[1] batch per step, {threads} threads; {what}"
     out = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(ts) * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU path on the box's host cores, rank 0 only; each step is a bounded sample"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+        "config": base_config(args),
+        "note": "CPU path on the box's host cores, rank 0 only (one host serves all N GPUs: the value does not scale with N)",
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "cpu_baseline_faithful": faithful_rate(),
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -235,170 +350,368 @@ def run_reference(args, rank):
 
 
 # --------------------------------------------------------------------------------------------
-# the other BASELINE configs that are benchmarks (not the driver's bench line)
+# shared measurement helpers (GPU arm)
 # --------------------------------------------------------------------------------------------
-def run_extra(args, rank, local_rank, world):
-    import ctypes as C
-    import torch
-    import torch.distributed as dist
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    gcs = importlib.import_module("2d_geometry_constraint_solver_b200")
-    capi, synth = gcs.capi, gcs.synth
-    shard = importlib.import_module("2d_geometry_constraint_solver_b200.shard")
-    capi.init([local_rank])
-    lib = capi.load()
-    warmup = max(args.warmup, 3)
-    stream = torch.cuda.current_stream(dev)
-
-    def barrier():
+class Ctx:
+    def __init__(self, args, rank, local_rank, world):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.args, self.rank, self.local_rank, self.world = args, rank, local_rank, world
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.gloo = None
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.gloo = dist.new_group(backend="gloo")  # host-side waits that must not occupy the GPUs
+        self.gcs = importlib.import_module("2d_geometry_constraint_solver_b200")
+        self.capi, self.synth = self.gcs.capi, self.gcs.synth
+        self.capi.init([local_rank])
+        self.lib = self.capi.load()
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.warmup = max(args.warmup, 3)
+        self._dfma = None
 
-    if args.workload == "multistart8":
-        n_total, scaling = (1 << 20) * world, "weak"
-        n = 1 << 20
-        hb = synth.make_pp(n, first=rank * n, n_seeds=8)
-        hb.variant = args.variant
-        db = capi.DeviceBatch(hb, dev, want_cand=False, variant=args.variant)
-        name = "configs[2]: 2^20 K1 clusters per GPU x 8 initial guesses, orientation-based root selection"
-        gen = None
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def host_barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.gloo)
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([float(v)], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(self, ok):
+        t = self.torch.tensor([1 if ok else 0], device=self.dev, dtype=self.torch.int32)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return int(t.item()) == 1
+
+    def dfma_peak(self):
+        if self._dfma is None:
+            self._dfma = self.lib.gcs_b200_fp64_probe(self.local_rank, 0)
+        return self._dfma
+
+    def time_launches(self, dbs, steps, warmup=3):
+        """`steps` passes over the device-resident batches `dbs`, L2 flushed between passes, CUDA
+        events around every launch on the launching stream.  Returns ms[len(dbs)][steps]."""
+        torch = self.torch
+        for _ in range(warmup):
+            self.flush.fill_(1)
+            for d in dbs:
+                d.solve()
+        self.barrier()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(dbs) + 1)] for _ in range(steps)]
+        for k in range(steps):
+            self.flush.fill_(k & 0xFF)  # evict the batch from L2 between timed steps (outside the events)
+            evs[k][0].record(self.stream)
+            for j, d in enumerate(dbs):
+                d.solve()
+                evs[k][j + 1].record(self.stream)
+        self.barrier()
+        return np.array([[e[j].elapsed_time(e[j + 1]) for e in evs] for j in range(len(dbs))])
+
+    def contract_check(self, a, b):
+        """Contracted batch `a` against bit-identical batch `b` (same inputs), on the device."""
+        torch = self.torch
+        same = bool(torch.equal(a.iters, b.iters)) and bool(torch.equal(a.converged, b.converged)) \
+            and bool(torch.equal(a.root_index, b.root_index))
+        cols = [c.abs() for c in a.cols if c is not None]
+        scale = torch.clamp(torch.stack(cols).max(dim=0).values, min=1.0)
+        worst = 0.0
+        for x, y in zip(a.out, b.out):
+            worst = max(worst, float(((x - y).abs() / torch.maximum(scale, y.abs())).max().item()))
+        return same, worst
+
+    def rerun_stats(self, dbs):
+        st = (C.c_uint64 * 8)()
+        self.lib.gcs_b200_contracted_stats_ex(self.local_rank, st, 1)
+        for d in dbs:
+            d.solve()
+        self.lib.gcs_b200_contracted_stats_ex(self.local_rank, st, 1)
+        return {"runs_per_step": int(sum(d.n * d.n_seeds for d in dbs)), "conditioning": int(st[0]), "selection": int(st[1]),
+                "bounce": int(st[2]), "band": int(st[3]), "cap": int(st[4]), "non_finite": int(st[5])}
+
+
+def pinned_batch(ctx, h, want_flags):
+    """`h` (HostBatch, possibly with NULL anchor columns) re-homed in page-locked memory from the
+    library's own allocator: one [present columns][n] slab up, one [out columns][n] slab down."""
+    capi = ctx.capi
+    keep = []
+    pres = [c for c, col in enumerate(h.cols) if col is not None]
+    slab = capi.PinnedArray((len(pres), h.n)); keep.append(slab)
+    for j, c in enumerate(pres):
+        slab.array[j] = h.cols[c]
+    cols = [None] * len(h.cols)
+    for j, c in enumerate(pres):
+        cols[c] = slab.array[j]
+    code = capi.PinnedArray(h.n, np.uint8); keep.append(code)
+    code.array[...] = h.code
+    hb = capi.HostBatch(h.kind, h.n_seeds, cols, code.array, None, h.variant, want_cand=False)
+    oslab = capi.PinnedArray((capi.OUT_COLS[h.kind], h.n)); keep.append(oslab)
+    hb.out = [oslab.array[c] for c in range(oslab.array.shape[0])]
+    root = capi.PinnedArray(h.n, np.uint8); keep.append(root)
+    hb.root_index = root.array
+    hb.cand = None
+    if want_flags:
+        it = capi.PinnedArray((h.n_seeds, h.n), np.int16); keep.append(it)
+        cv = capi.PinnedArray((h.n_seeds, h.n), np.uint8); keep.append(cv)
+        hb.iters, hb.converged = it.array, cv.array
     else:
-        n_total, scaling = 1 << 26, "strong"
-        lo, hi = shard.shard_range(n_total, rank, world)
-        n = hi - lo
-        hb = synth.make_pp(1)  # descriptor template; the columns are generated on the device
-        db = capi.DeviceBatch.empty(capi.KIND_PP, 2, n, dev, variant=args.variant)
-        ptrs = (C.c_void_p * 6)(*[c.data_ptr() for c in db.cols])
+        hb.iters = hb.converged = None
+    hb._keep = keep
+    return hb
 
-        def gen():
-            capi.check(lib.gcs_b200_synth_pp(local_rank, C.c_void_p(stream.cuda_stream), synth.BASE_SEED, lo, n, 4096, ptrs,
-                                             C.c_void_p(db.code.data_ptr())), "gcs_b200_synth_pp")
-        gen()
-        name = ("configs[4]: parametric sweep, 2^26 K1 instances = 4096 base clusters x 16384 perturbations (+-5% on ra, rb, d), "
-                "generated on the device, sharded by index over the ranks")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for _ in range(warmup):
-        flush.fill_(1)
-        db.solve()
-    barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    l0 = lib.gcs_b200_launch_count()
-    barrier()
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)
-        evs[k][0].record(stream)
-        db.solve()
-        evs[k][1].record(stream)
-    barrier()
-    launches = lib.gcs_b200_launch_count() - l0
-    ms = np.array([a.elapsed_time(b) for a, b in evs])
-    t = torch.tensor([float(ms.sum())], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = n_total * args.steps / (total_ms * 1e-3)
-    # work of this rank's launch from its measured iteration counts (device-side reduction)
-    it = db.iters
-    w = float((it.to(torch.int64) + 1).sum().item()) * synth.F_EVAL[1] + n * synth.F_SELECT[1]
-    ach = w / (float(ms.mean()) * 1e-3) / 1e12
-    conv = float(db.converged.to(torch.float32).mean().item())
-    # contracted variants: the same batch through the bit-identical kernels, and the contract between
-    # the two checked on this rank's whole batch (device-side comparison)
+
+def batch_d2h_bytes(capi, b):
+    return capi.OUT_COLS[b.kind] * 8 * b.n + (b.n if b.root_index is not None else 0) \
+        + (b.n_seeds * 2 * b.n if b.iters is not None else 0) + (b.n_seeds * b.n if b.converged is not None else 0)
+
+
+def time_e2e(ctx, batches, steps):
+    """Wall-clock solves/s of `steps` passes: gcs_b200_solve_host_async per batch + gcs_b200_wait."""
+    capi = ctx.capi
+
+    def one():
+        for b in batches:
+            capi.solve_host_async(b, ctx.local_rank)
+        capi.wait(ctx.local_rank)
+
+    for _ in range(3):
+        one()
+    l1 = ctx.lib.gcs_b200_launch_count()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    ctx.barrier()
+    dt = time.perf_counter() - t0
+    launches = ctx.lib.gcs_b200_launch_count() - l1
+    return ctx.max_over_ranks(dt), dt, int(launches)
+
+
+# --------------------------------------------------------------------------------------------
+# the other BASELINE configs (each also runnable alone with --workload)
+# --------------------------------------------------------------------------------------------
+def bench_multistart(ctx, steps):
+    """configs[2]: 2^20 K1 clusters per GPU x 8 initial guesses, orientation-based root selection."""
+    capi, synth, args = ctx.capi, ctx.synth, ctx.args
+    n = 1 << 20
+    hb = synth.make_pp(n, first=ctx.rank * n, n_seeds=8)
+    hb.variant = args.variant
+    db = capi.DeviceBatch(hb, ctx.dev, want_cand=False, variant=args.variant)
+    l0 = ctx.lib.gcs_b200_launch_count()
+    ms = ctx.time_launches([db], steps)[0]
+    launches = ctx.lib.gcs_b200_launch_count() - l0
+    total_ms = ctx.max_over_ranks(float(ms.sum()))
+    out = _extra_line(ctx, db, ms, total_ms, n * ctx.world, n, "weak",
+                      "configs[2]: 2^20 K1 clusters per GPU x 8 initial guesses, orientation-based root selection", 8, launches, steps)
     contract = None
     if args.variant >= 5:
-        if gen is None:
-            db0 = capi.DeviceBatch(hb, dev, want_cand=False, variant=0)
-        else:
-            db0 = capi.DeviceBatch.empty(capi.KIND_PP, 2, n, dev, variant=0)
-            for dst, src in zip(db0.cols, db.cols):
-                dst.copy_(src)
-            db0.code.copy_(db.code)
-        db.solve()
+        db0 = capi.DeviceBatch(hb, ctx.dev, want_cand=False, variant=0)
+        ms0 = ctx.time_launches([db0], max(2, steps // 2), warmup=1)[0]
+        same, worst = ctx.contract_check(db, db0)
+        contract = {"iters_flags_roots_equal": same, "max_rel_coordinate_error": worst, "tolerance": 1e-9, "solves_compared": n,
+                    "bit_identical_launch_ms": float(ms0.mean())}
+        del db0
+    out["contract_check_rank0"] = contract
+    # end to end: pinned host columns -> results in pinned host memory
+    pb = pinned_batch(ctx, hb, want_flags=False)
+    e2e_steps = 4
+    t_max, _, _ = time_e2e(ctx, [pb], e2e_steps)
+    out["e2e"] = {"value": n * ctx.world * e2e_steps / t_max, "unit": UNIT, "h2d_bytes_per_step": pb.input_bytes(),
+                  "d2h_bytes_per_step": batch_d2h_bytes(capi, pb), "api": "gcs_b200_solve_host_async + gcs_b200_wait (pinned)"}
+    return out
+
+
+def bench_sweep(ctx, steps):
+    """configs[4]: 2^26 perturbed K1 instances generated on the device, sharded by index over the ranks."""
+    capi, synth, args = ctx.capi, ctx.synth, ctx.args
+    torch = ctx.torch
+    shard = importlib.import_module("2d_geometry_constraint_solver_b200.shard")
+    n_total = 1 << 26
+    lo, hi = shard.shard_range(n_total, ctx.rank, ctx.world)
+    n = hi - lo
+    db = capi.DeviceBatch.empty(capi.KIND_PP, 2, n, ctx.dev, variant=args.variant)
+    ptrs = (C.c_void_p * 6)(*[c.data_ptr() for c in db.cols])
+
+    def gen():
+        capi.check(ctx.lib.gcs_b200_synth_pp(ctx.local_rank, C.c_void_p(ctx.stream.cuda_stream), synth.BASE_SEED, lo, n, 4096, ptrs,
+                                             C.c_void_p(db.code.data_ptr())), "gcs_b200_synth_pp")
+    gen()
+    l0 = ctx.lib.gcs_b200_launch_count()
+    ms = ctx.time_launches([db], steps, warmup=2)[0]
+    launches = ctx.lib.gcs_b200_launch_count() - l0
+    total_ms = ctx.max_over_ranks(float(ms.sum()))
+    out = _extra_line(ctx, db, ms, total_ms, n_total, n, "strong",
+                      "configs[4]: parametric sweep, 2^26 K1 instances = 4096 base clusters x 16384 perturbations (+-5% on ra, rb, d), "
+                      "generated on the device, sharded by index over the ranks", 2, launches, steps)
+    contract = None
+    if args.variant >= 5:
+        db0 = capi.DeviceBatch.empty(capi.KIND_PP, 2, n, ctx.dev, variant=0)
+        for dst, src in zip(db0.cols, db.cols):
+            dst.copy_(src)
+        db0.code.copy_(db.code)
         db0.solve()
-        torch.cuda.synchronize(dev)
-        same = bool(torch.equal(db.iters, db0.iters)) and bool(torch.equal(db.converged, db0.converged)) \
-            and bool(torch.equal(db.root_index, db0.root_index))
-        scale = torch.clamp(torch.stack([c.abs() for c in db.cols]).max(dim=0).values, min=1.0)
-        worst = max(float(((x - y).abs() / torch.maximum(scale, y.abs())).max().item()) for x, y in zip(db.out, db0.out))
-        ok = torch.tensor([1 if (same and worst <= 1e-9) else 0], device=dev, dtype=torch.int32)
-        if world > 1:
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            # never report a number from results that failed their check: rerun this workload on the
-            # bit-identical kernels (every rank takes this branch together)
-            print(f"[bench] CONTRACT VIOLATED by variant {args.variant} (discrete outputs equal = {same}, max relative error = "
-                  f"{worst:.3e}); rerunning on the bit-identical kernels", file=sys.stderr, flush=True)
-            if world > 1:
-                dist.destroy_process_group()
-            args.variant = 0
-            return run_extra(args, rank, local_rank, world)
+        torch.cuda.synchronize(ctx.dev)
+        same, worst = ctx.contract_check(db, db0)
         contract = {"iters_flags_roots_equal": same, "max_rel_coordinate_error": worst, "tolerance": 1e-9, "solves_compared": int(n)}
-        del db0, scale
-    # end to end: generation (sweep) or pinned H2D (multi-start), solve, results back to pinned host memory
-    e2e_steps = max(3, min(args.steps, 10))
-    if gen is None:
-        keep = []
-        slab = torch.empty((6, n), dtype=torch.float64, pin_memory=True); slab.numpy()[...] = np.stack(hb.cols)
-        code = torch.empty(n, dtype=torch.uint8, pin_memory=True); code.numpy()[...] = hb.code
-        oslab = torch.empty((2, n), dtype=torch.float64, pin_memory=True)
-        its = torch.empty((8, n), dtype=torch.int16, pin_memory=True)
-        cvs = torch.empty((8, n), dtype=torch.uint8, pin_memory=True)
-        root = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-        keep += [slab, code, oslab, its, cvs, root]
-        eb = capi.HostBatch(1, 8, [slab.numpy()[c] for c in range(6)], code.numpy(), None, args.variant, want_cand=False)
-        eb.out = [oslab.numpy()[c] for c in range(2)]
-        eb.iters, eb.converged, eb.root_index, eb.cand = its.numpy(), cvs.numpy(), root.numpy(), None
+        del db0
+    out["contract_check_rank0"] = contract
+    # end to end: generation + solve + (x, y, root) to pinned host memory
+    outs = [torch.empty(n, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+    roots = torch.empty(n, dtype=torch.uint8, pin_memory=True)
 
-        def e2e_step():
-            capi.solve_host(eb, local_rank)
-        h2d, d2h = 6 * 8 * n + n, 2 * 8 * n + 8 * 3 * n + n
-    else:
-        outs = [torch.empty(n, dtype=torch.float64, pin_memory=True) for _ in range(2)]
-        roots = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-
-        def e2e_step():
-            gen()
-            db.solve()
-            for o, dcol in zip(outs, db.out):
-                o.copy_(dcol, non_blocking=True)
-            roots.copy_(db.root_index, non_blocking=True)
-            torch.cuda.synchronize(dev)
-        h2d, d2h = 0, 17 * n
-    for _ in range(2):
-        e2e_step()
-    barrier()
+    def e2e_step():
+        gen()
+        db.solve()
+        for o, dcol in zip(outs, db.out):
+            o.copy_(dcol, non_blocking=True)
+        roots.copy_(db.root_index, non_blocking=True)
+        torch.cuda.synchronize(ctx.dev)
+    e2e_step()
+    ctx.barrier()
     t0 = time.perf_counter()
+    e2e_steps = 2
     for _ in range(e2e_steps):
         e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    et = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(et, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        dfma = lib.gcs_b200_fp64_probe(local_rank, 0)
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "solves_total": n_total, "solves_rank0": n, "l2": "256 MiB flush write between timed steps",
-                       "converged_fraction_rank0": conv, "mean_iters_per_seed_rank0": float(it.to(torch.float32).mean().item()),
-                       "variant": args.variant, "contract_check_rank0": contract},
-            "e2e": {"value": n_total * e2e_steps / float(et.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "gcs_b200_solve_host (pinned)" if gen is None else "gcs_b200_synth_pp + gcs_b200_solve + D2H of (x, y, root) to pinned memory"},
-            "gpu_launches": int(launches),
-            "roofline": {"kernel": lib.gcs_b200_kernel_name(1, 8 if gen is None else 2, args.variant).decode(), "bound": "fp64",
-                         "achieved": ach, "peak": dfma, "unit": "TFLOP/s", "frac": ach / dfma if dfma > 0 else None, "traffic": None,
-                         "algorithmic_flops_per_launch_rank0": w},
-            "cpu_baseline": None,
-        }), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.barrier()
+    t_max = ctx.max_over_ranks(time.perf_counter() - t0)
+    out["e2e"] = {"value": n_total * e2e_steps / t_max, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 17 * n,
+                  "api": "gcs_b200_synth_pp + gcs_b200_solve + D2H of (x, y, root) to pinned memory"}
+    return out
+
+
+def _extra_line(ctx, db, ms, total_ms, n_total, n_rank, scaling, name, n_seeds, launches, steps):
+    synth = ctx.synth
+    torch = ctx.torch
+    it = db.iters
+    w = float((it.to(torch.int64) + 1).sum().item()) * synth.F_EVAL[1] + n_rank * synth.F_SELECT[1]
+    ach = w / (float(ms.mean()) * 1e-3) / 1e12
+    dfma = ctx.dfma_peak()
+    return {
+        "metric": METRIC, "value": n_total * steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": ctx.world, "steps": steps,
+        "ms_per_step": total_ms / steps, "scaling": scaling,
+        "config": {"workload": name, "solves_total": n_total, "solves_rank0": int(n_rank), "l2": "256 MiB flush write between timed steps",
+                   "converged_fraction_rank0": float(db.converged.to(torch.float32).mean().item()),
+                   "mean_iters_per_seed_rank0": float(it.to(torch.float32).mean().item()),
+                   "variant": VARIANT_NAMES[ctx.args.variant]},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": ctx.lib.gcs_b200_kernel_name(1, n_seeds, ctx.args.variant).decode(), "bound": "fp64",
+                     "achieved": ach, "peak": dfma, "unit": "TFLOP/s", "frac": ach / dfma if dfma > 0 else None, "traffic": None,
+                     "launch_ms_rank0": float(ms.mean()), "algorithmic_flops_per_launch_rank0": w},
+    }
+
+
+def bench_kinds(ctx, steps=10):
+    """K2 / K3 / K4 kernel lines (2^19 sub-systems each, device-resident, L2 flushed): launch time,
+    algorithmic flops and bytes against the FP64 and HBM peaks, for the kernel class of the line and
+    for the bit-identical default.  K4 (two linear equations: two updates per seed) is the
+    HBM-leaning kind; its batch has no parallel line pairs (those never converge and run to the cap)."""
+    capi, synth, args = ctx.capi, ctx.synth, ctx.args
+    peaks, _ = load_peaks()
+    n = 1 << 19
+    out = {}
+    for kind in (2, 3, 4):
+        hb = synth.make_pll(n, parallel_every=0) if kind == 4 else synth.make(kind, n)
+        row = {"n": n}
+        dbs = {}
+        for label, variant in ([("line_variant", args.variant)] + ([("bit_identical", 0)] if args.variant >= 5 else [])):
+            db = dbs[label] = capi.DeviceBatch(hb, ctx.dev, want_cand=False, variant=variant)
+            ms = ctx.time_launches([db], steps, warmup=2)[0]
+            it = db.iters.cpu().numpy()
+            w = synth.algorithmic_flops(kind, it)
+            b = db.algorithmic_bytes()
+            t = float(np.mean(ms)) * 1e-3
+            dfma = ctx.dfma_peak()
+            row[label] = {"kernel": ctx.lib.gcs_b200_kernel_name(kind, 2, variant).decode(), "launch_ms": t * 1e3,
+                          "fp64_tflops": w / t / 1e12, "fp64_frac": w / t / 1e12 / dfma if dfma > 0 else None,
+                          "hbm_gbs": b / t / 1e9, "hbm_frac": b / t / 1e9 / peaks.get("hbm_gbs", 6650.0),
+                          "algorithmic_flops_per_launch": w, "algorithmic_bytes_per_launch": b,
+                          "mean_iters_per_seed": float(it.mean())}
+        if "bit_identical" in dbs:
+            same, worst = ctx.contract_check(dbs["line_variant"], dbs["bit_identical"])
+            row["contract_check"] = {"iters_flags_roots_equal": same, "max_rel_coordinate_error": worst}
+        row["bound"] = "hbm" if kind == 4 else "fp64"
+        out[f"K{kind}"] = row
+    return out
+
+
+def bench_sketch(ctx, n_points=100000):
+    """configs[3]: one rigidly well-constrained linkage of n_points points through the host mirror
+    (GeometricConstraintSystem -> decomposition -> wave-batched solveGcs on the device)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import host_lib as H
+    import sketch_gen as S
+    el, edges = S.make_linkage(n_points, seed=4)
+    H.system_solve_ex(el[:2000], [e for e in edges if max(e["a"], e["b"]) < 2000])  # warm-up (context, arena)
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        rc, got, stats = H.system_solve_ex(el, edges)
+        wall = time.perf_counter() - t0
+        if rc != 0:
+            return {"error": H.last_error()}
+        if best is None or stats["solve_us"] < best["solve_us"]:
+            best = dict(stats, wall_s_incl_python_marshalling=wall)
+    # every distance constraint of the sketch must hold in the result
+    pos = np.array([g["pos"][:2] for g in got])
+    a = np.array([e["a"] for e in edges]); b = np.array([e["b"] for e in edges]); v = np.array([e["value"] for e in edges])
+    resid = np.abs(np.hypot(*(pos[a] - pos[b]).T) - v)
+    return {"workload": f"configs[3]: linkage of {n_points} points, {len(edges)} distance constraints, through "
+                        "GeometricConstraintSystem::solveGeometricConstraintSystem", **best,
+            "leaves_per_s_solve": best["leaves"] / (best["solve_us"] * 1e-6),
+            "device_share_of_solve": best["device_us"] / max(best["solve_us"], 1),
+            "constraints_satisfied_to_1e-6": int((resid <= 1e-6 * np.maximum(1.0, v)).sum()), "constraints": len(edges),
+            "max_constraint_residual": float(resid.max())}
+
+
+def bench_sharded(ctx):
+    """N > 1: gcs_b200_solve_sharded inside ONE process (rank 0) over the N devices of the box, checked
+    bit for bit against the same batch on one device; the other ranks wait at a host-side barrier."""
+    if ctx.world == 1:
+        return None
+    out = None
+    ctx.barrier()
+    if ctx.rank == 0:
+        capi, synth = ctx.capi, ctx.synth
+        try:
+            capi.init(list(range(ctx.world)))
+            n = 1 << 20
+            res = {}
+            for kind in (1, 5):
+                a = synth.make(kind, n)
+                a.variant = ctx.args.variant
+                a.want_cand = False
+                pa = pinned_batch(ctx, a, want_flags=True)
+                capi.solve_sharded(pa, ctx.world)  # warm (arenas on every device)
+                t0 = time.perf_counter()
+                capi.solve_sharded(pa, ctx.world)
+                dt = time.perf_counter() - t0
+                b = synth.make(kind, n)
+                b.variant = ctx.args.variant
+                b.want_cand = False
+                pb = pinned_batch(ctx, b, want_flags=True)
+                capi.solve_host(pb, ctx.local_rank)
+                same = all(np.array_equal(x.view(np.uint64), y.view(np.uint64)) for x, y in zip(pa.out, pb.out)) \
+                    and np.array_equal(pa.iters, pb.iters) and np.array_equal(pa.converged, pb.converged) \
+                    and np.array_equal(pa.root_index, pb.root_index)
+                res[f"K{kind}"] = {"n": n, "devices": ctx.world, "identical_to_one_device": bool(same), "ms": dt * 1e3,
+                                   "solves_per_s": n / dt}
+            out = res
+        except Exception as ex:
+            out = {"error": repr(ex)[:300]}
+        finally:
+            capi.init([ctx.local_rank])
+    ctx.host_barrier()
+    return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -413,6 +726,7 @@ def _quiet_stdout():
 
 def main():
     args = parse()
+    args0 = argparse.Namespace(**vars(args))  # as given on the command line (args.variant changes if the contract check fails)
     _quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -420,167 +734,103 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    if args.workload != "configs1":
-        run_extra(args, rank, local_rank, world)
-        return
 
     import torch
-    import torch.distributed as dist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    ctx = Ctx(args, rank, local_rank, world)
+    dist = ctx.dist
+    if args.workload != "configs1":
+        line = bench_multistart(ctx, args.steps) if args.workload == "multistart8" else bench_sweep(ctx, args.steps)
+        if rank == 0:
+            line.update({"warmup": ctx.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                         "cpu_baseline": None})
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
-    gcs = importlib.import_module("2d_geometry_constraint_solver_b200")
-    capi, synth = gcs.capi, gcs.synth
-    capi.init([local_rank])
-    lib = capi.load()
-
+    capi, synth, lib, dev, stream = ctx.capi, ctx.synth, ctx.lib, ctx.dev, ctx.stream
     n = args.n
-    warmup = max(args.warmup, 3)
+    warmup = ctx.warmup
     host = make_batches(synth, n, rank)
     for h in host:
         h.variant = args.variant
     devb = [capi.DeviceBatch(h, dev, want_cand=False, variant=args.variant) for h in host]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    flush = ctx.flush
+    barrier = ctx.barrier
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    stream = torch.cuda.current_stream(dev)
-
-    def step(events=None):
-        if events:
-            events[0].record(stream)
-        devb[0].solve()
-        if events:
-            events[1].record(stream)
-        devb[1].solve()
-        if events:
-            events[2].record(stream)
+    # A step = the whole batch as ONE job through gcs_b200_solve_many (the library runs the K1 and
+    # the K5 launch concurrently on its own streams, stream-ordered as a whole on the caller's
+    # stream); CUDA events around the call on the launching stream.
+    def timed_jobs(dbs, steps, warm):
+        for _ in range(warm):
+            flush.fill_(1)
+            capi.solve_many(dbs)
+        barrier()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+        l0 = lib.gcs_b200_launch_count()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            flush.fill_(k & 0xFF)  # evict the batch from L2 between timed steps (outside the events)
+            evs[k][0].record(stream)
+            capi.solve_many(dbs)
+            evs[k][1].record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = np.array([e[0].elapsed_time(e[1]) for e in evs])
+        return ms, lib.gcs_b200_launch_count() - l0, wall
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(warmup):
-        flush.fill_(1)
-        step()
-    barrier()
-
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    l0 = lib.gcs_b200_launch_count()
     sampler.enter()
-    barrier()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)  # evict the batch from L2 between timed steps (outside the events)
-        step(evs[k])
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = lib.gcs_b200_launch_count() - l0
-
-    ms_k1 = np.array([e[0].elapsed_time(e[1]) for e in evs])
-    ms_k5 = np.array([e[1].elapsed_time(e[2]) for e in evs])
-    ms_step = ms_k1 + ms_k5
-    t_sum = torch.tensor([float(ms_step.sum())], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_sum, op=dist.ReduceOp.MAX)
-    total_ms = float(t_sum.item())
+    ms_job, launches, t_wall = timed_jobs(devb, args.steps, warmup)
+    total_ms = ctx.max_over_ranks(float(ms_job.sum()))
     value = (n * world * args.steps) / (total_ms * 1e-3)
 
-    # ---- the same step with the two launches on two streams (the kinds are independent batches):
-    #      one kernel's tail - the few warps that re-run a seed with the literal code, ~8 us of
-    #      dependent FP64 latency each - is covered by the other kernel.  Reported beside `value`,
-    #      which stays the sum of the per-launch times. ----
-    side = torch.cuda.Stream(device=dev)
-    fork = [torch.cuda.Event() for _ in range(args.steps)]
-    join = [torch.cuda.Event() for _ in range(args.steps)]
-    ev2 = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    # ---- the same launches one after the other on one stream, each between its own events: the
+    #      per-kernel durations the roofline is quoted on ----
+    ms_seq = ctx.time_launches(devb, args.steps, warmup)
+    ms_k1, ms_k5 = ms_seq[0], ms_seq[1]
+    seq_ms = ctx.max_over_ranks(float((ms_k1 + ms_k5).sum()))
+    sequential = {"value": (n * world * args.steps) / (seq_ms * 1e-3), "unit": UNIT, "ms_per_step": seq_ms / args.steps,
+                  "note": "the two launches of a step one after the other on one stream (gcs_b200_solve x2), sum of the per-launch event times"}
 
-    def step2(k):
-        ev2[k][0].record(stream)
-        fork[k].record(stream)
-        side.wait_event(fork[k])
-        devb[0].solve(stream)
-        devb[1].solve(side)
-        join[k].record(side)
-        stream.wait_event(join[k])
-        ev2[k][1].record(stream)
-
-    for k in range(min(3, args.steps)):
-        flush.fill_(1)
-        step2(k)
-    barrier()
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)
-        step2(k)
-    barrier()
-    ms2 = np.array([e[0].elapsed_time(e[1]) for e in ev2])
-    t2_sum = torch.tensor([float(ms2.sum())], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t2_sum, op=dist.ReduceOp.MAX)
-    two_stream = {"value": (n * world * args.steps) / (float(t2_sum.item()) * 1e-3), "unit": UNIT,
-                  "ms_per_step": float(t2_sum.item()) / args.steps,
-                  "note": "K1 and K5 launches of a step enqueued on two streams, CUDA events from fork to join on the launching stream"}
-
-    # ---- the bit-identical kernels on the same batches, timed the same way, and the contract
+    # ---- the bit-identical kernels on the same batches, timed the same two ways, and the contract
     #      between the two checked on the full batch (contracted variants only) ----
     bit_identical = None
     violation = None
     if args.variant >= 5:
         devb0 = [capi.DeviceBatch(h, dev, want_cand=False, variant=0) for h in host]
-        for _ in range(warmup):
-            flush.fill_(1)
-            for d in devb0:
-                d.solve()
-        barrier()
-        evs0 = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-        for k in range(args.steps):
-            flush.fill_(k & 0xFF)
-            evs0[k][0].record(stream)
-            devb0[0].solve()
-            evs0[k][1].record(stream)
-            devb0[1].solve()
-            evs0[k][2].record(stream)
-        barrier()
-        ms0_k1 = np.array([e[0].elapsed_time(e[1]) for e in evs0])
-        ms0_k5 = np.array([e[1].elapsed_time(e[2]) for e in evs0])
-        t0_sum = torch.tensor([float((ms0_k1 + ms0_k5).sum())], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t0_sum, op=dist.ReduceOp.MAX)
+        ms0_job, launches0, _ = timed_jobs(devb0, args.steps, warmup)
+        t0_job = ctx.max_over_ranks(float(ms0_job.sum()))
+        ms0 = ctx.time_launches(devb0, args.steps, warmup)
+        ms0_k1, ms0_k5 = ms0[0], ms0[1]
+        t0_sum = ctx.max_over_ranks(float((ms0_k1 + ms0_k5).sum()))
         same, worst = True, 0.0
-        for a, b, h in zip(devb, devb0, host):
-            same = same and bool(torch.equal(a.iters, b.iters)) and bool(torch.equal(a.converged, b.converged)) \
-                and bool(torch.equal(a.root_index, b.root_index))
-            scale = torch.clamp(torch.stack([c.abs() for c in a.cols]).max(dim=0).values, min=1.0)
-            for x, y in zip(a.out, b.out):
-                worst = max(worst, float(((x - y).abs() / torch.maximum(scale, y.abs())).max().item()))
+        for a, b in zip(devb, devb0):
+            s_, w_ = ctx.contract_check(a, b)
+            same, worst = same and s_, max(worst, w_)
         if os.environ.get("GCS_BENCH_TEST_VIOLATION"):  # exercises the fallback below
             same = False
-        ok = torch.tensor([1 if (same and worst <= 1e-9) else 0], device=dev, dtype=torch.int32)
-        if world > 1:
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
+        if not ctx.all_ok(same and worst <= 1e-9):
             # Never report a number from results that failed their check: the line falls back to the
             # bit-identical kernels (timed above, on the same batches) and says so.
             print(f"[bench] CONTRACT VIOLATED by variant {args.variant} on rank {rank}'s view (discrete outputs equal = {same}, "
                   f"max relative error = {worst:.3e}); reporting the bit-identical kernels instead", file=sys.stderr, flush=True)
             violation = {"variant": args.variant, "iters_flags_roots_equal_rank": same, "max_rel_coordinate_error_rank": worst}
             args.variant = 0
-            two_stream = None
-            devb, ms_k1, ms_k5 = devb0, ms0_k1, ms0_k5
-            total_ms = float(t0_sum.item())
+            devb, ms_k1, ms_k5, launches = devb0, ms0_k1, ms0_k5, launches0
+            total_ms = t0_job
             value = (n * world * args.steps) / (total_ms * 1e-3)
+            sequential["value"], sequential["ms_per_step"] = (n * world * args.steps) / (t0_sum * 1e-3), t0_sum / args.steps
             for h in host:
                 h.variant = 0
         bit_identical = {
-            "variant": "default (newton_sorted_kernel, literal Householder QR, no contraction)",
-            "value": (n * world * args.steps) / (float(t0_sum.item()) * 1e-3), "unit": UNIT,
-            "ms_per_step": float(t0_sum.item()) / args.steps,
+            "variant": "default (newton_sorted_kernel, literal Householder QR, no contraction): what GCS_VARIANT_DEFAULT and the host mirror run",
+            "value": (n * world * args.steps) / (t0_job * 1e-3), "unit": UNIT, "ms_per_step": t0_job / args.steps,
+            "sequential_launches": {"value": (n * world * args.steps) / (t0_sum * 1e-3), "ms_per_step": t0_sum / args.steps},
             "k1_launch_ms": float(ms0_k1.mean()), "k5_launch_ms": float(ms0_k5.mean()),
             "contract_check_rank0": {"iters_flags_roots_equal": same, "max_rel_coordinate_error": worst, "tolerance": 1e-9,
                                      "solves_compared": int(sum(d.n for d in devb))},
@@ -598,93 +848,82 @@ def main():
     b_k1 = devb[0].algorithmic_bytes()
     b_k5 = devb[1].algorithmic_bytes()
 
-    # ---- end to end through the host-buffer C-ABI calls, pinned host memory ----
-    def pin_like(a):
-        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].copy()).dtype, pin_memory=True)
-        v = t.numpy()
-        v[...] = a
-        return t, v
-
-    keep = []
+    # ---- end to end through the host-buffer C-ABI calls, pinned host memory.  Batches as the
+    #      packer emits them: the zero-fixed (anchored) shapes and the general shapes are different
+    #      solvers, hence different batches; the anchor columns are NULL (not stored, not copied).
+    #      What comes back is what the reference's solvers produce: the solved coordinates and the
+    #      chosen root (solve2D returns no iteration counts / flags, newton_raphson.hpp:97-101). ----
     e2e_batches = []
     for h in host:
-        # one pinned [columns][n] slab per direction: the library moves such slabs with strided copies
-        t, slab = pin_like(np.stack(h.cols)); keep.append(t)
-        cols = [slab[c] for c in range(slab.shape[0])]
-        t, code = pin_like(h.code); keep.append(t)
-        hb = capi.HostBatch(h.kind, h.n_seeds, cols, code, None, args.variant, want_cand=False)
-        m = hb.n
-        t, oslab = pin_like(np.zeros((capi.OUT_COLS[h.kind], m))); keep.append(t)
-        hb.out = [oslab[c] for c in range(oslab.shape[0])]
-        t, hb.iters = pin_like(np.zeros((h.n_seeds, m), np.int16)); keep.append(t)
-        t, hb.converged = pin_like(np.zeros((h.n_seeds, m), np.uint8)); keep.append(t)
-        t, hb.root_index = pin_like(np.zeros(m, np.uint8)); keep.append(t)
-        hb.cand = None
-        e2e_batches.append(hb)
-    h2d = sum(capi.IN_COLS[b.kind] * 8 * b.n + b.n for b in e2e_batches)
-    d2h = sum(capi.OUT_COLS[b.kind] * 8 * b.n + b.n_seeds * 3 * b.n + b.n for b in e2e_batches)
+        even = np.arange(0, h.n, 2)
+        odd = np.arange(1, h.n, 2)
+        for part in (h.take(even).anchored(), h.take(odd)):
+            part.variant = args.variant
+            e2e_batches.append(pinned_batch(ctx, part, want_flags=False))
+    # the larger uploads first: what trails the last upload is then the smallest batch's last range
+    e2e_batches.sort(key=lambda b: -b.input_bytes())
+    h2d = sum(b.input_bytes() for b in e2e_batches)
+    d2h = sum(batch_d2h_bytes(capi, b) for b in e2e_batches)
     e2e_steps = max(3, min(args.steps, 20))
-
-    def e2e_step():
-        for b in e2e_batches:
-            capi.solve_host_async(b, local_rank)
-        capi.wait(local_rank)
-
-    for _ in range(3):
-        e2e_step()
-    l1 = lib.gcs_b200_launch_count()
+    e2e_t, e2e_s, e2e_launches = time_e2e(ctx, e2e_batches, e2e_steps)
+    e2e_value = n * world * e2e_steps / e2e_t
+    # the e2e results must equal the device-resident ones (same inputs, same kernels)
+    for b in e2e_batches:
+        src = devb[0] if b.kind == 1 else devb[1]
+        sel = slice(0, None, 2) if any(c is None for c in b.cols) else slice(1, None, 2)
+        assert np.array_equal(b.out[0], src.out[0].cpu().numpy()[sel]), "e2e coordinates differ from the device-resident run"
+        assert np.array_equal(b.root_index, src.root_index.cpu().numpy()[sel]), "e2e roots differ from the device-resident run"
+    # the same step in the round-1 wire format (dense 6 / 13 columns, iteration counts and flags
+    # downloaded too), for continuity
+    dense = [pinned_batch(ctx, h, want_flags=True) for h in host]
+    dense_t, _, _ = time_e2e(ctx, dense, max(3, e2e_steps // 2))
+    dense_line = {"value": n * world * max(3, e2e_steps // 2) / dense_t, "unit": UNIT,
+                  "h2d_bytes_per_step": sum(b.input_bytes() for b in dense), "d2h_bytes_per_step": sum(batch_d2h_bytes(capi, b) for b in dense),
+                  "note": "round-1 wire format: anchor columns shipped as zeros, iteration counts and flags downloaded"}
+    del dense
+    # copy-only ceiling of the same byte counts, all ranks at once (one contiguous copy per direction
+    # and the pipeline's own granularity), on the library's copy streams
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    probe1 = capi.pcie_probe(local_rank, h2d, d2h, 1, False, 5)
     barrier()
-    e2e_s = time.perf_counter() - t0
+    probe_p = capi.pcie_probe(local_rank, h2d, d2h, 16, False, 5)
+    ceil_ms = ctx.max_over_ranks(probe1["both_ms_median"])
+    ceil_p_ms = ctx.max_over_ranks(probe_p["both_ms_median"])
+    e2e_ms = e2e_t / e2e_steps * 1e3
+    pcie = {"h2d_gbs_rank0": probe1["h2d_gbs"], "d2h_gbs_rank0": probe1["d2h_gbs"],
+            "ceiling_ms_per_step": ceil_ms, "ceiling_solves_per_s": n * world / (ceil_ms * 1e-3), "frac_of_ceiling": ceil_ms / e2e_ms,
+            "ceiling_ms_per_step_16_pieces": ceil_p_ms, "frac_of_ceiling_16_pieces": ceil_p_ms / e2e_ms,
+            "aggregate_gbs_at_ceiling": (h2d + d2h) * world / (ceil_ms * 1e-3) / 1e9,
+            "how": "gcs_b200_pcie_probe: the step's H2D and D2H byte counts as one contiguous copy per direction (and as 16 pieces) "
+                   "from / to pinned memory, both directions at once, every rank at the same time; max over ranks of the median"}
     sampler.leave()
-    e2e_launches = lib.gcs_b200_launch_count() - l1
-    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = n * world * e2e_steps / float(e2e_t.item())
-    # the e2e results must equal the device-resident ones (same inputs)
-    assert np.array_equal(e2e_batches[0].iters, it1) and np.array_equal(e2e_batches[1].iters, it5)
-    assert np.array_equal(e2e_batches[0].out[0], devb[0].out[0].cpu().numpy())
-
     clocks = sampler.stop()
 
     # ---- peaks (after the timed regions: the probe heats the chip) ----
-    dfma_peak = lib.gcs_b200_fp64_probe(local_rank, 0)
+    dfma_peak = ctx.dfma_peak()
     mix_peak = lib.gcs_b200_fp64_probe(local_rank, 1)
     peaks, peak_src = load_peaks()
     ach_tf = w_k1 / (k1_ms * 1e-3) / 1e12
-    traffic = load_traffic()
-    vname = {0: "default", 1: "static", 2: "refill", 3: "sorted", 4: "pair", 5: "contracted", 6: "contracted-static",
-             7: "contracted-sorted"}[args.variant]
-    rerun_stats = None
-    if args.variant >= 5:
-        import ctypes as C
-        st2 = (C.c_uint64 * 2)()
-        lib.gcs_b200_contracted_stats(local_rank, st2, 1)
-        step()
-        lib.gcs_b200_contracted_stats(local_rank, st2, 1)
-        rerun_stats = {"runs_per_step": int(sum(d.n * d.n_seeds for d in devb)), "redone_by_run_guards": int(st2[0]),
-                       "redone_by_selection_guard": int(st2[1])}
-    kernel_name = lib.gcs_b200_kernel_name(1, 2, args.variant).decode() if hasattr(lib, "gcs_b200_kernel_name") else vname
+    traffic, traffic_stale = load_traffic(lib)
+    vname = VARIANT_NAMES[args.variant]
+    rerun_stats = ctx.rerun_stats(devb) if args.variant >= 5 else None
+    kernel_name = lib.gcs_b200_kernel_name(1, 2, args.variant).decode()
+    fma_kernel = args.variant >= 5
     roofline = {
         "kernel": kernel_name,
         "bound": "fp64",
         "bound_note": "FP64 CUDA-core pipe (no tensor-core work on this path); the HBM side is under 'hbm'",
         "achieved": ach_tf, "peak": dfma_peak, "unit": "TFLOP/s", "frac": ach_tf / dfma_peak if dfma_peak > 0 else None,
         "peak_source": "measured live: gcs_b200_fp64_probe DFMA micro-benchmark (FMA = 2 flops); MEASURED_PEAKS.json has no FP64 entry",
-        "non_fma_peak": mix_peak,
-        "frac_of_non_fma_peak": ach_tf / mix_peak if mix_peak > 0 else None,
         "traffic": traffic.get(kernel_name, {}).get("dram_bytes_per_launch"),
         "traffic_source": traffic.get(kernel_name, {}).get("source"),
+        "traffic_capture_is_of_another_build": traffic_stale,
         "algorithmic_flops_per_launch": w_k1,
         "algorithmic_flops_note": ("SURVEY.md 8d work model: (iters+1) * 64 flops per seed + selection, from the measured iteration "
                                    "counts - the reference algorithm's work (Householder QR counted at 44 flops per update).  The "
                                    "contracted kernels reach the same iterates with a closed-form solve (~33 executed flops per update, "
-                                   "FMA = 2), so for them `achieved` is a rate of reference-algorithm work, not of executed flops; "
-                                   "executed flops per launch are in profiles/traffic.json" if args.variant >= 5 else
+                                   "FMA = 2), so for them `achieved` is a rate of reference-algorithm work, not of executed flops; see "
+                                   "executed_*" if fma_kernel else
                                    "SURVEY.md 8d work model from the measured iteration counts"),
         "executed_flops_per_launch": traffic.get(kernel_name, {}).get("executed_flops_per_launch"),
         "flops_per_solve": w_k1 / devb[0].n,
@@ -698,35 +937,74 @@ def main():
                           "hbm_gbs": b_k5 / (k5_ms * 1e-3) / 1e9, "mean_iters_per_seed": float(it5.mean()),
                           "algorithmic_flops_per_launch": w_k5, "algorithmic_bytes_per_launch": b_k5},
     }
+    ex = roofline["executed_flops_per_launch"]
+    if ex:
+        roofline["executed_tflops"] = ex / (k1_ms * 1e-3) / 1e12
+        roofline["executed_frac"] = ex / (k1_ms * 1e-3) / 1e12 / dfma_peak if dfma_peak > 0 else None
+    if not fma_kernel:
+        roofline["non_fma_peak"] = mix_peak
+        roofline["frac_of_non_fma_peak"] = ach_tf / mix_peak if mix_peak > 0 else None
 
-    cpu = None
+    # ---- the other BASELINE configs, measured in this run ----
+    configs = None
+    if not args.no_extras:
+        configs = {}
+        t_extra = time.perf_counter()
+        for name, fn in (("multistart8", lambda: bench_multistart(ctx, 5)), ("sweep64m", lambda: bench_sweep(ctx, 3)),
+                         ("kinds", lambda: bench_kinds(ctx))):
+            try:
+                configs[name] = fn()
+            except Exception as ex_:  # an extra may not take the line down
+                if world > 1:
+                    raise
+                configs[name] = {"error": repr(ex_)[:300]}
+        if rank == 0:
+            try:
+                configs["sketch100k"] = bench_sketch(ctx)
+            except Exception as ex_:
+                configs["sketch100k"] = {"error": repr(ex_)[:300]}
+        ctx.host_barrier()
+        configs["sharded"] = bench_sharded(ctx)
+        configs["seconds"] = time.perf_counter() - t_extra
+
+    cpu = faithful = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, kind, desc = cpu_rate(gcs, args.cpu_seconds)
+        v, cores, kind, desc = cpu_rate(ctx.gcs, args.cpu_seconds)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+        faithful = faithful_rate()
 
     if rank == 0:
+        cfg = base_config(args0)
+        run = {"variant": vname,
+               "parity_class": ("contract: iteration counts, convergence flags and root indices identical to the reference, "
+                                "coordinates within 1e-9 relative (checked in this run against the bit-identical kernels)"
+                                if fma_kernel else "bit-identical to the reference arithmetic"),
+               "literal_reruns": rerun_stats,
+               "contract_violation": violation,
+               "timing": "CUDA events around each step's gcs_b200_solve_many call on the launching stream, sum over steps, max over ranks",
+               "wall_s_timed_region_incl_flush": t_wall,
+               "library": lib.gcs_b200_version().decode()}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "solves_per_gpu": n, "l2": "256 MiB flush write between timed steps",
-                       "variant": vname,
-                       "parity_class": ("contract: iteration counts, convergence flags and root indices identical to the reference, "
-                                        "coordinates within 1e-9 relative (checked in this run against the bit-identical kernels)"
-                                        if args.variant >= 5 else "bit-identical to the reference arithmetic"),
-                       "literal_reruns": rerun_stats,
-                       "contract_violation": violation,
-                       "timing": "per-launch CUDA events on the launching stream, sum over steps, max over ranks",
-                       "wall_s_timed_region_incl_flush": t_wall},
+            "config": cfg,
+            "run": run,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "gpu_launches": int(e2e_launches),
-                    "api": "gcs_b200_solve_host_async x2 + gcs_b200_wait (pinned host buffers, wall clock incl. copies)"},
+                    "steps": e2e_steps, "ms_per_step": e2e_ms, "gpu_launches": int(e2e_launches),
+                    "api": "gcs_b200_solve_host_async x4 + gcs_b200_wait (pinned host buffers, wall clock incl. copies)",
+                    "device_api_of_value": "gcs_b200_solve_many([K1 batch, K5 batch]) per step",
+                    "wire_format": "one batch per solver shape (anchored K1 / general K1 / anchored K5 / general K5), anchor columns NULL; "
+                                   "down: solved coordinates + chosen root",
+                    "pcie": pcie, "dense_round1_format": dense_line},
             "gpu_launches": int(launches),
             "roofline": roofline,
-            "two_stream_step": two_stream,
+            "sequential_launches": sequential,
             "bit_identical": bit_identical,
+            "configs": configs,
             "cpu_baseline": cpu,
+            "cpu_baseline_faithful": faithful,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -198,6 +198,14 @@ GCS_B200_API const char* gcs_b200_version(void);
  * `Equations::solve2D` + `pickBy*` calls (newton_raphson.hpp:41-102, heuristics.hpp). */
 GCS_B200_API int gcs_b200_solve(const gcs_b200_batch* batch, int device, void* cuda_stream);
 
+/* Several device-resident batches as ONE job (e.g. one batch per equation kind of a dependency
+ * wave, or the K1 + K5 halves of a cluster batch): stream-ordered on `cuda_stream` as a whole -
+ * everything enqueued before the call precedes every launch, everything enqueued after it follows
+ * all of them - while inside the job the launches run concurrently on internal streams, so that one
+ * kernel's ramp-up, drain and literal re-runs are covered by its neighbours.  The batches must not
+ * alias each other's outputs. */
+GCS_B200_API int gcs_b200_solve_many(const gcs_b200_batch* const* batches, int count, int device, void* cuda_stream);
+
 /* Same with HOST buffers: copies inputs H2D, solves, copies outputs D2H and synchronises.
  * This is the call the host-side solver mirror makes. */
 GCS_B200_API int gcs_b200_solve_host(const gcs_b200_batch* batch, int device);

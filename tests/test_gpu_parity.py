@@ -460,3 +460,30 @@ def test_sharded_solve_takes_guesses_and_candidate_planes(gpu, gcs):
     ref = O.solve(capi.HostBatch(a.kind, 2, a.cols, a.code, a.guesses).alloc_outputs())
     assert_batches_identical(a, ref, f"sharded with guesses over {ndev} devices")
     capi.init([0])
+
+
+def test_solve_many_runs_independent_batches_as_one_stream_ordered_job(gpu, gcs):
+    """gcs_b200_solve_many: several device-resident batches as one job (the launches fan out over the
+    library's internal streams and are joined back into the caller's stream).  Same results as one
+    gcs_b200_solve per batch; stream order holds on both sides of the call."""
+    import torch
+    synth, capi = gcs.synth, gcs.capi
+    hosts = [synth.make(kind, n) for kind, n in ((1, 70001), (5, 50021), (2, 33333), (3, 20011), (4, 4099), (1, 129))]
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        many = [capi.DeviceBatch(h, "cuda:0", want_cand=True) for h in hosts]
+        for d in many:  # work enqueued BEFORE the call that the job must follow: poison the outputs
+            for o in d.out:
+                o.fill_(float("nan"))
+        capi.solve_many(many, st)
+        sums = [d.out[0].clone() for d in many]  # work enqueued AFTER the call that must follow the whole job
+    st.synchronize()
+    for h, d, s in zip(hosts, many, sums):
+        ref = O.solve(synth.make(h.kind, h.n).alloc_outputs())
+        got = d.to_host(synth.make(h.kind, h.n))
+        assert_batches_identical(got, ref, f"solve_many kind {h.kind} n {h.n}")
+        assert np.array_equal(bits(s.cpu().numpy()), bits(ref.out[0])), "a copy enqueued after the job ran before it finished"
+    # an empty job and a job of one
+    capi.check(capi.load().gcs_b200_solve_many(None, 0, 0, None))
+    capi.solve_many(many[:1])
+    torch.cuda.synchronize()
