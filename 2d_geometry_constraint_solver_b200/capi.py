@@ -81,6 +81,7 @@ EXPORTS = [
     "gcs_b200_fp64_probe", "gcs_b200_synth_pp", "gcs_b200_selftest", "gcs_b200_host_alloc", "gcs_b200_host_free",
     "gcs_b200_contracted_stats", "gcs_b200_contracted_stats_ex", "gcs_b200_column_may_be_null", "gcs_b200_host_alloc_ex",
     "gcs_b200_solve_host_range_async", "gcs_b200_pcie_probe", "gcs_b200_solve_many",
+    "gcs_b200_debug_path_buffer",
 ]
 
 
@@ -119,6 +120,7 @@ def load():
     lib.gcs_b200_host_alloc_ex.restype = C.c_void_p
     lib.gcs_b200_host_free.argtypes = [C.c_void_p]
     lib.gcs_b200_pcie_probe.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    lib.gcs_b200_debug_path_buffer.argtypes = [C.c_int, C.c_void_p, C.c_int64]
     lib.gcs_b200_fp64_probe.argtypes = [C.c_int, C.c_int]
     lib.gcs_b200_fp64_probe.restype = C.c_double
     lib.gcs_b200_selftest.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.POINTER(C.c_uint64)]

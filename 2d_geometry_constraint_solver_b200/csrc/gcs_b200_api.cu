@@ -66,6 +66,10 @@ struct DeviceState {
     // read-only afterwards: a few MB that stay in L2 and are shared by every NULL column of a batch)
     double* zeros = nullptr;
     size_t zeros_n = 0;
+    // test hook (gcs_b200_debug_path_buffer): where device-resident contracted launches report how
+    // each run was decided
+    uint8_t* dbg_path = nullptr;
+    long long dbg_path_cap = 0;
     std::atomic<unsigned> ticket_rr { 0 };
     // staging arena for the host-buffer entry points
     std::mutex arena_mu, zeros_mu;
@@ -341,6 +345,7 @@ int solve_on(DeviceState* d, const gcs_b200_batch* b, cudaStream_t st)
 {
     if (b->n == 0) return GCS_OK;
     BatchDev p = to_dev(b);
+    if (d->dbg_path && (long long)b->n * b->n_seeds <= d->dbg_path_cap) p.path = d->dbg_path;
     if (has_null_column(b)) {
         const int rc = ensure_zeros(d, (size_t)b->n);
         if (rc != GCS_OK) return rc;
@@ -714,16 +719,29 @@ int ensure_events(DeviceState* d, size_t count)
     return GCS_OK;
 }
 
-int64_t chunk_len(int64_t n, bool slabs)
+int64_t chunk_len(int64_t n, bool slabs, size_t up_bytes_per_row)
 {
-    // Ranges per batch: 4 when every range moves with a handful of strided copies, 3 when each
-    // column needs its own call; never below 32 Ki sub-systems nor above 256 Ki (pipeline ramp);
-    // multiples of 128 keep every slice 16-byte aligned
+    // Index ranges per batch.  Every copy costs a few microseconds of engine time whatever its
+    // size, and copies below a few MB do not reach the link rate, so a range is sized by the BYTES
+    // its upload moves (default 8 MB per stage; GCS_B200_STAGE_MB), never below 32 Ki sub-systems
+    // and never more than 16 ranges per batch (3 when every column needs its own copy call).  The
+    // caller halves the last range, so what trails the final upload is 1/2 .. 1/32 of the batch.
+    // Multiples of 128 keep every slice 16-byte aligned.
     static const int forced = getenv("GCS_B200_PARTS") ? atoi(getenv("GCS_B200_PARTS")) : 0;  // tuning knob, 1..64
-    const int parts = (forced > 0 && forced <= 64) ? forced : (slabs ? 4 : 3);
+    static const int stage_mb = getenv("GCS_B200_STAGE_MB") ? atoi(getenv("GCS_B200_STAGE_MB")) : 8;
+    int64_t parts;
+    if (forced > 0 && forced <= 64) {
+        parts = forced;
+    } else {
+        const size_t stage = (size_t)(stage_mb > 0 && stage_mb <= 1024 ? stage_mb : 8) << 20;
+        const size_t bytes = (size_t)n * (up_bytes_per_row ? up_bytes_per_row : 8);
+        parts = (int64_t)((bytes + stage - 1) / stage);
+        const int64_t max_parts = slabs ? 16 : 3;
+        if (parts > max_parts) parts = max_parts;
+        if (parts < 1) parts = 1;
+    }
     int64_t c = (n + parts - 1) / parts;
     if (c < 32768) c = 32768;
-    if (c > 262144) c = 262144;
     return (c + 127) / 128 * 128;
 }
 
@@ -799,7 +817,7 @@ int record_pipeline(DeviceState* d, const gcs_b200_batch* b, size_t off, int64_t
     const bool slabs = in_calls <= 2 && out_calls <= 2;
 
     // index ranges: equal steps, the last one halved so that less work trails the final upload
-    const int64_t step = chunk_len(count, slabs);
+    const int64_t step = chunk_len(count, slabs, (size_t)npres * 8 + 1 + (b->guesses ? 16u * (size_t)ns : 0u));
     std::vector<std::pair<int64_t, int64_t>> ranges;
     for (int64_t lo = 0; lo < count; lo += step) ranges.push_back({ lo, (count - lo < step) ? (count - lo) : step });
     if (ranges.size() >= 2 && ranges.back().second >= 65536) {
@@ -1001,6 +1019,18 @@ int gcs_b200_solve_sharded(const gcs_b200_batch* b, int n_dev)
 }
 
 int gcs_b200_contracted_stats_ex(int device, uint64_t out[8], int reset);
+
+int gcs_b200_debug_path_buffer(int device, uint8_t* dev_buf, int64_t capacity)
+{
+    int rc = ensure_init();
+    if (rc != GCS_OK) return rc;
+    DeviceState* d = find_dev(device);
+    if (!d) return fail(GCS_E_NO_DEVICE, "device %d not present", device);
+    if (capacity < 0) return fail(GCS_E_INVALID, "negative capacity");
+    d->dbg_path = capacity > 0 ? dev_buf : nullptr;
+    d->dbg_path_cap = d->dbg_path ? capacity : 0;
+    return GCS_OK;
+}
 
 int gcs_b200_contracted_stats(int device, uint64_t out[2], int reset)
 {

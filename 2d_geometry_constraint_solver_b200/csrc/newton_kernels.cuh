@@ -44,11 +44,21 @@ struct BatchDev {
     int16_t* iters;     // [NS][n] or null
     uint8_t* converged; // [NS][n] or null
     uint8_t* root;      // [n] or null
+    uint8_t* path;      // [NS][n] or null (test hook, contracted static kernels): how each run was decided, kPath*
     long long n;
     long long stride;  // distance between per-seed planes (== n unless this launch is a slice of a larger batch)
 };
 
 constexpr unsigned kFull = 0xffffffffu;
+
+// BatchDev::path values (gcs_b200_debug_path_buffer)
+enum : int {
+    kPathFirstLevel = 0,   // closed form; every decision by the integer first-level tests
+    kPathSecondLevel = 1,  // closed form; at least one decision by the second-level margin test
+    kPathCareful = 2,      // closed form; careful mode (every late decision by the margin test)
+    kPathLiteralRun = 3,   // redone by the literal code: a run-level guard fired
+    kPathLiteralSel = 4    // redone by the literal code: the selection guard fired
+};
 
 __device__ __forceinline__ unsigned lanemask_lt()
 {
@@ -101,6 +111,7 @@ __global__ void __launch_bounds__(128, RLX ? GCS_STATIC_RLX_MINB : GCS_STATIC_MI
     const double runtime_zero = (double)(p.n >> 62);  // 0.0 for every valid n, opaque to the compiler
     int it, conv;
     bool literal = !RLX;
+    int pathv = 0;
     if constexpr (RLX) {
         Rsys<KIND> rs;
         RelaxGuard g;
@@ -110,12 +121,14 @@ __global__ void __launch_bounds__(128, RLX ? GCS_STATIC_RLX_MINB : GCS_STATIC_MI
         // iteration 0 compares the guess with prev = (0, 0)
         if (!(fabs(0.0 - x) < kTol && fabs(0.0 - y) < kTol)) {
             double u0, u1;
-            state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1);
+            state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1, nullptr, p.path ? &pathv : nullptr);
         }
         conv = 1;
+        pathv = (pathv & 2) ? kPathCareful : (pathv & 1) ? kPathSecondLevel : kPathFirstLevel;
         if (state != kRlxConverged) {
             literal_rerun<KIND>(p.guesses, p.stride, i, k, seed, runtime_zero, x, y, it, conv, state - kRlxUncertain);
             literal = true;
+            pathv = kPathLiteralRun;
         }
     } else {
         FastConsts fc;
@@ -137,7 +150,10 @@ __global__ void __launch_bounds__(128, RLX ? GCS_STATIC_RLX_MINB : GCS_STATIC_MI
         int redo = (seed == 0 && !selection_is_robust<KIND, NS>(k, code, cx, cy)) ? 1 : 0;
         redo = __shfl_sync(kFull, redo, lead);
         if (__any_sync(kFull, redo)) {
-            if (redo && !literal) literal_rerun<KIND>(p.guesses, p.stride, i, k, seed, runtime_zero, x, y, it, conv, kWhySelection);
+            if (redo && !literal) {
+                literal_rerun<KIND>(p.guesses, p.stride, i, k, seed, runtime_zero, x, y, it, conv, kWhySelection);
+                pathv = kPathLiteralSel;
+            }
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 cx[s] = __shfl_sync(kFull, x, lead + s);
@@ -146,6 +162,8 @@ __global__ void __launch_bounds__(128, RLX ? GCS_STATIC_RLX_MINB : GCS_STATIC_MI
         }
     }
     if (valid) {
+        if constexpr (RLX)
+            if (p.path) p.path[(long long)seed * p.stride + sub] = (uint8_t)pathv;
         if (p.iters) p.iters[(long long)seed * p.stride + sub] = (int16_t)it;
         if (p.converged) p.converged[(long long)seed * p.stride + sub] = (uint8_t)conv;
         if (p.cand) {

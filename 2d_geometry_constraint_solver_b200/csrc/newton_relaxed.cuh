@@ -310,8 +310,10 @@ __device__ __forceinline__ bool rlx_uncertain(int state) { return state >= kRlxU
 // run to the next so that (G2) sees growth across the hand-off.
 template <int KIND, bool kTrack>
 __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard& g, double& x, double& y, int& it,
-    int limit, double& d2, double& d3, int* dmin_io = nullptr)
+    int limit, double& d2, double& d3, int* dmin_io = nullptr, int* trace = nullptr)
 {
+    // trace (test hook, rare path only): |= 1 when a decision went to the second-level margin test,
+    // |= 2 when the run entered careful mode
     unsigned span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
     // smallest hi(|det|) at the iterates after the seed, and its largest growth over that running
     // minimum; the determinant AT THE SEED (d1) counts for (G1) only: both arithmetics start from
@@ -417,12 +419,14 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
                 break;
             }
             careful = true;
+            if (trace) *trace |= 2;
         }
         if (!careful && mh < g.lo_h) {
             state = kRlxConverged;
             break;
         }
         const int verdict = g.precise(fmax(fabs(s0), fabs(s1)) * Rsys<KIND>::kStepScale, det);
+        if (trace) *trace |= 1;
         if (verdict >= 0) {
             state = verdict > 0 ? kRlxConverged : kRlxUncertain + kWhyBand;
             break;

@@ -245,6 +245,15 @@ GCS_B200_API int gcs_b200_contracted_stats(int device, uint64_t out[2], int rese
  * [6], [7] reserved (0) */
 GCS_B200_API int gcs_b200_contracted_stats_ex(int device, uint64_t out[8], int reset);
 
+/* Test hook: while set (dev_buf != NULL, capacity > 0), every gcs_b200_solve launch of a
+ * GCS_VARIANT_CONTRACTED[_STATIC] batch on `device` with n * n_seeds <= capacity also writes, per
+ * Newton run ([n_seeds][n] bytes at dev_buf), how the run was decided: 0 closed form, first-level
+ * tests only; 1 closed form, second-level margin test consulted; 2 closed form, careful mode;
+ * 3 redone literally by a run-level guard; 4 redone literally by the selection guard.
+ * tests/test_gpu_margins.py checks the runs the guards accepted against the CPU checker's own
+ * record of how close the literal trajectory came to each decision boundary. */
+GCS_B200_API int gcs_b200_debug_path_buffer(int device, uint8_t* dev_buf, int64_t capacity);
+
 /* FP64 pipe micro-benchmarks used as roofline denominators (seconds-scale, device `device`):
  *   what = 0: dependent-free DFMA throughput, returns TFLOP/s counting FMA = 2 flops
  *   what = 1: DADD/DMUL mix throughput (1 flop per instruction), TFLOP/s

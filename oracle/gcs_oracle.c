@@ -302,6 +302,40 @@ static seed_result newton2d(const system2* s, double gx, double gy)
     return out;
 }
 
+/* The same run, watching how close every convergence decision came to the threshold.  For the
+ * update k that led to iterate k+1 (Jacobian J_k), m_k = max(|dx_k|, |dy_k|) is what the reference
+ * compares with TOL one iteration later (newton_raphson.hpp:83-88).  The contracted kernels
+ * (csrc/newton_relaxed.cuh, G3) vouch for such a decision only if it is further from the threshold
+ * than     first level : band  = 2^-36 S + 2^-16 TOL            (integer tests in the hot loop)
+ *          second level: sdr / |det J_k| + 2^-40 TOL, sdr = 2^-44 S dr   (careful mode: every update)
+ * Returns in out[0] the minimum over k of |m_k - TOL| - min(band, second)/2 and in out[1] the minimum
+ * of |m_k - TOL| - second/2: how far the LITERAL trajectory stayed from every decision boundary in
+ * excess of half those margins (half: the two arithmetics' own m_k differ by a fraction of the margin).
+ * Negative: some decision of this run sat closer to the threshold than any arithmetic but the
+ * literal one may decide.  (tests/test_gpu_margins.py) */
+static void newton2d_decision_slack(const system2* s, double gx, double gy, double sdr, double band, double out[2])
+{
+    double x = gx, y = gy, px = 0.0, py = 0.0, det_prev = INFINITY;
+    out[0] = out[1] = INFINITY;
+    for (int i = 0; i < MAXIT; ++i) {
+        double f, g, J[4], s0, s1;
+        eval_system(s, x, y, &f, &g, J);
+        colpiv_householder_qr_solve_2x2(J[0], J[1], J[2], J[3], -f, -g, &s0, &s1);
+        if (i > 0) { /* i == 0 compares the seed itself with (0,0): the same exact numbers in any arithmetic */
+            const double m = fmax(fabs(px - x), fabs(py - y));
+            const double second = sdr / det_prev + 0x1p-40 * TOL;
+            const double gap = fabs(m - TOL);
+            const double a = gap - 0.5 * fmin(band, second), b2 = gap - 0.5 * second;
+            if (!(a >= out[0])) out[0] = a; /* NaN sticks */
+            if (!(b2 >= out[1])) out[1] = b2;
+        }
+        if (fabs(px - x) < TOL && fabs(py - y) < TOL) break;
+        det_prev = fabs(J[0] * J[3] - J[1] * J[2]);
+        px = x, py = y;
+        x += s0, y += s1;
+    }
+}
+
 int gcs_oracle_newton2d(int kind, const double* consts, double gx, double gy, double* x, double* y,
     int* iters, int* converged)
 {
@@ -424,6 +458,11 @@ static int pick_by_orientation(const seed_result* c, int ns, int canvas_sign, do
 }
 
 /* one full sub-system: solve2D over all seeds + selection (+ reconstruction) */
+/* gcs_oracle_decision_slack: where solve_one leaves each run's slack (NULL: not tracing) */
+static const double* g_trace_sdr = NULL;
+static const double* g_trace_band = NULL;
+static double* g_trace_slack = NULL; /* [2][n_seeds][n] */
+
 static void solve_one(const gcs_b200_batch* b, int64_t i)
 {
     const int ns = b->n_seeds;
@@ -496,6 +535,13 @@ static void solve_one(const gcs_b200_batch* b, int64_t i)
     }
 
     for (int k = 0; k < ns; ++k) cand[k] = newton2d(&s, g[k][0], g[k][1]);
+    if (g_trace_slack)
+        for (int k = 0; k < ns; ++k) {
+            double sl[2];
+            newton2d_decision_slack(&s, g[k][0], g[k][1], g_trace_sdr[i], g_trace_band[i], sl);
+            g_trace_slack[((int64_t)0 * ns + k) * n + i] = sl[0];
+            g_trace_slack[((int64_t)1 * ns + k) * n + i] = sl[1];
+        }
 
     switch (b->kind) {
     case GCS_KIND_PP:
@@ -620,4 +666,13 @@ int gcs_oracle_solve(const gcs_b200_batch* b, int threads)
 #endif
     for (int64_t i = 0; i < b->n; ++i) solve_one(b, i);
     return GCS_OK;
+}
+
+int gcs_oracle_decision_slack(const gcs_b200_batch* b, const double* sdr, const double* band, double* slack, int threads)
+{
+    if (!sdr || !band || !slack) return GCS_E_INVALID;
+    g_trace_sdr = sdr, g_trace_band = band, g_trace_slack = slack;
+    const int rc = gcs_oracle_solve(b, threads);
+    g_trace_sdr = g_trace_band = NULL, g_trace_slack = NULL;
+    return rc;
 }

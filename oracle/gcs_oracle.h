@@ -15,6 +15,12 @@ extern "C" {
 /* whole batch on the host; threads < 1 = all OpenMP threads, 1 = scalar */
 int gcs_oracle_solve(const gcs_b200_batch* batch, int threads);
 
+/* gcs_oracle_solve, plus per run (slack[2][n_seeds][n]) how far the literal trajectory's
+ * convergence decisions stayed from the threshold in excess of half the margins the contracted
+ * kernels claim: plane 0 against min(band[i], sdr[i] / |det J| + 2^-40 tol), plane 1 against the
+ * second term alone (see newton2d_decision_slack).  Not re-entrant. */
+int gcs_oracle_decision_slack(const gcs_b200_batch* batch, const double* sdr, const double* band, double* slack, int threads);
+
 /* one Newton run (newton_raphson.hpp:53-99) of kind `kind` with the kind's 12 evaluation
  * constants (see `system2` in gcs_oracle.c) from guess (gx, gy) */
 int gcs_oracle_newton2d(int kind, const double* consts, double gx, double gy, double* x, double* y,

@@ -26,6 +26,8 @@ def load():
         lib.gcs_oracle_newton2d.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_double, C.c_double,
                                             C.POINTER(C.c_double), C.POINTER(C.c_double),
                                             C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.gcs_oracle_decision_slack.argtypes = [C.POINTER(capi.CBatch), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                                  C.POINTER(C.c_double), C.c_int]
         lib.gcs_oracle_qr_solve_2x2.argtypes = [C.POINTER(C.c_double)] * 3
         lib.gcs_oracle_qr_solve_2x2.restype = None
         _lib = lib
@@ -41,6 +43,22 @@ def solve(batch, threads=0):
     if rc != 0:
         raise RuntimeError(f"gcs_oracle_solve -> {rc}")
     return batch
+
+
+def decision_slack(batch, sdr, band, threads=0):
+    """gcs_oracle_solve + slack[2][n_seeds][n]: how far the literal trajectory's convergence decisions
+    stayed from the threshold beyond half the margins the contracted kernels claim (gcs_oracle.c)."""
+    if not batch.out:
+        batch.alloc_outputs()
+    cb = batch.cbatch(dense=True)
+    sdr = np.ascontiguousarray(sdr, dtype=np.float64)
+    band = np.ascontiguousarray(band, dtype=np.float64)
+    slack = np.empty((2, batch.n_seeds, batch.n))
+    dp = C.POINTER(C.c_double)
+    rc = load().gcs_oracle_decision_slack(C.byref(cb), sdr.ctypes.data_as(dp), band.ctypes.data_as(dp), slack.ctypes.data_as(dp), threads)
+    if rc != 0:
+        raise RuntimeError(f"gcs_oracle_decision_slack -> {rc}")
+    return slack
 
 
 def newton2d(kind, consts, gx, gy):

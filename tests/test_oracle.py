@@ -180,3 +180,20 @@ def test_openmp_equals_scalar(gcs):
     a = O.solve(synth.make_pp(5000).alloc_outputs(), threads=1)
     b = O.solve(synth.make_pp(5000).alloc_outputs(), threads=0)
     assert np.array_equal(a.iters, b.iters) and all(np.array_equal(x, y) for x, y in zip(a.out, b.out))
+
+
+def test_decision_slack_trace_leaves_the_results_alone_and_orders_its_planes(gcs):
+    """gcs_oracle_decision_slack (used by tests/test_gpu_margins.py): same outputs as the plain solve;
+    plane 0 (against min(first level, second level) / 2) is never below plane 1 (second level / 2);
+    a huge margin makes every run's slack negative, a zero margin leaves the bare distance |m - tol|."""
+    synth = gcs.synth
+    a = O.solve(synth.make_pp(2000).alloc_outputs())
+    b = synth.make_pp(2000).alloc_outputs()
+    n = b.n
+    sl = O.decision_slack(b, np.full(n, 1e-9), np.full(n, 1e-12))
+    assert np.array_equal(a.iters, b.iters) and np.array_equal(a.out[0].view(np.uint64), b.out[0].view(np.uint64))
+    assert sl.shape == (2, 2, n) and (sl[0] >= sl[1]).all()
+    bare = O.decision_slack(synth.make_pp(2000).alloc_outputs(), np.zeros(n), np.zeros(n))
+    assert (bare[1] >= -1e-5 * 2.0 ** -41 * 1.0001).all() and (bare[1] < 1e9).all()
+    huge = O.decision_slack(synth.make_pp(2000).alloc_outputs(), np.full(n, 1e30), np.full(n, 1e30))
+    assert (huge[0] < 0).all()
