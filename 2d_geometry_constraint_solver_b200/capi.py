@@ -34,6 +34,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 VARIANT_DEFAULT, VARIANT_STATIC, VARIANT_REFILL, VARIANT_SORTED, VARIANT_PAIR = 0, 1, 2, 3, 4
 # tolerance-class arithmetic (discrete outputs identical, coordinates to 1e-9): auto / static / sorted
 VARIANT_CONTRACTED, VARIANT_CONTRACTED_STATIC, VARIANT_CONTRACTED_SORTED = 5, 6, 7
+VARIANT_CONTRACTED_SEQ, VARIANT_SEQ = 8, 9  # one lane per sub-system, seeds in sequence: contracted / bit-identical
 
 CODE_COLLINEAR = 0x10
 CODE_CANVAS_PARALLEL = 0x20
@@ -81,7 +82,7 @@ EXPORTS = [
     "gcs_b200_fp64_probe", "gcs_b200_synth_pp", "gcs_b200_selftest", "gcs_b200_host_alloc", "gcs_b200_host_free",
     "gcs_b200_contracted_stats", "gcs_b200_contracted_stats_ex", "gcs_b200_column_may_be_null", "gcs_b200_host_alloc_ex",
     "gcs_b200_solve_host_range_async", "gcs_b200_pcie_probe", "gcs_b200_solve_many",
-    "gcs_b200_debug_path_buffer",
+    "gcs_b200_debug_path_buffer", "gcs_b200_resolve_variant",
 ]
 
 
@@ -111,6 +112,7 @@ def load():
     lib.gcs_b200_kernel_name.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.gcs_b200_kernel_name.restype = C.c_char_p
     lib.gcs_b200_default_variant.argtypes = [C.c_int64, C.c_int]
+    lib.gcs_b200_resolve_variant.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int]
     lib.gcs_b200_contracted_stats.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.c_int]
     lib.gcs_b200_contracted_stats_ex.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.c_int]
     lib.gcs_b200_column_may_be_null.argtypes = [C.c_int, C.c_int]

@@ -44,14 +44,23 @@ int fail(int code, const char* fmt, ...)
 
 // GCS_VARIANT_DEFAULT: the sorted kernel from kSortedMinRuns Newton runs per launch (measured faster
 // on every kind and seed count there, profiles/), the static kernel below (a sorted CTA lives
-// twice as long as a static one, which shows while the launch does not fill the device)
+// twice as long as a static one, which shows while the launch does not fill the device).
+// K4 (two linear equations: two updates per seed, then a selection that costs as much) runs one
+// lane per sub-system with the seeds in sequence in both classes (K4, 2^19 sub-systems without
+// parallel rows: 28.7 us against 43.0 sorted / 36.9 contracted static); so does the contracted
+// 8-seed K1 (289 us against 371 per 2^20 x 8: a lane's eight runs add up to nearly the same
+// total in every lane, so hardly a lane-slot idles).
 constexpr long long kSortedMinRuns = 1ll << 18;
-inline int resolve_variant(int variant, long long n, int n_seeds)
+inline int resolve_variant(int variant, int kind, long long n, int n_seeds)
 {
-    // contracted arithmetic: the static kernel at every size (with a 55-cycle update the sort's
-    // bookkeeping costs more than the idle lanes it removes: K1 51 vs 57 us, K3 68 vs 84 us per 2^19)
-    if (variant == GCS_VARIANT_CONTRACTED) return GCS_VARIANT_CONTRACTED_STATIC;
+    if (variant == GCS_VARIANT_CONTRACTED) {
+        // contracted arithmetic otherwise: the static kernel at every size (with a 55-cycle update the
+        // sort's bookkeeping costs more than the idle lanes it removes: K1 51 vs 57 us, K3 68 vs 84 us per 2^19)
+        if (kind == GCS_KIND_PLL || (kind == GCS_KIND_PP && n_seeds == 8)) return GCS_VARIANT_CONTRACTED_SEQ;
+        return GCS_VARIANT_CONTRACTED_STATIC;
+    }
     if (variant != GCS_VARIANT_DEFAULT) return variant;
+    if (kind == GCS_KIND_PLL && n * n_seeds >= (1ll << 17)) return GCS_VARIANT_SEQ;
     return n * n_seeds >= kSortedMinRuns ? GCS_VARIANT_SORTED : GCS_VARIANT_STATIC;
 }
 constexpr int kTicketSlots = 64;
@@ -194,7 +203,7 @@ int validate(const gcs_b200_batch* b)
     if (!b) return fail(GCS_E_INVALID, "null batch");
     if (b->kind < 1 || b->kind > GCS_KIND_COUNT) return fail(GCS_E_INVALID, "unknown kind %d", b->kind);
     if (b->n < 0) return fail(GCS_E_INVALID, "negative n");
-    if (b->variant < GCS_VARIANT_DEFAULT || b->variant > GCS_VARIANT_CONTRACTED_SORTED)
+    if (b->variant < GCS_VARIANT_DEFAULT || b->variant > GCS_VARIANT_SEQ)
         return fail(GCS_E_INVALID, "unknown variant %d", b->variant);
     const bool column_guess = (b->kind == GCS_KIND_SDD || b->kind == GCS_KIND_ANG);
     if (column_guess) {
@@ -248,6 +257,17 @@ int launch_static(const BatchDev& p, cudaStream_t st)
     const long long grid = (threads + block - 1) / block;
     if (grid > 0x7fffffffLL) return fail(GCS_E_INVALID, "batch too large for one launch");
     newton_static_kernel<KIND, NS, RLX><<<(unsigned)grid, block, 0, st>>>(p);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCS_OK;
+}
+
+template <int KIND, int NS, bool RLX>
+int launch_seq(const BatchDev& p, cudaStream_t st)
+{
+    const long long grid = (p.n + 127) / 128;
+    if (grid > 0x7fffffffLL) return fail(GCS_E_INVALID, "batch too large for one launch");
+    newton_seq_kernel<KIND, NS, RLX><<<(unsigned)grid, 128, 0, st>>>(p);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return GCS_OK;
@@ -310,9 +330,11 @@ int launch_refill(DeviceState* d, const BatchDev& p, cudaStream_t st)
 template <int KIND>
 int launch_kind(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cudaStream_t st)
 {
-    const int variant = resolve_variant(b->variant, p.n, b->n_seeds);
+    const int variant = resolve_variant(b->variant, KIND, p.n, b->n_seeds);
     constexpr bool column_guess = (KIND == GCS_KIND_SDD || KIND == GCS_KIND_ANG);
     if (b->n_seeds == 2) {
+        if (variant == GCS_VARIANT_CONTRACTED_SEQ) return launch_seq<KIND, 2, true>(p, st);
+        if (variant == GCS_VARIANT_SEQ) return launch_seq<KIND, 2, false>(p, st);
         if (variant == GCS_VARIANT_CONTRACTED_SORTED) return launch_sorted<KIND, 2, true>(p, st);
         if (variant == GCS_VARIANT_CONTRACTED_STATIC) return launch_static<KIND, 2, true>(p, st);
         if (variant == GCS_VARIANT_SORTED) return launch_sorted<KIND, 2>(p, st);
@@ -320,6 +342,8 @@ int launch_kind(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cuda
         return variant == GCS_VARIANT_REFILL ? launch_refill<KIND, 2>(d, p, st) : launch_static<KIND, 2>(p, st);
     }
     if constexpr (!column_guess) {
+        if (variant == GCS_VARIANT_CONTRACTED_SEQ) return launch_seq<KIND, 8, true>(p, st);
+        if (variant == GCS_VARIANT_SEQ) return launch_seq<KIND, 8, false>(p, st);
         if (variant == GCS_VARIANT_CONTRACTED_SORTED) return launch_sorted<KIND, 8, true>(p, st);
         if (variant == GCS_VARIANT_CONTRACTED_STATIC) return launch_static<KIND, 8, true>(p, st);
         if (variant == GCS_VARIANT_SORTED) return launch_sorted<KIND, 8>(p, st);
@@ -519,13 +543,17 @@ const char* gcs_b200_version(void) { return "gcs_b200 0.2.0 (sm_100a, fp64, fmad
 
 int64_t gcs_b200_launch_count(void) { return g_launches.load(); }
 
-int gcs_b200_default_variant(int64_t n, int n_seeds) { return resolve_variant(GCS_VARIANT_DEFAULT, n, n_seeds); }
+int gcs_b200_default_variant(int64_t n, int n_seeds) { return resolve_variant(GCS_VARIANT_DEFAULT, GCS_KIND_PP, n, n_seeds); }
+
+int gcs_b200_resolve_variant(int variant, int kind, int64_t n, int n_seeds) { return resolve_variant(variant, kind, n, n_seeds); }
 
 const char* gcs_b200_kernel_name(int kind, int n_seeds, int variant)
 {
     static thread_local char name[96];
-    variant = resolve_variant(variant, kSortedMinRuns, 1);  // default: named for a launch that fills the device
+    variant = resolve_variant(variant, kind, kSortedMinRuns, n_seeds);  // default: named for a launch that fills the device
     const char* base = variant == GCS_VARIANT_REFILL ? "newton_refill_kernel"
+        : variant == GCS_VARIANT_CONTRACTED_SEQ      ? "newton_seq_kernel[contracted]"
+        : variant == GCS_VARIANT_SEQ                 ? "newton_seq_kernel"
         : variant == GCS_VARIANT_CONTRACTED_SORTED   ? "newton_sorted_kernel[contracted]"
         : variant == GCS_VARIANT_CONTRACTED_STATIC   ? "newton_static_kernel[contracted]"
         : variant == GCS_VARIANT_SORTED              ? "newton_sorted_kernel"
@@ -723,17 +751,17 @@ int64_t chunk_len(int64_t n, bool slabs, size_t up_bytes_per_row)
 {
     // Index ranges per batch.  Every copy costs a few microseconds of engine time whatever its
     // size, and copies below a few MB do not reach the link rate, so a range is sized by the BYTES
-    // its upload moves (default 8 MB per stage; GCS_B200_STAGE_MB), never below 32 Ki sub-systems
+    // its upload moves (default 32 MB per stage, measured best of 4..32; GCS_B200_STAGE_MB), never below 32 Ki sub-systems
     // and never more than 16 ranges per batch (3 when every column needs its own copy call).  The
     // caller halves the last range, so what trails the final upload is 1/2 .. 1/32 of the batch.
     // Multiples of 128 keep every slice 16-byte aligned.
     static const int forced = getenv("GCS_B200_PARTS") ? atoi(getenv("GCS_B200_PARTS")) : 0;  // tuning knob, 1..64
-    static const int stage_mb = getenv("GCS_B200_STAGE_MB") ? atoi(getenv("GCS_B200_STAGE_MB")) : 8;
+    static const int stage_mb = getenv("GCS_B200_STAGE_MB") ? atoi(getenv("GCS_B200_STAGE_MB")) : 32;
     int64_t parts;
     if (forced > 0 && forced <= 64) {
         parts = forced;
     } else {
-        const size_t stage = (size_t)(stage_mb > 0 && stage_mb <= 1024 ? stage_mb : 8) << 20;
+        const size_t stage = (size_t)(stage_mb > 0 && stage_mb <= 1024 ? stage_mb : 32) << 20;
         const size_t bytes = (size_t)n * (up_bytes_per_row ? up_bytes_per_row : 8);
         parts = (int64_t)((bytes + stage - 1) / stage);
         const int64_t max_parts = slabs ? 16 : 3;

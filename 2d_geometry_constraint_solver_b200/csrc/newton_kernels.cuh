@@ -122,6 +122,11 @@ __global__ void __launch_bounds__(128, RLX ? GCS_STATIC_RLX_MINB : GCS_STATIC_MI
         if (!(fabs(0.0 - x) < kTol && fabs(0.0 - y) < kTol)) {
             double u0, u1;
             state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1, nullptr, p.path ? &pathv : nullptr);
+            if (state == kRlxWantCareful) {  // ill conditioned, above the floor: replay with every decision margin-tested
+                run_seed<KIND>(p.guesses, p.stride, i, k, seed, x, y);
+                const CarefulOut o = relaxed_careful<KIND>(rs, g, x, y);
+                x = o.x, y = o.y, it = o.it, state = o.state, pathv |= o.trace;
+            }
         }
         conv = 1;
         pathv = (pathv & 2) ? kPathCareful : (pathv & 1) ? kPathSecondLevel : kPathFirstLevel;
@@ -178,6 +183,128 @@ __global__ void __launch_bounds__(128, RLX ? GCS_STATIC_RLX_MINB : GCS_STATIC_MI
             if (p.root) p.root[sub] = (uint8_t)root;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// sequential variant: one lane per sub-system, its seeds one after the other
+//
+// The static mapping gives every (sub-system, seed) its own lane: the columns of a sub-system are
+// requested by NS lanes, only one lane in NS selects the root, and a warp lasts as long as the
+// longest of its 32 runs.  Here a lane owns a whole sub-system: it loads the columns once (32
+// consecutive doubles per column and warp: full 256-byte requests), iterates seed 0, then seed 1
+// (..., seed 7), selects and stores - every lane busy in every phase, no shuffles.  A warp now
+// lasts as long as the largest SUM of iteration counts among its 32 sub-systems, and sums spread
+// less than single runs do (K1: runs of 11..18 updates, sums of 24..30), so fewer lane-slots idle;
+// for the short kinds (K4: two updates per seed; K2 / K5: five or six) the selection - a third to
+// a half of the work - no longer runs on half-empty warps.  The price: half as many threads per
+// batch (fewer CTAs to fill the last wave with) and twice the latency of a CTA.
+// The literal re-run of the contracted class is an out-of-line call here (it reloads the columns
+// itself), which keeps the closed-form path free of its registers.
+// ------------------------------------------------------------------------------------------
+struct RunOut {
+    double x, y;
+    int it, conv;
+};
+
+template <int KIND>
+static __device__ __noinline__ RunOut literal_run_from_global(const BatchDev& p, long long i, int seed, int why)
+{
+    using S = Sys<KIND>;
+    double k[S::kCols];
+#pragma unroll
+    for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + i);
+    RunOut r;
+    literal_rerun<KIND>(p.guesses, p.stride, i, k, seed, (double)(p.n >> 62), r.x, r.y, r.it, r.conv, why);
+    return r;
+}
+
+// contracted: held to 80 registers (6 CTAs per SM); measured 8 / 6 / 5 CTAs: K1 55.3 / 51.7 / 50.7 us,
+// K3 80.4 / 73.7 / 74.8 us per 2^19
+#ifndef GCS_SEQ_MINB
+#define GCS_SEQ_MINB 6
+#endif
+template <int KIND, int NS, bool RLX>
+__global__ void __launch_bounds__(128, RLX ? GCS_SEQ_MINB : 5) newton_seq_kernel(const __grid_constant__ BatchDev p)
+{
+    using S = Sys<KIND>;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    double k[S::kCols];
+#pragma unroll
+    for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + i);
+    const uint8_t code = p.code ? __ldg(p.code + i) : (uint8_t)GCS_MAKE_CODE(0, 0, 0);
+    const double runtime_zero = (double)(p.n >> 62);
+    double cx[NS], cy[NS];
+
+    auto one_seed = [&](int s) {
+        double x, y;
+        run_seed<KIND>(p.guesses, p.stride, i, k, s, x, y);
+        int it = 0, conv = 1, pathv = 0;
+        if constexpr (RLX) {
+            Rsys<KIND> rs;
+            RelaxGuard g;
+            rs.load(k, g);
+            int state = kRlxConverged;
+            // iteration 0 compares the guess with prev = (0, 0)
+            if (!(fabs(0.0 - x) < kTol && fabs(0.0 - y) < kTol)) {
+                double u0, u1;
+                state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1, nullptr, p.path ? &pathv : nullptr);
+                if (state == kRlxWantCareful) {
+                    run_seed<KIND>(p.guesses, p.stride, i, k, s, x, y);
+                    const CarefulOut o = relaxed_careful<KIND>(rs, g, x, y);
+                    x = o.x, y = o.y, it = o.it, state = o.state, pathv |= o.trace;
+                }
+            }
+            pathv = (pathv & 2) ? kPathCareful : (pathv & 1) ? kPathSecondLevel : kPathFirstLevel;
+            if (state != kRlxConverged) {
+                const RunOut r = literal_run_from_global<KIND>(p, i, s, state - kRlxUncertain);
+                x = r.x, y = r.y, it = r.it, conv = r.conv;
+                pathv = kPathLiteralRun;
+            }
+            if (p.path) p.path[(long long)s * p.stride + i] = (uint8_t)pathv;
+        } else {
+            S sys;
+            sys.load(k);
+            FastConsts fc;
+            fc.init(runtime_zero);
+            newton_run<KIND>(sys, fc, x, y, it, conv);
+        }
+        if (p.iters) p.iters[(long long)s * p.stride + i] = (int16_t)it;
+        if (p.converged) p.converged[(long long)s * p.stride + i] = (uint8_t)conv;
+        cx[s] = x, cy[s] = y;
+    };
+    if constexpr (NS == 2) {
+        one_seed(0);
+        one_seed(1);
+    } else {
+#pragma unroll 1
+        for (int s = 0; s < NS; ++s) one_seed(s);
+    }
+    if constexpr (RLX) {
+        // (G5) a selection the margins do not vouch for: every seed of the sub-system goes literal
+        if (!selection_is_robust<KIND, NS>(k, code, cx, cy)) {
+#pragma unroll 1
+            for (int s = 0; s < NS; ++s) {
+                const RunOut r = literal_run_from_global<KIND>(p, i, s, kWhySelection);
+                cx[s] = r.x, cy[s] = r.y;
+                if (p.iters) p.iters[(long long)s * p.stride + i] = (int16_t)r.it;
+                if (p.converged) p.converged[(long long)s * p.stride + i] = (uint8_t)r.conv;
+                if (p.path) p.path[(long long)s * p.stride + i] = (uint8_t)kPathLiteralSel;
+            }
+        }
+    }
+    if (p.cand) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            p.cand[((long long)s * 2 + 0) * p.stride + i] = cx[s];
+            p.cand[((long long)s * 2 + 1) * p.stride + i] = cy[s];
+        }
+    }
+    double out[4];
+    const int root = select_and_finish<KIND, NS>(k, code, cx, cy, out);
+#pragma unroll
+    for (int c = 0; c < S::kOut; ++c) p.out[c][i] = out[c];
+    if (p.root) p.root[i] = (uint8_t)root;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -470,6 +597,11 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
                         double u0, u1;
                         int dmin = s_dmin[r];
                         state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1, &dmin);
+                        if (state == kRlxWantCareful) {  // replayed from the seed, whatever phase A did with its first updates
+                            run_seed<KIND>(p.guesses, p.stride, base + sub, k, r / TILE, x, y);
+                            const CarefulOut o = relaxed_careful<KIND>(rs, g, x, y);
+                            x = o.x, y = o.y, it = o.it, state = o.state;
+                        }
                     }
                     if (state != kRlxConverged)
                         literal_rerun<KIND>(p.guesses, p.stride, base + sub, k, r / TILE, (double)(p.n >> 62), x, y, it, conv, state - kRlxUncertain);

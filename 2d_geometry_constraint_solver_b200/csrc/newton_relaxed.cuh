@@ -298,7 +298,7 @@ struct Rsys<GCS_KIND_ANG> {
 
 // Outcome of a stretch of closed-form updates.  Uncertain outcomes carry the reason:
 // state = kRlxUncertain + kWhy*.
-enum : int { kRlxRunning = 0, kRlxConverged = 1, kRlxUncertain = 2 };
+enum : int { kRlxRunning = 0, kRlxConverged = 1, kRlxUncertain = 2, kRlxWantCareful = 32 };
 __device__ __forceinline__ bool rlx_uncertain(int state) { return state >= kRlxUncertain; }
 
 // Up to `limit` closed-form updates from (x, y), `it` updates applied so far.  Returns
@@ -312,8 +312,7 @@ template <int KIND, bool kTrack>
 __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard& g, double& x, double& y, int& it,
     int limit, double& d2, double& d3, int* dmin_io = nullptr, int* trace = nullptr)
 {
-    // trace (test hook, rare path only): |= 1 when a decision went to the second-level margin test,
-    // |= 2 when the run entered careful mode
+    // trace (test hook, rare path only): |= 1 when a decision went to the second-level margin test
     unsigned span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
     // smallest hi(|det|) at the iterates after the seed, and its largest growth over that running
     // minimum; the determinant AT THE SEED (d1) counts for (G1) only: both arithmetics start from
@@ -321,14 +320,10 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
     // and then contracted) but has none to amplify, and |det| growing from the seed to the
     // landing point is routine (a seed that happens to lie near the singular line).
     int dmin = 0x7fffffff, grow = 0, d1 = 0x7fffffff;
-    // smallest length (high word) of the updates BEFORE the latest one: what lets a run whose
-    // conditioning falls under the (G1) line late be certified after the fact (careful mode below)
-    // instead of being redone.  Unknown (0) for a run continued from an earlier stretch.
-    int mmin = 0x7fffffff;
-    if (dmin_io && it > 0) dmin = *dmin_io, mmin = 0;  // a run continued from an earlier stretch (sorted kernel)
+    if (dmin_io && it > 0) dmin = *dmin_io;  // a run continued from an earlier stretch (sorted kernel)
     int state = kRlxRunning;
     if (it >= limit) return (limit >= kRelaxCap) ? kRlxUncertain + kWhyCap : kRlxRunning;
-    int mh = 0x7fffffff, dh;
+    int mh, dh;
     double s0, s1, det;
     // one closed-form update; leaves mh = larger high word of the update's components, dh = hi(|det|)
     auto update = [&](auto from_seed) {
@@ -365,63 +360,31 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
         d1 = dh;
         in_loop = (unsigned)(mh - g.hi_h) < span && it < limit;
     }
-    // Careful mode (the static kernels only: whole runs, every update's length on record).  A run
-    // whose |det J| falls under the (G1) line 2^-10 dr - flat triangles, lines that nearly touch
-    // their circle - used to be redone literally: one long chain of dependent FP64 operations that
-    // outlived its launch (the re-run tail).  Its decisions are still certifiable: the
-    // second-level margin of (G3) already scales with the actual conditioning, 2^-44 S dr/|det|.
-    // So down to |det| >= 2^-14 dr (the coordinates differ by ~8 (dr/|det|) 2^-52 S between the two
-    // arithmetics: 2^-35 S there, a factor 30 inside the 1e-9 tolerance; past it: literal) the run continues with EVERY update decided by that margin test, provided
-    // no earlier update - decided by the first-level band, which is only wide enough for
-    // dr/|det| <= 2^10 - was shorter than tol + the margin at the floor (mmin).
-    constexpr bool kCareful = !kTrack;
-    bool careful = false;
 #pragma unroll 1
     for (;;) {
-        if (!careful) {
-            // hot loop: one update per trip, left when the update is no longer longer than the
-            // threshold for certain (or is non-finite / huge), or at the limit
-            if (in_loop) {
+        // hot loop: one update per trip, left when the update is no longer longer than the
+        // threshold for certain (or is non-finite / huge), or at the limit
+        if (in_loop) {
 #pragma unroll 1
-                do {
-                    if constexpr (kCareful) mmin = min(mmin, mh);
-                    update(std::false_type {});
-                    grow = max(grow, dh - dmin);  // (G2), in high-word units (2^20 per binade)
-                    dmin = min(dmin, dh);
-                } while ((unsigned)(mh - g.hi_h) < span && it < limit);
-            }
-            in_loop = true;
-            // ---- rare from here ----
-            if ((unsigned)(mh - g.hi_h) < span) break;  // limit reached, every update longer than the threshold
-        } else {
-            if (it >= limit) break;
-            mmin = min(mmin, mh);
-            update(std::false_type {});
-            grow = max(grow, dh - dmin);
-            dmin = min(dmin, dh);
+            do {
+                update(std::false_type {});
+                grow = max(grow, dh - dmin);  // (G2), in high-word units (2^20 per binade)
+                dmin = min(dmin, dh);
+            } while ((unsigned)(mh - g.hi_h) < span && it < limit);
         }
-        const int dlow = min(dmin, d1);
+        in_loop = true;
+        // ---- rare from here ----
+        if ((unsigned)(mh - g.hi_h) < span) break;  // limit reached, every update longer than the threshold
         if (mh >= RelaxGuard::kBigH || grow > kBounce) {  // (G4) / (G2)
             state = kRlxUncertain + (mh >= RelaxGuard::kBigH ? kWhyHuge : kWhyBounce);
             break;
         }
-        if (dlow < g.det_h) {  // (G1)
-            bool ok = kCareful && kCarefulBinades > 0 && limit >= kRelaxCap && dlow >= g.det_h - (kCarefulBinades << 20);  // |det| >= 2^-14 dr
-            if (ok && !careful) {
-                // every earlier update longer, for certain, than tol + the widest margin careful mode admits
-                const double wide = g.carry < 0.5
-                    ? (kTol * (1.0 + 0x1p-39) + (double)(1 << (kCarefulBinades + 2)) * (g.band - 0x1p-16 * kTol)) / (1.0 - g.carry)
-                    : 0x1p900;
-                ok = mmin > hi_floor(wide * (1.0 / Rsys<KIND>::kStepScale)) + 1;
-            }
-            if (!ok) {
-                state = kRlxUncertain + kWhyCond;
-                break;
-            }
-            careful = true;
-            if (trace) *trace |= 2;
+        if (min(dmin, d1) < g.det_h) {  // (G1): careful mode if the caller runs whole runs and the floor holds, else literal
+            state = (!kTrack && kCarefulBinades > 0 && limit >= kRelaxCap && min(dmin, d1) >= g.det_h - (kCarefulBinades << 20))
+                ? kRlxWantCareful : kRlxUncertain + kWhyCond;
+            break;
         }
-        if (!careful && mh < g.lo_h) {
+        if (mh < g.lo_h) {
             state = kRlxConverged;
             break;
         }
@@ -433,13 +396,83 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
         }
         if (it >= limit) break;  // not converged for certain, and out of updates
     }
-    if (state == kRlxRunning) {
-        const int dlow = min(dmin, d1);
-        if ((dlow < g.det_h && !careful) || grow > kBounce || limit >= kRelaxCap)
-            state = kRlxUncertain + ((dlow < g.det_h && !careful) ? kWhyCond : grow > kBounce ? kWhyBounce : kWhyCap);
-    }
+    if (state == kRlxRunning && (min(dmin, d1) < g.det_h || grow > kBounce || limit >= kRelaxCap))
+        state = kRlxUncertain + (min(dmin, d1) < g.det_h ? kWhyCond : grow > kBounce ? kWhyBounce : kWhyCap);
     if (dmin_io) *dmin_io = dmin;
     return state;
+}
+
+// Careful mode: a whole run from its seed with EVERY convergence decision taken by the
+// conditioning-scaled margin test (RelaxGuard::precise) instead of the fixed first-level band.
+//
+// A run whose |det J| falls under the (G1) line 2^-10 dr - flat triangles, lines that nearly touch
+// their circle - used to be redone literally: one long chain of dependent FP64 operations that
+// outlived its launch (the re-run tail).  Its decisions are still certifiable: the
+// second-level margin of (G3), 2^-44 S dr/|det J| + 2^-40 tol (+ the carry term), scales with the
+// actual conditioning at every update; what does not is the first-level band of the hot loop, which
+// is only wide enough for dr/|det| <= 2^10.  So relaxed_updates hands such a run back
+// (kRlxWantCareful) and the caller replays it here: the closed-form arithmetic is deterministic, the
+// replay visits the same iterates, and now no decision rests on the fixed band.  The floor
+// |det| >= 2^-14 dr stays (the coordinates of the two arithmetics differ by ~8 (dr/|det|) 2^-52 S:
+// 2^-35 S there, a factor 30 inside the 1e-9 tolerance); below it, and for everything else the
+// guards do not vouch for, the literal code.  Out of line and by value: one run in a few thousand
+// comes here, and the hot loop of relaxed_updates keeps its registers.
+struct CarefulOut {
+    double x, y;
+    int it, state, trace;
+};
+
+template <int KIND>
+static __device__ __noinline__ CarefulOut relaxed_careful(Rsys<KIND> rs, RelaxGuard g, double x, double y)
+{
+    CarefulOut o;
+    o.trace = 2;
+    int it = 0, state = kRlxRunning;
+    int dmin = 0x7fffffff, grow = 0, d1 = 0x7fffffff;
+#pragma unroll 1
+    while (it < kRelaxCap) {
+        double a, b, c, d, r0, r1;
+        rs.eval(x, y, a, b, c, d, r0, r1);
+        const double det = __fma_rn(a, d, -(b * c));
+        const double r = rcp_relaxed(det);
+        if (it == 0) {
+            const double q = __fma_rn(a, a, __fma_rn(b, b, __fma_rn(c, c, d * d)));
+            g.add_carry(0x1p-48 * q * fabs(r), Rsys<KIND>::kStepScale);
+        }
+        const double n0 = __fma_rn(r0, d, -(r1 * b));
+        const double n1 = __fma_rn(a, r1, -(c * r0));
+        const double s0 = n0 * r, s1 = n1 * r;
+        if constexpr (Rsys<KIND>::kStepScale == 1.0) {
+            x += s0, y += s1;
+        } else {
+            x = __fma_rn(s0, Rsys<KIND>::kStepScale, x);
+            y = __fma_rn(s1, Rsys<KIND>::kStepScale, y);
+        }
+        const int dh = abs_hi(det), mh = max(abs_hi(s0), abs_hi(s1));
+        if (it == 0) {
+            d1 = dh;  // the determinant at the seed counts for the floor only (see relaxed_updates)
+        } else {
+            grow = max(grow, dh - dmin);
+            dmin = min(dmin, dh);
+        }
+        ++it;
+        if (mh >= RelaxGuard::kBigH || grow > kBounce) {  // (G4) / (G2)
+            state = kRlxUncertain + (mh >= RelaxGuard::kBigH ? kWhyHuge : kWhyBounce);
+            break;
+        }
+        if (min(dmin, d1) < g.det_h - (kCarefulBinades << 20)) {  // under the careful floor (or a degenerate scale)
+            state = kRlxUncertain + kWhyCond;
+            break;
+        }
+        const int verdict = g.precise(fmax(fabs(s0), fabs(s1)) * Rsys<KIND>::kStepScale, det);
+        if (verdict >= 0) {
+            state = verdict > 0 ? kRlxConverged : kRlxUncertain + kWhyBand;
+            break;
+        }
+    }
+    if (state == kRlxRunning) state = kRlxUncertain + kWhyCap;
+    o.x = x, o.y = y, o.it = it, o.state = state;
+    return o;
 }
 
 // seed `seed` of sub-system `gi` as the kernels take it

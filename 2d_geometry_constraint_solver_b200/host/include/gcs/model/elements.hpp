@@ -8,6 +8,8 @@
 //                      Element::updateElementPosition sets and the eight matches() predicates read.
 #pragma once
 
+#include <cstdint>
+
 #include <string>
 #include <utility>
 #include <variant>
@@ -98,9 +100,15 @@ public:
     std::string getElementName() const;
     std::string toString() const;
 
+    // Scratch word of the batched leaf scheduler (gcs/b200/leaf_batch.hpp): (epoch of the plan
+    // that last numbered this element) << 32 | its dense index in that plan.  Not part of the
+    // element's value; plans over the same elements must not run concurrently.
+    std::uint64_t& planTagWord() const { return m_planTag; }
+
 private:
     ElementVariant m_element;
     bool m_isSet = false;
+    alignas(8) mutable std::uint64_t m_planTag = 0;
 };
 
 }  // namespace Gcs

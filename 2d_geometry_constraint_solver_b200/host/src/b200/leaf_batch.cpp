@@ -14,6 +14,7 @@
 // Numerics on this side are plain IEEE doubles evaluated in the reference's order (one rounding
 // per operation; the host build uses -ffp-contract=off like the reference's baseline x86-64 build).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -66,6 +67,8 @@ Census census(const ConstraintGraph& g, const SetQuery& q)
 struct ConstraintCensus {
     int total = 0, distance = 0, angle = 0;
 };
+
+bool matchesCountsOn(SolverId id, int edgeCount, const Census& c, const ConstraintCensus& k);  // below, with the predicates
 
 ConstraintCensus constraintCensus(const ConstraintGraph& g)
 {
@@ -432,6 +435,187 @@ struct Plan {
     std::exception_ptr error;          // what the reference's loop would have thrown at leaf `stop`
 };
 
+// ---------------------------------------------------------------------------------------------
+// The symbolic pass in two steps.
+//  (A) per leaf, independent of every other leaf (hence over all host threads): the three
+//      elements in ascending node id, their types, the constraint on each of the three node pairs
+//      (kind, value, orientation flag; virtual and missing edges carry none), the counts the eight
+//      predicates ask for.  This is where the graph containers are walked.
+//  (B) one sequential sweep over those facts with the PREDICTED solved flags: the reference's
+//      first-match dispatch (component_solver.hpp:31-66), its role loops, the read / write footprint
+//      and the wave of every leaf.  No container is touched here; elements are numbered on first
+//      sight through a tag kept in the Element itself.
+// A leaf the facts cannot describe (not three nodes, a role whose constraint is missing, ...) goes
+// through the general code (classify / assignRoles on the graph), which raises what the reference
+// raises.
+// ---------------------------------------------------------------------------------------------
+struct LeafFacts {
+    Element* e[3] = { nullptr, nullptr, nullptr };
+    bool isPoint[3] = {}, isLine[3] = {}, setNow[3] = {};
+    // node pairs (0,1), (0,2), (1,2): a real constraint with a value sits on the edge
+    bool has[3] = {}, flip[3] = {};
+    double val[3] = {};
+    int slot[3] = { -1, -1, -1 };  // dense index of each element in this plan (Element::planTag)
+    int edgeCount = 0;
+    ConstraintCensus k;
+    bool simple = false;
+};
+
+// Dense index of an element in the plan of `epoch`, handed out on first sight from `next` - from
+// any thread: the tag word is claimed by compare-and-swap (a slot number lost to a race is simply
+// never used).
+int planSlot(const Element* e, std::uint32_t epoch, std::atomic<int>& next)
+{
+    std::atomic_ref<std::uint64_t> tag(e->planTagWord());
+    std::uint64_t seen = tag.load(std::memory_order_relaxed);
+    while (static_cast<std::uint32_t>(seen >> 32) != epoch) {
+        const std::uint64_t mine = (static_cast<std::uint64_t>(epoch) << 32) | static_cast<std::uint32_t>(next.fetch_add(1));
+        if (tag.compare_exchange_strong(seen, mine, std::memory_order_relaxed)) return static_cast<int>(mine & 0xffffffffu);
+    }
+    return static_cast<int>(seen & 0xffffffffu);
+}
+
+inline int pairIndex(int a, int b) { return a + b - 1; }  // {0,1} -> 0, {0,2} -> 1, {1,2} -> 2
+
+LeafFacts gatherFacts(const ConstraintGraph& g, std::uint32_t epoch, std::atomic<int>& nextSlot)
+{
+    LeafFacts f;
+    if (g.nodeCount() != 3) return f;
+    NodeId node[3];
+    int n = 0;
+    for (const auto& [nd, el] : g.getElementMap()) {
+        if (n == 3 || !el) return f;
+        node[n] = nd;
+        f.e[n] = el.get();
+        f.isPoint[n] = el->isElementType<Point>();
+        f.isLine[n] = el->isElementType<Line>();
+        f.setNow[n] = el->isElementSet();
+        f.slot[n] = planSlot(el.get(), epoch, nextSlot);
+        ++n;
+    }
+    if (n != 3) return f;
+    f.edgeCount = static_cast<int>(g.edgeCount());
+    f.k = constraintCensus(g);
+    const auto& cmap = g.getConstraintMap();
+    for (int a = 0; a < 3; ++a)
+        for (int b = a + 1; b < 3; ++b) {
+            const int p = pairIndex(a, b);
+            const auto edge = g.getEdgeBetween(node[a], node[b]);
+            if (!edge.has_value()) continue;
+            const auto c = cmap.get(edge.value());
+            if (!c.has_value() || !c.value().get()) continue;
+            const Constraint& con = *c.value().get();
+            const auto v = con.getConstraintValue();
+            if (!v.has_value()) continue;
+            f.has[p] = true;
+            f.val[p] = v.value();
+            const auto* ang = con.getConstraintAs<AngleConstraint>();
+            f.flip[p] = ang != nullptr && ang->flipOrientation;
+        }
+    f.simple = true;
+    return f;
+}
+
+// classify() on facts: same counts, same order
+SolverId classifyFacts(const LeafFacts& f, const bool set[3])
+{
+    Census c;
+    for (int i = 0; i < 3; ++i) {
+        c.solved += set[i] ? 1 : 0;
+        if (f.isPoint[i]) {
+            ++c.points;
+            ++(set[i] ? c.solvedPoints : c.unsolvedPoints);
+        } else if (f.isLine[i]) {
+            ++c.lines;
+            ++(set[i] ? c.solvedLines : c.unsolvedLines);
+        }
+    }
+    static constexpr SolverId order[] = { SolverId::ZeroFixedPointsTriangle, SolverId::ZeroFixedPPLTriangle,
+        SolverId::ZeroFixedLLPAngleTriangle, SolverId::TwoFixedPointsDistance, SolverId::TwoFixedPointsLine,
+        SolverId::FixedPointAndLineFreePoint, SolverId::TwoFixedLinesFreePoint, SolverId::FixedLineAndPointFreeLine };
+    for (SolverId id : order)
+        if (matchesCountsOn(id, f.edgeCount, c, f.k)) return id;
+    return SolverId::None;
+}
+
+// assignRoles() on facts.  Returns false when a constraint a role needs is not there (the general
+// code then raises the reference's exception) or the shape is one the role loops do not fill.
+bool rolesFromFacts(SolverId id, const LeafFacts& f, const bool set[3], Roles& r)
+{
+    r = Roles {};
+    r.id = id;
+    int ia = -1, ib = -1, ic = -1;
+    auto firstSecond = [&](auto pred, int& first, int& second) {  // "if (!haveA) a = e else b = e" over ascending ids
+        for (int i = 0; i < 3; ++i)
+            if (pred(i)) {
+                if (first < 0)
+                    first = i;
+                else
+                    second = i;
+            }
+    };
+    auto last = [&](auto pred, int& slot) {
+        for (int i = 0; i < 3; ++i)
+            if (pred(i)) slot = i;
+    };
+    auto value = [&](int a, int b, double& out, bool* flip = nullptr) {
+        if (a < 0 || b < 0 || a == b) return false;
+        const int p = pairIndex(a < b ? a : b, a < b ? b : a);
+        if (!f.has[p]) return false;
+        out = f.val[p];
+        if (flip) *flip = f.flip[p];
+        return true;
+    };
+    bool ok = true;
+    switch (id) {
+    case SolverId::ZeroFixedPointsTriangle:
+        ia = 0, ib = 1, ic = 2;
+        ok = value(ia, ib, r.v0) && value(ia, ic, r.v1) && value(ib, ic, r.v2);
+        break;
+    case SolverId::ZeroFixedPPLTriangle:
+    case SolverId::TwoFixedPointsLine:
+        last([&](int i) { return f.isLine[i]; }, ic);
+        firstSecond([&](int i) { return !f.isLine[i] && f.isPoint[i]; }, ia, ib);
+        if (id == SolverId::ZeroFixedPPLTriangle) ok = value(ia, ib, r.v0);
+        ok = ok && value(ia, ic, r.v1) && value(ib, ic, r.v2);
+        break;
+    case SolverId::ZeroFixedLLPAngleTriangle:
+        last([&](int i) { return f.isPoint[i]; }, ib);
+        firstSecond([&](int i) { return !f.isPoint[i] && f.isLine[i]; }, ia, ic);
+        ok = value(ia, ic, r.v0, &r.flip) && value(ib, ia, r.v1) && value(ib, ic, r.v2);
+        break;
+    case SolverId::TwoFixedPointsDistance:
+        firstSecond([&](int i) { return set[i]; }, ia, ib);
+        last([&](int i) { return !set[i]; }, ic);
+        if (ic < 0) return false;  // all three solved: the general code raises the reference's failure
+        ok = value(ia, ic, r.v1) && value(ib, ic, r.v2);
+        break;
+    case SolverId::FixedPointAndLineFreePoint:
+        last([&](int i) { return f.isLine[i]; }, ib);
+        last([&](int i) { return !f.isLine[i] && f.isPoint[i] && set[i]; }, ia);
+        last([&](int i) { return !f.isLine[i] && f.isPoint[i] && !set[i]; }, ic);
+        ok = value(ia, ic, r.v1) && value(ib, ic, r.v2);
+        break;
+    case SolverId::TwoFixedLinesFreePoint:
+        last([&](int i) { return f.isPoint[i]; }, ic);
+        firstSecond([&](int i) { return !f.isPoint[i] && f.isLine[i]; }, ia, ib);
+        ok = value(ia, ic, r.v1) && value(ib, ic, r.v2);
+        break;
+    case SolverId::FixedLineAndPointFreeLine:
+        last([&](int i) { return f.isPoint[i]; }, ib);
+        last([&](int i) { return !f.isPoint[i] && f.isLine[i] && set[i]; }, ia);
+        last([&](int i) { return !f.isPoint[i] && f.isLine[i] && !set[i]; }, ic);
+        ok = value(ia, ic, r.v0, &r.flip) && value(ib, ic, r.v2);
+        break;
+    case SolverId::None: return false;
+    }
+    if (!ok || ia < 0 || ib < 0 || ic < 0) return false;
+    r.a = f.e[ia], r.b = f.e[ib], r.c = f.e[ic];
+    return true;
+}
+
+std::atomic<std::uint32_t> g_planEpoch { 0 };
+
 Plan makePlan(const std::vector<ConstraintGraph>& leaves)
 {
     Plan plan;
@@ -439,81 +623,124 @@ Plan makePlan(const std::vector<ConstraintGraph>& leaves)
     plan.report.leaves = n;
     plan.report.level.assign(n, -1);
     plan.report.solver.assign(n, SolverId::None);
-    plan.report.results.assign(n, SolveResult::unsupported("No solver matches this component configuration"));
+    // (a result is a status + a message string: 1e5 copies of the 46-character "unsupported" message
+    // were 1e5 heap allocations, undone one by one below; leaves without a solver get it where they are found)
+    plan.report.results.assign(n, SolveResult::success());
     plan.roles.resize(n);
     plan.stop = n;
+    static const char* const kNoSolver = "No solver matches this component configuration";
 
-    // Every element gets a dense index on first sight; what the symbolic pass knows about it
-    // (solved once the leaves so far have run; wave of its last write / last read) lives in flat
-    // arrays.  One hash lookup per element of a leaf - the predicates and the role assignment then
-    // ask a three-entry table.
-    std::unordered_map<const Element*, int> indexOf;
-    indexOf.reserve(2 * n + 16);
-    std::vector<char> predicted;
-    std::vector<int> lastWrite, lastRead;
-    const Element* leafEl[3] = { nullptr, nullptr, nullptr };
-    int leafIx[3] = { -1, -1, -1 };
-    int leafCount = 0;
-    auto slotOf = [&](const Element* e) {
-        for (int k = 0; k < leafCount; ++k)
-            if (leafEl[k] == e) return leafIx[k];
-        const auto it = indexOf.find(e);  // not an element of the current leaf: cannot happen for 3-node leaves
-        return it == indexOf.end() ? -1 : it->second;
-    };
-    const SetQuery q = [&](const Element* e) {
-        if (e->isElementSet()) return true;
-        const int ix = slotOf(e);
-        return ix >= 0 && predicted[static_cast<std::size_t>(ix)] != 0;
+    // (A) per-leaf facts, every host thread
+    const auto tA = std::chrono::steady_clock::now();
+    const std::uint32_t epoch = ++g_planEpoch;
+    std::atomic<int> nextSlot { 0 };
+    std::vector<LeafFacts> facts(n);
+    const long long nn = static_cast<long long>(n);
+#pragma omp parallel for schedule(static) if (nn > 2048)
+    for (long long i = 0; i < nn; ++i) {
+        try {
+            facts[static_cast<std::size_t>(i)] = gatherFacts(leaves[static_cast<std::size_t>(i)], epoch, nextSlot);
+        } catch (...) {
+            facts[static_cast<std::size_t>(i)] = LeafFacts {};  // not simple: the general code decides (and raises) in step (B)
+        }
+    }
+
+    // (B) the sequential sweep.  What the symbolic pass knows about an element (solved once the
+    // leaves so far have run; wave of its last write / last read) lives in flat arrays under the
+    // element's dense index of step (A); the index is kept in the element itself (Element::planTag:
+    // epoch of this plan + slot), so no table is searched and this loop touches no element at all
+    // for the leaves step (A) could describe.  Plans over the same elements must not run
+    // concurrently (the reference's containers are not thread safe either).
+    const auto tB = std::chrono::steady_clock::now();
+    std::vector<char> predicted(static_cast<std::size_t>(nextSlot.load()), 0);
+    std::vector<int> lastWrite(predicted.size(), -1), lastRead(predicted.size(), -1);
+    auto slotOfElement = [&](const Element* e) {
+        const int slot = planSlot(e, epoch, nextSlot);
+        if (static_cast<std::size_t>(slot) >= predicted.size()) {
+            const auto want = static_cast<std::size_t>(nextSlot.load());
+            predicted.resize(want, 0), lastWrite.resize(want, -1), lastRead.resize(want, -1);
+        }
+        return slot;
     };
     int top = -1;
     for (std::size_t i = 0; i < n; ++i) {
-        leafCount = 0;
-        for (const auto& [node, e] : leaves[i].getElementMap()) {
-            const auto [it, fresh] = indexOf.try_emplace(e.get(), static_cast<int>(predicted.size()));
-            if (fresh) predicted.push_back(0), lastWrite.push_back(-1), lastRead.push_back(-1);
-            if (leafCount < 3) leafEl[leafCount] = e.get(), leafIx[leafCount] = it->second, ++leafCount;
+        const LeafFacts& f = facts[i];
+        SolverId id = SolverId::None;
+        bool haveRoles = false;
+        if (f.simple) {
+            bool set[3];
+            for (int k = 0; k < 3; ++k) set[k] = f.setNow[k] || predicted[static_cast<std::size_t>(f.slot[k])] != 0;
+            id = classifyFacts(f, set);
+            if (id != SolverId::None) haveRoles = rolesFromFacts(id, f, set, plan.roles[i]);
+        } else {
+            for (const auto& [node, e] : leaves[i].getElementMap())
+                if (e) slotOfElement(e.get());
         }
-        const SolverId id = classify(leaves[i], q);
+        if (!haveRoles && (!f.simple || id != SolverId::None)) {
+            // the general code: same decisions on the graph itself, raising what the reference raises
+            const SetQuery q = [&](const Element* e) {
+                return e->isElementSet() || predicted[static_cast<std::size_t>(slotOfElement(e))] != 0;
+            };
+            id = classify(leaves[i], q);
+            if (id != SolverId::None) {
+                try {
+                    plan.roles[i] = assignRoles(id, leaves[i], q);
+                } catch (...) {
+                    plan.error = std::current_exception();
+                    plan.stop = i;
+                    plan.report.solver[i] = SolverId::None;
+                    break;
+                }
+            }
+        }
         plan.report.solver[i] = id;
         if (id == SolverId::None) {
             ++plan.report.unsupported;
+            plan.report.results[i] = SolveResult::unsupported(kNoSolver);
             continue;
         }
-        try {
-            plan.roles[i] = assignRoles(id, leaves[i], q);
-        } catch (...) {
-            plan.error = std::current_exception();
-            plan.stop = i;
-            plan.report.solver[i] = SolverId::None;
-            break;
+        // read / write footprint as dense indices (footprintOf: the zero-fixed shapes write all three
+        // elements, the others read a, b and write c)
+        const Roles& r = plan.roles[i];
+        int rs[2], ws[3], nr = 0, nw = 0;
+        auto slotOfRole = [&](const Element* e) {
+            if (f.simple)
+                for (int k = 0; k < 3; ++k)
+                    if (f.e[k] == e) return f.slot[k];
+            return slotOfElement(e);
+        };
+        if (zeroFixed(r.id)) {
+            ws[nw++] = slotOfRole(r.a), ws[nw++] = slotOfRole(r.b), ws[nw++] = slotOfRole(r.c);
+        } else {
+            rs[nr++] = slotOfRole(r.a), rs[nr++] = slotOfRole(r.b);
+            ws[nw++] = slotOfRole(r.c);
         }
-        const Footprint f = footprintOf(plan.roles[i]);
         int lvl = -1;
-        for (int k = 0; k < f.nReads; ++k) lvl = std::max(lvl, lastWrite[static_cast<std::size_t>(slotOf(f.reads[k]))]);
-        for (int k = 0; k < f.nWrites; ++k) {
-            const auto w = static_cast<std::size_t>(slotOf(f.writes[k]));
-            lvl = std::max({ lvl, lastWrite[w], lastRead[w] });
-        }
+        for (int k = 0; k < nr; ++k) lvl = std::max(lvl, lastWrite[static_cast<std::size_t>(rs[k])]);
+        for (int k = 0; k < nw; ++k) lvl = std::max({ lvl, lastWrite[static_cast<std::size_t>(ws[k])], lastRead[static_cast<std::size_t>(ws[k])] });
         ++lvl;
         plan.report.level[i] = lvl;
         top = std::max(top, lvl);
-        for (int k = 0; k < f.nReads; ++k) {
-            int& r = lastRead[static_cast<std::size_t>(slotOf(f.reads[k]))];
-            r = std::max(r, lvl);
+        for (int k = 0; k < nr; ++k) {
+            int& rd = lastRead[static_cast<std::size_t>(rs[k])];
+            rd = std::max(rd, lvl);
         }
-        for (int k = 0; k < f.nWrites; ++k) {
-            const auto w = static_cast<std::size_t>(slotOf(f.writes[k]));
-            lastWrite[w] = lvl;
-            predicted[w] = 1;
+        for (int k = 0; k < nw; ++k) {
+            lastWrite[static_cast<std::size_t>(ws[k])] = lvl;
+            predicted[static_cast<std::size_t>(ws[k])] = 1;
         }
-        plan.report.results[i] = SolveResult::success();
         ++plan.report.solved;
     }
     for (std::size_t i = plan.stop; i < n; ++i) {
         plan.report.level[i] = -1;
+        plan.report.results[i] = SolveResult::unsupported(kNoSolver);
         if (i > plan.stop) plan.report.solver[i] = SolverId::None;
     }
     plan.report.waves = static_cast<std::size_t>(top + 1);
+    if (std::getenv("GCS_HOST_TRACE"))
+        std::fprintf(stderr, "[host] plan: facts %.1f ms, sweep %.1f ms, %zu leaves\n",
+            std::chrono::duration<double>(tB - tA).count() * 1e3,
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - tB).count() * 1e3, n);
     return plan;
 }
 
@@ -554,16 +781,16 @@ int kindOf(SolverId id)
 namespace {
 
 // the eight matches() predicates on the counts of one leaf
-bool matchesCounts(SolverId id, const ConstraintGraph& g, const Census& c, const ConstraintCensus& k)
+bool matchesCountsOn(SolverId id, int edgeCount, const Census& c, const ConstraintCensus& k)
 {
     const bool allDistance = k.distance == k.total;
     switch (id) {
     case SolverId::ZeroFixedPointsTriangle:
-        return g.edgeCount() == 3 && c.solved == 0 && c.points == 3 && allDistance;
+        return edgeCount == 3 && c.solved == 0 && c.points == 3 && allDistance;
     case SolverId::ZeroFixedPPLTriangle:
-        return g.edgeCount() == 3 && c.solved == 0 && c.points == 2 && c.lines == 1 && allDistance;
+        return edgeCount == 3 && c.solved == 0 && c.points == 2 && c.lines == 1 && allDistance;
     case SolverId::ZeroFixedLLPAngleTriangle:
-        return g.edgeCount() == 3 && c.solved == 0 && c.points == 1 && c.lines == 2 && k.angle == 1 && k.distance == 2;
+        return edgeCount == 3 && c.solved == 0 && c.points == 1 && c.lines == 2 && k.angle == 1 && k.distance == 2;
     case SolverId::TwoFixedPointsDistance:
         return c.solved >= 2 && c.points == 3 && allDistance;
     case SolverId::TwoFixedPointsLine:
@@ -579,6 +806,11 @@ bool matchesCounts(SolverId id, const ConstraintGraph& g, const Census& c, const
     case SolverId::None: break;
     }
     return false;
+}
+
+bool matchesCounts(SolverId id, const ConstraintGraph& g, const Census& c, const ConstraintCensus& k)
+{
+    return matchesCountsOn(id, static_cast<int>(g.edgeCount()), c, k);
 }
 
 }  // namespace
@@ -719,13 +951,28 @@ BatchReport solveLeaves(std::vector<ConstraintGraph>& leaves, int device)
     for (std::size_t i = 0; i < plan.stop; ++i)
         if (rep.level[i] >= 0) byWave[static_cast<std::size_t>(rep.level[i])].push_back(i);
     KindBatch batches[GCS_KIND_COUNT + 1];
+    std::vector<PackedLeaf> rows;
     for (const auto& wave : byWave) {
         t0 = Clock::now();
         for (int k = 1; k <= GCS_KIND_COUNT; ++k) batches[k] = KindBatch(k);
-        for (std::size_t i : wave) {
-            const PackedLeaf row = packNumeric(plan.roles[i]);
-            batches[row.kind].push(row);
+        // The leaves of a wave touch disjoint elements wherever one of them writes (that is what a
+        // wave is: nobody reads or writes what another leaf of the wave writes - the anchors the
+        // zero-fixed shapes place included), so their rows are packed on every host thread; the
+        // rows then enter the kind batches in input order.
+        rows.resize(wave.size());
+        const long long m = static_cast<long long>(wave.size());
+        std::exception_ptr packError;
+#pragma omp parallel for schedule(static) if (m > 1024)
+        for (long long j = 0; j < m; ++j) {
+            try {
+                rows[static_cast<std::size_t>(j)] = packNumeric(plan.roles[wave[static_cast<std::size_t>(j)]]);
+            } catch (...) {
+#pragma omp critical
+                if (!packError) packError = std::current_exception();
+            }
         }
+        if (packError) std::rethrow_exception(packError);
+        for (const PackedLeaf& row : rows) batches[row.kind].push(row);
         rep.packSeconds += since(t0);
         for (int k = 1; k <= GCS_KIND_COUNT; ++k) {
             if (batches[k].size() == 0) continue;

@@ -143,7 +143,8 @@ extern "C" {
 
 /* kernel selection.  Variants 0-4 produce bit-identical results (same device functions, same
  * operation order per Newton run); they differ in how runs are mapped to lanes.
- * DEFAULT = SORTED for launches of at least 2^18 runs (n * n_seeds), STATIC below. */
+ * DEFAULT = SORTED for launches of at least 2^18 runs (n * n_seeds), STATIC below; K4 from 2^17
+ * runs: SEQ. */
 #define GCS_VARIANT_DEFAULT 0
 #define GCS_VARIANT_STATIC 1 /* one lane per (sub-system, seed), static mapping */
 #define GCS_VARIANT_REFILL 2 /* persistent CTAs, TMA-staged tiles, warp-level lane refill */
@@ -158,11 +159,13 @@ extern "C" {
  * tests/test_gpu_soak.py and the soaks of profiles/ (> 1e8 sub-systems without a difference; an
  * earlier soak did find one, which is why the carry term exists) - NOT a machine-checked proof.
  * Opt-in: DEFAULT never resolves to it, and the host mirror stays on the bit-identical kernels.
- * CONTRACTED = CONTRACTED_STATIC (measured fastest at every size); CONTRACTED_SORTED maps the same
- * arithmetic onto the sorted tiles. */
+ * CONTRACTED = CONTRACTED_STATIC (measured fastest at every size) except K4 and the 8-seed K1, which
+ * take CONTRACTED_SEQ; CONTRACTED_SORTED maps the same arithmetic onto the sorted tiles. */
 #define GCS_VARIANT_CONTRACTED 5
 #define GCS_VARIANT_CONTRACTED_STATIC 6
 #define GCS_VARIANT_CONTRACTED_SORTED 7
+#define GCS_VARIANT_CONTRACTED_SEQ 8 /* contracted arithmetic, one lane per sub-system, seeds one after the other */
+#define GCS_VARIANT_SEQ 9            /* bit-identical arithmetic in the same mapping */
 
 typedef struct gcs_b200_batch {
     int32_t kind;    /* GCS_KIND_* */
@@ -233,8 +236,11 @@ GCS_B200_API int gcs_b200_solve_sharded(const gcs_b200_batch* batch, int n_dev);
 GCS_B200_API int64_t gcs_b200_launch_count(void);
 /* name of the kernel a batch of this kind / seed count / variant is solved by (thread-local string) */
 GCS_B200_API const char* gcs_b200_kernel_name(int kind, int n_seeds, int variant);
-/* the variant GCS_VARIANT_DEFAULT resolves to for a launch of n sub-systems x n_seeds seeds */
+/* the variant GCS_VARIANT_DEFAULT resolves to for a K1 launch of n sub-systems x n_seeds seeds */
 GCS_B200_API int gcs_b200_default_variant(int64_t n, int n_seeds);
+/* the kernel mapping `variant` (GCS_VARIANT_DEFAULT / GCS_VARIANT_CONTRACTED / an explicit one)
+ * resolves to for a launch of n sub-systems of `kind` x n_seeds seeds */
+GCS_B200_API int gcs_b200_resolve_variant(int variant, int kind, int64_t n, int n_seeds);
 
 /* GCS_VARIANT_CONTRACTED*: cumulative number of Newton runs on `device` that the guards handed to
  * the literal code since the last call with reset != 0: out[0] run-level guards (conditioning,

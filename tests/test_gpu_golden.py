@@ -7,7 +7,7 @@ from test_golden import check_against_golden, check_against_golden_contract, loa
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 9])
 @pytest.mark.parametrize("kind", [1, 2, 3, 4, 5])
 def test_cuda_matches_reference_golden(gpu, gcs, kind, variant):
     hb, z = load_numeric(gcs.capi, kind)
@@ -16,7 +16,7 @@ def test_cuda_matches_reference_golden(gpu, gcs, kind, variant):
     check_against_golden(hb, z, kind, f"cuda kind {kind} variant {variant}")
 
 
-@pytest.mark.parametrize("variant", [5, 6, 7])
+@pytest.mark.parametrize("variant", [5, 6, 7, 8])
 @pytest.mark.parametrize("kind", [1, 2, 3, 4, 5])
 def test_contracted_cuda_matches_reference_golden_to_the_contract(gpu, gcs, kind, variant):
     """The contracted variants against the golden vectors of the reference's own code: iteration

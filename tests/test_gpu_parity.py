@@ -14,7 +14,7 @@ from util import assert_batches_identical, assert_batches_within_contract, bits,
 pytestmark = pytest.mark.gpu
 
 KINDS = [1, 2, 3, 4, 5]
-VARIANTS = [1, 2, 3, 4]  # static, refill, sorted, pair
+VARIANTS = [1, 2, 3, 4, 9]  # static, refill, sorted, pair, sequential
 
 
 def _solve_pair(gpu, synth, kind, n, variant, **kw):
@@ -149,7 +149,7 @@ def test_device_resident_batch_on_torch_stream(gpu, gcs):
     db = capi.DeviceBatch(hb, "cuda:0", want_cand=True)
     s = torch.cuda.Stream(device="cuda:0")
     with torch.cuda.stream(s):
-        for variant in (1, 2, 3, 4):
+        for variant in (1, 2, 3, 4, 9):
             db.set_variant(variant)
             db.solve()
             s.synchronize()
@@ -212,7 +212,7 @@ def test_error_paths(gpu, gcs):
     cb.kind = 9
     assert lib.gcs_b200_solve_host(C.byref(cb), 0) == capi.GCS_E_INVALID
     cb = hb.cbatch()
-    cb.variant = 8
+    cb.variant = 99
     assert lib.gcs_b200_solve_host(C.byref(cb), 0) == capi.GCS_E_INVALID
     assert b"unknown variant" in lib.gcs_b200_last_error()
     cb = hb.cbatch()
@@ -406,11 +406,11 @@ def test_null_anchor_columns_are_columns_of_zeros(gpu, gcs):
         sparse = dense.anchored()
         assert [c for c, col in enumerate(sparse.cols) if col is None] == nulls, kind
         ref = O.solve(full.take(even).alloc_outputs())
-        for variant in (capi.VARIANT_STATIC, capi.VARIANT_SORTED, capi.VARIANT_REFILL, capi.VARIANT_PAIR):
+        for variant in (capi.VARIANT_STATIC, capi.VARIANT_SORTED, capi.VARIANT_REFILL, capi.VARIANT_PAIR, capi.VARIANT_SEQ):
             sparse.variant = variant
             capi.solve_host(sparse.alloc_outputs(), 0)
             assert_batches_identical(sparse, ref, f"NULL anchor columns, kind {kind} variant {variant}")
-        for variant in (capi.VARIANT_CONTRACTED_STATIC, capi.VARIANT_CONTRACTED_SORTED):
+        for variant in (capi.VARIANT_CONTRACTED_STATIC, capi.VARIANT_CONTRACTED_SORTED, capi.VARIANT_CONTRACTED_SEQ):
             sparse.variant = variant
             capi.solve_host(sparse.alloc_outputs(), 0)
             assert_batches_within_contract(sparse, ref, f"NULL anchor columns, kind {kind} variant {variant}")

@@ -16,7 +16,7 @@ from util import assert_batches_identical, assert_batches_within_contract, bits
 pytestmark = pytest.mark.gpu
 
 KINDS = [1, 2, 3, 4, 5]
-VARIANTS = [6, 7]  # contracted static, contracted sorted
+VARIANTS = [6, 7, 8]  # contracted static, contracted sorted, contracted sequential (one lane per sub-system)
 
 
 def _solve_pair(gpu, synth, kind, n, variant, **kw):
@@ -155,7 +155,7 @@ def test_contract_device_resident_batch_and_default_is_still_bit_identical(gpu, 
     hb = synth.make_ang(70001)
     db = capi.DeviceBatch(hb, "cuda:0", want_cand=True)
     ref = O.solve(synth.make_ang(70001).alloc_outputs())
-    for variant in (5, 6, 7):
+    for variant in (5, 6, 7, 8):
         db.set_variant(variant)
         db.solve()
         torch.cuda.synchronize()
