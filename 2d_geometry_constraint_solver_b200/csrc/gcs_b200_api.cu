@@ -249,8 +249,31 @@ inline int static_block_size()
     return (v == 32 || v == 64 || v == 96 || v == 128) ? v : 128;
 }
 
+// GCS_B200_PREFETCH (tuning knob): waves of look-ahead of the L2 prefetch (0 = off, default 1)
+inline int prefetch_waves()
+{
+    static const int v = [] {
+        const char* e = getenv("GCS_B200_PREFETCH");
+        const int w = e ? atoi(e) : 1;
+        return (w >= 0 && w <= 8) ? w : 1;
+    }();
+    return v;
+}
+
+// sub-systems one wave of resident CTAs of `kern` covers on this device
+template <typename Kern>
+long long wave_subs(DeviceState* d, Kern kern, int block, int subs_per_block)
+{
+    int bps = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, block, 0) != cudaSuccess || bps < 1) {
+        cudaGetLastError();
+        return 0;
+    }
+    return (long long)d->sm_count * bps * subs_per_block;
+}
+
 template <int KIND, int NS, bool RLX = false>
-int launch_static(const BatchDev& p, cudaStream_t st)
+int launch_static(DeviceState*, const BatchDev& p, cudaStream_t st)
 {
     const long long threads = p.n * NS;
     static const int block = static_block_size();
@@ -263,10 +286,16 @@ int launch_static(const BatchDev& p, cudaStream_t st)
 }
 
 template <int KIND, int NS, bool RLX>
-int launch_seq(const BatchDev& p, cudaStream_t st)
+int launch_seq(DeviceState* d, BatchDev p, cudaStream_t st)
 {
     const long long grid = (p.n + 127) / 128;
     if (grid > 0x7fffffffLL) return fail(GCS_E_INVALID, "batch too large for one launch");
+    static thread_local long long wave[64] = {};
+    if (prefetch_waves() > 0) {
+        long long& w = wave[d->device & 63];
+        if (w == 0) w = wave_subs(d, newton_seq_kernel<KIND, NS, RLX>, 128, 128);
+        p.pf = w * prefetch_waves();
+    }
     newton_seq_kernel<KIND, NS, RLX><<<(unsigned)grid, 128, 0, st>>>(p);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
@@ -333,21 +362,21 @@ int launch_kind(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cuda
     const int variant = resolve_variant(b->variant, KIND, p.n, b->n_seeds);
     constexpr bool column_guess = (KIND == GCS_KIND_SDD || KIND == GCS_KIND_ANG);
     if (b->n_seeds == 2) {
-        if (variant == GCS_VARIANT_CONTRACTED_SEQ) return launch_seq<KIND, 2, true>(p, st);
-        if (variant == GCS_VARIANT_SEQ) return launch_seq<KIND, 2, false>(p, st);
+        if (variant == GCS_VARIANT_CONTRACTED_SEQ) return launch_seq<KIND, 2, true>(d, p, st);
+        if (variant == GCS_VARIANT_SEQ) return launch_seq<KIND, 2, false>(d, p, st);
         if (variant == GCS_VARIANT_CONTRACTED_SORTED) return launch_sorted<KIND, 2, true>(p, st);
-        if (variant == GCS_VARIANT_CONTRACTED_STATIC) return launch_static<KIND, 2, true>(p, st);
+        if (variant == GCS_VARIANT_CONTRACTED_STATIC) return launch_static<KIND, 2, true>(d, p, st);
         if (variant == GCS_VARIANT_SORTED) return launch_sorted<KIND, 2>(p, st);
         if (variant == GCS_VARIANT_PAIR) return launch_pair<KIND>(p, st);
-        return variant == GCS_VARIANT_REFILL ? launch_refill<KIND, 2>(d, p, st) : launch_static<KIND, 2>(p, st);
+        return variant == GCS_VARIANT_REFILL ? launch_refill<KIND, 2>(d, p, st) : launch_static<KIND, 2>(d, p, st);
     }
     if constexpr (!column_guess) {
-        if (variant == GCS_VARIANT_CONTRACTED_SEQ) return launch_seq<KIND, 8, true>(p, st);
-        if (variant == GCS_VARIANT_SEQ) return launch_seq<KIND, 8, false>(p, st);
+        if (variant == GCS_VARIANT_CONTRACTED_SEQ) return launch_seq<KIND, 8, true>(d, p, st);
+        if (variant == GCS_VARIANT_SEQ) return launch_seq<KIND, 8, false>(d, p, st);
         if (variant == GCS_VARIANT_CONTRACTED_SORTED) return launch_sorted<KIND, 8, true>(p, st);
-        if (variant == GCS_VARIANT_CONTRACTED_STATIC) return launch_static<KIND, 8, true>(p, st);
+        if (variant == GCS_VARIANT_CONTRACTED_STATIC) return launch_static<KIND, 8, true>(d, p, st);
         if (variant == GCS_VARIANT_SORTED) return launch_sorted<KIND, 8>(p, st);
-        return variant == GCS_VARIANT_REFILL ? launch_refill<KIND, 8>(d, p, st) : launch_static<KIND, 8>(p, st);
+        return variant == GCS_VARIANT_REFILL ? launch_refill<KIND, 8>(d, p, st) : launch_static<KIND, 8>(d, p, st);
     }
     return fail(GCS_E_INVALID, "unsupported seed count");
 }

@@ -145,9 +145,11 @@ struct RelaxGuard {
     // (newton_relaxed.cuh header; dr/|det| <= 2^10 by G1).  With 32x margin:
     //     | m - tol | > 2^-44 S dr/|det| + 2^-40 tol   ->   `m < tol` is the literal code's decision too.
     // Returns +1 converged for certain, -1 not converged for certain, 0 undecided.
-    __device__ __forceinline__ int precise(double m, double det) const
+    // `extra`: an absolute term on top (the deviation carried over from the PREVIOUS update, see
+    // relaxed_updates: carry * |previous update|, which matters when that update dwarfs this one).
+    __device__ __forceinline__ int precise(double m, double det, double extra = 0.0) const
     {
-        const double margin = __fma_rn(carry, m, __fma_rn(pm, rcp_relaxed(fabs(det)), 0x1p-40 * kTol));
+        const double margin = __fma_rn(carry, m, __fma_rn(pm, rcp_relaxed(fabs(det)), 0x1p-40 * kTol)) + extra;
         const double gap = m - kTol;
         if (gap > margin) return -1;
         if (-gap > margin) return 1;
@@ -355,10 +357,34 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
         mh = max(abs_hi(s0), abs_hi(s1));
     };
     bool in_loop = true;
+    // The update AFTER the one from the seed is decided with a wider margin.  From the same iterate
+    // the two arithmetics' updates differ by ~eps cond (|this update| + |previous update|): the part
+    // that scales with the previous update is the rounding of the step before, re-solved now.  Where
+    // updates shrink by halves or faster that is covered by the carry * m term; it is not when the
+    // update from the seed dwarfs what follows - a LINEAR pair (K4) lands on its solution at once,
+    // from a seed 1e9 away with an error of eps cond 1e9 ~ 1e-6 .. 1e-4, and its second update is that
+    // error: pure rounding noise sitting around the threshold (found by tests/test_gpu_soak.py: one
+    // run in 65536 with a different iteration count).  So the second update, peeled like the first,
+    // is compared against a band widened by w1 = carry * |first update|, and so is its margin test.
+    double extra = 0.0;   // absolute add-on of the decision in flight (w1 for the second update, else 0)
+    int lo_cur = g.lo_h;  // "converged for certain" threshold of the decision in flight
     if (it == 0) {  // the update from the seed, peeled (see above)
         update(std::true_type {});
         d1 = dh;
         in_loop = (unsigned)(mh - g.hi_h) < span && it < limit;
+        if (in_loop) {
+            const double w1 = g.carry * fmax(fabs(s0), fabs(s1)) * Rsys<KIND>::kStepScale;
+            RelaxGuard g2 = g;
+            g2.set_band(__fma_rn(g.carry, kTol, g.band) + w1, Rsys<KIND>::kStepScale);
+            update(std::false_type {});
+            dmin = min(dmin, dh);  // first iterate after the seed: nothing to have grown from yet
+            if ((unsigned)(mh - g2.hi_h) < (unsigned)(RelaxGuard::kBigH - g2.hi_h)) {
+                in_loop = it < limit;  // longer than the threshold for certain, carried deviation included
+            } else {
+                in_loop = false;  // decided below, against the widened band and margin
+                extra = fmax(w1, 0x1p-1000), lo_cur = g2.lo_h;
+            }
+        }
     }
 #pragma unroll 1
     for (;;) {
@@ -374,7 +400,7 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
         }
         in_loop = true;
         // ---- rare from here ----
-        if ((unsigned)(mh - g.hi_h) < span) break;  // limit reached, every update longer than the threshold
+        if (extra == 0.0 && (unsigned)(mh - g.hi_h) < span) break;  // limit reached, every update longer than the threshold
         if (mh >= RelaxGuard::kBigH || grow > kBounce) {  // (G4) / (G2)
             state = kRlxUncertain + (mh >= RelaxGuard::kBigH ? kWhyHuge : kWhyBounce);
             break;
@@ -384,16 +410,17 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
                 ? kRlxWantCareful : kRlxUncertain + kWhyCond;
             break;
         }
-        if (mh < g.lo_h) {
+        if (mh < lo_cur) {
             state = kRlxConverged;
             break;
         }
-        const int verdict = g.precise(fmax(fabs(s0), fabs(s1)) * Rsys<KIND>::kStepScale, det);
+        const int verdict = g.precise(fmax(fabs(s0), fabs(s1)) * Rsys<KIND>::kStepScale, det, extra);
         if (trace) *trace |= 1;
         if (verdict >= 0) {
             state = verdict > 0 ? kRlxConverged : kRlxUncertain + kWhyBand;
             break;
         }
+        extra = 0.0, lo_cur = g.lo_h;
         if (it >= limit) break;  // not converged for certain, and out of updates
     }
     if (state == kRlxRunning && (min(dmin, d1) < g.det_h || grow > kBounce || limit >= kRelaxCap))
@@ -429,6 +456,7 @@ static __device__ __noinline__ CarefulOut relaxed_careful(Rsys<KIND> rs, RelaxGu
     o.trace = 2;
     int it = 0, state = kRlxRunning;
     int dmin = 0x7fffffff, grow = 0, d1 = 0x7fffffff;
+    double mprev = 0.0;  // length of the previous update: its rounding is what this update re-solves (see relaxed_updates)
 #pragma unroll 1
     while (it < kRelaxCap) {
         double a, b, c, d, r0, r1;
@@ -464,7 +492,9 @@ static __device__ __noinline__ CarefulOut relaxed_careful(Rsys<KIND> rs, RelaxGu
             state = kRlxUncertain + kWhyCond;
             break;
         }
-        const int verdict = g.precise(fmax(fabs(s0), fabs(s1)) * Rsys<KIND>::kStepScale, det);
+        const double m = fmax(fabs(s0), fabs(s1)) * Rsys<KIND>::kStepScale;
+        const int verdict = g.precise(m, det, g.carry * mprev);
+        mprev = m;
         if (verdict >= 0) {
             state = verdict > 0 ? kRlxConverged : kRlxUncertain + kWhyBand;
             break;

@@ -913,11 +913,15 @@ gcs_b200_batch KindBatch::descriptor()
 
 void KindBatch::applyAll()
 {
+    // the rows of a batch write distinct elements (one wave of the scheduler, or the independent
+    // candidates of a merge): every host thread
     const int nout = gcs_b200_kind_out_cols(m_kind);
-    for (std::size_t i = 0; i < m_leaves.size(); ++i) {
+    const long long m = static_cast<long long>(m_leaves.size());
+#pragma omp parallel for schedule(static) if (m > 1024)
+    for (long long i = 0; i < m; ++i) {
         double o[GCS_MAX_OUT_COLS] = {};
-        for (int c = 0; c < nout; ++c) o[c] = m_out[static_cast<std::size_t>(c)][i];
-        apply(m_leaves[i], o);
+        for (int c = 0; c < nout; ++c) o[c] = m_out[static_cast<std::size_t>(c)][static_cast<std::size_t>(i)];
+        apply(m_leaves[static_cast<std::size_t>(i)], o);
     }
 }
 

@@ -22,6 +22,7 @@
 #include <gcs/model/gcs_data_structures.hpp>
 #include <gcs/orchestration/geometric_constraint_system.hpp>
 
+#include "solving/bottom_up/merge3_ppp_batched.hpp"
 #include "solving/bottom_up/merge3_solver_common.hpp"
 #include "solving/component_solver.hpp"
 #include "solving/equations/newton_raphson.hpp"
@@ -509,6 +510,64 @@ GCS_API double gcs_host_m3_score(int n_el, const int32_t* type, const double* ca
             merged.emplace(node, Bu::LinePose { Vector2d(p[0], p[1]), Vector2d(p[2], p[3]) });
     }
     return Bu::scoreMergedPose(g, merged);
+}
+
+// Gcs::B200::solveMerge3Ppp (solving/bottom_up/merge3_ppp_batched.hpp) on three child clusters of one
+// sketch: the batched form of the reference's Merge3PppSolver::solve enumeration loop.  Same flat
+// layout as the reference-side test driver: elements i = 0..n_el-1 (type 0 point / 1 line, canvas4),
+// cluster c = 0..2 holds counts[c] elements (ids / pose4 concatenated, in insertion order).
+// Returns the size of the merged pose (0: no candidate; -1: error), out_ids ascending; stats[3] =
+// candidates solved, candidates scored, kernel launches; *score = the winning score.
+GCS_API int gcs_host_m3_ppp_merge(int n_el, const int32_t* type, const double* canvas4, const int32_t* counts, const int32_t* ids,
+    const double* pose4, int32_t* out_ids, double* out_pose4, double* score, int64_t* stats)
+{
+    namespace Bu = Gcs::Solvers::BottomUp;
+    try {
+        Gcs::ConstraintGraph g;
+        std::vector<Gcs::ConstraintGraph::NodeIdType> nodes;
+        for (int i = 0; i < n_el; ++i) {
+            const double* c = canvas4 + 4 * i;
+            nodes.push_back(g.getGraph().addNode());
+            if (type[i] == 0)
+                g.addElement(nodes.back(), std::make_shared<Gcs::Element>(Gcs::Point(Vector2d(c[0], c[1]))));
+            else
+                g.addElement(nodes.back(), std::make_shared<Gcs::Element>(Gcs::Line(Vector2d(c[0], c[1]), Vector2d(c[2], c[3]))));
+        }
+        Bu::ClusterPose pose[3];
+        int at = 0;
+        for (int c = 0; c < 3; ++c)
+            for (int k = 0; k < counts[c]; ++k, ++at) {
+                const double* p = pose4 + 4 * at;
+                const auto node = nodes.at(static_cast<std::size_t>(ids[at]));
+                if (type[ids[at]] == 0)
+                    pose[c].emplace(node, Bu::PointPose { Vector2d(p[0], p[1]) });
+                else
+                    pose[c].emplace(node, Bu::LinePose { Vector2d(p[0], p[1]), Vector2d(p[2], p[3]) });
+            }
+        Gcs::B200::Merge3PppReport rep;
+        const auto merged = Gcs::B200::solveMerge3Ppp(g, { &pose[0], &pose[1], &pose[2] }, 0, &rep);
+        if (stats) stats[0] = static_cast<int64_t>(rep.candidates), stats[1] = static_cast<int64_t>(rep.scored), stats[2] = static_cast<int64_t>(rep.launches);
+        if (score) *score = rep.bestScore;
+        if (!merged) return 0;
+        int n = 0;
+        for (int i = 0; i < n_el; ++i) {
+            const auto it = merged->find(nodes[static_cast<std::size_t>(i)]);
+            if (it == merged->end()) continue;
+            out_ids[n] = i;
+            double* o = out_pose4 + 4 * n;
+            o[0] = o[1] = o[2] = o[3] = 0.0;
+            if (const auto* pp = std::get_if<Bu::PointPose>(&it->second))
+                o[0] = pp->position.x(), o[1] = pp->position.y();
+            else {
+                const auto& l = std::get<Bu::LinePose>(it->second);
+                o[0] = l.p1.x(), o[1] = l.p1.y(), o[2] = l.p2.x(), o[3] = l.p2.y();
+            }
+            ++n;
+        }
+        return n;
+    } catch (const std::exception& ex) {
+        return fail(ex);
+    }
 }
 
 // The step after the solve (gcs/b200/canvas_transform.hpp): elements with is_set != 0 carry solver

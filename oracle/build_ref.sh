@@ -23,6 +23,7 @@ CXX="${GCS_REF_CXX:-/usr/bin/g++}"
   "$here/ref_driver.cpp" "$here/ref_merge3_driver.cpp" "$here/ref_model_driver.cpp" "$here/ref_graph_members.cpp" \
   "$ref/gui/src/constraint_model.cpp" \
   "$cs/src/solving/bottom_up/merge3_solver_common.cpp" \
+  "$cs/src/solving/bottom_up/merge3_ppp_solver.cpp" \
   "$cs/src/model/elements.cpp" "$cs/src/model/constraints.cpp" \
   "$cs/src/solving/solvers/point_point_solvers.cpp" \
   "$cs/src/solving/solvers/point_line_solvers.cpp" \

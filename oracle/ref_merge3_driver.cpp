@@ -8,6 +8,7 @@
 //   solveFreePointFromFixedLines          merge3_solver_common.cpp:564-608
 //   estimateRigidTransform / applyRigidTransform   :96-160, :162-178
 //   scoreMergedPose                       :411-456
+//   Merge3PppSolver::solve (the whole enumeration loop)   merge3_ppp_solver.cpp:18-214
 // The point-from-two-points step is inlined in Merge3PppSolver::solve (merge3_ppp_solver.cpp:135-153);
 // gcs_ref_m3_point_pp repeats those three calls on the reference's own functions.
 // Third-party arithmetic (Eigen's JacobiSVD, ColPivHouseholderQR, autodiff) is the stand-ins'.
@@ -15,8 +16,10 @@
 #include <cstdint>
 #include <limits>
 #include <memory>
+#include <unordered_map>
 #include <vector>
 
+#include "solving/bottom_up/merge3_ppp_solver.hpp"
 #include "solving/bottom_up/merge3_solver_common.hpp"
 #include "solving/equations/equation_primitives.hpp"
 #include "solving/equations/newton_raphson.hpp"
@@ -115,4 +118,60 @@ REF_API double gcs_ref_m3_score(int n_el, const int32_t* type, const double* can
             merged.emplace(node, ln(p));
     }
     return Bu::scoreMergedPose(g, merged);
+}
+
+// The reference's own Merge3PppSolver::solve on three child clusters of one sketch.
+// Elements i = 0..n_el-1 (type 0 point: canvas x,y; 1 line: x1,y1,x2,y2).  Cluster c = 0..2 holds
+// counts[c] elements: ids / pose4 concatenated in the order they are inserted into the cluster's
+// pose map.  Returns the size of the merged pose (0: no candidate), out_ids ascending, out_pose4 per id.
+REF_API int gcs_ref_m3_ppp_merge(int n_el, const int32_t* type, const double* canvas4, const int32_t* counts, const int32_t* ids,
+    const double* pose4, int32_t* out_ids, double* out_pose4)
+{
+    Gcs::ConstraintGraph g;
+    std::vector<Gcs::ConstraintGraph::NodeIdType> nodes;
+    for (int i = 0; i < n_el; ++i) {
+        const double* c = canvas4 + 4 * i;
+        nodes.push_back(g.getGraph().addNode());
+        if (type[i] == 0)
+            g.addElement(nodes.back(), std::make_shared<Gcs::Element>(Gcs::Point(v2(c))));
+        else
+            g.addElement(nodes.back(), std::make_shared<Gcs::Element>(Gcs::Line(v2(c), v2(c + 2))));
+    }
+    std::unordered_map<MathUtils::GeneralTreeNodeId, Bu::ClusterPose> poses;
+    std::vector<MathUtils::GeneralTreeNodeId> children;
+    int at = 0;
+    for (int c = 0; c < 3; ++c) {
+        Bu::ClusterPose pose;
+        for (int k = 0; k < counts[c]; ++k, ++at) {
+            const double* p = pose4 + 4 * at;
+            if (type[ids[at]] == 0)
+                pose.emplace(nodes[ids[at]], Bu::PointPose { .position = v2(p) });
+            else
+                pose.emplace(nodes[ids[at]], ln(p));
+        }
+        const MathUtils::GeneralTreeNodeId child { c + 1 };
+        children.push_back(child);
+        poses.emplace(child, std::move(pose));
+    }
+    Gcs::PlanNode node { .kind = Gcs::PlanNodeKind::Merge3,
+        .info = Gcs::Merge3Info { .output = Gcs::ClusterId { 9 }, .inputs = { Gcs::ClusterId { 1 }, Gcs::ClusterId { 2 }, Gcs::ClusterId { 3 } }, .outputElements = {} } };
+    const Bu::Merge3Context context { .sourceGraph = g, .node = node, .children = children, .solvedNodePose = poses };
+    const auto merged = Bu::Merge3PppSolver::solve(context);
+    if (!merged) return 0;
+    int n = 0;
+    for (int i = 0; i < n_el; ++i) {
+        const auto it = merged->find(nodes[i]);
+        if (it == merged->end()) continue;
+        out_ids[n] = i;
+        double* o = out_pose4 + 4 * n;
+        o[0] = o[1] = o[2] = o[3] = 0.0;
+        if (const auto* pp = std::get_if<Bu::PointPose>(&it->second))
+            o[0] = pp->position.x(), o[1] = pp->position.y();
+        else {
+            const auto& l = std::get<Bu::LinePose>(it->second);
+            o[0] = l.p1.x(), o[1] = l.p1.y(), o[2] = l.p2.x(), o[3] = l.p2.y();
+        }
+        ++n;
+    }
+    return n;
 }

@@ -12,9 +12,17 @@ gcs = importlib.import_module("2d_geometry_constraint_solver_b200")
 capi = gcs.capi
 capi.init([local])
 rows = []
-for up, down, what in ((80740352, 32505856, "bench step r1"), (62 << 20, 25 << 20, "bench step compact"), (256 << 20, 256 << 20, "256 MiB")):
-    for pieces in (1, 4, 10):
-        for wc in (False, True):
+quick = os.environ.get("PROBE_QUICK")
+if quick:
+    plan = [(66060288, 26214400, "bench step (compact wire format)", 1, False), (66060288, 26214400, "bench step (compact wire format)", 16, False),
+            (66060288, 26214400, "bench step (compact wire format)", 1, True), (256 << 20, 256 << 20, "256 MiB", 1, False)]
+else:
+    plan = [(up, down, what, pieces, wc)
+            for up, down, what in ((80740352, 32505856, "bench step r1"), (62 << 20, 25 << 20, "bench step compact"), (256 << 20, 256 << 20, "256 MiB"))
+            for pieces in (1, 4, 10) for wc in (False, True)]
+for up, down, what, pieces, wc in plan:
+    if True:
+        if True:
             if world > 1:
                 dist.barrier()
             r = capi.pcie_probe(local, up, down, pieces, wc, 6)

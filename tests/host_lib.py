@@ -49,6 +49,9 @@ def load():
             lib.gcs_host_m3_score.argtypes = [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                               C.POINTER(C.c_uint8)]
             lib.gcs_host_m3_score.restype = C.c_double
+        if hasattr(lib, "gcs_host_m3_ppp_merge"):
+            ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+            lib.gcs_host_m3_ppp_merge.argtypes = [C.c_int, ip, dp, ip, ip, dp, ip, dp, dp, C.POINTER(C.c_int64)]
         _lib = lib
     return _lib
 
@@ -207,6 +210,29 @@ def m3_score(types, canvas4, pose4, in_pose):
     in_pose = np.ascontiguousarray(in_pose, dtype=np.uint8)
     return load().gcs_host_m3_score(len(types), types.ctypes.data_as(C.POINTER(C.c_int32)), _dp(canvas4), _dp(pose4),
                                     in_pose.ctypes.data_as(C.POINTER(C.c_uint8)))
+
+
+def _m3_ppp_args(types, canvas4, clusters):
+    """clusters: three lists of (element id, pose4) in insertion order."""
+    types = np.ascontiguousarray(types, dtype=np.int32)
+    canvas4 = np.ascontiguousarray(canvas4, dtype=np.float64)
+    counts = np.array([len(c) for c in clusters], dtype=np.int32)
+    ids = np.array([i for c in clusters for i, _ in c], dtype=np.int32)
+    pose4 = np.ascontiguousarray([p for c in clusters for _, p in c], dtype=np.float64).reshape(-1, 4)
+    out_ids = np.zeros(len(types), dtype=np.int32)
+    out_pose = np.zeros((len(types), 4))
+    ip = C.POINTER(C.c_int32)
+    return types, canvas4, counts, ids, pose4, out_ids, out_pose, ip
+
+
+def m3_ppp_merge(types, canvas4, clusters):
+    """Gcs::B200::solveMerge3Ppp.  Returns (n merged or 0 / -1, ids, pose4, score, (candidates, scored, launches))."""
+    types, canvas4, counts, ids, pose4, out_ids, out_pose, ip = _m3_ppp_args(types, canvas4, clusters)
+    score = C.c_double()
+    stats = (C.c_int64 * 3)()
+    n = load().gcs_host_m3_ppp_merge(len(types), types.ctypes.data_as(ip), _dp(canvas4), counts.ctypes.data_as(ip), ids.ctypes.data_as(ip),
+                                     _dp(pose4), out_ids.ctypes.data_as(ip), _dp(out_pose), C.byref(score), stats)
+    return n, out_ids[:max(n, 0)].copy(), out_pose[:max(n, 0)].copy(), score.value, tuple(stats)
 
 
 def canvas_transform(elements):

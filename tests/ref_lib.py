@@ -45,6 +45,9 @@ def load():
             lib.gcs_ref_m3_rigid_transform.argtypes = [C.c_int, dp, dp, dp]
             lib.gcs_ref_m3_score.argtypes = [C.c_int, C.POINTER(C.c_int32), dp, dp, bp]
             lib.gcs_ref_m3_score.restype = C.c_double
+        if hasattr(lib, "gcs_ref_m3_ppp_merge"):
+            ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+            lib.gcs_ref_m3_ppp_merge.argtypes = [C.c_int, ip, dp, ip, ip, dp, ip, dp]
         if hasattr(lib, "gcs_ref_model_solve_transform"):
             dp, bp, ip = C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
             lib.gcs_ref_model_solve_transform.argtypes = [C.c_int, ip, dp, dp, bp, C.c_int, ip, dp, dp, dp]
@@ -125,6 +128,16 @@ def m3_solve(kase, rows):
     else:
         {2: lib.gcs_ref_m3_free_line, 3: lib.gcs_ref_m3_point_pl, 4: lib.gcs_ref_m3_point_ll}[kase](n, _dp(rows), _dp(out), okp)
     return out, ok
+
+
+def m3_ppp_merge(types, canvas4, clusters):
+    """The reference's own Merge3PppSolver::solve.  Returns (n merged or 0, ids, pose4).  Its progress
+    lines go to stderr."""
+    import host_lib as H
+    types, canvas4, counts, ids, pose4, out_ids, out_pose, ip = H._m3_ppp_args(types, canvas4, clusters)
+    n = load().gcs_ref_m3_ppp_merge(len(types), types.ctypes.data_as(ip), _dp(canvas4), counts.ctypes.data_as(ip), ids.ctypes.data_as(ip),
+                                    _dp(pose4), out_ids.ctypes.data_as(ip), _dp(out_pose))
+    return n, out_ids[:max(n, 0)].copy(), out_pose[:max(n, 0)].copy()
 
 
 def m3_rigid_transform(src, dst):

@@ -164,3 +164,27 @@ def test_contract_device_resident_batch_and_default_is_still_bit_identical(gpu, 
     db.solve()
     torch.cuda.synchronize()
     assert_batches_identical(db.to_host(synth.make_ang(70001)), ref, "default variant")
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("kind", [1, 3, 4])
+def test_contract_seeds_so_far_away_that_the_landing_error_straddles_the_threshold(gpu, gcs, kind, variant):
+    """A linear pair (K4) lands on its solution with its first update, from any seed; from a seed
+    1e8 .. 1e11 away it lands with an error of eps * cond * |seed| ~ 1e-8 .. 1e-3, and the SECOND update
+    is that error - rounding noise of the first update, different in any other arithmetic, sitting
+    around the threshold 1e-5.  The margin of that decision must carry the first update's length
+    (newton_relaxed.cuh: w1); found by tests/test_gpu_soak.py on a fresh stream (one run in 65536 with
+    a different iteration count before w1 existed).  K1 / K3 from the same seeds halve their way in and
+    never decide anything there: they ride along as controls."""
+    n = 1 << 17
+    rng = np.random.default_rng(4040 + kind)
+    g = rng.uniform(-1.0, 1.0, size=(2, 2, n)) * 10.0 ** rng.uniform(7, 11, size=(2, 1, n))
+    hb = gcs.synth.make(kind, n, seed=0xFA5 + kind)
+    hb.guesses, hb.variant = np.ascontiguousarray(g), variant
+    gpu.solve_host(hb.alloc_outputs(), 0)
+    ref = gcs.synth.make(kind, n, seed=0xFA5 + kind)
+    ref.guesses = hb.guesses
+    O.solve(ref.alloc_outputs())
+    assert_batches_within_contract(hb, ref, f"kind {kind} variant {variant} far seeds")
+    if kind == 4:
+        assert len(np.unique(ref.iters)) >= 2  # the landing error really decides: some runs need a third update

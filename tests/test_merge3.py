@@ -148,3 +148,94 @@ def test_cuda_batch_equals_reference_build_on_fresh_rows(gpu, host):
         assert rc == 0 and launches == 1
         assert np.array_equal(ok, exp_ok)
         assert same(out[exp_ok == 1], exp[exp_ok == 1]).all(), kase
+
+
+def _ppp_scenario(rng, n_ref_only=1, n_shared_ra=2, n_shared_rb=2, n_free=2, n_a_only=1, n_b_only=1, lines=True, coincide=False):
+    """Three solved clusters of one sketch: a reference cluster and two moving clusters that share
+    points with it and with each other.  Every cluster holds the true layout under its own rigid
+    motion (a solved cluster is rigid; its frame is arbitrary); the canvas is the true layout under
+    another motion, with noise.  Returns (types, canvas4, [cluster 0, 1, 2] as (id, pose4) lists)."""
+    groups = {}
+    nid = 0
+    for name, k in (("r", n_ref_only), ("ra", n_shared_ra), ("rb", n_shared_rb), ("f", n_free), ("a", n_a_only), ("b", n_b_only)):
+        groups[name] = list(range(nid, nid + k))
+        nid += k
+    line_ids = []
+    if lines:  # a line inside moving cluster A and one inside the reference: transformed and scored, never an anchor
+        line_ids = [nid, nid + 1]
+        nid += 2
+    true = rng.uniform(-300, 300, size=(nid, 4))
+    types = np.zeros(nid, dtype=np.int32)
+    for l in line_ids:
+        types[l] = 1
+    if coincide and groups["f"]:  # a free candidate sitting on a fixed point of A: distance < EPSILON, skipped by the loop
+        true[groups["f"][0], :2] = true[groups["ra"][0], :2]
+
+    def motion():
+        th = rng.uniform(0, 2 * np.pi)
+        c, s = np.cos(th), np.sin(th)
+        t = rng.uniform(-500, 500, size=2)
+        return lambda p: np.array([c * p[0] - s * p[1] + t[0], s * p[0] + c * p[1] + t[1]])
+
+    def pose_of(ids, mv):
+        out = []
+        for i in ids:
+            p4 = np.zeros(4)
+            p4[:2] = mv(true[i, :2])
+            if types[i] == 1:
+                p4[2:] = mv(true[i, 2:])
+            out.append((int(i), p4))
+        return out
+
+    ref_ids = groups["r"] + groups["ra"] + groups["rb"] + line_ids[1:2]
+    a_ids = groups["ra"] + groups["f"] + groups["a"] + line_ids[0:1]
+    b_ids = groups["rb"] + groups["f"] + groups["b"]
+    clusters = [pose_of(list(rng.permutation(ids)), motion()) for ids in (ref_ids, a_ids, b_ids)]
+    order = rng.permutation(3)  # which child is the reference must not matter: the loop tries all three
+    clusters = [clusters[k] for k in order]
+    cm = motion()
+    canvas4 = np.zeros((nid, 4))
+    for i in range(nid):
+        canvas4[i, :2] = cm(true[i, :2]) + rng.normal(0, 2.0, size=2)
+        if types[i] == 1:
+            canvas4[i, 2:] = cm(true[i, 2:]) + rng.normal(0, 2.0, size=2)
+    return types, canvas4, clusters
+
+
+@pytest.mark.gpu
+def test_ppp_merge_enumeration_loop_equals_the_reference_solver(gpu, host):
+    """The reference's real candidate enumeration (Merge3PppSolver::solve, merge3_ppp_solver.cpp:18-214:
+    reference cluster x shared fixed points x free candidates, one solve2D + pickByTriangleOrientation
+    per candidate, two-point anchor placement, merge, score, first best wins) against its batched form
+    Gcs::B200::solveMerge3Ppp, which collects every candidate of a merge in a Merge3Batch and solves
+    them with ONE kernel launch: the merged pose must come out bit for bit, over scenarios with
+    8..72 candidates, lines riding along, a coincident candidate the loop skips, and merges without
+    any candidate."""
+    import ref_lib as R
+    if not R.available() or not hasattr(R.load(), "gcs_ref_m3_ppp_merge"):
+        pytest.skip("oracle/_ref (with the reference's merge3_ppp_solver.cpp) not present on this box")
+    rng = np.random.default_rng(77)
+    shapes = [dict(), dict(n_shared_ra=3, n_shared_rb=2, n_free=3), dict(n_shared_ra=1, n_shared_rb=1, n_free=1, lines=False),
+              dict(n_free=0), dict(n_shared_rb=0), dict(coincide=True), dict(n_shared_ra=3, n_shared_rb=3, n_free=4, n_ref_only=3)]
+    total = 0
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(2)
+    os.dup2(devnull, 2)  # the reference prints a line per candidate
+    try:
+        for rep in range(6):
+            for kw in shapes:
+                types, canvas4, clusters = _ppp_scenario(rng, **kw)
+                n_ref, ids_ref, pose_ref = R.m3_ppp_merge(types, canvas4, clusters)
+                n, ids, pose, score, (cands, scored, launches) = H.m3_ppp_merge(types, canvas4, clusters)
+                assert n >= 0, H.last_error()
+                assert n == n_ref and np.array_equal(ids, ids_ref), (kw, n, n_ref)
+                assert same(pose, pose_ref).all(), (kw, pose, pose_ref)
+                assert launches == (1 if cands else 0), "every candidate of a merge goes through one launch"
+                if kw.get("n_free") == 0 or kw.get("n_shared_rb") == 0:
+                    assert cands == 0 or n >= 0
+                total += cands
+    finally:
+        os.dup2(saved, 2)
+        os.close(devnull)
+        os.close(saved)
+    assert total > 500
