@@ -56,7 +56,11 @@ inline int resolve_variant(int variant, int kind, long long n, int n_seeds)
     if (variant == GCS_VARIANT_CONTRACTED) {
         // contracted arithmetic otherwise: the static kernel at every size (with a 55-cycle update the
         // sort's bookkeeping costs more than the idle lanes it removes: K1 51 vs 57 us, K3 68 vs 84 us per 2^19)
-        if (kind == GCS_KIND_PLL || (kind == GCS_KIND_PP && n_seeds == 8)) return GCS_VARIANT_CONTRACTED_SEQ;
+        // K4: two updates per seed leave the closed-form update nothing to win back for its guards'
+        // set-up - the bit-identical sequential kernel is the faster one (30.2 against 32.9 us per 2^19)
+        // and trivially within the contract
+        if (kind == GCS_KIND_PLL) return n * n_seeds >= (1ll << 17) ? GCS_VARIANT_SEQ : GCS_VARIANT_CONTRACTED_STATIC;
+        if (kind == GCS_KIND_PP && n_seeds == 8) return GCS_VARIANT_CONTRACTED_SEQ;
         return GCS_VARIANT_CONTRACTED_STATIC;
     }
     if (variant != GCS_VARIANT_DEFAULT) return variant;

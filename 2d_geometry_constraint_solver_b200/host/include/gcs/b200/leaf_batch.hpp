@@ -114,6 +114,7 @@ GCS_API SolveResult solveSingle(SolverId id, ConstraintGraph& component, int dev
 
 struct BatchReport {
     std::size_t leaves = 0, solved = 0, unsupported = 0, waves = 0, launches = 0;
+    std::size_t shardedLaunches = 0;  // launches of a kind batch that went over several devices (solveLeavesOnDevices)
     double planSeconds = 0, packSeconds = 0, deviceSeconds = 0, applySeconds = 0;  // where solveLeaves spent its time
     std::vector<SolveResult> results;  // per leaf, in input order
     std::vector<int> level;            // wave of each leaf (-1 = unsupported)
@@ -125,6 +126,13 @@ struct BatchReport {
 GCS_API BatchReport planLeaves(const std::vector<ConstraintGraph>& leaves);
 // Batched solve with the reference's sequential semantics; one launch per kind per wave.
 GCS_API BatchReport solveLeaves(std::vector<ConstraintGraph>& leaves, int device = 0);
+// The same with one sketch's waves spread over several GPUs: a wave's batch of a kind with at least
+// `minRowsPerDevice` rows per device is cut into contiguous index ranges over the first nDevices
+// devices of gcs_b200_init (gcs_b200_solve_sharded: one pipeline per device, no collective; the
+// solved positions meet again in the host's elements, which is where the next wave is packed from -
+// the "separator exchange" of SURVEY.md section 8f rank 1 is that write-back).  Smaller batches stay
+// on the first device.  Results do not depend on nDevices.
+GCS_API BatchReport solveLeavesOnDevices(std::vector<ConstraintGraph>& leaves, int nDevices, std::size_t minRowsPerDevice = 16384);
 
 // Kernel class of every batch the host mirror launches: GCS_VARIANT_DEFAULT (bit-identical to the
 // reference arithmetic; the default) or GCS_VARIANT_CONTRACTED (iteration counts, flags and roots

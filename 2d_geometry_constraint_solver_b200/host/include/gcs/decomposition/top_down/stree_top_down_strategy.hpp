@@ -30,10 +30,14 @@ public:
     // what the last solveGcs did (leaves, waves, launches, per-leaf results)
     const B200::BatchReport& lastReport() const { return m_report; }
     void setDevice(int device) { m_device = device; }
+    // spread every wave over the first n devices of gcs_b200_init (B200::solveLeavesOnDevices); 1 = one device
+    void setDeviceCount(int n, std::size_t minRowsPerDevice = 16384) { m_devices = n < 1 ? 1 : n, m_minRows = minRowsPerDevice; }
 
 private:
     B200::BatchReport m_report;
     int m_device = 0;
+    int m_devices = 1;
+    std::size_t m_minRows = 16384;
 };
 
 }  // namespace Gcs

@@ -942,7 +942,19 @@ BatchReport planLeaves(const std::vector<ConstraintGraph>& leaves)
     return rep;
 }
 
-BatchReport solveLeaves(std::vector<ConstraintGraph>& leaves, int device)
+namespace {
+BatchReport solveLeavesImpl(std::vector<ConstraintGraph>& leaves, int device, int nDevices, std::size_t minRowsPerDevice);
+}
+
+BatchReport solveLeaves(std::vector<ConstraintGraph>& leaves, int device) { return solveLeavesImpl(leaves, device, 1, 0); }
+
+BatchReport solveLeavesOnDevices(std::vector<ConstraintGraph>& leaves, int nDevices, std::size_t minRowsPerDevice)
+{
+    return solveLeavesImpl(leaves, 0, nDevices < 1 ? 1 : nDevices, minRowsPerDevice);
+}
+
+namespace {
+BatchReport solveLeavesImpl(std::vector<ConstraintGraph>& leaves, int device, int nDevices, std::size_t minRowsPerDevice)
 {
     using Clock = std::chrono::steady_clock;
     auto since = [](Clock::time_point t) { return std::chrono::duration<double>(Clock::now() - t).count(); };
@@ -982,10 +994,12 @@ BatchReport solveLeaves(std::vector<ConstraintGraph>& leaves, int device)
             if (batches[k].size() == 0) continue;
             t0 = Clock::now();
             gcs_b200_batch d = batches[k].descriptor();
-            const int rc = gcs_b200_solve_host(&d, device);
+            const bool shard = nDevices > 1 && batches[k].size() >= minRowsPerDevice * static_cast<std::size_t>(nDevices);
+            const int rc = shard ? gcs_b200_solve_sharded(&d, nDevices) : gcs_b200_solve_host(&d, device);
             if (rc != GCS_OK)
                 throw std::runtime_error(std::string("gcs_b200_solve_host failed (") + std::to_string(rc) + "): "
                     + gcs_b200_last_error() + " - the sub-problem solvers run on the CUDA path only");
+            if (shard) ++rep.shardedLaunches;
             const double call = since(t0);
             rep.deviceSeconds += call;
             if (std::getenv("GCS_HOST_TRACE"))
@@ -999,5 +1013,6 @@ BatchReport solveLeaves(std::vector<ConstraintGraph>& leaves, int device)
     if (plan.error) std::rethrow_exception(plan.error);
     return rep;
 }
+}  // namespace
 
 }  // namespace Gcs::B200

@@ -271,7 +271,8 @@ GCS_API int gcs_host_solve2d(int pair, const double* p, const double* guesses, d
 // sketches go through the degree-2 peeling of gcs/b200/peel_decomposition.hpp - config 4), then
 // the batched solveGcs.  stats (may be NULL): [0] leaves, [1] waves, [2] launches, [3] solved,
 // [4] microseconds in check + decomposition, [5] microseconds in solveGcs, of which [6] planning
-// (symbolic classification + wave levels), [7] packing, [8] device calls, [9] write-back.
+// (symbolic classification + wave levels), [7] packing, [8] device calls, [9] write-back, [10] launches that
+// went over several devices (GCS_HOST_DEVICES).  stats holds 12 values.
 GCS_API int gcs_host_system_solve_ex(int n_el, gcs_host_element* el, int n_edges, const gcs_host_edge* edges, int64_t* stats)
 {
     try {
@@ -300,6 +301,11 @@ GCS_API int gcs_host_system_solve_ex(int n_el, gcs_host_element* el, int n_edges
         // the three steps of GeometricConstraintSystem::solveGeometricConstraintSystem, timed apart
         auto strategy = std::make_unique<Gcs::DeficitStreeBasedTopDownStrategy>();
         Gcs::DeficitStreeBasedTopDownStrategy* st = strategy.get();
+        // GCS_HOST_DEVICES = n: every wave over the first n devices of gcs_b200_init (bench / tests)
+        if (const char* e = std::getenv("GCS_HOST_DEVICES")) {
+            const char* m = std::getenv("GCS_HOST_MIN_ROWS");
+            st->setDeviceCount(std::atoi(e), m ? static_cast<std::size_t>(std::atoll(m)) : 16384);
+        }
         const auto t0 = std::chrono::steady_clock::now();
         if (st->checkConstraintGraphConstrainedness(g) != Gcs::Constrainedness::WELL_CONSTRAINED && !st->resolve(g))
             throw std::runtime_error("Gcs is not well-constrained, current algorithms do not support such inputs");
@@ -315,6 +321,7 @@ GCS_API int gcs_host_system_solve_ex(int n_el, gcs_host_element* el, int n_edges
             stats[5] = std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
             stats[6] = static_cast<int64_t>(rep.planSeconds * 1e6), stats[7] = static_cast<int64_t>(rep.packSeconds * 1e6);
             stats[8] = static_cast<int64_t>(rep.deviceSeconds * 1e6), stats[9] = static_cast<int64_t>(rep.applySeconds * 1e6);
+            stats[10] = static_cast<int64_t>(rep.shardedLaunches);
         }
         for (int i = 0; i < n_el; ++i) readBack(*elems[static_cast<std::size_t>(i)], el[i]);
         return 0;

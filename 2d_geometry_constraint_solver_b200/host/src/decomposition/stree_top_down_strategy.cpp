@@ -30,7 +30,7 @@ std::vector<ConstraintGraph> DeficitStreeBasedTopDownStrategy::decomposeConstrai
 void DeficitStreeBasedTopDownStrategy::solveGcs(std::vector<ConstraintGraph>& splitComponents)
 {
     // reference: std::ranges::for_each(splitComponents, classifyAndSolve), results discarded
-    m_report = B200::solveLeaves(splitComponents, m_device);
+    m_report = m_devices > 1 ? B200::solveLeavesOnDevices(splitComponents, m_devices, m_minRows) : B200::solveLeaves(splitComponents, m_device);
 }
 
 }  // namespace Gcs

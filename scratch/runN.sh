@@ -7,7 +7,7 @@ for N in 2 4 8; do
   PROBE_QUICK=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N scratch/pcie_probe2.py > gpurun_out/r2_pcie_n$N.jsonl 2>> gpurun_out/r2_pcie.err
 done
 cat gpurun_out/r2_pcie_n*.jsonl | cut -c1-330
-python -m pytest tests/test_gpu_parity.py -m gpu -q -k "sharded or index_ranges" 2>&1 | tail -3
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_host.py -m gpu -q -k "sharded or index_ranges or several_devices" 2>&1 | tail -3
 for N in 8 4 2; do
   ( time python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2952$N bench.py --gpus $N --steps 20 --warmup 3 ) > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err
   tail -4 gpurun_out/r2_bench_n$N.err

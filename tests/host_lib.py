@@ -101,9 +101,10 @@ def system_solve(elements, edges):
 def system_solve_ex(elements, edges):
     """Whole sketch through check -> decompose -> batched solveGcs.  Returns (rc, elements, stats dict)."""
     els, eds = to_c(elements, edges)
-    stats = (C.c_int64 * 10)()
+    stats = (C.c_int64 * 12)()
     rc = load().gcs_host_system_solve_ex(len(elements), els, len(edges), eds, stats)
-    keys = ("leaves", "waves", "launches", "solved", "decompose_us", "solve_us", "plan_us", "pack_us", "device_us", "apply_us")
+    keys = ("leaves", "waves", "launches", "solved", "decompose_us", "solve_us", "plan_us", "pack_us", "device_us", "apply_us",
+            "sharded_launches")
     return rc, from_c(elements, els), dict(zip(keys, list(stats)))
 
 

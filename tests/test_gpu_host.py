@@ -276,3 +276,28 @@ def test_unchecked_linkage_runs_into_the_cap_like_the_reference(host):
     assert rc == 0
     for g, e in zip(got, exp):
         assert same_pos(g["pos"], e["pos"])
+
+
+def test_one_sketch_over_several_devices_equals_one_device(host, gcs):
+    """DeficitStreeBasedTopDownStrategy::setDeviceCount / solveLeavesOnDevices: the waves of ONE sketch
+    cut into index ranges over the GPUs of the box (gcs_b200_solve_sharded per kind batch; the solved
+    positions meet again in the host's elements).  Same result as on one device, bit for bit.  On a
+    one-GPU box the device list has one entry and the call degenerates to the single-device path."""
+    capi = gcs.capi
+    ndev = capi.load().gcs_b200_device_count()
+    capi.init(list(range(ndev)))
+    el, edges = S.make_linkage(20000, seed=6)
+    try:
+        os.environ["GCS_HOST_DEVICES"], os.environ["GCS_HOST_MIN_ROWS"] = str(ndev), "64"
+        rc, many, st_many = H.system_solve_ex(el, edges)
+        assert rc == 0, H.last_error()
+    finally:
+        os.environ.pop("GCS_HOST_DEVICES", None), os.environ.pop("GCS_HOST_MIN_ROWS", None)
+        capi.init([0])
+    rc, one, st_one = H.system_solve_ex(el, edges)
+    assert rc == 0, H.last_error()
+    assert st_one["sharded_launches"] == 0
+    if ndev > 1:
+        assert st_many["sharded_launches"] > 0
+    for a, b in zip(many, one):
+        assert a["is_set"] and same_pos(a["pos"], b["pos"])
