@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <exception>
+#include <memory>
 #include <stdexcept>
 #include <unordered_map>
 #include <unordered_set>
@@ -450,15 +451,16 @@ struct Plan {
 // raises.
 // ---------------------------------------------------------------------------------------------
 struct LeafFacts {
-    Element* e[3] = { nullptr, nullptr, nullptr };
-    bool isPoint[3] = {}, isLine[3] = {}, setNow[3] = {};
-    // node pairs (0,1), (0,2), (1,2): a real constraint with a value sits on the edge
-    bool has[3] = {}, flip[3] = {};
-    double val[3] = {};
-    int slot[3] = { -1, -1, -1 };  // dense index of each element in this plan (Element::planTag)
-    int edgeCount = 0;
+    // no member initialisers: the array of facts is allocated untouched and first written by the
+    // thread that gathers the leaf (gatherFacts value-initialises what it returns)
+    Element* e[3];
+    double val[3];   // node pairs (0,1), (0,2), (1,2): value of the real constraint on the edge, if has[]
+    int slot[3];     // dense index of each element in this plan (Element::planTag)
+    int edgeCount;
     ConstraintCensus k;
-    bool simple = false;
+    bool isPoint[3], isLine[3], setNow[3];
+    bool has[3], flip[3];
+    bool simple;
 };
 
 // Dense index of an element in the plan of `epoch`, handed out on first sight from `next` - from
@@ -479,7 +481,8 @@ inline int pairIndex(int a, int b) { return a + b - 1; }  // {0,1} -> 0, {0,2} -
 
 LeafFacts gatherFacts(const ConstraintGraph& g, std::uint32_t epoch, std::atomic<int>& nextSlot)
 {
-    LeafFacts f;
+    LeafFacts f {};
+    f.slot[0] = f.slot[1] = f.slot[2] = -1;
     if (g.nodeCount() != 3) return f;
     NodeId node[3];
     int n = 0;
@@ -634,14 +637,16 @@ Plan makePlan(const std::vector<ConstraintGraph>& leaves)
     const auto tA = std::chrono::steady_clock::now();
     const std::uint32_t epoch = ++g_planEpoch;
     std::atomic<int> nextSlot { 0 };
-    std::vector<LeafFacts> facts(n);
+    const std::unique_ptr<LeafFacts[]> facts(new LeafFacts[n ? n : 1]);  // untouched: first written in the parallel loop
     const long long nn = static_cast<long long>(n);
 #pragma omp parallel for schedule(static) if (nn > 2048)
     for (long long i = 0; i < nn; ++i) {
         try {
             facts[static_cast<std::size_t>(i)] = gatherFacts(leaves[static_cast<std::size_t>(i)], epoch, nextSlot);
         } catch (...) {
-            facts[static_cast<std::size_t>(i)] = LeafFacts {};  // not simple: the general code decides (and raises) in step (B)
+            LeafFacts none {};  // not simple: the general code decides (and raises) in step (B)
+            none.slot[0] = none.slot[1] = none.slot[2] = -1;
+            facts[static_cast<std::size_t>(i)] = none;
         }
     }
 

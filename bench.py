@@ -884,18 +884,20 @@ def main():
     # copy-only ceiling of the same byte counts, all ranks at once (one contiguous copy per direction
     # and the pipeline's own granularity), on the library's copy streams
     barrier()
-    probe1 = capi.pcie_probe(local_rank, h2d, d2h, 1, False, 5)
+    probe1 = capi.pcie_probe(local_rank, h2d, d2h, 1, False, 9)
     barrier()
-    probe_p = capi.pcie_probe(local_rank, h2d, d2h, 16, False, 5)
-    ceil_ms = ctx.max_over_ranks(probe1["both_ms_median"])
-    ceil_p_ms = ctx.max_over_ranks(probe_p["both_ms_median"])
+    probe_p = capi.pcie_probe(local_rank, h2d, d2h, 16, False, 9)
     e2e_ms = e2e_t / e2e_steps * 1e3
+    best_ms = ctx.max_over_ranks(min(probe1["both_ms_best"], probe_p["both_ms_best"]))
+    typical_ms = ctx.max_over_ranks(min(probe1["both_ms_median"], probe_p["both_ms_median"]))
     pcie = {"h2d_gbs_rank0": probe1["h2d_gbs"], "d2h_gbs_rank0": probe1["d2h_gbs"],
-            "ceiling_ms_per_step": ceil_ms, "ceiling_solves_per_s": n * world / (ceil_ms * 1e-3), "frac_of_ceiling": ceil_ms / e2e_ms,
-            "ceiling_ms_per_step_16_pieces": ceil_p_ms, "frac_of_ceiling_16_pieces": ceil_p_ms / e2e_ms,
-            "aggregate_gbs_at_ceiling": (h2d + d2h) * world / (ceil_ms * 1e-3) / 1e9,
-            "how": "gcs_b200_pcie_probe: the step's H2D and D2H byte counts as one contiguous copy per direction (and as 16 pieces) "
-                   "from / to pinned memory, both directions at once, every rank at the same time; max over ranks of the median"}
+            "ceiling_ms_per_step": best_ms, "ceiling_solves_per_s": n * world / (best_ms * 1e-3), "frac_of_ceiling": best_ms / e2e_ms,
+            "typical_copy_only_ms_per_step": typical_ms, "frac_of_typical_copy_only": typical_ms / e2e_ms,
+            "aggregate_gbs_at_ceiling": (h2d + d2h) * world / (best_ms * 1e-3) / 1e9,
+            "how": "gcs_b200_pcie_probe: the step's H2D and D2H byte counts from / to pinned memory, both directions at once, every rank "
+                   "at the same time, as one contiguous copy per direction and as 16 pieces (the faster of the two); ceiling = the best of "
+                   "9 repetitions, typical = their median (under contention between ranks the two differ by 1.6x); max over ranks. "
+                   "Standalone sweep: profiles/r2_pcie_probe.md"}
     sampler.leave()
     clocks = sampler.stop()
 

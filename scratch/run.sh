@@ -1,11 +1,8 @@
 set -x
 mkdir -p gpurun_out
-python scratch/repro_k4.py 2>&1 | tail -5
-( time python -m pytest tests -m gpu -x -q ) > gpurun_out/r2h_pytest.log 2>&1; tail -6 gpurun_out/r2h_pytest.log
-python scratch/kbench.py 5 1,2,3,5 524288 > gpurun_out/r2h_kbench.log 2>&1
-python scratch/k4_hbm.py >> gpurun_out/r2h_kbench.log 2>&1
-python scratch/soak_relaxed.py 1048576 0x200 >> gpurun_out/r2h_kbench.log 2>&1
-python scratch/soak_relaxed_guesses.py 262144 >> gpurun_out/r2h_kbench.log 2>&1
-grep -v "variant [13]:" gpurun_out/r2h_kbench.log | cut -c1-260
-python bench.py --workload sweep64m --steps 5 --warmup 3 2>/dev/null | python -c "
-import json,sys; b=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('sweep', b['value'], b['ms_per_step'], b['roofline']['frac'])"
+( time python -m pytest tests -m gpu -x -q ) > gpurun_out/r2j_pytest.log 2>&1; tail -5 gpurun_out/r2j_pytest.log
+python scratch/norerun.py > gpurun_out/r2j_norerun.log 2>&1; tail -30 gpurun_out/r2j_norerun.log
+( time python bench.py --steps 20 --warmup 5 ) > gpurun_out/r2j_bench_n1.json 2> gpurun_out/r2j_bench_n1.err; tail -3 gpurun_out/r2j_bench_n1.err
+( time python bench.py --impl reference --steps 20 --warmup 5 ) > gpurun_out/r2j_ref_n1.json 2> gpurun_out/r2j_ref_n1.err; cut -c1-200 gpurun_out/r2j_ref_n1.json
+GCS_HOST_TRACE=1 python profiles/sketch_bench.py 100000 2>&1 | grep -v "wave launch" | tail -4 | cut -c1-900
+python -c "import __graft_entry__ as e; e.smoke()" 2>&1 | tail -1
