@@ -238,8 +238,11 @@ static __device__ __noinline__ RunOut literal_run_from_global(const BatchDev& p,
 #ifndef GCS_SEQ_MINB
 #define GCS_SEQ_MINB 6
 #endif
+#ifndef GCS_SEQ_LIT_MINB
+#define GCS_SEQ_LIT_MINB 5
+#endif
 template <int KIND, int NS, bool RLX>
-__global__ void __launch_bounds__(128, RLX ? GCS_SEQ_MINB : 5) newton_seq_kernel(const __grid_constant__ BatchDev p)
+__global__ void __launch_bounds__(128, RLX ? GCS_SEQ_MINB : GCS_SEQ_LIT_MINB) newton_seq_kernel(const __grid_constant__ BatchDev p)
 {
     using S = Sys<KIND>;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -471,7 +474,11 @@ __global__ void __launch_bounds__(THREADS, kSortedMinBlocks<KIND>) newton_sorted
     __shared__ unsigned short s_order[RUNS];
     __shared__ unsigned char s_cv[RUNS];
     __shared__ double s_carry[RLX ? RUNS : 1];  // RLX: each run's carry term (RelaxGuard::add_carry) at the hand-off
-    __shared__ int s_dmin[RLX ? RUNS : 1];  // running minimum of hi(|det|) of each run at the hand-off (guard G2)
+    // running minimum of hi(|det|) of each run at the hand-off (guard G2).  The growth value itself needs
+    // no slot: growth inside phase A's stretch is judged when that stretch ends (relaxed_updates turns a
+    // stretch with grow > kBounce into "uncertain"), and growth in phase C is measured against this
+    // carried minimum, i.e. against the smallest |det| of the whole run so far.
+    __shared__ int s_dmin[RLX ? RUNS : 1];
     __shared__ int s_bin[kSortBins];   // live runs per sort key
     __shared__ int s_fill[kSortBins];  // slots handed out per sort key during the scatter
 

@@ -1,8 +1,6 @@
 set -x
 mkdir -p gpurun_out
-( time python -m pytest tests -m gpu -x -q ) > gpurun_out/r2j_pytest.log 2>&1; tail -5 gpurun_out/r2j_pytest.log
-python scratch/norerun.py > gpurun_out/r2j_norerun.log 2>&1; tail -30 gpurun_out/r2j_norerun.log
-( time python bench.py --steps 20 --warmup 5 ) > gpurun_out/r2j_bench_n1.json 2> gpurun_out/r2j_bench_n1.err; tail -3 gpurun_out/r2j_bench_n1.err
-( time python bench.py --impl reference --steps 20 --warmup 5 ) > gpurun_out/r2j_ref_n1.json 2> gpurun_out/r2j_ref_n1.err; cut -c1-200 gpurun_out/r2j_ref_n1.json
-GCS_HOST_TRACE=1 python profiles/sketch_bench.py 100000 2>&1 | grep -v "wave launch" | tail -4 | cut -c1-900
-python -c "import __graft_entry__ as e; e.smoke()" 2>&1 | tail -1
+python scratch/small_launch.py || exit 1
+ncu --set full --clock-control none --import-source on -k regex:newton_static_kernel -s 3 -c 1 -f -o gpurun_out/r2_prof_small python scratch/small_launch.py > gpurun_out/r2_ncu_small.log 2>&1
+ncu --set full --clock-control none --cache-control none --import-source on -k regex:newton_static_kernel -s 3 -c 1 -f -o gpurun_out/r2_prof_small_nocc python scratch/small_launch.py > gpurun_out/r2_ncu_small2.log 2>&1
+ls -la gpurun_out/r2_prof_small*

@@ -80,6 +80,33 @@ def test_null_columns_only_where_the_shape_is_anchored(gcs, built):
                 assert rc == capi.GCS_E_INVALID and b"anchor" in lib.gcs_b200_last_error()
 
 
+def test_argument_checks_of_the_round_2_entry_points_need_no_device(gcs, built):
+    """Validation comes before any device is touched: bad index ranges, bad batch lists, host pointers
+    handed to the device entry points and unknown variants are GCS_E_INVALID here as on a GPU box."""
+    capi, synth = gcs.capi, gcs.synth
+    lib = capi.load()
+    hb = synth.make_pp(16).alloc_outputs()
+    cb = hb.cbatch()
+    for first, count in ((-1, 4), (0, 17), (12, 5), (17, 0), (3, -1)):
+        assert lib.gcs_b200_solve_host_range_async(C.byref(cb), 0, first, count) == capi.GCS_E_INVALID, (first, count)
+        assert b"index range" in lib.gcs_b200_last_error()
+    assert lib.gcs_b200_solve_many(None, 0, 0, None) == capi.GCS_OK          # an empty job is a no-op anywhere
+    assert lib.gcs_b200_solve_many(None, 2, 0, None) == capi.GCS_E_INVALID
+    arr = (C.POINTER(capi.CBatch) * 2)(C.pointer(cb), C.pointer(cb))
+    assert lib.gcs_b200_solve_many(arr, 2, 0, None) == capi.GCS_E_INVALID    # host pointers
+    assert b"device pointers" in lib.gcs_b200_last_error()
+    cb.variant = 10
+    assert lib.gcs_b200_solve_host(C.byref(cb), 0) == capi.GCS_E_INVALID and b"unknown variant" in lib.gcs_b200_last_error()
+    # kernel mapping a class resolves to: K4 and the 8-seed K1 take the sequential kernel
+    R = lib.gcs_b200_resolve_variant
+    assert R(capi.VARIANT_DEFAULT, 1, 1 << 19, 2) == capi.VARIANT_SORTED and R(capi.VARIANT_DEFAULT, 1, 1000, 2) == capi.VARIANT_STATIC
+    assert R(capi.VARIANT_DEFAULT, 4, 1 << 19, 2) == capi.VARIANT_SEQ and R(capi.VARIANT_CONTRACTED, 4, 1 << 19, 2) == capi.VARIANT_SEQ
+    assert R(capi.VARIANT_CONTRACTED, 1, 1 << 19, 2) == capi.VARIANT_CONTRACTED_STATIC
+    assert R(capi.VARIANT_CONTRACTED, 1, 1 << 19, 8) == capi.VARIANT_CONTRACTED_SEQ
+    assert R(capi.VARIANT_REFILL, 3, 5, 2) == capi.VARIANT_REFILL
+    assert lib.gcs_b200_pcie_probe(0, 0, 1, 1, 0, 1, (C.c_double * 4)()) == capi.GCS_E_INVALID
+
+
 def test_library_is_built_from_the_sources_in_the_tree(gcs, built):
     """gcs_b200_version() carries the hash of csrc/*, the header and the flags it was compiled
     from: a stale libgcs_b200.so (the .so is not in git but travels to the GPU box) fails here."""
