@@ -1,6 +1,7 @@
 // Degree-2 peeling decomposition (see gcs/b200/peel_decomposition.hpp).
 #include <algorithm>
 #include <array>
+#include <exception>
 #include <functional>
 #include <map>
 #include <set>
@@ -151,10 +152,24 @@ std::vector<ConstraintGraph> decomposeByPeeling(const ConstraintGraph& gcs, Peel
         }
         leaves.push_back(makeLeaf(gcs, base, std::vector<EdgeId>(edges.begin(), edges.end()), nullptr));
     }
-    for (auto it = peels.rbegin(); it != peels.rend(); ++it) {
-        const std::pair<NodeId, NodeId> pair { it->a, it->b };
-        leaves.push_back(makeLeaf(gcs, { it->a, it->b, it->v }, { it->va, it->vb }, &pair));
+    // the peeled leaves, in reverse peel order (= solve order).  Each is a small graph of its own
+    // (a dozen allocations, shared_ptr copies of its elements and constraints) built from read-only
+    // looks at the sketch: every host thread builds its share.
+    const long long np = static_cast<long long>(peels.size());
+    leaves.resize(static_cast<std::size_t>(np) + 1);
+    std::exception_ptr failure;
+#pragma omp parallel for schedule(static) if (np > 2048)
+    for (long long k = 0; k < np; ++k) {
+        const Peel& p = peels[static_cast<std::size_t>(np - 1 - k)];
+        try {
+            const std::pair<NodeId, NodeId> pair { p.a, p.b };
+            leaves[static_cast<std::size_t>(k) + 1] = makeLeaf(gcs, { p.a, p.b, p.v }, { p.va, p.vb }, &pair);
+        } catch (...) {
+#pragma omp critical
+            if (!failure) failure = std::current_exception();
+        }
     }
+    if (failure) std::rethrow_exception(failure);
     if (stats) *stats = { graph.nodeCount(), graph.edgeCount(), leaves.size() };
     return leaves;
 }
