@@ -1,11 +1,12 @@
 set -x
 mkdir -p gpurun_out
-for off in 0x1000 0x2000 0x3000; do python scratch/soak_relaxed.py 2097152 $off 2>&1 | tail -1; done > gpurun_out/r2l_soak.log 2>&1
-python scratch/soak_relaxed_guesses.py 1048576 2>&1 | tail -1 >> gpurun_out/r2l_soak.log
-python scratch/soak_relaxed_scaled.py 1048576 2>&1 | tail -1 >> gpurun_out/r2l_soak.log
-python scratch/soak.py 2>&1 | tail -1 >> gpurun_out/r2l_soak.log
-cat gpurun_out/r2l_soak.log
-GCS_BENCH_TEST_VIOLATION=1 python bench.py --steps 5 --warmup 3 --no-extras --no-cpu-baseline 2> gpurun_out/r2l_viol.err | python -c "
-import json,sys; b=json.loads(sys.stdin.read()); print('violation run:', b['run']['variant'], b['run']['contract_violation'], b['value'], b['roofline']['kernel'], b['config']['gpu_kernel_class'][:40])"
-tail -2 gpurun_out/r2l_viol.err
-python -m pytest tests/test_capi_load.py tests/test_gpu_parity.py -q -x 2>&1 | tail -2
+( time python -m pytest tests -m gpu -x -q ) > gpurun_out/r2m_pytest.log 2>&1; tail -5 gpurun_out/r2m_pytest.log
+python -c "import __graft_entry__ as e; e.smoke()" 2>&1 | tail -1
+( time python bench.py --impl reference --steps 20 --warmup 5 ) > gpurun_out/r2m_ref_n1.json 2> gpurun_out/r2m_ref_n1.err; cut -c1-160 gpurun_out/r2m_ref_n1.json
+( time python bench.py --steps 20 --warmup 5 ) > gpurun_out/r2m_bench_n1.json 2> gpurun_out/r2m_bench_n1.err; tail -3 gpurun_out/r2m_bench_n1.err
+python - <<'PY'
+import json
+b=json.loads(open('gpurun_out/r2m_bench_n1.json').read().strip().splitlines()[-1])
+print('value',b['value'],'e2e',b['e2e']['value'],b['e2e']['pcie']['frac_of_ceiling'],'k1',b['roofline']['launch_ms'],b['roofline']['frac'],'traffic stale',b['roofline']['traffic_capture_is_of_another_build'])
+print('sketch',{k:v for k,v in b['configs']['sketch100k'].items() if k!='workload'})
+PY
