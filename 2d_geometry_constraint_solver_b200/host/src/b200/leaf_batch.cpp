@@ -995,25 +995,40 @@ BatchReport solveLeavesImpl(std::vector<ConstraintGraph>& leaves, int device, in
         if (packError) std::rethrow_exception(packError);
         for (const PackedLeaf& row : rows) batches[row.kind].push(row);
         rep.packSeconds += since(t0);
+        // The kind batches of a wave are independent jobs: all of them are queued (upload / kernel /
+        // download pipelines on the library's streams) before any is waited for, then written back.
+        t0 = Clock::now();
+        auto failed = [&](const char* what, int rc) {
+            gcs_b200_wait(device);  // leave nothing in flight behind the exception
+            throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + gcs_b200_last_error()
+                + " - the sub-problem solvers run on the CUDA path only");
+        };
+        int queued = 0;
         for (int k = 1; k <= GCS_KIND_COUNT; ++k) {
             if (batches[k].size() == 0) continue;
-            t0 = Clock::now();
             gcs_b200_batch d = batches[k].descriptor();
             const bool shard = nDevices > 1 && batches[k].size() >= minRowsPerDevice * static_cast<std::size_t>(nDevices);
-            const int rc = shard ? gcs_b200_solve_sharded(&d, nDevices) : gcs_b200_solve_host(&d, device);
-            if (rc != GCS_OK)
-                throw std::runtime_error(std::string("gcs_b200_solve_host failed (") + std::to_string(rc) + "): "
-                    + gcs_b200_last_error() + " - the sub-problem solvers run on the CUDA path only");
-            if (shard) ++rep.shardedLaunches;
-            const double call = since(t0);
-            rep.deviceSeconds += call;
-            if (std::getenv("GCS_HOST_TRACE"))
-                std::fprintf(stderr, "[host] wave launch kind %d rows %zu: %.1f us\n", k, batches[k].size(), call * 1e6);
-            t0 = Clock::now();
-            batches[k].applyAll();
-            rep.applySeconds += since(t0);
+            if (shard) {
+                const int rc = gcs_b200_solve_sharded(&d, nDevices);
+                if (rc != GCS_OK) failed("gcs_b200_solve_sharded", rc);
+                ++rep.shardedLaunches;
+            } else {
+                const int rc = gcs_b200_solve_host_async(&d, device);
+                if (rc != GCS_OK) failed("gcs_b200_solve_host_async", rc);
+                ++queued;
+            }
             ++rep.launches;
+            if (std::getenv("GCS_HOST_TRACE")) std::fprintf(stderr, "[host] wave launch kind %d rows %zu\n", k, batches[k].size());
         }
+        if (queued) {
+            const int rc = gcs_b200_wait(device);
+            if (rc != GCS_OK) failed("gcs_b200_wait", rc);
+        }
+        rep.deviceSeconds += since(t0);
+        t0 = Clock::now();
+        for (int k = 1; k <= GCS_KIND_COUNT; ++k)
+            if (batches[k].size() != 0) batches[k].applyAll();
+        rep.applySeconds += since(t0);
     }
     if (plan.error) std::rethrow_exception(plan.error);
     return rep;
