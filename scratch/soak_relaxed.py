@@ -25,7 +25,7 @@ cases.append((3, dict(seed=31338 + off, n_seeds=8)))
 for kind, kw in cases:
     m = n // 4 if kw.get("n_seeds") == 8 else n
     a = synth.make(kind, m, **kw)
-    a.variant = capi.VARIANT_CONTRACTED
+    a.variant = int(os.environ.get("SOAK_VARIANT", capi.VARIANT_CONTRACTED))
     a.alloc_outputs()
     b = synth.make(kind, m, **kw).alloc_outputs()
     capi.solve_host(a, 0)

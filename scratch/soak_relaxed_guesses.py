@@ -53,7 +53,7 @@ for kind in (1, 2, 3, 4, 5):
     for mode in ("box", "wide", "near_root", "tiny", "singular"):
         g = np.ascontiguousarray(guesses(kind, mode, base))
         a = synth.make(kind, n, seed=0xC0DE + kind)
-        a.guesses, a.variant, a.want_cand = g, capi.VARIANT_CONTRACTED, True
+        a.guesses, a.variant, a.want_cand = g, int(os.environ.get("SOAK_VARIANT", capi.VARIANT_CONTRACTED)), True
         b = synth.make(kind, n, seed=0xC0DE + kind)
         b.guesses, b.want_cand = g, True
         capi.solve_host(a.alloc_outputs(), 0)
