@@ -100,15 +100,33 @@ public:
     std::string getElementName() const;
     std::string toString() const;
 
-    // Scratch word of the batched leaf scheduler (gcs/b200/leaf_batch.hpp): (epoch of the plan
-    // that last numbered this element) << 32 | its dense index in that plan.  Not part of the
-    // element's value; plans over the same elements must not run concurrently.
-    std::uint64_t& planTagWord() const { return m_planTag; }
+    // Serial number of this Element OBJECT: unique in the process, handed out in construction order,
+    // so the elements of one sketch sit in a narrow range of it.  The batched leaf scheduler
+    // (gcs/b200/leaf_batch.hpp) indexes its per-element tables by it instead of hashing pointers.
+    // Not part of the element's value: a copy is a new object with a new number, assignment keeps
+    // the number of the object assigned to.
+    std::uint64_t serial() const { return m_serial; }
+    // leaves `count` numbers unused (tests: elements whose numbers lie far apart)
+    static void skipSerials(std::uint64_t count);
+
+    Element(const Element& other) : m_element(other.m_element), m_isSet(other.m_isSet) {}
+    Element(Element&& other) noexcept : m_element(std::move(other.m_element)), m_isSet(other.m_isSet) {}
+    Element& operator=(const Element& other)
+    {
+        m_element = other.m_element, m_isSet = other.m_isSet;
+        return *this;
+    }
+    Element& operator=(Element&& other) noexcept
+    {
+        m_element = std::move(other.m_element), m_isSet = other.m_isSet;
+        return *this;
+    }
 
 private:
     ElementVariant m_element;
     bool m_isSet = false;
-    alignas(8) mutable std::uint64_t m_planTag = 0;
+    const std::uint64_t m_serial = nextSerial();
+    static std::uint64_t nextSerial();
 };
 
 }  // namespace Gcs

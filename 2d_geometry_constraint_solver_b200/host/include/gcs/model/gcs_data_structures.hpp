@@ -5,6 +5,7 @@
 #pragma once
 
 #include <cstddef>
+#include <cstdint>
 #include <expected>
 #include <memory>
 #include <unordered_set>
@@ -19,6 +20,20 @@
 namespace Gcs {
 
 enum class ConstraintGraphError { OK, NodeNotFound, EdgeNotFound };
+
+// What the batched leaf scheduler (gcs/b200/leaf_batch.hpp) reads from a three-element component,
+// kept in the graph object itself so that planning 1e5 leaves is one pass over the vector of
+// leaves instead of a walk through five small containers per leaf: the elements in ascending node
+// id and, for each node pair, the constraint on the edge between them (null: no edge, a virtual
+// edge, or an edge without a constraint).  Pointers only - element flags and constraint values are
+// read through them when a plan is made.  `simple` is false for anything else than three nodes
+// with at most one edge per node pair (such components go through the container walk).
+struct TriangleDigest {
+    Element* element[3] {};
+    const Constraint* constraint[3] {};  // node pairs (0,1), (0,2), (1,2)
+    int edgeCount = 0;                   // virtual edges included
+    bool simple = false;
+};
 
 class GCS_API ConstraintGraph final {
 public:
@@ -60,6 +75,11 @@ public:
     bool isVirtualEdge(EdgeIdType edge) const { return m_virtualEdges.count(edge) != 0; }
     const std::unordered_set<EdgeIdType>& getVirtualEdges() const { return m_virtualEdges; }
 
+    // Derived from the containers above on first use and again after any change to them (through
+    // this class or through getGraph()); the decomposition asks for it while the leaf it has just
+    // built is still in cache.  Not thread safe on one graph object, like the rest of the class.
+    const TriangleDigest& triangleDigest() const;
+
     // 2n - 3 - edges, in int (the reference's strategy computes it in size_t and wraps)
     int getDeficit() const { return (2 * static_cast<int>(nodeCount()) - 3) - static_cast<int>(edgeCount()); }
 
@@ -68,6 +88,9 @@ private:
     ElementMap m_elementNodeMap;
     ConstraintMap m_constraintEdgeMap;
     std::unordered_set<EdgeIdType> m_virtualEdges;
+    unsigned m_version = 0;  // changes to the property maps / virtual-edge set (the graph counts its own)
+    mutable TriangleDigest m_digest;
+    mutable std::uint64_t m_digestStamp = ~std::uint64_t { 0 };  // (graph version, m_version) the digest was taken at
 };
 
 }  // namespace Gcs

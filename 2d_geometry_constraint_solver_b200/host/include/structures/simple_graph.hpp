@@ -106,6 +106,7 @@ public:
     {
         const NodeId id { m_nextNode++ };
         m_incident.put(id, EdgeList {});
+        ++m_version;
         return id;
     }
 
@@ -117,6 +118,7 @@ public:
         m_ends.put(id, std::make_pair(s, t));
         is->second.push_back(id);  // the newest id is the largest: lists stay ascending
         if (it != is) it->second.push_back(id);
+        ++m_version;
         return id;
     }
 
@@ -129,6 +131,7 @@ public:
             if (in != m_incident.end()) std::erase(in->second, e);
         }
         m_ends.erase(e);
+        ++m_version;
         return {};
     }
 
@@ -139,6 +142,7 @@ public:
         const EdgeList gone = f->second;
         for (EdgeId e : gone) removeEdge(e);
         m_incident.erase(n);
+        ++m_version;
         return {};
     }
 
@@ -195,9 +199,13 @@ public:
     }
     bool hasEdgeBetween(NodeId s, NodeId t) const { return getEdgeBetween(s, t).has_value(); }
 
+    // counts the structural changes made so far (what ConstraintGraph keys its derived digest on)
+    unsigned version() const { return m_version; }
+
 private:
     int m_nextNode { 0 };
     int m_nextEdge { 0 };
+    unsigned m_version { 0 };
     detail::FlatTable<NodeId, EdgeList> m_incident;
     detail::FlatTable<EdgeId, std::pair<NodeId, NodeId>> m_ends;
 };

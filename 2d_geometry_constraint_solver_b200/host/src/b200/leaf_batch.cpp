@@ -455,68 +455,70 @@ struct LeafFacts {
     // thread that gathers the leaf (gatherFacts value-initialises what it returns)
     Element* e[3];
     double val[3];   // node pairs (0,1), (0,2), (1,2): value of the real constraint on the edge, if has[]
-    int slot[3];     // dense index of each element in this plan (Element::planTag)
+    std::uint64_t serial[3];  // Element::serial(): what the sweep's per-element tables are indexed by
     int edgeCount;
-    ConstraintCensus k;
+    int total, distance, angle;  // constraintCensus()
+    std::uint32_t shapeKey;      // shapeKeyOf(): what the sweep's classification depends on besides the solved flags
     bool isPoint[3], isLine[3], setNow[3];
     bool has[3], flip[3];
     bool simple;
 };
 
-// Dense index of an element in the plan of `epoch`, handed out on first sight from `next` - from
-// any thread: the tag word is claimed by compare-and-swap (a slot number lost to a race is simply
-// never used).
-int planSlot(const Element* e, std::uint32_t epoch, std::atomic<int>& next)
-{
-    std::atomic_ref<std::uint64_t> tag(e->planTagWord());
-    std::uint64_t seen = tag.load(std::memory_order_relaxed);
-    while (static_cast<std::uint32_t>(seen >> 32) != epoch) {
-        const std::uint64_t mine = (static_cast<std::uint64_t>(epoch) << 32) | static_cast<std::uint32_t>(next.fetch_add(1));
-        if (tag.compare_exchange_strong(seen, mine, std::memory_order_relaxed)) return static_cast<int>(mine & 0xffffffffu);
-    }
-    return static_cast<int>(seen & 0xffffffffu);
-}
-
 inline int pairIndex(int a, int b) { return a + b - 1; }  // {0,1} -> 0, {0,2} -> 1, {1,2} -> 2
 
-LeafFacts gatherFacts(const ConstraintGraph& g, std::uint32_t epoch, std::atomic<int>& nextSlot)
+std::uint32_t shapeKeyOf(const LeafFacts& f);  // below, next to what reads it
+
+LeafFacts gatherFacts(const ConstraintGraph& g)
 {
     LeafFacts f {};
-    f.slot[0] = f.slot[1] = f.slot[2] = -1;
-    if (g.nodeCount() != 3) return f;
-    NodeId node[3];
-    int n = 0;
-    for (const auto& [nd, el] : g.getElementMap()) {
-        if (n == 3 || !el) return f;
-        node[n] = nd;
-        f.e[n] = el.get();
+    // the graph's own digest: three elements in ascending node id, the constraint of each node pair
+    // (ConstraintGraph::triangleDigest; the decomposition left it warm).  Flags, kinds and values are
+    // read here, through the pointers: they may have changed since the digest was taken.
+    const TriangleDigest& d = g.triangleDigest();
+    if (!d.simple) return f;
+    for (int n = 0; n < 3; ++n) {
+        Element* el = d.element[n];
+        f.e[n] = el;
         f.isPoint[n] = el->isElementType<Point>();
         f.isLine[n] = el->isElementType<Line>();
         f.setNow[n] = el->isElementSet();
-        f.slot[n] = planSlot(el.get(), epoch, nextSlot);
-        ++n;
+        f.serial[n] = el->serial();
     }
-    if (n != 3) return f;
-    f.edgeCount = static_cast<int>(g.edgeCount());
-    f.k = constraintCensus(g);
-    const auto& cmap = g.getConstraintMap();
-    for (int a = 0; a < 3; ++a)
-        for (int b = a + 1; b < 3; ++b) {
-            const int p = pairIndex(a, b);
-            const auto edge = g.getEdgeBetween(node[a], node[b]);
-            if (!edge.has_value()) continue;
-            const auto c = cmap.get(edge.value());
-            if (!c.has_value() || !c.value().get()) continue;
-            const Constraint& con = *c.value().get();
-            const auto v = con.getConstraintValue();
-            if (!v.has_value()) continue;
-            f.has[p] = true;
-            f.val[p] = v.value();
-            const auto* ang = con.getConstraintAs<AngleConstraint>();
-            f.flip[p] = ang != nullptr && ang->flipOrientation;
-        }
+    f.edgeCount = d.edgeCount;
+    for (int p = 0; p < 3; ++p) {
+        const Constraint* con = d.constraint[p];
+        if (!con) continue;
+        ++f.total;  // constraintCensus(): every real constraint, with or without a value
+        const auto* ang = con->getConstraintAs<AngleConstraint>();
+        if (con->isConstraintType<DistanceConstraint>())
+            ++f.distance;
+        else if (ang)
+            ++f.angle;
+        const auto v = con->getConstraintValue();
+        if (!v.has_value()) continue;
+        f.has[p] = true;
+        f.val[p] = v.value();
+        f.flip[p] = ang != nullptr && ang->flipOrientation;
+    }
     f.simple = true;
+    f.shapeKey = shapeKeyOf(f);
     return f;
+}
+
+constexpr long long kFactsLookAhead = 12;
+
+void prefetchFacts(const ConstraintGraph& g)
+{
+    const TriangleDigest& d = g.triangleDigest();
+    if (!d.simple) return;
+    for (int n = 0; n < 3; ++n) {
+        // kind, solved flag and serial number sit behind the shape's coordinates
+        const char* tail = reinterpret_cast<const char*>(d.element[n]) + sizeof(Element) - 1;
+        __builtin_prefetch(tail);
+        __builtin_prefetch(tail - 23);
+    }
+    for (int p = 0; p < 3; ++p)
+        if (d.constraint[p]) __builtin_prefetch(d.constraint[p]);
 }
 
 // classify() on facts: same counts, same order
@@ -536,18 +538,18 @@ SolverId classifyFacts(const LeafFacts& f, const bool set[3])
     static constexpr SolverId order[] = { SolverId::ZeroFixedPointsTriangle, SolverId::ZeroFixedPPLTriangle,
         SolverId::ZeroFixedLLPAngleTriangle, SolverId::TwoFixedPointsDistance, SolverId::TwoFixedPointsLine,
         SolverId::FixedPointAndLineFreePoint, SolverId::TwoFixedLinesFreePoint, SolverId::FixedLineAndPointFreeLine };
+    const ConstraintCensus k { f.total, f.distance, f.angle };
     for (SolverId id : order)
-        if (matchesCountsOn(id, f.edgeCount, c, f.k)) return id;
+        if (matchesCountsOn(id, f.edgeCount, c, k)) return id;
     return SolverId::None;
 }
 
-// assignRoles() on facts.  Returns false when a constraint a role needs is not there (the general
-// code then raises the reference's exception) or the shape is one the role loops do not fill.
-bool rolesFromFacts(SolverId id, const LeafFacts& f, const bool set[3], Roles& r)
+// assignRoles() on facts, in two halves.  Who plays which part depends only on what the memo key
+// below holds (element kinds and solved flags); the constraint values are fetched per leaf.
+// roleIndices: false when the shape is one the role loops do not fill.
+bool roleIndices(SolverId id, const LeafFacts& f, const bool set[3], int& ia, int& ib, int& ic)
 {
-    r = Roles {};
-    r.id = id;
-    int ia = -1, ib = -1, ic = -1;
+    ia = ib = ic = -1;
     auto firstSecond = [&](auto pred, int& first, int& second) {  // "if (!haveA) a = e else b = e" over ascending ids
         for (int i = 0; i < 3; ++i)
             if (pred(i)) {
@@ -561,8 +563,47 @@ bool rolesFromFacts(SolverId id, const LeafFacts& f, const bool set[3], Roles& r
         for (int i = 0; i < 3; ++i)
             if (pred(i)) slot = i;
     };
+    switch (id) {
+    case SolverId::ZeroFixedPointsTriangle: ia = 0, ib = 1, ic = 2; break;
+    case SolverId::ZeroFixedPPLTriangle:
+    case SolverId::TwoFixedPointsLine:
+        last([&](int i) { return f.isLine[i]; }, ic);
+        firstSecond([&](int i) { return !f.isLine[i] && f.isPoint[i]; }, ia, ib);
+        break;
+    case SolverId::ZeroFixedLLPAngleTriangle:
+        last([&](int i) { return f.isPoint[i]; }, ib);
+        firstSecond([&](int i) { return !f.isPoint[i] && f.isLine[i]; }, ia, ic);
+        break;
+    case SolverId::TwoFixedPointsDistance:
+        firstSecond([&](int i) { return set[i]; }, ia, ib);
+        last([&](int i) { return !set[i]; }, ic);  // all three solved: ic stays -1, the general code raises the reference's failure
+        break;
+    case SolverId::FixedPointAndLineFreePoint:
+        last([&](int i) { return f.isLine[i]; }, ib);
+        last([&](int i) { return !f.isLine[i] && f.isPoint[i] && set[i]; }, ia);
+        last([&](int i) { return !f.isLine[i] && f.isPoint[i] && !set[i]; }, ic);
+        break;
+    case SolverId::TwoFixedLinesFreePoint:
+        last([&](int i) { return f.isPoint[i]; }, ic);
+        firstSecond([&](int i) { return !f.isPoint[i] && f.isLine[i]; }, ia, ib);
+        break;
+    case SolverId::FixedLineAndPointFreeLine:
+        last([&](int i) { return f.isPoint[i]; }, ib);
+        last([&](int i) { return !f.isPoint[i] && f.isLine[i] && set[i]; }, ia);
+        last([&](int i) { return !f.isPoint[i] && f.isLine[i] && !set[i]; }, ic);
+        break;
+    case SolverId::None: return false;
+    }
+    return ia >= 0 && ib >= 0 && ic >= 0 && ia != ib && ia != ic && ib != ic;
+}
+
+// roleValues: false when a constraint a role needs is not there (the general code then raises the
+// reference's exception).
+bool roleValues(SolverId id, int ia, int ib, int ic, const LeafFacts& f, Roles& r)
+{
+    r = Roles {};
+    r.id = id;
     auto value = [&](int a, int b, double& out, bool* flip = nullptr) {
-        if (a < 0 || b < 0 || a == b) return false;
         const int p = pairIndex(a < b ? a : b, a < b ? b : a);
         if (!f.has[p]) return false;
         out = f.val[p];
@@ -572,55 +613,86 @@ bool rolesFromFacts(SolverId id, const LeafFacts& f, const bool set[3], Roles& r
     bool ok = true;
     switch (id) {
     case SolverId::ZeroFixedPointsTriangle:
-        ia = 0, ib = 1, ic = 2;
-        ok = value(ia, ib, r.v0) && value(ia, ic, r.v1) && value(ib, ic, r.v2);
-        break;
-    case SolverId::ZeroFixedPPLTriangle:
-    case SolverId::TwoFixedPointsLine:
-        last([&](int i) { return f.isLine[i]; }, ic);
-        firstSecond([&](int i) { return !f.isLine[i] && f.isPoint[i]; }, ia, ib);
-        if (id == SolverId::ZeroFixedPPLTriangle) ok = value(ia, ib, r.v0);
-        ok = ok && value(ia, ic, r.v1) && value(ib, ic, r.v2);
-        break;
-    case SolverId::ZeroFixedLLPAngleTriangle:
-        last([&](int i) { return f.isPoint[i]; }, ib);
-        firstSecond([&](int i) { return !f.isPoint[i] && f.isLine[i]; }, ia, ic);
-        ok = value(ia, ic, r.v0, &r.flip) && value(ib, ia, r.v1) && value(ib, ic, r.v2);
-        break;
+    case SolverId::ZeroFixedPPLTriangle: ok = value(ia, ib, r.v0) && value(ia, ic, r.v1) && value(ib, ic, r.v2); break;
+    case SolverId::ZeroFixedLLPAngleTriangle: ok = value(ia, ic, r.v0, &r.flip) && value(ib, ia, r.v1) && value(ib, ic, r.v2); break;
     case SolverId::TwoFixedPointsDistance:
-        firstSecond([&](int i) { return set[i]; }, ia, ib);
-        last([&](int i) { return !set[i]; }, ic);
-        if (ic < 0) return false;  // all three solved: the general code raises the reference's failure
-        ok = value(ia, ic, r.v1) && value(ib, ic, r.v2);
-        break;
+    case SolverId::TwoFixedPointsLine:
     case SolverId::FixedPointAndLineFreePoint:
-        last([&](int i) { return f.isLine[i]; }, ib);
-        last([&](int i) { return !f.isLine[i] && f.isPoint[i] && set[i]; }, ia);
-        last([&](int i) { return !f.isLine[i] && f.isPoint[i] && !set[i]; }, ic);
-        ok = value(ia, ic, r.v1) && value(ib, ic, r.v2);
-        break;
-    case SolverId::TwoFixedLinesFreePoint:
-        last([&](int i) { return f.isPoint[i]; }, ic);
-        firstSecond([&](int i) { return !f.isPoint[i] && f.isLine[i]; }, ia, ib);
-        ok = value(ia, ic, r.v1) && value(ib, ic, r.v2);
-        break;
-    case SolverId::FixedLineAndPointFreeLine:
-        last([&](int i) { return f.isPoint[i]; }, ib);
-        last([&](int i) { return !f.isPoint[i] && f.isLine[i] && set[i]; }, ia);
-        last([&](int i) { return !f.isPoint[i] && f.isLine[i] && !set[i]; }, ic);
-        ok = value(ia, ic, r.v0, &r.flip) && value(ib, ic, r.v2);
-        break;
+    case SolverId::TwoFixedLinesFreePoint: ok = value(ia, ic, r.v1) && value(ib, ic, r.v2); break;
+    case SolverId::FixedLineAndPointFreeLine: ok = value(ia, ic, r.v0, &r.flip) && value(ib, ic, r.v2); break;
     case SolverId::None: return false;
     }
-    if (!ok || ia < 0 || ib < 0 || ic < 0) return false;
+    if (!ok) return false;
     r.a = f.e[ia], r.b = f.e[ib], r.c = f.e[ic];
     return true;
 }
 
-std::atomic<std::uint32_t> g_planEpoch { 0 };
+// What the sweep decides for a leaf from its facts and the predicted solved flags, remembered per
+// distinct (kinds, counts, flags) combination: a sketch has a handful of them.
+struct Verdict {
+    SolverId id = SolverId::None;
+    std::int8_t ia = -1, ib = -1, ic = -1;
+    bool roles = false;
+};
+
+Verdict decide(const LeafFacts& f, const bool set[3])
+{
+    Verdict v;
+    v.id = classifyFacts(f, set);
+    if (v.id == SolverId::None) return v;
+    int ia, ib, ic;
+    v.roles = roleIndices(v.id, f, set, ia, ib, ic);
+    v.ia = static_cast<std::int8_t>(ia), v.ib = static_cast<std::int8_t>(ib), v.ic = static_cast<std::int8_t>(ic);
+    return v;
+}
+
+// everything decide() reads from the facts, in 14 bits (a digest-described leaf has at most three edges)
+std::uint32_t shapeKeyOf(const LeafFacts& f)
+{
+    std::uint32_t k = 0;
+    for (int i = 0; i < 3; ++i) k = (k << 2) | (f.isPoint[i] ? 1u : f.isLine[i] ? 2u : 0u);
+    k = (k << 2) | static_cast<std::uint32_t>(f.edgeCount & 3);
+    k = (k << 2) | static_cast<std::uint32_t>(f.total & 3);
+    k = (k << 2) | static_cast<std::uint32_t>(f.distance & 3);
+    k = (k << 2) | static_cast<std::uint32_t>(f.angle & 3);
+    return k;
+}
+
+class VerdictMemo {
+public:
+    const Verdict& get(const LeafFacts& f, const bool set[3])
+    {
+        const std::uint32_t key = (f.shapeKey << 3) | (set[0] ? 4u : 0u) | (set[1] ? 2u : 0u) | (set[2] ? 1u : 0u);
+        Entry& e = m_rows[(key * 2654435761u) >> 24];
+        if (e.key != key) e.key = key, e.verdict = decide(f, set);
+        return e.verdict;
+    }
+
+private:
+    struct Entry {
+        std::uint32_t key = ~0u;
+        Verdict verdict;
+    };
+    Entry m_rows[256];
+};
+
+// Element serial -> index into the sweep's per-element tables.  The elements of one sketch were
+// constructed together, so their serials fill a narrow range and the index is a subtraction; a
+// plan over elements scattered through the life of the process falls back to a hash table.
+struct SlotIndex {
+    std::uint64_t lo = 0;
+    bool direct = true;
+    std::unordered_map<std::uint64_t, int> sparse;
+    int of(std::uint64_t serial)
+    {
+        if (direct) return static_cast<int>(serial - lo);
+        return sparse.try_emplace(serial, static_cast<int>(sparse.size())).first->second;
+    }
+};
 
 Plan makePlan(const std::vector<ConstraintGraph>& leaves)
 {
+    const auto t0 = std::chrono::steady_clock::now();
     Plan plan;
     const std::size_t n = leaves.size();
     plan.report.leaves = n;
@@ -633,53 +705,68 @@ Plan makePlan(const std::vector<ConstraintGraph>& leaves)
     plan.stop = n;
     static const char* const kNoSolver = "No solver matches this component configuration";
 
-    // (A) per-leaf facts, every host thread
+    // (A) per-leaf facts, every host thread.  Nothing is written to but the facts: a pass that tags
+    // the elements (an index claimed by compare-and-swap) spent its time moving their cache lines
+    // from core to core and did not get faster with more threads.
     const auto tA = std::chrono::steady_clock::now();
-    const std::uint32_t epoch = ++g_planEpoch;
-    std::atomic<int> nextSlot { 0 };
-    const std::unique_ptr<LeafFacts[]> facts(new LeafFacts[n ? n : 1]);  // untouched: first written in the parallel loop
+    struct FreeFacts {
+        void operator()(LeafFacts* p) const { std::free(p); }
+    };
+    // untouched memory: first written, page by page, by the thread that gathers the leaf
+    const std::unique_ptr<LeafFacts[], FreeFacts> facts(static_cast<LeafFacts*>(std::malloc(sizeof(LeafFacts) * (n ? n : 1))));
+    if (!facts) throw std::bad_alloc();
     const long long nn = static_cast<long long>(n);
-#pragma omp parallel for schedule(static) if (nn > 2048)
+    unsigned long long lo = ~0ull, hi = 0;
+#pragma omp parallel for schedule(static) reduction(min : lo) reduction(max : hi) if (nn > 2048)
     for (long long i = 0; i < nn; ++i) {
+        LeafFacts& f = facts[static_cast<std::size_t>(i)];
         try {
-            facts[static_cast<std::size_t>(i)] = gatherFacts(leaves[static_cast<std::size_t>(i)], epoch, nextSlot);
+            // the leaves lie one after the other, what they point to does not: ask for the elements
+            // and constraints of a leaf a few iterations before they are read
+            if (i + kFactsLookAhead < nn) prefetchFacts(leaves[static_cast<std::size_t>(i + kFactsLookAhead)]);
+            f = gatherFacts(leaves[static_cast<std::size_t>(i)]);
         } catch (...) {
-            LeafFacts none {};  // not simple: the general code decides (and raises) in step (B)
-            none.slot[0] = none.slot[1] = none.slot[2] = -1;
-            facts[static_cast<std::size_t>(i)] = none;
+            f = LeafFacts {};  // not simple: the general code decides (and raises) in step (B)
+        }
+        if (f.simple) {
+            for (int k = 0; k < 3; ++k) lo = std::min<unsigned long long>(lo, f.serial[k]), hi = std::max<unsigned long long>(hi, f.serial[k]);
+        } else {
+            for (const auto& [node, e] : leaves[static_cast<std::size_t>(i)].getElementMap())
+                if (e) lo = std::min<unsigned long long>(lo, e->serial()), hi = std::max<unsigned long long>(hi, e->serial());
         }
     }
 
     // (B) the sequential sweep.  What the symbolic pass knows about an element (solved once the
-    // leaves so far have run; wave of its last write / last read) lives in flat arrays under the
-    // element's dense index of step (A); the index is kept in the element itself (Element::planTag:
-    // epoch of this plan + slot), so no table is searched and this loop touches no element at all
-    // for the leaves step (A) could describe.  Plans over the same elements must not run
-    // concurrently (the reference's containers are not thread safe either).
+    // leaves so far have run; wave of its last write / last read) lives in flat arrays indexed by
+    // the element's serial number, so no table is searched and this loop touches no element at all
+    // for the leaves step (A) could describe.
     const auto tB = std::chrono::steady_clock::now();
-    std::vector<char> predicted(static_cast<std::size_t>(nextSlot.load()), 0);
+    SlotIndex index;
+    index.lo = lo;
+    const std::uint64_t span = hi >= lo ? hi - lo + 1 : 0;
+    index.direct = span <= 16 * static_cast<std::uint64_t>(n) + 65536;
+    std::vector<char> predicted(index.direct ? static_cast<std::size_t>(span) : 0, 0);
     std::vector<int> lastWrite(predicted.size(), -1), lastRead(predicted.size(), -1);
-    auto slotOfElement = [&](const Element* e) {
-        const int slot = planSlot(e, epoch, nextSlot);
-        if (static_cast<std::size_t>(slot) >= predicted.size()) {
-            const auto want = static_cast<std::size_t>(nextSlot.load());
-            predicted.resize(want, 0), lastWrite.resize(want, -1), lastRead.resize(want, -1);
-        }
+    auto slotOfSerial = [&](std::uint64_t serial) {
+        const int slot = index.of(serial);
+        if (static_cast<std::size_t>(slot) >= predicted.size()) predicted.push_back(0), lastWrite.push_back(-1), lastRead.push_back(-1);
         return slot;
     };
+    auto slotOfElement = [&](const Element* e) { return slotOfSerial(e->serial()); };
+    VerdictMemo memo;
     int top = -1;
     for (std::size_t i = 0; i < n; ++i) {
         const LeafFacts& f = facts[i];
         SolverId id = SolverId::None;
         bool haveRoles = false;
+        int slot3[3] = { -1, -1, -1 };
         if (f.simple) {
             bool set[3];
-            for (int k = 0; k < 3; ++k) set[k] = f.setNow[k] || predicted[static_cast<std::size_t>(f.slot[k])] != 0;
-            id = classifyFacts(f, set);
-            if (id != SolverId::None) haveRoles = rolesFromFacts(id, f, set, plan.roles[i]);
-        } else {
-            for (const auto& [node, e] : leaves[i].getElementMap())
-                if (e) slotOfElement(e.get());
+            for (int k = 0; k < 3; ++k) slot3[k] = slotOfSerial(f.serial[k]);
+            for (int k = 0; k < 3; ++k) set[k] = f.setNow[k] || predicted[static_cast<std::size_t>(slot3[k])] != 0;
+            const Verdict& v = memo.get(f, set);
+            id = v.id;
+            if (v.roles) haveRoles = roleValues(id, v.ia, v.ib, v.ic, f, plan.roles[i]);
         }
         if (!haveRoles && (!f.simple || id != SolverId::None)) {
             // the general code: same decisions on the graph itself, raising what the reference raises
@@ -711,7 +798,7 @@ Plan makePlan(const std::vector<ConstraintGraph>& leaves)
         auto slotOfRole = [&](const Element* e) {
             if (f.simple)
                 for (int k = 0; k < 3; ++k)
-                    if (f.e[k] == e) return f.slot[k];
+                    if (f.e[k] == e) return slot3[k];
             return slotOfElement(e);
         };
         if (zeroFixed(r.id)) {
@@ -743,8 +830,8 @@ Plan makePlan(const std::vector<ConstraintGraph>& leaves)
     }
     plan.report.waves = static_cast<std::size_t>(top + 1);
     if (std::getenv("GCS_HOST_TRACE"))
-        std::fprintf(stderr, "[host] plan: facts %.1f ms, sweep %.1f ms, %zu leaves\n",
-            std::chrono::duration<double>(tB - tA).count() * 1e3,
+        std::fprintf(stderr, "[host] plan: set-up %.1f ms, facts %.1f ms, sweep %.1f ms, %zu leaves\n",
+            std::chrono::duration<double>(tA - t0).count() * 1e3, std::chrono::duration<double>(tB - tA).count() * 1e3,
             std::chrono::duration<double>(std::chrono::steady_clock::now() - tB).count() * 1e3, n);
     return plan;
 }

@@ -61,6 +61,9 @@ std::shared_ptr<Gcs::Element> makeElement(const gcs_host_element& e)
         el = std::make_shared<Gcs::Element>(Gcs::Line(Vector2d(e.canvas[0], e.canvas[1]), Vector2d(e.canvas[2], e.canvas[3])));
         if (e.is_set) el->updateElementPosition(Vector2d(e.pos[0], e.pos[1]), Vector2d(e.pos[2], e.pos[3]));
     }
+    // tests: GCS_HOST_SERIAL_STRIDE = k leaves k element serial numbers unused after every element,
+    // which takes the leaf scheduler off its dense per-element tables (leaf_batch.cpp, SlotIndex)
+    if (const char* stride = std::getenv("GCS_HOST_SERIAL_STRIDE")) Gcs::Element::skipSerials(std::strtoull(stride, nullptr, 10));
     return el;
 }
 
@@ -120,6 +123,68 @@ int fail(const std::exception& ex)
 extern "C" {
 
 GCS_API const char* gcs_host_last_error(void) { return g_msg; }
+
+// Self-check of ConstraintGraph::triangleDigest (the per-leaf summary the scheduler plans from):
+// it must follow every change made to the graph, through the class or through getGraph(), and
+// copies of elements must be new objects to the scheduler.  Returns 0, or the number of the
+// first check that failed.
+GCS_API int gcs_host_selftest_digest(void)
+{
+    using namespace Gcs;
+    try {
+        ConstraintGraph g;
+        std::vector<std::shared_ptr<Element>> el;
+        std::vector<ConstraintGraph::NodeIdType> nd;
+        for (int i = 0; i < 3; ++i) {
+            el.push_back(std::make_shared<Element>(Point(Vector2d(i, 2 * i))));
+            nd.push_back(g.getGraph().addNode());
+            if (g.triangleDigest().simple) return 1;  // fewer than three elements
+            g.addElement(nd.back(), el.back());
+        }
+        const TriangleDigest* d = &g.triangleDigest();
+        if (!d->simple || d->edgeCount != 0 || d->element[0] != el[0].get() || d->element[2] != el[2].get()) return 2;
+        const auto e01 = g.getGraph().addEdge(nd[0], nd[1]).value();  // behind the class's back
+        d = &g.triangleDigest();
+        if (!d->simple || d->edgeCount != 1 || d->constraint[0] != nullptr) return 3;
+        auto c01 = std::make_shared<Constraint>(DistanceConstraint(3.0));
+        g.addConstraint(e01, c01);
+        d = &g.triangleDigest();
+        if (!d->simple || d->constraint[0] != c01.get() || d->constraint[1] || d->constraint[2]) return 4;
+        const auto v12 = g.addVirtualEdge(nd[1], nd[2]);
+        d = &g.triangleDigest();
+        if (!d->simple || d->edgeCount != 2 || d->constraint[2] != nullptr) return 5;
+        const auto e02 = g.getGraph().addEdge(nd[0], nd[2]).value();
+        auto c02 = std::make_shared<Constraint>(AngleConstraint(0.5, true));
+        g.addConstraint(e02, c02);
+        d = &g.triangleDigest();
+        if (!d->simple || d->edgeCount != 3 || d->constraint[1] != c02.get()) return 6;
+        ConstraintGraph copy = g;  // a copy shares elements and constraints, and answers for itself afterwards
+        g.removeVirtualEdge(v12);
+        if (g.triangleDigest().edgeCount != 2 || copy.triangleDigest().edgeCount != 3) return 7;
+        const auto p01 = copy.getGraph().addEdge(nd[0], nd[1]).value();  // a second edge on one pair: not simple any more
+        if (copy.triangleDigest().simple) return 8;
+        copy.removeConstraintEdge(p01);
+        if (!copy.triangleDigest().simple) return 9;
+        g.removeConstraintEdge(e01);
+        d = &g.triangleDigest();
+        if (!d->simple || d->edgeCount != 1 || d->constraint[0] || d->constraint[1] != c02.get()) return 10;
+        g.removeElement(nd[2]);
+        if (g.triangleDigest().simple) return 11;
+        // element serial numbers: unique per object, ascending, untouched by assignment
+        Element a(Point(Vector2d(1, 2))), b(a);
+        if (a.serial() == b.serial() || b.serial() < a.serial()) return 12;
+        const auto sb = b.serial();
+        b = *el[1];
+        if (b.serial() != sb || !b.isElementType<Point>()) return 13;
+        Element::skipSerials(1000);
+        Element c(Line(Vector2d(0, 0), Vector2d(1, 1)));
+        if (c.serial() < sb + 1000) return 14;
+        return 0;
+    } catch (const std::exception& ex) {
+        fail(ex);
+        return -1;
+    }
+}
 
 // Kernel class of the host mirror's launches (Gcs::B200::setKernelVariant); returns the previous one.
 GCS_API int gcs_host_set_variant(int variant) { return Gcs::B200::setKernelVariant(variant); }

@@ -49,6 +49,7 @@ ConstraintGraph makeLeaf(const ConstraintGraph& g, std::array<NodeId, 3> nodes, 
         }
     }
     if (virtualPair) leaf.addVirtualEdge(toLocal(virtualPair->first), toLocal(virtualPair->second));
+    (void)leaf.triangleDigest();  // what the leaf scheduler will read, taken while the leaf is in this thread's cache
     return leaf;
 }
 

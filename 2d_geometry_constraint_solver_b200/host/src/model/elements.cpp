@@ -3,6 +3,7 @@
 // :636-673; line_angle_solvers.cpp:551), so those keep Eigen's operation order: norm =
 // sqrt(x*x + y*y), normalized = v / norm when the squared norm is positive, midpoint =
 // (p1 + p2) / 2.0.  The text forms are the reference's, character for character.
+#include <atomic>
 #include <format>
 
 #include <gcs/model/elements.hpp>
@@ -77,6 +78,14 @@ Vec Line::normal() const
 Vec Line::midpoint() const { return (p1 + p2) / 2.0; }
 
 // ---- Element: forwards to the active alternative ----
+namespace {
+std::atomic<std::uint64_t> g_serial { 1 };
+}
+
+std::uint64_t Element::nextSerial() { return g_serial.fetch_add(1, std::memory_order_relaxed); }
+
+void Element::skipSerials(std::uint64_t count) { g_serial.fetch_add(count, std::memory_order_relaxed); }
+
 std::string Element::getElementName() const
 {
     return std::visit([](const auto& shape) { return shape.getTypeName(); }, m_element);

@@ -141,6 +141,58 @@ def test_plan_levels_follow_data_dependences(host):
     assert r["solved"] == 0 and r["level"] == [-1] * 6
 
 
+def test_the_digest_the_plan_reads_follows_every_change_to_a_leaf(host):
+    """ConstraintGraph::triangleDigest - the summary the scheduler plans from instead of walking a
+    leaf's containers - tracks edges added behind the class's back (getGraph()), constraints, virtual
+    edges, removals and copies; Element serial numbers are per object."""
+    assert H.load().gcs_host_selftest_digest() == 0, H.last_error()
+
+
+def test_plan_does_not_depend_on_how_the_elements_are_numbered(host, monkeypatch):
+    """The sweep indexes its per-element tables by Element::serial(): a subtraction when the numbers
+    are close together, a hash table when they are not.  Same sketches, same plans."""
+    import sketch_gen as S
+    data = json.load(open(os.path.join(GOLD, "sketch_leaves.json")))["items"]
+    cases = [(sk["elements"], sk["leaves"]) for sk in data]
+    el, lv = S.make_sketch(3000, seed=5, first_shape=2, p_line=0.3)
+    cases.append((el, lv))
+    for els, leaves in cases:
+        monkeypatch.delenv("GCS_HOST_SERIAL_STRIDE", raising=False)
+        dense = H.leaves_solve([dict(e) for e in els], leaves, mode=2)
+        monkeypatch.setenv("GCS_HOST_SERIAL_STRIDE", "1000003")
+        sparse = H.leaves_solve([dict(e) for e in els], leaves, mode=2)
+        assert dense["rc"] == sparse["rc"] == 0
+        for key in ("solver", "level", "status", "waves", "solved"):
+            assert dense[key] == sparse[key], key
+
+
+def test_leaves_the_digest_cannot_describe_take_the_container_walk(host):
+    """Two edges on one node pair: not a `simple` triangle, so the general classification (the
+    reference's own counts over the containers) decides - next to ordinary leaves in one plan.
+    The two-fixed predicates do not look at the edge count (point_point_solvers.cpp:87-95), so such a
+    leaf is solved like any other; a leaf whose three points are all solved by the time its turn
+    comes makes the reference dereference a null free point (:110-127): the loop stops there.
+    (Expected values: the plan of the round-1 build, which walked the containers of every leaf.)"""
+    P = lambda x, y: dict(type=0, canvas=[x, y])
+    D = lambda a, b, v: dict(a=a, b=b, type=0, value=v)
+    V = lambda a, b: dict(a=a, b=b, type=2)
+    els = [P(0, 0), P(10, 0), P(5, 8), P(15, 8), P(-5, 8), P(3, 3)]
+    leaves = [
+        {"elems": [0, 1, 2], "edges": [D(0, 1, 10), D(0, 2, 9), D(1, 2, 9)]},
+        {"elems": [1, 2, 3], "edges": [D(1, 3, 9), D(2, 3, 10), D(2, 3, 10), V(1, 2)]},  # 4 edges
+        {"elems": [0, 2, 4], "edges": [D(0, 4, 9), D(2, 4, 10), V(0, 2)]},
+        {"elems": [3, 4, 5], "edges": [D(3, 5, 9), D(3, 5, 9), D(4, 5, 10)]},            # a double edge, reads waves 1
+        {"elems": [1, 2, 3], "edges": [D(1, 3, 9), D(1, 3, 9), D(2, 3, 10)]},            # all three solved by now
+        {"elems": [0, 1, 5], "edges": [D(0, 5, 9), D(1, 5, 10)]},
+    ]
+    plan = H.leaves_solve(els, leaves, mode=2)
+    assert plan["rc"] == 0
+    assert plan["solver"] == [1, 4, 4, 4, 0, 0]
+    assert plan["level"] == [0, 1, 1, 2, -1, -1]
+    assert plan["status"] == [0, 0, 0, 0, 1, 1]
+    assert plan["waves"] == 3 and plan["solved"] == 4
+
+
 def test_wave_plan_reproduces_the_reference_loop_on_golden_sketches(gcs, host):
     """tests/golden/sketch_leaves.json: 4 sketches x (120..300) leaves solved by the reference's
     sequential loop.  Here: plan on the host (solver + wave per leaf), then replay the waves -
