@@ -80,32 +80,49 @@ struct PackedLeaf {
 GCS_API PackedLeaf pack(SolverId id, ConstraintGraph& component);
 GCS_API void apply(const PackedLeaf& leaf, const double out[GCS_MAX_OUT_COLS]);
 
-// Structure-of-arrays batch of one kind.
+// Structure-of-arrays batch of one kind, in ONE block of host memory: input columns, output columns
+// and the code column at a constant spacing, so a call moves them with one strided copy each way
+// (gcs_b200.h, "host buffers"), page-locked once the batch is large enough for that to matter
+// (gcs_b200_host_alloc; ordinary memory when there is no device).  Blocks are recycled through a
+// small process-wide pool: a solve of many waves, or many solves, allocate once.
 class GCS_API KindBatch {
 public:
     explicit KindBatch(int kind = 0);
+    ~KindBatch();
+    KindBatch(KindBatch&& other) noexcept;
+    KindBatch& operator=(KindBatch&& other) noexcept;
+    KindBatch(const KindBatch&) = delete;
+    KindBatch& operator=(const KindBatch&) = delete;
+
     int kind() const { return m_kind; }
-    std::size_t size() const { return m_code.size(); }
-    void clear();
+    std::size_t size() const { return m_size; }
+    void clear();                     // keeps the storage
+    void reserve(std::size_t rows);   // the kind must be known
     void push(const PackedLeaf& leaf);
-    // descriptor over the current contents (host pointers, 2 seeds, default guesses);
-    // allocates the output columns
+    // rows [0, rows) to be filled with set() - from any thread, each row once
+    void resize(std::size_t rows);
+    void set(std::size_t row, const PackedLeaf& leaf);
+    // descriptor over the current contents (host pointers, 2 seeds, default guesses; the flag
+    // columns are not asked for: write-back needs the positions only)
     gcs_b200_batch descriptor();
     // after a solve: hand every row's output to its target element
     void applyAll();
-    const std::vector<double>& column(int c) const { return m_in[c]; }
-    const std::vector<std::uint8_t>& codes() const { return m_code; }
-    std::vector<double>& out(int c) { return m_out[c]; }
-    const std::vector<PackedLeaf>& leaves() const { return m_leaves; }
+    const double* column(int c) const { return doubles() + static_cast<std::size_t>(c) * m_cap; }
+    const double* out(int c) const { return doubles() + (static_cast<std::size_t>(m_nin) + static_cast<std::size_t>(c)) * m_cap; }
+    const std::uint8_t* codes() const { return m_slab + static_cast<std::size_t>(m_nin + m_nout) * m_cap * sizeof(double); }
+    Element* target(std::size_t row) const { return m_target[row]; }
+    bool pageLocked() const { return m_pinned; }
 
 private:
+    const double* doubles() const { return reinterpret_cast<const double*>(m_slab); }
+    void grow(std::size_t rows);
+    void release();
     int m_kind;
-    std::array<std::vector<double>, GCS_MAX_IN_COLS> m_in;
-    std::vector<std::uint8_t> m_code;
-    std::array<std::vector<double>, GCS_MAX_OUT_COLS> m_out;
-    std::vector<std::int16_t> m_iters;
-    std::vector<std::uint8_t> m_conv, m_root;
-    std::vector<PackedLeaf> m_leaves;
+    int m_nin = 0, m_nout = 0;
+    std::size_t m_size = 0, m_cap = 0, m_bytes = 0;
+    unsigned char* m_slab = nullptr;
+    bool m_pinned = false;
+    std::vector<Element*> m_target;
 };
 
 // One leaf through the CUDA path (batch of one).  Throws std::runtime_error when the CUDA

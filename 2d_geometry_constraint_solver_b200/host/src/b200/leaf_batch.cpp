@@ -18,6 +18,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <cstring>
 #include <cmath>
 #include <exception>
 #include <memory>
@@ -940,23 +942,158 @@ void apply(const PackedLeaf& leaf, const double out[GCS_MAX_OUT_COLS])
         leaf.target->updateElementPosition(Vector2d { out[0], out[1] }, Vector2d { out[2], out[3] });
 }
 
+// ---- storage of a KindBatch ------------------------------------------------------------------
+namespace {
+
+struct Block {
+    unsigned char* p = nullptr;
+    std::size_t bytes = 0;
+    bool pinned = false;
+};
+
+// Page-locking memory costs a system call and a driver call per block (hundreds of microseconds):
+// blocks go back to this pool instead of to the system.  Never destroyed (freeing page-locked
+// memory from a static destructor would run after the CUDA runtime has shut down).
+struct BlockPool {
+    std::mutex mu;
+    std::vector<Block> idle;
+    std::size_t idleBytes = 0;
+};
+BlockPool& pool()
+{
+    static BlockPool* p = new BlockPool;
+    return *p;
+}
+constexpr std::size_t kPinFrom = 16 * 1024;            // smaller batches (single leaves, merge candidates) stay in ordinary memory
+constexpr std::size_t kPoolBytes = std::size_t { 256 } << 20;
+constexpr std::size_t kPoolBlocks = 32;
+
+Block acquireBlock(std::size_t bytes)
+{
+    if (bytes >= kPinFrom) {
+        BlockPool& bp = pool();
+        std::lock_guard<std::mutex> lk(bp.mu);
+        std::size_t best = bp.idle.size();
+        for (std::size_t i = 0; i < bp.idle.size(); ++i)
+            if (bp.idle[i].bytes >= bytes && bp.idle[i].bytes <= 4 * bytes && (best == bp.idle.size() || bp.idle[i].bytes < bp.idle[best].bytes))
+                best = i;
+        if (best != bp.idle.size()) {
+            const Block b = bp.idle[best];
+            bp.idle.erase(bp.idle.begin() + static_cast<std::ptrdiff_t>(best));
+            bp.idleBytes -= b.bytes;
+            return b;
+        }
+    }
+    Block b;
+    b.bytes = bytes;
+    if (bytes >= kPinFrom) b.p = static_cast<unsigned char*>(gcs_b200_host_alloc(bytes));  // NULL without a device
+    b.pinned = b.p != nullptr;
+    if (!b.p) b.p = static_cast<unsigned char*>(std::aligned_alloc(256, (bytes + 255) / 256 * 256));
+    if (!b.p) throw std::bad_alloc();
+    return b;
+}
+
+void releaseBlock(const Block& b)
+{
+    if (!b.p) return;
+    if (b.pinned) {
+        BlockPool& bp = pool();
+        std::lock_guard<std::mutex> lk(bp.mu);
+        if (bp.idle.size() < kPoolBlocks && bp.idleBytes + b.bytes <= kPoolBytes) {
+            bp.idle.push_back(b);
+            bp.idleBytes += b.bytes;
+            return;
+        }
+    }
+    if (b.pinned)
+        gcs_b200_host_free(b.p);
+    else
+        std::free(b.p);
+}
+
+}  // namespace
+
 KindBatch::KindBatch(int kind) : m_kind(kind) {}
+
+KindBatch::~KindBatch() { release(); }
+
+KindBatch::KindBatch(KindBatch&& o) noexcept
+    : m_kind(o.m_kind), m_nin(o.m_nin), m_nout(o.m_nout), m_size(o.m_size), m_cap(o.m_cap), m_bytes(o.m_bytes), m_slab(o.m_slab),
+      m_pinned(o.m_pinned), m_target(std::move(o.m_target))
+{
+    o.m_slab = nullptr, o.m_cap = o.m_size = o.m_bytes = 0, o.m_pinned = false;
+}
+
+KindBatch& KindBatch::operator=(KindBatch&& o) noexcept
+{
+    if (this != &o) {
+        release();
+        m_kind = o.m_kind, m_nin = o.m_nin, m_nout = o.m_nout, m_size = o.m_size, m_cap = o.m_cap, m_bytes = o.m_bytes;
+        m_slab = o.m_slab, m_pinned = o.m_pinned, m_target = std::move(o.m_target);
+        o.m_slab = nullptr, o.m_cap = o.m_size = o.m_bytes = 0, o.m_pinned = false;
+    }
+    return *this;
+}
+
+void KindBatch::release()
+{
+    releaseBlock(Block { m_slab, m_bytes, m_pinned });
+    m_slab = nullptr, m_cap = m_bytes = 0, m_pinned = false;
+}
 
 void KindBatch::clear()
 {
-    for (auto& c : m_in) c.clear();
-    for (auto& c : m_out) c.clear();
-    m_code.clear(), m_iters.clear(), m_conv.clear(), m_root.clear(), m_leaves.clear();
+    m_size = 0;
+    m_target.clear();
+}
+
+// capacity for `rows` rows: a new block (columns of the old one copied over), 64-row granules so
+// that every column starts on a 512-byte boundary
+void KindBatch::grow(std::size_t rows)
+{
+    if (m_kind < 1 || m_kind > GCS_KIND_COUNT) throw std::invalid_argument("KindBatch: storage asked for before the kind is known");
+    m_nin = gcs_b200_kind_in_cols(m_kind), m_nout = gcs_b200_kind_out_cols(m_kind);
+    const std::size_t cap = (std::max<std::size_t>(rows, 64) + 63) / 64 * 64;
+    const std::size_t ncol = static_cast<std::size_t>(m_nin + m_nout);
+    const Block nb = acquireBlock(ncol * cap * sizeof(double) + cap);
+    // a recycled block may be larger than asked for: the spacing follows what was asked, the rest is slack
+    if (m_slab && m_size) {
+        for (int c = 0; c < m_nin; ++c)
+            std::memcpy(nb.p + static_cast<std::size_t>(c) * cap * sizeof(double), column(c), m_size * sizeof(double));
+        std::memcpy(nb.p + ncol * cap * sizeof(double), codes(), m_size);
+    }
+    release();
+    m_slab = nb.p, m_bytes = nb.bytes, m_pinned = nb.pinned, m_cap = cap;
+}
+
+void KindBatch::reserve(std::size_t rows)
+{
+    if (rows > m_cap) grow(rows);
+}
+
+void KindBatch::resize(std::size_t rows)
+{
+    reserve(rows);
+    m_size = rows;
+    m_target.assign(rows, nullptr);
+}
+
+void KindBatch::set(std::size_t row, const PackedLeaf& leaf)
+{
+    if (leaf.kind != m_kind) throw std::invalid_argument("KindBatch::set: leaf of another kind");
+    double* cols = reinterpret_cast<double*>(m_slab);
+    for (int c = 0; c < m_nin; ++c) cols[static_cast<std::size_t>(c) * m_cap + row] = leaf.in[c];
+    m_slab[static_cast<std::size_t>(m_nin + m_nout) * m_cap * sizeof(double) + row] = leaf.code;
+    m_target[row] = leaf.target;
 }
 
 void KindBatch::push(const PackedLeaf& leaf)
 {
     if (m_kind == 0) m_kind = leaf.kind;
     if (leaf.kind != m_kind) throw std::invalid_argument("KindBatch::push: leaf of another kind");
-    const int nin = gcs_b200_kind_in_cols(m_kind);
-    for (int c = 0; c < nin; ++c) m_in[static_cast<std::size_t>(c)].push_back(leaf.in[c]);
-    m_code.push_back(leaf.code);
-    m_leaves.push_back(leaf);
+    if (m_size == m_cap) grow(std::max<std::size_t>(2 * m_cap, 64));
+    m_target.push_back(nullptr);
+    set(m_size++, leaf);
 }
 
 namespace {
@@ -981,25 +1118,18 @@ int setKernelVariant(int variant)
 gcs_b200_batch KindBatch::descriptor()
 {
     gcs_b200_batch d {};
-    const std::size_t n = size();
     d.kind = m_kind;
     d.n_seeds = 2;  // Equations::solve2D runs exactly two guesses (newton_raphson.hpp:42-53)
-    d.n = static_cast<std::int64_t>(n);
+    d.n = static_cast<std::int64_t>(m_size);
     d.mem = GCS_MEM_HOST;
     d.variant = variantSetting();
-    const int nin = gcs_b200_kind_in_cols(m_kind), nout = gcs_b200_kind_out_cols(m_kind);
-    for (int c = 0; c < nin; ++c) d.in[c] = m_in[static_cast<std::size_t>(c)].data();
-    d.code = m_code.data();
+    if (m_size == 0) return d;
+    for (int c = 0; c < m_nin; ++c) d.in[c] = column(c);
+    d.code = codes();
     d.guesses = nullptr;
-    for (int c = 0; c < nout; ++c) {
-        m_out[static_cast<std::size_t>(c)].assign(n, 0.0);
-        d.out[c] = m_out[static_cast<std::size_t>(c)].data();
-    }
-    m_iters.assign(2 * n, 0), m_conv.assign(2 * n, 0), m_root.assign(n, 0);
-    d.cand = nullptr;
-    d.iters = m_iters.data();
-    d.converged = m_conv.data();
-    d.root_index = m_root.data();
+    for (int c = 0; c < m_nout; ++c) d.out[c] = const_cast<double*>(out(c));
+    // candidates, iteration counts, flags and root indices stay on the device: nothing here reads them
+    d.cand = nullptr, d.iters = nullptr, d.converged = nullptr, d.root_index = nullptr;
     return d;
 }
 
@@ -1007,13 +1137,15 @@ void KindBatch::applyAll()
 {
     // the rows of a batch write distinct elements (one wave of the scheduler, or the independent
     // candidates of a merge): every host thread
-    const int nout = gcs_b200_kind_out_cols(m_kind);
-    const long long m = static_cast<long long>(m_leaves.size());
-#pragma omp parallel for schedule(static) if (m > 1024)
+    const long long m = static_cast<long long>(m_size);
+    PackedLeaf shape;
+    shape.kind = m_kind;
+#pragma omp parallel for schedule(static) firstprivate(shape) if (m > 1024)
     for (long long i = 0; i < m; ++i) {
         double o[GCS_MAX_OUT_COLS] = {};
-        for (int c = 0; c < nout; ++c) o[c] = m_out[static_cast<std::size_t>(c)][static_cast<std::size_t>(i)];
-        apply(m_leaves[static_cast<std::size_t>(i)], o);
+        for (int c = 0; c < m_nout; ++c) o[c] = out(c)[static_cast<std::size_t>(i)];
+        shape.target = m_target[static_cast<std::size_t>(i)];
+        apply(shape, o);
     }
 }
 
@@ -1059,28 +1191,42 @@ BatchReport solveLeavesImpl(std::vector<ConstraintGraph>& leaves, int device, in
     for (std::size_t i = 0; i < plan.stop; ++i)
         if (rep.level[i] >= 0) byWave[static_cast<std::size_t>(rep.level[i])].push_back(i);
     KindBatch batches[GCS_KIND_COUNT + 1];
-    std::vector<PackedLeaf> rows;
+    for (int k = 1; k <= GCS_KIND_COUNT; ++k) batches[k] = KindBatch(k);
+    {  // one block per kind for the whole solve: the largest wave decides
+        std::vector<std::array<std::size_t, GCS_KIND_COUNT + 1>> count(rep.waves);
+        for (std::size_t i = 0; i < plan.stop; ++i)
+            if (rep.level[i] >= 0) ++count[static_cast<std::size_t>(rep.level[i])][static_cast<std::size_t>(kindOf(plan.roles[i].id))];
+        for (int k = 1; k <= GCS_KIND_COUNT; ++k) {
+            std::size_t most = 0;
+            for (const auto& c : count) most = std::max(most, c[static_cast<std::size_t>(k)]);
+            if (most) batches[k].reserve(most);
+        }
+    }
+    std::vector<std::size_t> rowOf;
     for (const auto& wave : byWave) {
         t0 = Clock::now();
-        for (int k = 1; k <= GCS_KIND_COUNT; ++k) batches[k] = KindBatch(k);
+        // rows of the kind batches in input order
+        std::size_t rowsOfKind[GCS_KIND_COUNT + 1] = {};
+        rowOf.resize(wave.size());
+        for (std::size_t j = 0; j < wave.size(); ++j) rowOf[j] = rowsOfKind[kindOf(plan.roles[wave[j]].id)]++;
+        for (int k = 1; k <= GCS_KIND_COUNT; ++k) batches[k].resize(rowsOfKind[k]);
         // The leaves of a wave touch disjoint elements wherever one of them writes (that is what a
         // wave is: nobody reads or writes what another leaf of the wave writes - the anchors the
-        // zero-fixed shapes place included), so their rows are packed on every host thread; the
-        // rows then enter the kind batches in input order.
-        rows.resize(wave.size());
+        // zero-fixed shapes place included), so their rows are packed on every host thread,
+        // straight into the kind batches.
         const long long m = static_cast<long long>(wave.size());
         std::exception_ptr packError;
 #pragma omp parallel for schedule(static) if (m > 1024)
         for (long long j = 0; j < m; ++j) {
             try {
-                rows[static_cast<std::size_t>(j)] = packNumeric(plan.roles[wave[static_cast<std::size_t>(j)]]);
+                const PackedLeaf row = packNumeric(plan.roles[wave[static_cast<std::size_t>(j)]]);
+                batches[row.kind].set(rowOf[static_cast<std::size_t>(j)], row);
             } catch (...) {
 #pragma omp critical
                 if (!packError) packError = std::current_exception();
             }
         }
         if (packError) std::rethrow_exception(packError);
-        for (const PackedLeaf& row : rows) batches[row.kind].push(row);
         rep.packSeconds += since(t0);
         // The kind batches of a wave are independent jobs: all of them are queued (upload / kernel /
         // download pipelines on the library's streams) before any is waited for, then written back.
@@ -1112,6 +1258,7 @@ BatchReport solveLeavesImpl(std::vector<ConstraintGraph>& leaves, int device, in
             if (rc != GCS_OK) failed("gcs_b200_wait", rc);
         }
         rep.deviceSeconds += since(t0);
+        if (std::getenv("GCS_HOST_TRACE")) std::fprintf(stderr, "[host] wave of %zu leaves: device calls %.1f us\n", wave.size(), since(t0) * 1e6);
         t0 = Clock::now();
         for (int k = 1; k <= GCS_KIND_COUNT; ++k)
             if (batches[k].size() != 0) batches[k].applyAll();

@@ -1,6 +1,9 @@
 // Degree-2 peeling decomposition (see gcs/b200/peel_decomposition.hpp).
 #include <algorithm>
 #include <array>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <exception>
 #include <functional>
 #include <map>
@@ -58,6 +61,7 @@ ConstraintGraph makeLeaf(const ConstraintGraph& g, std::array<NodeId, 3> nodes, 
 std::vector<ConstraintGraph> decomposeByPeeling(const ConstraintGraph& gcs, PeelStats* stats)
 {
     const auto& graph = gcs.getGraph();
+    const auto t0 = std::chrono::steady_clock::now();
     if (graph.nodeCount() < 3) throw std::runtime_error("decomposeByPeeling: fewer than three elements");
 
     // live adjacency in flat arrays over the dense positions of the nodes in ascending id order:
@@ -98,6 +102,7 @@ std::vector<ConstraintGraph> decomposeByPeeling(const ConstraintGraph& gcs, Peel
         if (inc[i].size() == 2) push(i);
     std::vector<std::size_t> parked;  // degree-2 slots whose two edges form a double edge (skipped, kept)
 
+    const auto t1 = std::chrono::steady_clock::now();
     std::vector<Peel> peels;
     peels.reserve(nn);
     std::size_t remaining = nn;
@@ -136,6 +141,7 @@ std::vector<ConstraintGraph> decomposeByPeeling(const ConstraintGraph& gcs, Peel
         for (std::size_t sl : { sa, sb })
             if (inc[sl].size() == 2) push(sl);
     }
+    const auto t2 = std::chrono::steady_clock::now();
     // what the base-leaf code below iterates: the three remaining nodes with their live edges
     std::map<NodeId, std::set<EdgeId>> incident;
     for (std::size_t i = 0; i < nn; ++i)
@@ -171,6 +177,12 @@ std::vector<ConstraintGraph> decomposeByPeeling(const ConstraintGraph& gcs, Peel
         }
     }
     if (failure) std::rethrow_exception(failure);
+    if (std::getenv("GCS_HOST_TRACE")) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count() * 1e3; };
+        std::fprintf(stderr, "[host] peel: adjacency %.1f ms, peel order %.1f ms, leaf graphs %.1f ms, %zu leaves\n", ms(t0, t1), ms(t1, t2),
+            ms(t2, t3), leaves.size());
+    }
     if (stats) *stats = { graph.nodeCount(), graph.edgeCount(), leaves.size() };
     return leaves;
 }

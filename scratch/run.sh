@@ -1,5 +1,6 @@
 set -x
 mkdir -p gpurun_out
-nproc
-GCS_HOST_TRACE=1 python scratch/sketch_time.py 100000 6 > gpurun_out/r2s_sketch.log 2>&1; grep -E "plan:|^rc|generated" gpurun_out/r2s_sketch.log
-python -m pytest tests/test_gpu_host.py -x -q > gpurun_out/r2s_host.log 2>&1; tail -5 gpurun_out/r2s_host.log
+python -m pytest tests/test_gpu_host.py tests/test_merge3.py -x -q > gpurun_out/r2v_host.log 2>&1; tail -5 gpurun_out/r2v_host.log
+GCS_HOST_TRACE=1 python scratch/sketch_time.py 100000 6 > gpurun_out/r2v_trace.log 2>&1
+grep -E "^rc" gpurun_out/r2v_trace.log | sed 's/.*decompose_us/decompose_us/'
+grep -E "wave of|peel:|plan:" gpurun_out/r2v_trace.log | tail -56 | head -54 | awk 'NR%4==0'

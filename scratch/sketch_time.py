@@ -2,6 +2,8 @@
 import os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
 import sketch_gen as S, host_lib as H
+if os.environ.get("GCS_HOST_SO"):
+    H.HOST_SO = os.path.join(H.HOST_DIR, os.environ["GCS_HOST_SO"])  # A/B against another build of the host library
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 t = time.time()
 el, ed = S.make_linkage(n, seed=4)
