@@ -133,7 +133,13 @@ struct BatchReport {
     std::size_t leaves = 0, solved = 0, unsupported = 0, waves = 0, launches = 0;
     std::size_t shardedLaunches = 0;  // launches of a kind batch that went over several devices (solveLeavesOnDevices)
     double planSeconds = 0, packSeconds = 0, deviceSeconds = 0, applySeconds = 0;  // where solveLeaves spent its time
-    std::vector<SolveResult> results;  // per leaf, in input order
+    std::vector<SolveStatus> status;   // per leaf, in input order
+    // what classifyAndSolve would have returned for the leaf (the message is made here, on demand)
+    SolveResult result(std::size_t leaf) const
+    {
+        if (status.at(leaf) == SolveStatus::Success) return SolveResult::success();
+        return { status[leaf], "No solver matches this component configuration" };
+    }
     std::vector<int> level;            // wave of each leaf (-1 = unsupported)
     std::vector<SolverId> solver;      // solver chosen per leaf
 };

@@ -431,13 +431,6 @@ void solveBatchOnDevice(KindBatch& batch, int device)
     batch.applyAll();
 }
 
-struct Plan {
-    BatchReport report;
-    std::vector<Roles> roles;          // per leaf (id None = unsupported)
-    std::size_t stop = 0;              // leaves [0, stop) are solved; == leaves.size() when no leaf throws
-    std::exception_ptr error;          // what the reference's loop would have thrown at leaf `stop`
-};
-
 // ---------------------------------------------------------------------------------------------
 // The symbolic pass in two steps.
 //  (A) per leaf, independent of every other leaf (hence over all host threads): the three
@@ -452,59 +445,91 @@ struct Plan {
 // through the general code (classify / assignRoles on the graph), which raises what the reference
 // raises.
 // ---------------------------------------------------------------------------------------------
-struct LeafFacts {
-    // no member initialisers: the array of facts is allocated untouched and first written by the
-    // thread that gathers the leaf (gatherFacts value-initialises what it returns)
-    Element* e[3];
-    double val[3];   // node pairs (0,1), (0,2), (1,2): value of the real constraint on the edge, if has[]
+//
+// The facts of a leaf come in two parts.  What the sweep reads for every leaf is 32 bytes (element
+// numbers, the kinds / counts of the leaf folded into a key, which elements are solved already,
+// which node pairs carry a value); pointers and constraint values are only read again when the
+// leaf's row is packed, on whatever thread packs it.
+struct HotFacts {
     std::uint64_t serial[3];  // Element::serial(): what the sweep's per-element tables are indexed by
-    int edgeCount;
-    int total, distance, angle;  // constraintCensus()
-    std::uint32_t shapeKey;      // shapeKeyOf(): what the sweep's classification depends on besides the solved flags
-    bool isPoint[3], isLine[3], setNow[3];
-    bool has[3], flip[3];
-    bool simple;
+    std::uint32_t shapeKey;   // Shape::key(): what classification depends on besides the solved flags
+    std::uint8_t setNow;      // bit 2 - k: element k is solved already
+    std::uint8_t has;         // bit p: node pair p - (0,1), (0,2), (1,2) - has a constraint with a value
+    std::uint8_t simple;      // 0: the general code decides (and raises what the reference raises)
+    std::uint8_t pad;
+};
+struct ColdFacts {
+    Element* e[3];
+    double val[3];    // node pairs (0,1), (0,2), (1,2): value of the real constraint on the edge, if `has`
+    std::uint8_t flip;  // bit p: AngleConstraint::flipOrientation of pair p
 };
 
 inline int pairIndex(int a, int b) { return a + b - 1; }  // {0,1} -> 0, {0,2} -> 1, {1,2} -> 2
 
-std::uint32_t shapeKeyOf(const LeafFacts& f);  // below, next to what reads it
+// kinds and counts of a three-element leaf: everything the eight predicates ask besides the solved flags
+struct Shape {
+    bool isPoint[3] = {}, isLine[3] = {};
+    int edgeCount = 0;                     // virtual edges included; at most three in a digest-described leaf
+    int total = 0, distance = 0, angle = 0;  // constraintCensus()
+    std::uint32_t key() const
+    {
+        std::uint32_t k = 0;
+        for (int i = 0; i < 3; ++i) k = (k << 2) | (isPoint[i] ? 1u : isLine[i] ? 2u : 0u);
+        k = (k << 2) | static_cast<std::uint32_t>(edgeCount & 3);
+        k = (k << 2) | static_cast<std::uint32_t>(total & 3);
+        k = (k << 2) | static_cast<std::uint32_t>(distance & 3);
+        return (k << 2) | static_cast<std::uint32_t>(angle & 3);
+    }
+    static Shape ofKey(std::uint32_t k)
+    {
+        Shape s;
+        s.angle = static_cast<int>(k & 3), k >>= 2;
+        s.distance = static_cast<int>(k & 3), k >>= 2;
+        s.total = static_cast<int>(k & 3), k >>= 2;
+        s.edgeCount = static_cast<int>(k & 3), k >>= 2;
+        for (int i = 2; i >= 0; --i) s.isPoint[i] = (k & 3) == 1, s.isLine[i] = (k & 3) == 2, k >>= 2;
+        return s;
+    }
+};
 
-LeafFacts gatherFacts(const ConstraintGraph& g)
+// false: the leaf is not one the digest describes
+bool gatherFacts(const ConstraintGraph& g, HotFacts& hot, ColdFacts& cold)
 {
-    LeafFacts f {};
+    hot = HotFacts {};
     // the graph's own digest: three elements in ascending node id, the constraint of each node pair
     // (ConstraintGraph::triangleDigest; the decomposition left it warm).  Flags, kinds and values are
     // read here, through the pointers: they may have changed since the digest was taken.
     const TriangleDigest& d = g.triangleDigest();
-    if (!d.simple) return f;
+    if (!d.simple) return false;
+    cold = ColdFacts {};
+    Shape shape;
     for (int n = 0; n < 3; ++n) {
         Element* el = d.element[n];
-        f.e[n] = el;
-        f.isPoint[n] = el->isElementType<Point>();
-        f.isLine[n] = el->isElementType<Line>();
-        f.setNow[n] = el->isElementSet();
-        f.serial[n] = el->serial();
+        cold.e[n] = el;
+        shape.isPoint[n] = el->isElementType<Point>();
+        shape.isLine[n] = el->isElementType<Line>();
+        if (el->isElementSet()) hot.setNow |= static_cast<std::uint8_t>(4 >> n);
+        hot.serial[n] = el->serial();
     }
-    f.edgeCount = d.edgeCount;
+    shape.edgeCount = d.edgeCount;
     for (int p = 0; p < 3; ++p) {
         const Constraint* con = d.constraint[p];
         if (!con) continue;
-        ++f.total;  // constraintCensus(): every real constraint, with or without a value
+        ++shape.total;  // constraintCensus(): every real constraint, with or without a value
         const auto* ang = con->getConstraintAs<AngleConstraint>();
         if (con->isConstraintType<DistanceConstraint>())
-            ++f.distance;
+            ++shape.distance;
         else if (ang)
-            ++f.angle;
+            ++shape.angle;
         const auto v = con->getConstraintValue();
         if (!v.has_value()) continue;
-        f.has[p] = true;
-        f.val[p] = v.value();
-        f.flip[p] = ang != nullptr && ang->flipOrientation;
+        hot.has |= static_cast<std::uint8_t>(1 << p);
+        cold.val[p] = v.value();
+        if (ang != nullptr && ang->flipOrientation) cold.flip |= static_cast<std::uint8_t>(1 << p);
     }
-    f.simple = true;
-    f.shapeKey = shapeKeyOf(f);
-    return f;
+    hot.shapeKey = shape.key();
+    hot.simple = 1;
+    return true;
 }
 
 constexpr long long kFactsLookAhead = 12;
@@ -523,8 +548,8 @@ void prefetchFacts(const ConstraintGraph& g)
         if (d.constraint[p]) __builtin_prefetch(d.constraint[p]);
 }
 
-// classify() on facts: same counts, same order
-SolverId classifyFacts(const LeafFacts& f, const bool set[3])
+// classify() on a shape: same counts, same order
+SolverId classifyShape(const Shape& f, const bool set[3])
 {
     Census c;
     for (int i = 0; i < 3; ++i) {
@@ -546,10 +571,9 @@ SolverId classifyFacts(const LeafFacts& f, const bool set[3])
     return SolverId::None;
 }
 
-// assignRoles() on facts, in two halves.  Who plays which part depends only on what the memo key
-// below holds (element kinds and solved flags); the constraint values are fetched per leaf.
-// roleIndices: false when the shape is one the role loops do not fill.
-bool roleIndices(SolverId id, const LeafFacts& f, const bool set[3], int& ia, int& ib, int& ic)
+// assignRoles() on a shape: who plays which part (indices into the leaf's three elements).
+// false when the shape is one the role loops do not fill.
+bool roleIndices(SolverId id, const Shape& f, const bool set[3], int& ia, int& ib, int& ic)
 {
     ia = ib = ic = -1;
     auto firstSecond = [&](auto pred, int& first, int& second) {  // "if (!haveA) a = e else b = e" over ascending ids
@@ -599,74 +623,65 @@ bool roleIndices(SolverId id, const LeafFacts& f, const bool set[3], int& ia, in
     return ia >= 0 && ib >= 0 && ic >= 0 && ia != ib && ia != ic && ib != ic;
 }
 
-// roleValues: false when a constraint a role needs is not there (the general code then raises the
-// reference's exception).
-bool roleValues(SolverId id, int ia, int ib, int ic, const LeafFacts& f, Roles& r)
+// Which constraint feeds which value of a solver: v0 / v1 / v2 of Roles, as node pairs of the roles
+// (-1: the solver does not read that value).  The reference's solve() bodies, e.g.
+// point_point_solvers.cpp:48-50, line_angle_solvers.cpp:322-333.
+struct ValuePairs {
+    int v0 = -1, v1 = -1, v2 = -1;  // pairIndex() of the two elements
+    bool flipFromV0 = false;
+};
+ValuePairs valuePairs(SolverId id, int ia, int ib, int ic)
 {
-    r = Roles {};
-    r.id = id;
-    auto value = [&](int a, int b, double& out, bool* flip = nullptr) {
-        const int p = pairIndex(a < b ? a : b, a < b ? b : a);
-        if (!f.has[p]) return false;
-        out = f.val[p];
-        if (flip) *flip = f.flip[p];
-        return true;
-    };
-    bool ok = true;
+    auto pair = [](int a, int b) { return pairIndex(a < b ? a : b, a < b ? b : a); };
+    ValuePairs v;
     switch (id) {
     case SolverId::ZeroFixedPointsTriangle:
-    case SolverId::ZeroFixedPPLTriangle: ok = value(ia, ib, r.v0) && value(ia, ic, r.v1) && value(ib, ic, r.v2); break;
-    case SolverId::ZeroFixedLLPAngleTriangle: ok = value(ia, ic, r.v0, &r.flip) && value(ib, ia, r.v1) && value(ib, ic, r.v2); break;
+    case SolverId::ZeroFixedPPLTriangle: v.v0 = pair(ia, ib), v.v1 = pair(ia, ic), v.v2 = pair(ib, ic); break;
+    case SolverId::ZeroFixedLLPAngleTriangle: v.v0 = pair(ia, ic), v.flipFromV0 = true, v.v1 = pair(ib, ia), v.v2 = pair(ib, ic); break;
     case SolverId::TwoFixedPointsDistance:
     case SolverId::TwoFixedPointsLine:
     case SolverId::FixedPointAndLineFreePoint:
-    case SolverId::TwoFixedLinesFreePoint: ok = value(ia, ic, r.v1) && value(ib, ic, r.v2); break;
-    case SolverId::FixedLineAndPointFreeLine: ok = value(ia, ic, r.v0, &r.flip) && value(ib, ic, r.v2); break;
-    case SolverId::None: return false;
+    case SolverId::TwoFixedLinesFreePoint: v.v1 = pair(ia, ic), v.v2 = pair(ib, ic); break;
+    case SolverId::FixedLineAndPointFreeLine: v.v0 = pair(ia, ic), v.flipFromV0 = true, v.v2 = pair(ib, ic); break;
+    case SolverId::None: break;
     }
-    if (!ok) return false;
-    r.a = f.e[ia], r.b = f.e[ib], r.c = f.e[ic];
-    return true;
-}
-
-// What the sweep decides for a leaf from its facts and the predicted solved flags, remembered per
-// distinct (kinds, counts, flags) combination: a sketch has a handful of them.
-struct Verdict {
-    SolverId id = SolverId::None;
-    std::int8_t ia = -1, ib = -1, ic = -1;
-    bool roles = false;
-};
-
-Verdict decide(const LeafFacts& f, const bool set[3])
-{
-    Verdict v;
-    v.id = classifyFacts(f, set);
-    if (v.id == SolverId::None) return v;
-    int ia, ib, ic;
-    v.roles = roleIndices(v.id, f, set, ia, ib, ic);
-    v.ia = static_cast<std::int8_t>(ia), v.ib = static_cast<std::int8_t>(ib), v.ic = static_cast<std::int8_t>(ic);
     return v;
 }
 
-// everything decide() reads from the facts, in 14 bits (a digest-described leaf has at most three edges)
-std::uint32_t shapeKeyOf(const LeafFacts& f)
+// What the sweep decides for a leaf from its shape and the predicted solved flags, remembered per
+// distinct combination: a sketch has a handful of them.
+struct Verdict {
+    SolverId id = SolverId::None;
+    std::int8_t ia = -1, ib = -1, ic = -1;
+    bool roles = false;      // ia, ib, ic are valid
+    std::uint8_t need = 0;   // bit p: node pair p must carry a value (else the general code raises the reference's exception)
+};
+
+Verdict decide(std::uint32_t shapeKey, unsigned setBits)
 {
-    std::uint32_t k = 0;
-    for (int i = 0; i < 3; ++i) k = (k << 2) | (f.isPoint[i] ? 1u : f.isLine[i] ? 2u : 0u);
-    k = (k << 2) | static_cast<std::uint32_t>(f.edgeCount & 3);
-    k = (k << 2) | static_cast<std::uint32_t>(f.total & 3);
-    k = (k << 2) | static_cast<std::uint32_t>(f.distance & 3);
-    k = (k << 2) | static_cast<std::uint32_t>(f.angle & 3);
-    return k;
+    const Shape shape = Shape::ofKey(shapeKey);
+    const bool set[3] = { (setBits & 4) != 0, (setBits & 2) != 0, (setBits & 1) != 0 };
+    Verdict v;
+    v.id = classifyShape(shape, set);
+    if (v.id == SolverId::None) return v;
+    int ia, ib, ic;
+    v.roles = roleIndices(v.id, shape, set, ia, ib, ic);
+    v.ia = static_cast<std::int8_t>(ia), v.ib = static_cast<std::int8_t>(ib), v.ic = static_cast<std::int8_t>(ic);
+    if (v.roles) {
+        const ValuePairs vp = valuePairs(v.id, ia, ib, ic);
+        for (int p : { vp.v0, vp.v1, vp.v2 })
+            if (p >= 0) v.need |= static_cast<std::uint8_t>(1 << p);
+    }
+    return v;
 }
 
 class VerdictMemo {
 public:
-    const Verdict& get(const LeafFacts& f, const bool set[3])
+    const Verdict& get(std::uint32_t shapeKey, unsigned setBits)
     {
-        const std::uint32_t key = (f.shapeKey << 3) | (set[0] ? 4u : 0u) | (set[1] ? 2u : 0u) | (set[2] ? 1u : 0u);
+        const std::uint32_t key = (shapeKey << 3) | setBits;
         Entry& e = m_rows[(key * 2654435761u) >> 24];
-        if (e.key != key) e.key = key, e.verdict = decide(f, set);
+        if (e.key != key) e.key = key, e.verdict = decide(shapeKey, setBits);
         return e.verdict;
     }
 
@@ -677,6 +692,23 @@ private:
     };
     Entry m_rows[256];
 };
+
+// The roles of a leaf the sweep decided from its facts: put together where the row is packed.
+// code: ia | ib << 2 | ic << 4 (kRolesStored: the general code stored them in Plan::roles instead).
+constexpr std::uint8_t kRolesStored = 0xff;
+Roles rolesFromFacts(SolverId id, std::uint8_t code, const ColdFacts& f)
+{
+    const int ia = code & 3, ib = (code >> 2) & 3, ic = (code >> 4) & 3;
+    const ValuePairs vp = valuePairs(id, ia, ib, ic);
+    Roles r;
+    r.id = id;
+    r.a = f.e[ia], r.b = f.e[ib], r.c = f.e[ic];
+    if (vp.v0 >= 0) r.v0 = f.val[vp.v0];
+    if (vp.v1 >= 0) r.v1 = f.val[vp.v1];
+    if (vp.v2 >= 0) r.v2 = f.val[vp.v2];
+    r.flip = vp.flipFromV0 && ((f.flip >> vp.v0) & 1) != 0;
+    return r;
+}
 
 // Element serial -> index into the sweep's per-element tables.  The elements of one sketch were
 // constructed together, so their serials fill a narrow range and the index is a subtraction; a
@@ -692,6 +724,57 @@ struct SlotIndex {
     }
 };
 
+// Working memory of a plan, kept by the thread between plans: a sketch is solved again and again
+// while it is edited, and fresh memory for 1e5 leaves costs more in page faults (~3 ms) than the
+// facts pass takes.  Buffers that have grown far beyond what the last plans needed are given back.
+struct PlanScratch {
+    template <typename T>
+    struct Buffer {
+        T* p = nullptr;
+        std::size_t cap = 0;
+        int idle = 0;  // plans in a row that used less than a quarter
+        T* get(std::size_t n)
+        {
+            idle = (cap > 65536 && n < cap / 4) ? idle + 1 : 0;
+            if (n > cap || idle >= 8) {
+                std::free(p);
+                cap = std::max<std::size_t>(n + n / 4, 64);
+                p = static_cast<T*>(std::malloc(sizeof(T) * cap));
+                if (!p) {
+                    cap = 0;
+                    throw std::bad_alloc();
+                }
+                idle = 0;
+            }
+            return p;
+        }
+        ~Buffer() { std::free(p); }
+    };
+    Buffer<HotFacts> hot;
+    Buffer<ColdFacts> cold;
+    Buffer<Roles> roles;
+    Buffer<std::uint8_t> roleCode;
+    std::vector<char> predicted;
+    std::vector<int> lastWrite, lastRead;
+};
+thread_local PlanScratch t_planScratch;
+
+struct Plan {
+    BatchReport report;
+    // per solved leaf: roleCode[i] says who plays which part among cold[i].e (the sweep decided from
+    // the facts), or kRolesStored: the general code left the roles in roles[i].  All three live in
+    // the thread's PlanScratch.
+    const ColdFacts* cold = nullptr;
+    const std::uint8_t* roleCode = nullptr;
+    const Roles* roles = nullptr;
+    std::size_t stop = 0;              // leaves [0, stop) are solved; == leaves.size() when no leaf throws
+    std::exception_ptr error;          // what the reference's loop would have thrown at leaf `stop`
+    Roles rolesOf(std::size_t i) const
+    {
+        return roleCode[i] == kRolesStored ? roles[i] : rolesFromFacts(report.solver[i], roleCode[i], cold[i]);
+    }
+};
+
 Plan makePlan(const std::vector<ConstraintGraph>& leaves)
 {
     const auto t0 = std::chrono::steady_clock::now();
@@ -700,38 +783,37 @@ Plan makePlan(const std::vector<ConstraintGraph>& leaves)
     plan.report.leaves = n;
     plan.report.level.assign(n, -1);
     plan.report.solver.assign(n, SolverId::None);
-    // (a result is a status + a message string: 1e5 copies of the 46-character "unsupported" message
-    // were 1e5 heap allocations, undone one by one below; leaves without a solver get it where they are found)
-    plan.report.results.assign(n, SolveResult::success());
-    plan.roles.resize(n);
+    // (per leaf a status; the one message there is - "no solver matches" - is put together by
+    // BatchReport::result() when somebody asks)
+    plan.report.status.assign(n, SolveStatus::Success);
+    PlanScratch& scratch = t_planScratch;
+    HotFacts* const hot = scratch.hot.get(n);
+    ColdFacts* const cold = scratch.cold.get(n);
+    Roles* const roles = scratch.roles.get(n);  // written for the few leaves the general code decides
+    std::uint8_t* const roleCode = scratch.roleCode.get(n);
+    plan.cold = cold, plan.roles = roles, plan.roleCode = roleCode;
     plan.stop = n;
-    static const char* const kNoSolver = "No solver matches this component configuration";
 
     // (A) per-leaf facts, every host thread.  Nothing is written to but the facts: a pass that tags
     // the elements (an index claimed by compare-and-swap) spent its time moving their cache lines
     // from core to core and did not get faster with more threads.
     const auto tA = std::chrono::steady_clock::now();
-    struct FreeFacts {
-        void operator()(LeafFacts* p) const { std::free(p); }
-    };
-    // untouched memory: first written, page by page, by the thread that gathers the leaf
-    const std::unique_ptr<LeafFacts[], FreeFacts> facts(static_cast<LeafFacts*>(std::malloc(sizeof(LeafFacts) * (n ? n : 1))));
-    if (!facts) throw std::bad_alloc();
     const long long nn = static_cast<long long>(n);
     unsigned long long lo = ~0ull, hi = 0;
 #pragma omp parallel for schedule(static) reduction(min : lo) reduction(max : hi) if (nn > 2048)
     for (long long i = 0; i < nn; ++i) {
-        LeafFacts& f = facts[static_cast<std::size_t>(i)];
+        HotFacts& h = hot[static_cast<std::size_t>(i)];
+        bool simple = false;
         try {
             // the leaves lie one after the other, what they point to does not: ask for the elements
             // and constraints of a leaf a few iterations before they are read
             if (i + kFactsLookAhead < nn) prefetchFacts(leaves[static_cast<std::size_t>(i + kFactsLookAhead)]);
-            f = gatherFacts(leaves[static_cast<std::size_t>(i)]);
+            simple = gatherFacts(leaves[static_cast<std::size_t>(i)], h, cold[static_cast<std::size_t>(i)]);
         } catch (...) {
-            f = LeafFacts {};  // not simple: the general code decides (and raises) in step (B)
+            h = HotFacts {};  // not simple: the general code decides (and raises) in step (B)
         }
-        if (f.simple) {
-            for (int k = 0; k < 3; ++k) lo = std::min<unsigned long long>(lo, f.serial[k]), hi = std::max<unsigned long long>(hi, f.serial[k]);
+        if (simple) {
+            for (int k = 0; k < 3; ++k) lo = std::min<unsigned long long>(lo, h.serial[k]), hi = std::max<unsigned long long>(hi, h.serial[k]);
         } else {
             for (const auto& [node, e] : leaves[static_cast<std::size_t>(i)].getElementMap())
                 if (e) lo = std::min<unsigned long long>(lo, e->serial()), hi = std::max<unsigned long long>(hi, e->serial());
@@ -741,14 +823,16 @@ Plan makePlan(const std::vector<ConstraintGraph>& leaves)
     // (B) the sequential sweep.  What the symbolic pass knows about an element (solved once the
     // leaves so far have run; wave of its last write / last read) lives in flat arrays indexed by
     // the element's serial number, so no table is searched and this loop touches no element at all
-    // for the leaves step (A) could describe.
+    // for the leaves step (A) could describe: 32 bytes read and 13 written per leaf.
     const auto tB = std::chrono::steady_clock::now();
     SlotIndex index;
     index.lo = lo;
     const std::uint64_t span = hi >= lo ? hi - lo + 1 : 0;
     index.direct = span <= 16 * static_cast<std::uint64_t>(n) + 65536;
-    std::vector<char> predicted(index.direct ? static_cast<std::size_t>(span) : 0, 0);
-    std::vector<int> lastWrite(predicted.size(), -1), lastRead(predicted.size(), -1);
+    std::vector<char>& predicted = scratch.predicted;
+    std::vector<int>&lastWrite = scratch.lastWrite, &lastRead = scratch.lastRead;
+    predicted.assign(index.direct ? static_cast<std::size_t>(span) : 0, 0);
+    lastWrite.assign(predicted.size(), -1), lastRead.assign(predicted.size(), -1);
     auto slotOfSerial = [&](std::uint64_t serial) {
         const int slot = index.of(serial);
         if (static_cast<std::size_t>(slot) >= predicted.size()) predicted.push_back(0), lastWrite.push_back(-1), lastRead.push_back(-1);
@@ -758,19 +842,30 @@ Plan makePlan(const std::vector<ConstraintGraph>& leaves)
     VerdictMemo memo;
     int top = -1;
     for (std::size_t i = 0; i < n; ++i) {
-        const LeafFacts& f = facts[i];
+        const HotFacts& h = hot[i];
         SolverId id = SolverId::None;
         bool haveRoles = false;
         int slot3[3] = { -1, -1, -1 };
-        if (f.simple) {
-            bool set[3];
-            for (int k = 0; k < 3; ++k) slot3[k] = slotOfSerial(f.serial[k]);
-            for (int k = 0; k < 3; ++k) set[k] = f.setNow[k] || predicted[static_cast<std::size_t>(slot3[k])] != 0;
-            const Verdict& v = memo.get(f, set);
+        int rs[2], ws[3], nr = 0, nw = 0;  // read / write footprint as table indices
+        if (h.simple) {
+            for (int k = 0; k < 3; ++k) slot3[k] = slotOfSerial(h.serial[k]);
+            const unsigned setBits = h.setNow | (predicted[static_cast<std::size_t>(slot3[0])] ? 4u : 0u)
+                | (predicted[static_cast<std::size_t>(slot3[1])] ? 2u : 0u) | (predicted[static_cast<std::size_t>(slot3[2])] ? 1u : 0u);
+            const Verdict& v = memo.get(h.shapeKey, setBits);
             id = v.id;
-            if (v.roles) haveRoles = roleValues(id, v.ia, v.ib, v.ic, f, plan.roles[i]);
+            if (v.roles && (v.need & ~h.has) == 0) {
+                haveRoles = true;
+                roleCode[i] = static_cast<std::uint8_t>(v.ia | (v.ib << 2) | (v.ic << 4));
+                // footprintOf(): the zero-fixed shapes write all three elements, the others read a, b and write c
+                if (zeroFixed(id)) {
+                    ws[nw++] = slot3[v.ia], ws[nw++] = slot3[v.ib], ws[nw++] = slot3[v.ic];
+                } else {
+                    rs[nr++] = slot3[v.ia], rs[nr++] = slot3[v.ib];
+                    ws[nw++] = slot3[v.ic];
+                }
+            }
         }
-        if (!haveRoles && (!f.simple || id != SolverId::None)) {
+        if (!haveRoles && (!h.simple || id != SolverId::None)) {
             // the general code: same decisions on the graph itself, raising what the reference raises
             const SetQuery q = [&](const Element* e) {
                 return e->isElementSet() || predicted[static_cast<std::size_t>(slotOfElement(e))] != 0;
@@ -778,36 +873,27 @@ Plan makePlan(const std::vector<ConstraintGraph>& leaves)
             id = classify(leaves[i], q);
             if (id != SolverId::None) {
                 try {
-                    plan.roles[i] = assignRoles(id, leaves[i], q);
+                    roles[i] = assignRoles(id, leaves[i], q);
                 } catch (...) {
                     plan.error = std::current_exception();
                     plan.stop = i;
-                    plan.report.solver[i] = SolverId::None;
                     break;
+                }
+                roleCode[i] = kRolesStored;
+                const Roles& r = roles[i];
+                if (zeroFixed(id)) {
+                    ws[nw++] = slotOfElement(r.a), ws[nw++] = slotOfElement(r.b), ws[nw++] = slotOfElement(r.c);
+                } else {
+                    rs[nr++] = slotOfElement(r.a), rs[nr++] = slotOfElement(r.b);
+                    ws[nw++] = slotOfElement(r.c);
                 }
             }
         }
         plan.report.solver[i] = id;
         if (id == SolverId::None) {
             ++plan.report.unsupported;
-            plan.report.results[i] = SolveResult::unsupported(kNoSolver);
+            plan.report.status[i] = SolveStatus::Unsupported;
             continue;
-        }
-        // read / write footprint as dense indices (footprintOf: the zero-fixed shapes write all three
-        // elements, the others read a, b and write c)
-        const Roles& r = plan.roles[i];
-        int rs[2], ws[3], nr = 0, nw = 0;
-        auto slotOfRole = [&](const Element* e) {
-            if (f.simple)
-                for (int k = 0; k < 3; ++k)
-                    if (f.e[k] == e) return slot3[k];
-            return slotOfElement(e);
-        };
-        if (zeroFixed(r.id)) {
-            ws[nw++] = slotOfRole(r.a), ws[nw++] = slotOfRole(r.b), ws[nw++] = slotOfRole(r.c);
-        } else {
-            rs[nr++] = slotOfRole(r.a), rs[nr++] = slotOfRole(r.b);
-            ws[nw++] = slotOfRole(r.c);
         }
         int lvl = -1;
         for (int k = 0; k < nr; ++k) lvl = std::max(lvl, lastWrite[static_cast<std::size_t>(rs[k])]);
@@ -827,8 +913,8 @@ Plan makePlan(const std::vector<ConstraintGraph>& leaves)
     }
     for (std::size_t i = plan.stop; i < n; ++i) {
         plan.report.level[i] = -1;
-        plan.report.results[i] = SolveResult::unsupported(kNoSolver);
-        if (i > plan.stop) plan.report.solver[i] = SolverId::None;
+        plan.report.status[i] = SolveStatus::Unsupported;
+        plan.report.solver[i] = SolverId::None;
     }
     plan.report.waves = static_cast<std::size_t>(top + 1);
     if (std::getenv("GCS_HOST_TRACE"))
@@ -1182,6 +1268,8 @@ BatchReport solveLeavesImpl(std::vector<ConstraintGraph>& leaves, int device, in
 {
     using Clock = std::chrono::steady_clock;
     auto since = [](Clock::time_point t) { return std::chrono::duration<double>(Clock::now() - t).count(); };
+    if (const char* reps = std::getenv("GCS_HOST_PLAN_REPS"))  // measurement aid: the plan alone, repeated (GCS_HOST_TRACE prints its split)
+        for (int k = std::atoi(reps); k > 0; --k) (void)makePlan(leaves);
     auto t0 = Clock::now();
     Plan plan = makePlan(leaves);
     BatchReport& rep = plan.report;
@@ -1195,7 +1283,7 @@ BatchReport solveLeavesImpl(std::vector<ConstraintGraph>& leaves, int device, in
     {  // one block per kind for the whole solve: the largest wave decides
         std::vector<std::array<std::size_t, GCS_KIND_COUNT + 1>> count(rep.waves);
         for (std::size_t i = 0; i < plan.stop; ++i)
-            if (rep.level[i] >= 0) ++count[static_cast<std::size_t>(rep.level[i])][static_cast<std::size_t>(kindOf(plan.roles[i].id))];
+            if (rep.level[i] >= 0) ++count[static_cast<std::size_t>(rep.level[i])][static_cast<std::size_t>(kindOf(rep.solver[i]))];
         for (int k = 1; k <= GCS_KIND_COUNT; ++k) {
             std::size_t most = 0;
             for (const auto& c : count) most = std::max(most, c[static_cast<std::size_t>(k)]);
@@ -1208,7 +1296,7 @@ BatchReport solveLeavesImpl(std::vector<ConstraintGraph>& leaves, int device, in
         // rows of the kind batches in input order
         std::size_t rowsOfKind[GCS_KIND_COUNT + 1] = {};
         rowOf.resize(wave.size());
-        for (std::size_t j = 0; j < wave.size(); ++j) rowOf[j] = rowsOfKind[kindOf(plan.roles[wave[j]].id)]++;
+        for (std::size_t j = 0; j < wave.size(); ++j) rowOf[j] = rowsOfKind[kindOf(rep.solver[wave[j]])]++;
         for (int k = 1; k <= GCS_KIND_COUNT; ++k) batches[k].resize(rowsOfKind[k]);
         // The leaves of a wave touch disjoint elements wherever one of them writes (that is what a
         // wave is: nobody reads or writes what another leaf of the wave writes - the anchors the
@@ -1219,7 +1307,7 @@ BatchReport solveLeavesImpl(std::vector<ConstraintGraph>& leaves, int device, in
 #pragma omp parallel for schedule(static) if (m > 1024)
         for (long long j = 0; j < m; ++j) {
             try {
-                const PackedLeaf row = packNumeric(plan.roles[wave[static_cast<std::size_t>(j)]]);
+                const PackedLeaf row = packNumeric(plan.rolesOf(wave[static_cast<std::size_t>(j)]));
                 batches[row.kind].set(rowOf[static_cast<std::size_t>(j)], row);
             } catch (...) {
 #pragma omp critical

@@ -285,7 +285,7 @@ GCS_API int gcs_host_leaves_solve(int n_el, gcs_host_element* el, int n_leaves, 
             }
             for (int l = 0; l < n_leaves; ++l) {
                 const auto i = static_cast<std::size_t>(l);
-                if (status) status[l] = static_cast<int32_t>(rep.results[i].status);
+                if (status) status[l] = static_cast<int32_t>(rep.status[i]);
                 if (level) level[l] = rep.level[i];
                 if (solver) solver[l] = static_cast<int32_t>(rep.solver[i]);
             }
