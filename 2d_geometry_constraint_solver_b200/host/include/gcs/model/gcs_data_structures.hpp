@@ -8,7 +8,6 @@
 #include <cstdint>
 #include <expected>
 #include <memory>
-#include <unordered_set>
 #include <vector>
 
 #include <gcs/export.hpp>
@@ -42,10 +41,19 @@ public:
     using EdgeIdType = Graph::EdgeIdType;
     using ElementMap = MathUtils::NodePropertyMap<std::shared_ptr<Element>>;
     using ConstraintMap = MathUtils::EdgePropertyMap<std::shared_ptr<Constraint>>;
+    // (an std::unordered_set in the reference: two heap blocks for the one member a leaf has)
+    using VirtualEdgeSet = MathUtils::detail::FlatSet<EdgeIdType>;
 
     // ---- the underlying graph (nodes and edges are created there, then decorated here) ----
     Graph& getGraph() { return m_constraintGraph; }
     const Graph& getGraph() const { return m_constraintGraph; }
+    // storage for a graph of this size in one allocation per container (a decomposition builds 1e5
+    // three-element leaves); `degree`: edges expected at every node
+    void reserve(std::size_t nodes, std::size_t edges, std::size_t degree = 0)
+    {
+        m_constraintGraph.reserve(nodes, edges, degree);
+        m_elementNodeMap.reserve(nodes), m_constraintEdgeMap.reserve(edges), m_virtualEdges.reserve(2);
+    }
     std::size_t nodeCount() const { return m_constraintGraph.nodeCount(); }
     std::size_t edgeCount() const { return m_constraintGraph.edgeCount(); }  // virtual edges included
     std::expected<EdgeIdType, ConstraintGraphError> getEdgeBetween(NodeIdType s, NodeIdType t) const;
@@ -73,7 +81,7 @@ public:
     ConstraintGraphError removeVirtualEdge(EdgeIdType virtualEdge);
     bool hasVirtualEdge() const { return !m_virtualEdges.empty(); }
     bool isVirtualEdge(EdgeIdType edge) const { return m_virtualEdges.count(edge) != 0; }
-    const std::unordered_set<EdgeIdType>& getVirtualEdges() const { return m_virtualEdges; }
+    const VirtualEdgeSet& getVirtualEdges() const { return m_virtualEdges; }
 
     // Derived from the containers above on first use and again after any change to them (through
     // this class or through getGraph()); the decomposition asks for it while the leaf it has just
@@ -87,7 +95,7 @@ private:
     Graph m_constraintGraph;
     ElementMap m_elementNodeMap;
     ConstraintMap m_constraintEdgeMap;
-    std::unordered_set<EdgeIdType> m_virtualEdges;
+    VirtualEdgeSet m_virtualEdges;
     unsigned m_version = 0;  // changes to the property maps / virtual-edge set (the graph counts its own)
     mutable TriangleDigest m_digest;
     mutable std::uint64_t m_digestStamp = ~std::uint64_t { 0 };  // (graph version, m_version) the digest was taken at

@@ -44,6 +44,7 @@ public:
         return {};
     }
     void clear() { m_data.clear(); }
+    void reserve(std::size_t n) { m_data.reserve(n); }
     bool contains(const KeyId& id) const { return m_data.contains(id); }
     std::size_t size() const { return m_data.size(); }
     bool empty() const { return m_data.empty(); }

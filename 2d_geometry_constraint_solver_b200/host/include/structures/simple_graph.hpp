@@ -53,6 +53,7 @@ public:
     std::size_t size() const { return m_rows.size(); }
     bool empty() const { return m_rows.empty(); }
     void clear() { m_rows.clear(); }
+    void reserve(std::size_t n) { m_rows.reserve(n); }
 
     const_iterator find(const Key& k) const { return locate(m_rows.begin(), m_rows.end(), k); }
     iterator find(const Key& k) { return locate(m_rows.begin(), m_rows.end(), k); }
@@ -94,6 +95,41 @@ private:
     std::vector<Entry> m_rows;
 };
 
+// A set of ids in a sorted vector (the virtual-edge set of a constraint graph: one or two members).
+template <typename Key>
+class FlatSet {
+public:
+    using const_iterator = typename std::vector<Key>::const_iterator;
+    const_iterator begin() const { return m_keys.begin(); }
+    const_iterator end() const { return m_keys.end(); }
+    std::size_t size() const { return m_keys.size(); }
+    bool empty() const { return m_keys.empty(); }
+    void reserve(std::size_t n) { m_keys.reserve(n); }
+    std::size_t count(const Key& k) const { return std::binary_search(m_keys.begin(), m_keys.end(), k) ? 1 : 0; }
+    bool contains(const Key& k) const { return count(k) != 0; }
+    bool insert(const Key& k)
+    {
+        if (m_keys.empty() || m_keys.back() < k) {
+            m_keys.push_back(k);
+            return true;
+        }
+        const auto it = std::lower_bound(m_keys.begin(), m_keys.end(), k);
+        if (it != m_keys.end() && *it == k) return false;
+        m_keys.insert(it, k);
+        return true;
+    }
+    std::size_t erase(const Key& k)
+    {
+        const auto it = std::lower_bound(m_keys.begin(), m_keys.end(), k);
+        if (it == m_keys.end() || !(*it == k)) return 0;
+        m_keys.erase(it);
+        return 1;
+    }
+
+private:
+    std::vector<Key> m_keys;
+};
+
 }  // namespace detail
 
 class SimpleGraph {
@@ -102,10 +138,18 @@ public:
     using EdgeIdType = EdgeId;
     using EdgeList = std::vector<EdgeId>;  // ascending
 
+    // room for this many nodes / edges, and for `degree` edges at every node added from now on
+    void reserve(std::size_t nodes, std::size_t edges, std::size_t degree = 0)
+    {
+        m_incident.reserve(nodes), m_ends.reserve(edges);
+        m_degreeHint = degree;
+    }
+
     NodeId addNode()
     {
         const NodeId id { m_nextNode++ };
-        m_incident.put(id, EdgeList {});
+        EdgeList& list = m_incident.put(id, EdgeList {}).second;
+        if (m_degreeHint) list.reserve(m_degreeHint);
         ++m_version;
         return id;
     }
@@ -206,6 +250,7 @@ private:
     int m_nextNode { 0 };
     int m_nextEdge { 0 };
     unsigned m_version { 0 };
+    std::size_t m_degreeHint { 0 };
     detail::FlatTable<NodeId, EdgeList> m_incident;
     detail::FlatTable<EdgeId, std::pair<NodeId, NodeId>> m_ends;
 };
