@@ -478,11 +478,21 @@ def batch_d2h_bytes(capi, b):
 def time_e2e(ctx, batches, steps):
     """Wall-clock solves/s of `steps` passes: gcs_b200_solve_host_async per batch + gcs_b200_wait."""
     capi = ctx.capi
+    # the C descriptors are built once (a caller in C has them on its stack): the loop below is the
+    # C-ABI calls and nothing else
+    lib, dev = ctx.lib, ctx.local_rank
+    for b in batches:
+        if not b.out:
+            b.alloc_outputs()
+    descs = [b.cbatch() for b in batches]
+    refs = [C.byref(d) for d in descs]
 
     def one():
-        for b in batches:
-            capi.solve_host_async(b, ctx.local_rank)
-        capi.wait(ctx.local_rank)
+        for r in refs:
+            rc = lib.gcs_b200_solve_host_async(r, dev)
+            if rc:
+                capi.check(rc, "gcs_b200_solve_host_async")
+        capi.check(lib.gcs_b200_wait(dev), "gcs_b200_wait")
 
     for _ in range(3):
         one()
