@@ -135,8 +135,7 @@ __global__ void __launch_bounds__(128, RLX ? GCS_STATIC_RLX_MINB : GCS_STATIC_MI
         int state = kRlxConverged;
         // iteration 0 compares the guess with prev = (0, 0)
         if (!(fabs(0.0 - x) < kTol && fabs(0.0 - y) < kTol)) {
-            double u0, u1;
-            state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1, nullptr, p.path ? &pathv : nullptr);
+            state = relaxed_run<KIND>(rs, k, g, x, y, it, p.path ? &pathv : nullptr);
             if (state == kRlxWantCareful) {  // ill conditioned, above the floor: replay with every decision margin-tested
                 run_seed<KIND>(p.guesses, p.stride, i, k, seed, x, y);
                 const CarefulOut o = relaxed_careful<KIND>(rs, g, x, y);
@@ -269,8 +268,7 @@ __global__ void __launch_bounds__(128, RLX ? GCS_SEQ_MINB : GCS_SEQ_LIT_MINB) ne
             int state = kRlxConverged;
             // iteration 0 compares the guess with prev = (0, 0)
             if (!(fabs(0.0 - x) < kTol && fabs(0.0 - y) < kTol)) {
-                double u0, u1;
-                state = relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1, nullptr, p.path ? &pathv : nullptr);
+                state = relaxed_run<KIND>(rs, k, g, x, y, it, p.path ? &pathv : nullptr);
                 if (state == kRlxWantCareful) {
                     run_seed<KIND>(p.guesses, p.stride, i, k, s, x, y);
                     const CarefulOut o = relaxed_careful<KIND>(rs, g, x, y);

@@ -429,6 +429,262 @@ __device__ __forceinline__ int relaxed_updates(const Rsys<KIND>& rs, RelaxGuard&
     return state;
 }
 
+// ------------------------------------------------------------------------------------------
+// The line form of a run.
+//
+// Every equation pair with a quadratic in it is a circle and a line (K2, K3, K5), or two circles
+// whose difference is a line (K1: the radical line).  Newton's method is affine covariant: the
+// update from the seed lands ON that line, and from there on the iteration is the scalar map of
+// this file's header,
+//        w  <-  w - (w^2 - h^2) / (2 w),
+// w the coordinate along the line from the foot F of the circle's centre, +-h the two roots.  The
+// literal arithmetic walks the same points with a 2x2 solve per update; the closed form above it
+// (relaxed_updates) with Cramer's rule, 21 FP64 operations per update.  The scalar map needs 8, and
+// its deviation from the literal arithmetic is of the kind the guards already budget for:
+//   * the landing point of the first update is projected onto the line; what is dropped is the
+//     component ACROSS the line, which is the landing's own rounding error (eps cond(J_seed) times
+//     the first update): the literal arithmetic removes it with its second update, whose length
+//     therefore differs from the scalar map's by at most that much - exactly the w1 term the second
+//     update's band and margin are widened by (relaxed_updates);
+//   * from the same point on the line the two arithmetics' updates differ by the rounding of F, of
+//     the direction and of h^2 (a few ulp of the coordinate scale, amplified by the conditioning the
+//     way a 2x2 solve amplifies its own rounding) - the O(cond eps S) of the header, under the
+//     first-level band for cond <= 2^10 (G1) and scaled with the actual conditioning by the
+//     second-level margin;
+//   * |det J| at F + w u is |w| times a constant of the system (RLine::dscale), so (G1) and (G2)
+//     watch the same quantity as before.
+// The guards, their thresholds and the order of the decisions are those of relaxed_updates, line
+// for line; careful mode and the literal re-run are unchanged (both restart from the seed).
+// An argument backed by the same tests and soaks, not a proof - like the rest of this file.
+// ------------------------------------------------------------------------------------------
+template <int KIND>
+struct RLine {
+    static constexpr bool kHas = false;
+};
+
+// |v|^-1/2 refined to ~2^-60 relative (MUFU.RSQ64H seed, one cubic step)
+__device__ __forceinline__ double rsqrt_relaxed(double v)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+    const double e = __fma_rn(-v * r, r, 1.0);           // 1 - v r^2
+    return __fma_rn(r * __fma_rn(0.375, e, 0.5), e, r);  // r (1 + e/2 + 3 e^2 / 8)
+}
+
+struct RLineData {
+    double fx, fy;   // foot of the circle's centre on the line
+    double ux, uy;   // unit direction of the line
+    double h2;       // squared half chord (negative: the line misses the circle, no real root)
+    double dscale;   // |det| of the matrix the closed form solves, at F + w u, is |w| dscale
+    double mscale;   // larger component of what that solve returns is |(w^2 - h^2) / w| mscale
+    __device__ __forceinline__ double project(double x, double y) const { return __fma_rn(x - fx, ux, (y - fy) * uy); }
+    __device__ __forceinline__ void point(double w, double& x, double& y) const { x = __fma_rn(w, ux, fx), y = __fma_rn(w, uy, fy); }
+};
+
+// How the constants are formed matters as much as the map.  The half chord h enters every late
+// update as (w^2 - h^2) / w, so an absolute error dh in it moves those updates by ~2 dh: it has to
+// stay within what the guards budget, eps S cond.  "h^2 = ra^2 - t0^2" does not: next to one of the
+// centres (P close to B: rb << ra) it cancels to eps ra^2 / (2 h), orders of magnitude over the
+// literal arithmetic's own error there (the first soak of this form: coordinates 1.1e-9 off on flat
+// triangles).  So h^2 comes from factors that are each a sum of INPUTS (Heron's product for K1,
+// (r - c)(r + c) for a circle of radius r at distance c from the line): relative error
+// eps S / (smallest factor), and h / (smallest factor) <= 2 dr / |det| at the roots - the same
+// amplification a 2x2 solve applies to its own rounding (checked for the needle P -> B and the
+// flat P -> AB shapes in DESIGN.md).  The foot likewise from (ra - rb)(ra + rb), not qa - qb.
+
+// K1: the radical line of the two circles, perpendicular to A -> B at t0 = (d^2 + ra^2 - rb^2) / (2 d) from A
+template <>
+struct RLine<GCS_KIND_PP> : RLineData {
+    static constexpr bool kHas = true;
+    __device__ __forceinline__ void set(const Rsys<GCS_KIND_PP>& rs, const double* k)
+    {
+        const double dx = rs.bx - rs.ax, dy = rs.by - rs.ay;
+        const double d2 = __fma_rn(dx, dx, dy * dy);
+        const double rd = rsqrt_relaxed(d2);  // concentric circles: inf -> NaN everywhere -> (G4)
+        const double d = d2 * rd;
+        const double px = dx * rd, py = dy * rd;
+        const double ra = fabs(k[2]), rb = fabs(k[5]);
+        const double sum = ra + rb, dif = ra - rb;
+        const double hr = 0.5 * rd;
+        const double t0 = __fma_rn(dif, sum, d2) * hr;
+        fx = __fma_rn(t0, px, rs.ax), fy = __fma_rn(t0, py, rs.ay);
+        ux = -py, uy = px;
+        // 16 area^2 = (ra + rb - d)(ra + rb + d)(d + ra - rb)(d - ra + rb);  h = 2 area / d
+        h2 = (((sum - d) * (sum + d)) * hr) * (((d + dif) * (d - dif)) * hr);
+        dscale = d;                            // det(J/2) = (P - A) x (P - B) = w d
+        mscale = fmax(fabs(ux), fabs(uy));     // the solve of J/2 returns twice the step
+    }
+};
+
+// the unit circle and the line N . n = t0, N = (nx, ny) / |(nx, ny)| (K2, K5: the unknown is a unit normal)
+struct RLineUnit : RLineData {
+    __device__ __forceinline__ void set_unit(double nx, double ny, double c)  // line: nx x + ny y = c
+    {
+        const double l2 = __fma_rn(nx, nx, ny * ny);
+        const double rl = rsqrt_relaxed(l2);
+        const double Nx = nx * rl, Ny = ny * rl;
+        const double t0 = c * rl;
+        fx = t0 * Nx, fy = t0 * Ny;
+        ux = -Ny, uy = Nx;
+        h2 = (1.0 - t0) * (1.0 + t0);
+        dscale = 2.0 * (l2 * rl);              // det J = 2 |(nx, ny)| w
+        mscale = 0.5 * fmax(fabs(ux), fabs(uy));
+    }
+};
+
+// K2: dX x + dY y + c0 = 0 and the unit circle
+template <>
+struct RLine<GCS_KIND_SDD> : RLineUnit {
+    static constexpr bool kHas = true;
+    __device__ __forceinline__ void set(const Rsys<GCS_KIND_SDD>& rs, const double*) { set_unit(rs.dX, rs.dY, -rs.c0); }
+};
+
+// K5: fdy x - fdx y = cos(A) |fd| and the unit circle
+template <>
+struct RLine<GCS_KIND_ANG> : RLineUnit {
+    static constexpr bool kHas = true;
+    __device__ __forceinline__ void set(const Rsys<GCS_KIND_ANG>& rs, const double*) { set_unit(rs.fdy, -rs.fdx, rs.cl); }
+};
+
+// K3: the circle (C, r) and the line at signed distance -s from A -> B
+template <>
+struct RLine<GCS_KIND_PPL> : RLineData {
+    static constexpr bool kHas = true;
+    __device__ __forceinline__ void set(const Rsys<GCS_KIND_PPL>& rs, const double* k)
+    {
+        const double l2 = __fma_rn(rs.l.ex, rs.l.ex, rs.l.ey * rs.l.ey);
+        const double rl = rsqrt_relaxed(l2);
+        ux = rs.l.ex * rl, uy = rs.l.ey * rl;
+        // offset of the centre from the line along N = (uy, -ux):  N . (C - A) + s
+        const double c = __fma_rn(rs.px - rs.l.xa, uy, __fma_rn(-(rs.py - rs.l.ya), ux, k[7]));
+        fx = __fma_rn(-c, uy, rs.px), fy = __fma_rn(c, ux, rs.py);
+        const double r = fabs(k[2]), ca = fabs(c);
+        h2 = (r - ca) * (r + ca);
+        dscale = 2.0 * (l2 * rl);              // det J = 2 (P - C) . e = 2 |e| w
+        mscale = 0.5 * fmax(fabs(ux), fabs(uy));
+    }
+};
+
+// relaxed_updates for a whole run (it == 0 on entry) of a kind with a line form: the update from the
+// seed in closed form, everything after it on the line.  Same outcomes, same guards.
+template <int KIND>
+__device__ __forceinline__ int relaxed_updates_line(const Rsys<KIND>& rs, const double* k, RelaxGuard& g, double& x, double& y,
+    int& it, int limit, int* trace = nullptr)
+{
+    static_assert(RLine<KIND>::kHas, "no line form for this kind");
+    int dmin = 0x7fffffff, grow = 0, d1 = 0x7fffffff;
+    int state = kRlxRunning;
+    if (it >= limit) return (limit >= kRelaxCap) ? kRlxUncertain + kWhyCap : kRlxRunning;
+    int mh, dh;
+    double sm, det;  // larger component of the update in flight, in the units of the closed-form solve; det at its iterate
+    {  // the update from the seed (relaxed_updates, update(true_type))
+        double a, b, c, d, r0, r1;
+        rs.eval(x, y, a, b, c, d, r0, r1);
+        det = __fma_rn(a, d, -(b * c));
+        const double r = rcp_relaxed(det);
+        const double q = __fma_rn(a, a, __fma_rn(b, b, __fma_rn(c, c, d * d)));
+        g.add_carry(0x1p-48 * q * fabs(r), Rsys<KIND>::kStepScale);
+        const double s0 = __fma_rn(r0, d, -(r1 * b)) * r, s1 = __fma_rn(a, r1, -(c * r0)) * r;
+        if constexpr (Rsys<KIND>::kStepScale == 1.0) {
+            x += s0, y += s1;
+        } else {
+            x = __fma_rn(s0, Rsys<KIND>::kStepScale, x);
+            y = __fma_rn(s1, Rsys<KIND>::kStepScale, y);
+        }
+        ++it;
+        sm = fmax(fabs(s0), fabs(s1));
+        dh = abs_hi(det);
+        mh = max(abs_hi(s0), abs_hi(s1));
+    }
+    const unsigned span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
+    d1 = dh;
+    bool in_loop = (unsigned)(mh - g.hi_h) < span && it < limit;
+    RLine<KIND> ln;
+    ln.set(rs, k);
+    double w = ln.project(x, y);
+    // one update on the line; leaves mh, dh, sm, det like the closed-form update does
+    auto update = [&]() {
+        const double f = __fma_rn(w, w, -ln.h2);
+        det = w * ln.dscale;
+        const double t = f * rcp_relaxed(w);
+        w = __fma_rn(-0.5, t, w);
+        ++it;
+        sm = t * ln.mscale;
+        dh = abs_hi(det);
+        mh = abs_hi(sm);
+    };
+    double extra = 0.0;   // absolute add-on of the decision in flight (w1 for the second update, else 0)
+    int lo_cur = g.lo_h;  // "converged for certain" threshold of the decision in flight
+    if (in_loop) {  // the second update, against a band widened by w1 (see relaxed_updates)
+        const double w1 = g.carry * sm * Rsys<KIND>::kStepScale;
+        RelaxGuard g2 = g;
+        g2.set_band(__fma_rn(g.carry, kTol, g.band) + w1, Rsys<KIND>::kStepScale);
+        update();
+        dmin = min(dmin, dh);  // first iterate after the seed: nothing to have grown from yet
+        if ((unsigned)(mh - g2.hi_h) < (unsigned)(RelaxGuard::kBigH - g2.hi_h)) {
+            in_loop = it < limit;
+        } else {
+            in_loop = false;
+            extra = fmax(w1, 0x1p-1000), lo_cur = g2.lo_h;
+        }
+    }
+#pragma unroll 1
+    for (;;) {
+        if (in_loop) {
+#pragma unroll 1
+            do {
+                update();
+                grow = max(grow, dh - dmin);  // (G2), in high-word units (2^20 per binade)
+                dmin = min(dmin, dh);
+            } while ((unsigned)(mh - g.hi_h) < span && it < limit);
+        }
+        in_loop = true;
+        // ---- rare from here: relaxed_updates' decisions, in its order ----
+        if (extra == 0.0 && (unsigned)(mh - g.hi_h) < span) break;
+        if (mh >= RelaxGuard::kBigH || grow > kBounce) {
+            state = kRlxUncertain + (mh >= RelaxGuard::kBigH ? kWhyHuge : kWhyBounce);
+            break;
+        }
+        if (min(dmin, d1) < g.det_h) {
+            state = (kCarefulBinades > 0 && limit >= kRelaxCap && min(dmin, d1) >= g.det_h - (kCarefulBinades << 20))
+                ? kRlxWantCareful : kRlxUncertain + kWhyCond;
+            break;
+        }
+        if (mh < lo_cur) {
+            state = kRlxConverged;
+            break;
+        }
+        const int verdict = g.precise(fabs(sm) * Rsys<KIND>::kStepScale, det, extra);
+        if (trace) *trace |= 1;
+        if (verdict >= 0) {
+            state = verdict > 0 ? kRlxConverged : kRlxUncertain + kWhyBand;
+            break;
+        }
+        extra = 0.0, lo_cur = g.lo_h;
+        if (it >= limit) break;
+    }
+    if (state == kRlxRunning && (min(dmin, d1) < g.det_h || grow > kBounce || limit >= kRelaxCap))
+        state = kRlxUncertain + (min(dmin, d1) < g.det_h ? kWhyCond : grow > kBounce ? kWhyBounce : kWhyCap);
+    ln.point(w, x, y);
+    return state;
+}
+
+// whole runs: the line form where the kind has one (GCS_RELAX_LINE=0 builds without it)
+#ifndef GCS_RELAX_LINE
+#define GCS_RELAX_LINE 1
+#endif
+template <int KIND>
+__device__ __forceinline__ int relaxed_run(const Rsys<KIND>& rs, const double* k, RelaxGuard& g, double& x, double& y, int& it,
+    int* trace)
+{
+    if constexpr (RLine<KIND>::kHas && GCS_RELAX_LINE) {
+        return relaxed_updates_line<KIND>(rs, k, g, x, y, it, kRelaxCap, trace);
+    } else {
+        double u0, u1;
+        return relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1, nullptr, trace);
+    }
+}
+
 // Careful mode: a whole run from its seed with EVERY convergence decision taken by the
 // conditioning-scaled margin test (RelaxGuard::precise) instead of the fixed first-level band.
 //
