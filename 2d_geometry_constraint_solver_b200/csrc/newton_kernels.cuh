@@ -128,17 +128,17 @@ __global__ void __launch_bounds__(128, RLX ? GCS_STATIC_RLX_MINB : GCS_STATIC_MI
     bool literal = !RLX;
     int pathv = 0;
     if constexpr (RLX) {
-        Rsys<KIND> rs;
-        RelaxGuard g;
-        rs.load(k, g);
+        RelaxedSystem<KIND> sysr;
+        sysr.load(k);
+        RelaxGuard g = sysr.g0;
         it = 0;
         int state = kRlxConverged;
         // iteration 0 compares the guess with prev = (0, 0)
         if (!(fabs(0.0 - x) < kTol && fabs(0.0 - y) < kTol)) {
-            state = relaxed_run<KIND>(rs, k, g, x, y, it, p.path ? &pathv : nullptr);
+            state = sysr.run(g, x, y, it, p.path ? &pathv : nullptr);
             if (state == kRlxWantCareful) {  // ill conditioned, above the floor: replay with every decision margin-tested
                 run_seed<KIND>(p.guesses, p.stride, i, k, seed, x, y);
-                const CarefulOut o = relaxed_careful<KIND>(rs, g, x, y);
+                const CarefulOut o = relaxed_careful<KIND>(sysr.rs, g, x, y);
                 x = o.x, y = o.y, it = o.it, state = o.state, pathv |= o.trace;
             }
         }
@@ -256,22 +256,23 @@ __global__ void __launch_bounds__(128, RLX ? GCS_SEQ_MINB : GCS_SEQ_LIT_MINB) ne
         for (int c = 0; c < S::kCols; ++c) prefetch_l2(p.in[c] + i + p.pf);
     }
     double cx[NS], cy[NS];
+    // contracted: what the seeds of a sub-system share (equations, guard, line constants) is set once
+    std::conditional_t<RLX, RelaxedSystem<KIND>, int> sysr;
+    if constexpr (RLX) sysr.load(k);
 
     auto one_seed = [&](int s) {
         double x, y;
         run_seed<KIND>(p.guesses, p.stride, i, k, s, x, y);
         int it = 0, conv = 1, pathv = 0;
         if constexpr (RLX) {
-            Rsys<KIND> rs;
-            RelaxGuard g;
-            rs.load(k, g);
+            RelaxGuard g = sysr.g0;
             int state = kRlxConverged;
             // iteration 0 compares the guess with prev = (0, 0)
             if (!(fabs(0.0 - x) < kTol && fabs(0.0 - y) < kTol)) {
-                state = relaxed_run<KIND>(rs, k, g, x, y, it, p.path ? &pathv : nullptr);
+                state = sysr.run(g, x, y, it, p.path ? &pathv : nullptr);
                 if (state == kRlxWantCareful) {
                     run_seed<KIND>(p.guesses, p.stride, i, k, s, x, y);
-                    const CarefulOut o = relaxed_careful<KIND>(rs, g, x, y);
+                    const CarefulOut o = relaxed_careful<KIND>(sysr.rs, g, x, y);
                     x = o.x, y = o.y, it = o.it, state = o.state, pathv |= o.trace;
                 }
             }

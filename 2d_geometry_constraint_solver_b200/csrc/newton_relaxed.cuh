@@ -568,7 +568,7 @@ struct RLine<GCS_KIND_PPL> : RLineData {
 // relaxed_updates for a whole run (it == 0 on entry) of a kind with a line form: the update from the
 // seed in closed form, everything after it on the line.  Same outcomes, same guards.
 template <int KIND>
-__device__ __forceinline__ int relaxed_updates_line(const Rsys<KIND>& rs, const double* k, RelaxGuard& g, double& x, double& y,
+__device__ __forceinline__ int relaxed_updates_line(const Rsys<KIND>& rs, const RLine<KIND>& ln, RelaxGuard& g, double& x, double& y,
     int& it, int limit, int* trace = nullptr)
 {
     static_assert(RLine<KIND>::kHas, "no line form for this kind");
@@ -599,8 +599,6 @@ __device__ __forceinline__ int relaxed_updates_line(const Rsys<KIND>& rs, const 
     const unsigned span = (unsigned)(RelaxGuard::kBigH - g.hi_h);
     d1 = dh;
     bool in_loop = (unsigned)(mh - g.hi_h) < span && it < limit;
-    RLine<KIND> ln;
-    ln.set(rs, k);
     double w = ln.project(x, y);
     // one update on the line; leaves mh, dh, sm, det like the closed-form update does
     auto update = [&]() {
@@ -673,17 +671,31 @@ __device__ __forceinline__ int relaxed_updates_line(const Rsys<KIND>& rs, const 
 #ifndef GCS_RELAX_LINE
 #define GCS_RELAX_LINE 1
 #endif
+// What a sub-system's runs share: the equations on fused multiply-adds, the guard before any run's own
+// carry term, the constants of the line form.  One per (sub-system, seed) lane in the static mapping,
+// one per sub-system - set once, used by every seed - in the sequential one.
 template <int KIND>
-__device__ __forceinline__ int relaxed_run(const Rsys<KIND>& rs, const double* k, RelaxGuard& g, double& x, double& y, int& it,
-    int* trace)
-{
-    if constexpr (RLine<KIND>::kHas && GCS_RELAX_LINE) {
-        return relaxed_updates_line<KIND>(rs, k, g, x, y, it, kRelaxCap, trace);
-    } else {
-        double u0, u1;
-        return relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1, nullptr, trace);
+struct RelaxedSystem {
+    static constexpr bool kLine = RLine<KIND>::kHas && GCS_RELAX_LINE;
+    Rsys<KIND> rs;
+    RelaxGuard g0;
+    RLine<KIND> ln;
+    __device__ __forceinline__ void load(const double* k)
+    {
+        rs.load(k, g0);
+        if constexpr (kLine) ln.set(rs, k);
     }
-}
+    // one run from (x, y) with it == 0; g: the run's own guard (a copy of g0 on entry)
+    __device__ __forceinline__ int run(RelaxGuard& g, double& x, double& y, int& it, int* trace) const
+    {
+        if constexpr (kLine) {
+            return relaxed_updates_line<KIND>(rs, ln, g, x, y, it, kRelaxCap, trace);
+        } else {
+            double u0, u1;
+            return relaxed_updates<KIND, false>(rs, g, x, y, it, kRelaxCap, u0, u1, nullptr, trace);
+        }
+    }
+};
 
 // Careful mode: a whole run from its seed with EVERY convergence decision taken by the
 // conditioning-scaled margin test (RelaxGuard::precise) instead of the fixed first-level band.

@@ -188,3 +188,32 @@ def test_contract_seeds_so_far_away_that_the_landing_error_straddles_the_thresho
     assert_batches_within_contract(hb, ref, f"kind {kind} variant {variant} far seeds")
     if kind == 4:
         assert len(np.unique(ref.iters)) >= 2  # the landing error really decides: some runs need a third update
+
+
+@pytest.mark.parametrize("variant", VARIANTS + [5])
+def test_contract_roots_next_to_a_centre(gpu, gcs, variant):
+    """Needle triangles: the free point lies 1e-6 .. 1e-2 from one of the two fixed points (one radius
+    is orders of magnitude under the other and under the base).  The system is WELL conditioned there
+    (the circles cross at the angle phi), so the runs stay on the closed-form path - and a line form
+    that takes the half chord from `ra^2 - t0^2` cancels to eps ra^2 / (2 h): coordinates 1e-9 .. 1e-6
+    off and late updates moved by more than the guards' band (scratch/soak_relaxed.py found it on
+    the flat-triangle case: 1.1e-9 on the 0.1 % of rows with the apex next to A or B).  RLine<K1>
+    builds h^2 from Heron's factors instead; this is the regression test."""
+    n = 1 << 18
+    rng = np.random.default_rng(9091)
+    hb = gcs.synth.make(1, n, seed=0xC0FFEE)
+    ax, ay, ra, bx, by, rb = hb.cols
+    rho = 10.0 ** rng.uniform(-6, -2, size=n)
+    phi = rng.uniform(0.02, np.pi - 0.02, size=n) * np.where(rng.random(n) < 0.5, 1.0, -1.0)
+    near_b = rng.random(n) < 0.5
+    cx, cy = np.where(near_b, bx, ax), np.where(near_b, by, ay)
+    px, py = cx + rho * np.cos(phi), cy + rho * np.sin(phi)
+    ra[:] = np.hypot(px - ax, py - ay)
+    rb[:] = np.hypot(px - bx, py - by)
+    hb.variant = variant
+    gpu.solve_host(hb.alloc_outputs(), 0)
+    ref = gcs.capi.HostBatch(1, 2, [c.copy() for c in hb.cols], hb.code.copy())
+    O.solve(ref.alloc_outputs())
+    worst = assert_batches_within_contract(hb, ref, f"needle triangles, variant {variant}")
+    assert worst <= 1e-10  # the closed form is far inside the contract here, as the Cramer form was
+    assert (ref.converged == 1).mean() > 0.99
