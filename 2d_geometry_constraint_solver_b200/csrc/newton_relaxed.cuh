@@ -91,6 +91,15 @@ __device__ __forceinline__ double rcp_relaxed(double b)
     return __fma_rn(r, e, r);
 }
 
+// |v|^-1/2 refined to an ulp or two (MUFU.RSQ64H seed, one cubic step: 2^-60 before the roundings of the step itself)
+__device__ __forceinline__ double rsqrt_relaxed(double v)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+    const double e = __fma_rn(-v * r, r, 1.0);           // 1 - v r^2
+    return __fma_rn(r * __fma_rn(0.375, e, 0.5), e, r);  // r (1 + e/2 + 3 e^2 / 8)
+}
+
 __device__ __forceinline__ int abs_hi(double v) { return __double2hiint(v) & 0x7fffffff; }
 
 // high word of a non-negative double, rounded outwards (thresholds of integer comparisons)
@@ -212,12 +221,16 @@ struct Rsys<GCS_KIND_SDD> {
 };
 
 struct RP2L {
-    double xa, ya, ex, ey, ld, len;
+    double xa, ya, ex, ey, ld, len, rl;
     __device__ __forceinline__ void set(double xa_, double ya_, double xb_, double yb_, double s_)
     {
         xa = xa_, ya = ya_;
         ex = xb_ - xa_, ey = yb_ - ya_;
-        len = sqrt(__fma_rn(ex, ex, ey * ey));
+        // |e| to an ulp or two without the 40 instructions of an IEEE square root (the literal code's
+        // length is correctly rounded: the difference is an ulp of the coordinate scale, in the budget)
+        const double l2 = __fma_rn(ex, ex, ey * ey);
+        rl = rsqrt_relaxed(l2);  // a point for a line: inf, len = NaN -> (G4)
+        len = l2 * rl;
         ld = len * s_;
     }
     // -f of pointToLineDistance: ld - uy ex + ux ey
@@ -278,13 +291,15 @@ struct Rsys<GCS_KIND_PLL> {
 template <>
 struct Rsys<GCS_KIND_ANG> {
     static constexpr double kStepScale = 1.0;
-    double fdx, fdy, cl;
+    double fdx, fdy, cl, len, rl;
     // kGuard = false: only the system's constants (the guard comes from where it was stashed)
     template <bool kGuard = true>
     __device__ __forceinline__ void load(const double* k, RelaxGuard& g)
     {
         fdx = k[0], fdy = k[1];
-        const double len = sqrt(__fma_rn(fdx, fdx, fdy * fdy));
+        const double l2 = __fma_rn(fdx, fdx, fdy * fdy);
+        rl = rsqrt_relaxed(l2);  // see RP2L::set
+        len = l2 * rl;
         cl = k[2] * len;
         // unit normals; the linear residual is L (cos(phi) - cosA): scale 2; det J = 2 L sin(.)
         if constexpr (kGuard) g.init(2.0, 2.0 * len, kStepScale);
@@ -462,15 +477,6 @@ struct RLine {
     static constexpr bool kHas = false;
 };
 
-// |v|^-1/2 refined to ~2^-60 relative (MUFU.RSQ64H seed, one cubic step)
-__device__ __forceinline__ double rsqrt_relaxed(double v)
-{
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
-    const double e = __fma_rn(-v * r, r, 1.0);           // 1 - v r^2
-    return __fma_rn(r * __fma_rn(0.375, e, 0.5), e, r);  // r (1 + e/2 + 3 e^2 / 8)
-}
-
 struct RLineData {
     double fx, fy;   // foot of the circle's centre on the line
     double ux, uy;   // unit direction of the line
@@ -522,12 +528,16 @@ struct RLineUnit : RLineData {
     {
         const double l2 = __fma_rn(nx, nx, ny * ny);
         const double rl = rsqrt_relaxed(l2);
+        set_unit(nx, ny, c, l2 * rl, rl);
+    }
+    __device__ __forceinline__ void set_unit(double nx, double ny, double c, double len, double rl)  // len = |(nx, ny)| = 1 / rl
+    {
         const double Nx = nx * rl, Ny = ny * rl;
         const double t0 = c * rl;
         fx = t0 * Nx, fy = t0 * Ny;
         ux = -Ny, uy = Nx;
         h2 = (1.0 - t0) * (1.0 + t0);
-        dscale = 2.0 * (l2 * rl);              // det J = 2 |(nx, ny)| w
+        dscale = 2.0 * len;                    // det J = 2 |(nx, ny)| w
         mscale = 0.5 * fmax(fabs(ux), fabs(uy));
     }
 };
@@ -543,7 +553,7 @@ struct RLine<GCS_KIND_SDD> : RLineUnit {
 template <>
 struct RLine<GCS_KIND_ANG> : RLineUnit {
     static constexpr bool kHas = true;
-    __device__ __forceinline__ void set(const Rsys<GCS_KIND_ANG>& rs, const double*) { set_unit(rs.fdy, -rs.fdx, rs.cl); }
+    __device__ __forceinline__ void set(const Rsys<GCS_KIND_ANG>& rs, const double*) { set_unit(rs.fdy, -rs.fdx, rs.cl, rs.len, rs.rl); }
 };
 
 // K3: the circle (C, r) and the line at signed distance -s from A -> B
@@ -552,15 +562,13 @@ struct RLine<GCS_KIND_PPL> : RLineData {
     static constexpr bool kHas = true;
     __device__ __forceinline__ void set(const Rsys<GCS_KIND_PPL>& rs, const double* k)
     {
-        const double l2 = __fma_rn(rs.l.ex, rs.l.ex, rs.l.ey * rs.l.ey);
-        const double rl = rsqrt_relaxed(l2);
-        ux = rs.l.ex * rl, uy = rs.l.ey * rl;
+        ux = rs.l.ex * rs.l.rl, uy = rs.l.ey * rs.l.rl;
         // offset of the centre from the line along N = (uy, -ux):  N . (C - A) + s
         const double c = __fma_rn(rs.px - rs.l.xa, uy, __fma_rn(-(rs.py - rs.l.ya), ux, k[7]));
         fx = __fma_rn(-c, uy, rs.px), fy = __fma_rn(c, ux, rs.py);
         const double r = fabs(k[2]), ca = fabs(c);
         h2 = (r - ca) * (r + ca);
-        dscale = 2.0 * (l2 * rl);              // det J = 2 (P - C) . e = 2 |e| w
+        dscale = 2.0 * rs.l.len;               // det J = 2 (P - C) . e = 2 |e| w
         mscale = 0.5 * fmax(fabs(ux), fabs(uy));
     }
 };
