@@ -35,6 +35,7 @@ VARIANT_DEFAULT, VARIANT_STATIC, VARIANT_REFILL, VARIANT_SORTED, VARIANT_PAIR = 
 # tolerance-class arithmetic (discrete outputs identical, coordinates to 1e-9): auto / static / sorted
 VARIANT_CONTRACTED, VARIANT_CONTRACTED_STATIC, VARIANT_CONTRACTED_SORTED = 5, 6, 7
 VARIANT_CONTRACTED_SEQ, VARIANT_SEQ = 8, 9  # one lane per sub-system, seeds in sequence: contracted / bit-identical
+VARIANT_CONTRACTED_LINEAR = 10  # K4 in the contracted class: closed form, decisions certified (other kinds: as VARIANT_CONTRACTED)
 
 CODE_COLLINEAR = 0x10
 CODE_CANVAS_PARALLEL = 0x20

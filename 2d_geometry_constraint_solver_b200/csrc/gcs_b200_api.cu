@@ -56,13 +56,12 @@ inline int resolve_variant(int variant, int kind, long long n, int n_seeds)
     if (variant == GCS_VARIANT_CONTRACTED) {
         // contracted arithmetic otherwise: the static kernel at every size (with a 55-cycle update the
         // sort's bookkeeping costs more than the idle lanes it removes: K1 51 vs 57 us, K3 68 vs 84 us per 2^19)
-        // K4: two updates per seed leave the closed-form update nothing to win back for its guards'
-        // set-up - the bit-identical sequential kernel is the faster one (30.2 against 32.9 us per 2^19)
-        // and trivially within the contract
-        if (kind == GCS_KIND_PLL) return n * n_seeds >= (1ll << 17) ? GCS_VARIANT_SEQ : GCS_VARIANT_CONTRACTED_STATIC;
+        // K4: a linear pair needs no iteration in this class (newton_linear_kernel)
+        if (kind == GCS_KIND_PLL) return GCS_VARIANT_CONTRACTED_LINEAR;
         if (kind == GCS_KIND_PP && n_seeds == 8) return GCS_VARIANT_CONTRACTED_SEQ;
         return GCS_VARIANT_CONTRACTED_STATIC;
     }
+    if (variant == GCS_VARIANT_CONTRACTED_LINEAR && kind != GCS_KIND_PLL) return resolve_variant(GCS_VARIANT_CONTRACTED, kind, n, n_seeds);
     if (variant != GCS_VARIANT_DEFAULT) return variant;
     if (kind == GCS_KIND_PLL && n * n_seeds >= (1ll << 17)) return GCS_VARIANT_SEQ;
     return n * n_seeds >= kSortedMinRuns ? GCS_VARIANT_SORTED : GCS_VARIANT_STATIC;
@@ -207,7 +206,7 @@ int validate(const gcs_b200_batch* b)
     if (!b) return fail(GCS_E_INVALID, "null batch");
     if (b->kind < 1 || b->kind > GCS_KIND_COUNT) return fail(GCS_E_INVALID, "unknown kind %d", b->kind);
     if (b->n < 0) return fail(GCS_E_INVALID, "negative n");
-    if (b->variant < GCS_VARIANT_DEFAULT || b->variant > GCS_VARIANT_SEQ)
+    if (b->variant < GCS_VARIANT_DEFAULT || b->variant > GCS_VARIANT_CONTRACTED_LINEAR)
         return fail(GCS_E_INVALID, "unknown variant %d", b->variant);
     const bool column_guess = (b->kind == GCS_KIND_SDD || b->kind == GCS_KIND_ANG);
     if (column_guess) {
@@ -306,6 +305,23 @@ int launch_seq(DeviceState* d, BatchDev p, cudaStream_t st)
     return GCS_OK;
 }
 
+template <int NS>
+int launch_linear(DeviceState* d, BatchDev p, cudaStream_t st)
+{
+    const long long grid = (p.n + 127) / 128;
+    if (grid > 0x7fffffffLL) return fail(GCS_E_INVALID, "batch too large for one launch");
+    static thread_local long long wave[64] = {};
+    if (prefetch_waves() > 0) {
+        long long& w = wave[d->device & 63];
+        if (w == 0) w = wave_subs(d, newton_linear_kernel<NS>, 128, 128);
+        p.pf = w * prefetch_waves();
+    }
+    newton_linear_kernel<NS><<<(unsigned)grid, 128, 0, st>>>(p);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return GCS_OK;
+}
+
 template <int KIND>
 int launch_pair(const BatchDev& p, cudaStream_t st)
 {
@@ -365,6 +381,9 @@ int launch_kind(DeviceState* d, const gcs_b200_batch* b, const BatchDev& p, cuda
 {
     const int variant = resolve_variant(b->variant, KIND, p.n, b->n_seeds);
     constexpr bool column_guess = (KIND == GCS_KIND_SDD || KIND == GCS_KIND_ANG);
+    if constexpr (KIND == GCS_KIND_PLL) {
+        if (variant == GCS_VARIANT_CONTRACTED_LINEAR) return b->n_seeds == 2 ? launch_linear<2>(d, p, st) : launch_linear<8>(d, p, st);
+    }
     if (b->n_seeds == 2) {
         if (variant == GCS_VARIANT_CONTRACTED_SEQ) return launch_seq<KIND, 2, true>(d, p, st);
         if (variant == GCS_VARIANT_SEQ) return launch_seq<KIND, 2, false>(d, p, st);
@@ -585,6 +604,7 @@ const char* gcs_b200_kernel_name(int kind, int n_seeds, int variant)
     static thread_local char name[96];
     variant = resolve_variant(variant, kind, kSortedMinRuns, n_seeds);  // default: named for a launch that fills the device
     const char* base = variant == GCS_VARIANT_REFILL ? "newton_refill_kernel"
+        : variant == GCS_VARIANT_CONTRACTED_LINEAR   ? "newton_linear_kernel[contracted]"
         : variant == GCS_VARIANT_CONTRACTED_SEQ      ? "newton_seq_kernel[contracted]"
         : variant == GCS_VARIANT_SEQ                 ? "newton_seq_kernel"
         : variant == GCS_VARIANT_CONTRACTED_SORTED   ? "newton_sorted_kernel[contracted]"

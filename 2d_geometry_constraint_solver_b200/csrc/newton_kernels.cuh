@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(128, RLX ? GCS_SEQ_MINB : GCS_SEQ_LIT_MINB) ne
 
     auto one_seed = [&](int s) {
         double x, y;
-        run_seed<KIND>(p.guesses, p.stride, i, k, s, x, y);
+        run_seed<KIND, (NS > 2)>(p.guesses, p.stride, i, k, s, x, y);
         int it = 0, conv = 1, pathv = 0;
         if constexpr (RLX) {
             RelaxGuard g = sysr.g0;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(128, RLX ? GCS_SEQ_MINB : GCS_SEQ_LIT_MINB) ne
             if (!(fabs(0.0 - x) < kTol && fabs(0.0 - y) < kTol)) {
                 state = sysr.run(g, x, y, it, p.path ? &pathv : nullptr);
                 if (state == kRlxWantCareful) {
-                    run_seed<KIND>(p.guesses, p.stride, i, k, s, x, y);
+                    run_seed<KIND, (NS > 2)>(p.guesses, p.stride, i, k, s, x, y);
                     const CarefulOut o = relaxed_careful<KIND>(sysr.rs, g, x, y);
                     x = o.x, y = o.y, it = o.it, state = o.state, pathv |= o.trace;
                 }
@@ -326,6 +326,136 @@ __global__ void __launch_bounds__(128, RLX ? GCS_SEQ_MINB : GCS_SEQ_LIT_MINB) ne
 #pragma unroll
     for (int c = 0; c < S::kOut; ++c) p.out[c][i] = out[c];
     if (p.root) p.root[i] = (uint8_t)root;
+}
+
+// ------------------------------------------------------------------------------------------
+// linear variant (K4, contracted class): one lane per sub-system, no iteration at all
+//
+// K4 is two point-to-line equations: a LINEAR pair with a constant Jacobian.  Newton's method lands
+// on the solution P with its first update from any seed; the second update is the landing's own
+// rounding error and ends the run: iters = 2, converged, candidate = P for EVERY seed.  Reproducing
+// that literally costs two Householder-QR updates per seed plus the line-intersection frame of the
+// selection (three IEEE divisions, a square root): ~900 warp instructions per 32 sub-systems, which
+// makes the kind the survey expected to bind on HBM bind on instruction issue instead.
+// The contract (iteration counts, flags, root identical; coordinates to 1e-9) needs none of it:
+//   * P in closed form (Cramer on fused multiply-adds, origin moved to the first line's anchor);
+//   * per seed, the two decisions certified instead of computed:
+//       - the update from the seed is longer than the threshold: m1 = |P - seed|_max > 2 tol;
+//       - the second update is shorter: it is the first update's rounding error, at most
+//         ~ eps cond (m1 + S) in any backward-stable arithmetic (cond = |J|_F^2 / |det|, S the
+//         coordinate scale; the contracted guards' carry / w1 terms budget 32 eps cond m1 for the
+//         DIFFERENCE of two arithmetics there) - required: 2^-46 cond (m1 + S) < tol / 4, i.e. a
+//         factor 512 between the bound and the threshold;
+//       - a seed inside the iteration-0 box, or within 2 tol of P, is not certified;
+//   * the root: every candidate is P and the orientation the reference tests is, exactly, the first
+//     equation's signed distance s1 (P lies at signed distance s1 from line 1, and the frame's origin
+//     is on line 1) - the reference computes it through the lines' intersection A, with an error of a
+//     few ulp of |A| + |P|: required |s1| > 2^-24 (2 |A| + 2 + |P|), the margin of selection_is_robust;
+//     nearest-to-canvas sub-systems (collinear / parallel codes, |cross| under the reference's absolute
+//     epsilon) are not certified: their rule compares two noise-level distances;
+//   * (G1) |det| >= 2^-10 |e1| |e2| as everywhere in the class, and cond < 2^16 (coordinates: the two
+//     arithmetics' P differ by a few eps cond S); NaN / inf fail every comparison.
+// A sub-system that is not certified - every seed of it - goes to the literal code (out of line, as
+// in the sequential kernel), so degenerate inputs come out bit for bit.
+// ------------------------------------------------------------------------------------------
+// every seed of sub-system i by the literal code, then the literal selection (out of line: reloads the
+// columns, keeps the certified path free of its registers and stack)
+template <int NS>
+static __device__ __noinline__ void linear_fallback(const BatchDev& p, long long i, uint8_t code)
+{
+    constexpr int KIND = GCS_KIND_PLL;
+    using S = Sys<KIND>;
+    double cx[NS], cy[NS];
+#pragma unroll 1
+    for (int s = 0; s < NS; ++s) {
+        const RunOut r = literal_run_from_global<KIND>(p, i, s, kWhyCond);
+        cx[s] = r.x, cy[s] = r.y;
+        if (p.iters) p.iters[(long long)s * p.stride + i] = (int16_t)r.it;
+        if (p.converged) p.converged[(long long)s * p.stride + i] = (uint8_t)r.conv;
+        if (p.path) p.path[(long long)s * p.stride + i] = (uint8_t)kPathLiteralRun;
+        if (p.cand) {
+            p.cand[((long long)s * 2 + 0) * p.stride + i] = r.x;
+            p.cand[((long long)s * 2 + 1) * p.stride + i] = r.y;
+        }
+    }
+    double k[S::kCols];
+#pragma unroll
+    for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + i);
+    double out[4];
+    const int root = select_and_finish<KIND, NS>(k, code, cx, cy, out);
+    p.out[0][i] = out[0], p.out[1][i] = out[1];
+    if (p.root) p.root[i] = (uint8_t)root;
+}
+
+#ifndef GCS_LINEAR_MINB
+#define GCS_LINEAR_MINB 8
+#endif
+template <int NS>
+__global__ void __launch_bounds__(128, GCS_LINEAR_MINB) newton_linear_kernel(const __grid_constant__ BatchDev p)
+{
+    constexpr int KIND = GCS_KIND_PLL;
+    using S = Sys<KIND>;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    double k[S::kCols];
+#pragma unroll
+    for (int c = 0; c < S::kCols; ++c) k[c] = __ldg(p.in[c] + i);
+    const uint8_t code = p.code ? __ldg(p.code + i) : (uint8_t)GCS_MAKE_CODE(0, 0, 0);
+    if (p.pf > 0 && i + p.pf < p.n) {
+#pragma unroll
+        for (int c = 0; c < S::kCols; ++c) prefetch_l2(p.in[c] + i + p.pf);
+    }
+    const double e1x = k[2] - k[0], e1y = k[3] - k[1];
+    const double e2x = k[7] - k[5], e2y = k[8] - k[6];
+    const double q1 = __fma_rn(e1x, e1x, e1y * e1y), q2 = __fma_rn(e2x, e2x, e2y * e2y);
+    const double r1 = rsqrt_relaxed(q1), r2 = rsqrt_relaxed(q2);
+    const double len1 = q1 * r1, len2 = q2 * r2;
+    const double cross_lit = e1x * e2y - e1y * e2x;  // heuristics.hpp:171-173, the reference's roundings
+    const double det = __fma_rn(e1x, e2y, -(e1y * e2x));
+    const double rdet = rcp_relaxed(det);
+    // P - A1 from  -e1y x' + e1x y' = len1 s1,   -e2y x' + e2x y' = len2 s2 + (-e2y dlx + e2x dly),  dl = A2 - A1
+    const double dlx = k[5] - k[0], dly = k[6] - k[1];
+    const double c1 = len1 * k[4];
+    const double c2 = __fma_rn(len2, k[9], __fma_rn(e2x, dly, -(e2y * dlx)));
+    const double px = __fma_rn(__fma_rn(c1, e2x, -(e1x * c2)), rdet, k[0]);
+    const double py = __fma_rn(__fma_rn(c1, e2y, -(e1y * c2)), rdet, k[1]);
+    // the frame's origin A = A1 + t e1 (heuristics.hpp:165-181), for the margin of the orientation only
+    const double t = __fma_rn(dlx, e2y, -(dly * e2x)) * rdet;
+    const double sa = 2.0 * (fabs(__fma_rn(t, e1x, k[0])) + fabs(__fma_rn(t, e1y, k[1]))) + 2.0;
+    const double cond = (q1 + q2) * fabs(rdet);
+    const double scale = fabs(k[0]) + fabs(k[1]) + fabs(k[5]) + fabs(k[6]) + fabs(k[4]) + fabs(k[9]);
+    bool ok = !(code & (GCS_CODE_COLLINEAR | GCS_CODE_CANVAS_PARALLEL)) && !(fabs(cross_lit) < GCS_PARALLEL_EPSILON)
+        && fabs(det) >= 0x1p-10 * (len1 * len2) && fabs(k[4]) > 0x1p-24 * (sa + fabs(px) + fabs(py)) && cond < 0x1p16;
+    const double nb = 0x1p-46 * cond;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        double gx, gy;
+        if (p.guesses) {
+            gx = __ldg(p.guesses + ((long long)s * 2 + 0) * p.stride + i);
+            gy = __ldg(p.guesses + ((long long)s * 2 + 1) * p.stride + i);
+        } else {
+            default_seed(s, gx, gy);
+        }
+        const double m1 = fmax(fabs(px - gx), fabs(py - gy));
+        ok = ok && !(fabs(gx) < 2.0 * kTol && fabs(gy) < 2.0 * kTol) && m1 > 2.0 * kTol && nb * (m1 + scale) < 0.25 * kTol;
+    }
+    if (ok) {
+        const int root = (GCS_CODE_SIGN0(code) == sgn3(k[4])) ? 0 : NS - 1;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            if (p.iters) p.iters[(long long)s * p.stride + i] = (int16_t)2;
+            if (p.converged) p.converged[(long long)s * p.stride + i] = (uint8_t)1;
+            if (p.path) p.path[(long long)s * p.stride + i] = (uint8_t)kPathFirstLevel;
+            if (p.cand) {
+                p.cand[((long long)s * 2 + 0) * p.stride + i] = px;
+                p.cand[((long long)s * 2 + 1) * p.stride + i] = py;
+            }
+        }
+        p.out[0][i] = px, p.out[1][i] = py;
+        if (p.root) p.root[i] = (uint8_t)root;
+        return;
+    }
+    linear_fallback<NS>(p, i, code);  // not certified: the reference's arithmetic for every seed of the sub-system
 }
 
 // ------------------------------------------------------------------------------------------

@@ -781,8 +781,9 @@ static __device__ __noinline__ CarefulOut relaxed_careful(Rsys<KIND> rs, RelaxGu
     return o;
 }
 
-// seed `seed` of sub-system `gi` as the kernels take it
-template <int KIND>
+// seed `seed` of sub-system `gi` as the kernels take it (kUniformSeed: `seed` is the same in every
+// lane of the warp and not a compile-time constant - the sequential kernel's loop over seeds)
+template <int KIND, bool kUniformSeed = false>
 __device__ __forceinline__ void run_seed(
     const double* guesses, long long stride, long long gi, const double* k, int seed, double& x, double& y)
 {
@@ -791,6 +792,8 @@ __device__ __forceinline__ void run_seed(
         y = __ldg(guesses + ((long long)seed * 2 + 1) * stride + gi);
     } else if constexpr (Sys<KIND>::kGuessFromCols) {
         column_seed<KIND>(k, seed, x, y);
+    } else if constexpr (kUniformSeed) {
+        default_seed_uniform(seed, x, y);
     } else {
         default_seed(seed, x, y);
     }

@@ -159,13 +159,17 @@ extern "C" {
  * tests/test_gpu_soak.py and the soaks of profiles/ (> 1e8 sub-systems without a difference; an
  * earlier soak did find one, which is why the carry term exists) - NOT a machine-checked proof.
  * Opt-in: DEFAULT never resolves to it, and the host mirror stays on the bit-identical kernels.
- * CONTRACTED = CONTRACTED_STATIC (measured fastest at every size) except K4 and the 8-seed K1, which
- * take CONTRACTED_SEQ; CONTRACTED_SORTED maps the same arithmetic onto the sorted tiles. */
+ * CONTRACTED = CONTRACTED_STATIC (measured fastest at every size) except the 8-seed K1, which takes
+ * CONTRACTED_SEQ, and K4, which takes CONTRACTED_LINEAR; CONTRACTED_SORTED maps the same arithmetic
+ * onto the sorted tiles. */
 #define GCS_VARIANT_CONTRACTED 5
 #define GCS_VARIANT_CONTRACTED_STATIC 6
 #define GCS_VARIANT_CONTRACTED_SORTED 7
 #define GCS_VARIANT_CONTRACTED_SEQ 8 /* contracted arithmetic, one lane per sub-system, seeds one after the other */
 #define GCS_VARIANT_SEQ 9            /* bit-identical arithmetic in the same mapping */
+/* K4 only (a linear pair): the solution in closed form, every seed's two decisions certified instead
+ * of iterated, uncertified sub-systems redone literally; any other kind resolves as CONTRACTED */
+#define GCS_VARIANT_CONTRACTED_LINEAR 10
 
 typedef struct gcs_b200_batch {
     int32_t kind;    /* GCS_KIND_* */

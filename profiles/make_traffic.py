@@ -1,8 +1,8 @@
 """Rebuilds profiles/traffic.json and the round-2 ncu summaries from the .ncu-rep files of one capture
-session (gpurun_out/r2_prof_*.ncu-rep, written by scratch/run.sh) and stamps them with the source
-hash of the library the capture ran (gpurun_out/r2_ncu_libversion.txt), so that bench.py can tell
+session (gpurun_out/<prefix>_prof_*.ncu-rep, written by scratch/run.sh) and stamps them with the source
+hash of the library the capture ran (gpurun_out/<prefix>_ncu_libversion.txt), so that bench.py can tell
 whether the library it runs is the build the traffic figures belong to.
-Usage: python profiles/make_traffic.py"""
+Usage: python profiles/make_traffic.py [prefix]      (r2: the Cramer-form build; r2f: the line-form build)"""
 import csv
 import json
 import os
@@ -41,37 +41,38 @@ def summary(rep, title, dst):
 
 
 def main():
-    lib = open(os.path.join(OUT, "r2_ncu_libversion.txt")).read().strip()
+    P = sys.argv[1] if len(sys.argv) > 1 else "r2f"
+    lib = open(os.path.join(OUT, f"{P}_ncu_libversion.txt")).read().strip()
     h = re.search(r"src ([0-9a-f]+)", lib).group(1)
     t = {"_src_hash": h, "_library": lib,
-         "_note": "per-launch DRAM bytes and executed FP64 flops from the round-2 `ncu --set full` captures (profiles/r2_ncu_*.md); bench.py "
+         "_note": f"per-launch DRAM bytes and executed FP64 flops from the round-2 `ncu --set full` captures (profiles/{P}_ncu_*.md); bench.py "
                   "reports `traffic_capture_is_of_another_build` when the library it runs carries another source hash"}
-    st = raw(os.path.join(OUT, "r2_prof_static.ncu-rep"))
-    t["newton_static_kernel[contracted]<K1,2 seeds>"] = entry(st[0], "profiles/r2_ncu_contracted.md", "37.7 MB (the 12 MB of outputs are still in the 126 MB L2 when the kernel ends)")
-    t["newton_static_kernel[contracted]<K5,2 seeds>"] = entry(st[1], "profiles/r2_ncu_contracted.md", "75.5 MB")
-    so = raw(os.path.join(OUT, "r2_prof_sorted.ncu-rep"))
-    t["newton_sorted_kernel<K1,2 seeds>"] = entry(so[0], "profiles/r2_ncu_sorted.md", "37.7 MB")
-    t["newton_sorted_kernel<K5,2 seeds>"] = entry(so[1], "profiles/r2_ncu_sorted.md", "75.5 MB")
-    k4 = raw(os.path.join(OUT, "r2_prof_seq_k4.ncu-rep"))
+    st = raw(os.path.join(OUT, f"{P}_prof_static.ncu-rep"))
+    t["newton_static_kernel[contracted]<K1,2 seeds>"] = entry(st[0], f"profiles/{P}_ncu_contracted.md", "37.7 MB (the 12 MB of outputs are still in the 126 MB L2 when the kernel ends)")
+    t["newton_static_kernel[contracted]<K5,2 seeds>"] = entry(st[1], f"profiles/{P}_ncu_contracted.md", "75.5 MB")
+    so = raw(os.path.join(OUT, f"{P}_prof_sorted.ncu-rep"))
+    t["newton_sorted_kernel<K1,2 seeds>"] = entry(so[0], f"profiles/{P}_ncu_sorted.md", "37.7 MB")
+    t["newton_sorted_kernel<K5,2 seeds>"] = entry(so[1], f"profiles/{P}_ncu_sorted.md", "75.5 MB")
+    k4 = raw(os.path.join(OUT, f"{P}_prof_seq_k4.ncu-rep"))
     name = "newton_seq_kernel<K4,2 seeds>" if "false" in k4[0]["Kernel Name"] or ", 0>" in k4[0]["Kernel Name"] else "newton_seq_kernel[contracted]<K4,2 seeds>"
-    t[name] = entry(k4[0], "profiles/r2_ncu_seq_k4.md", "62.9 MB")
-    k8 = raw(os.path.join(OUT, "r2_prof_seq_k1x8.ncu-rep"))
-    t["newton_seq_kernel[contracted]<K1,8 seeds>"] = entry(k8[0], "profiles/r2_ncu_seq_k1x8.md", "2^20 x (48 + 1 + 16 + 1 + 24) B = 94.4 MB")
+    t[name] = entry(k4[0], f"profiles/{P}_ncu_seq_k4.md", "62.9 MB")
+    k8 = raw(os.path.join(OUT, f"{P}_prof_seq_k1x8.ncu-rep"))
+    t["newton_seq_kernel[contracted]<K1,8 seeds>"] = entry(k8[0], f"profiles/{P}_ncu_seq_k1x8.md", "2^20 x (48 + 1 + 16 + 1 + 24) B = 94.4 MB")
     json.dump(t, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     cmd = "ncu --set full --clock-control none --import-source on"
-    summary(os.path.join(OUT, "r2_prof_static.ncu-rep"),
+    summary(os.path.join(OUT, f"{P}_prof_static.ncu-rep"),
             f"Contracted static kernels (GCS_VARIANT_CONTRACTED for K1 / K5 with 2 seeds = newton_static_kernel<KIND, 2, true>), round 2\n\nlibrary: {lib}\n\n"
             f"command: `{cmd} -k regex:newton_static_kernel -s 10 -c 2 python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline` (after the same "
-            "command exited 0 without ncu); launch list of the same command: `profiles/r2_launches.csv`", "r2_ncu_contracted.md")
-    summary(os.path.join(OUT, "r2_prof_sorted.ncu-rep"),
+            f"command exited 0 without ncu); launch list of the same command: `profiles/{P}_launches.csv`", f"{P}_ncu_contracted.md")
+    summary(os.path.join(OUT, f"{P}_prof_sorted.ncu-rep"),
             f"Bit-identical default kernels (GCS_VARIANT_DEFAULT at 2^19 = newton_sorted_kernel<KIND, 2, 128, 128, false>), round 2\n\nlibrary: {lib}\n\n"
-            f"command: `{cmd} -k regex:newton_sorted_kernel -s 4 -c 2 python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline`", "r2_ncu_sorted.md")
-    summary(os.path.join(OUT, "r2_prof_seq_k4.ncu-rep"),
+            f"command: `{cmd} -k regex:newton_sorted_kernel -s 4 -c 2 python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline`", f"{P}_ncu_sorted.md")
+    summary(os.path.join(OUT, f"{P}_prof_seq_k4.ncu-rep"),
             f"Sequential kernel on K4 (newton_seq_kernel<4, 2, .>, 2^19 sub-systems without parallel line pairs), round 2\n\nlibrary: {lib}\n\n"
-            f"command: `{cmd} -k regex:newton_seq_kernel -s 4 -c 1 python scratch/k4_hbm.py`", "r2_ncu_seq_k4.md")
-    summary(os.path.join(OUT, "r2_prof_seq_k1x8.ncu-rep"),
+            f"command: `{cmd} -k regex:newton_seq_kernel -s 4 -c 1 python scratch/k4_hbm.py`", f"{P}_ncu_seq_k4.md")
+    summary(os.path.join(OUT, f"{P}_prof_seq_k1x8.ncu-rep"),
             f"Sequential kernel on the 8-seed K1 (newton_seq_kernel<1, 8, true>, 2^20 sub-systems x 8 seeds: configs[2]), round 2\n\nlibrary: {lib}\n\n"
-            f"command: `{cmd} -k regex:newton_seq_kernel -s 3 -c 1 python scratch/kbench.py 5 1 1048576 8`", "r2_ncu_seq_k1x8.md")
+            f"command: `{cmd} -k regex:newton_seq_kernel -s 3 -c 1 python scratch/kbench.py 5 1 1048576 8`", f"{P}_ncu_seq_k1x8.md")
     for k, v in t.items():
         if isinstance(v, dict):
             print(k, v["dram_bytes_per_launch"], f"{v['executed_flops_per_launch']:.3e}", v["launch_us_under_ncu"])

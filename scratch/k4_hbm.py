@@ -10,7 +10,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = torch.cuda.current_stream()
 for n in (1 << 19, 1 << 22):
     hb = synth.make_pll(n, parallel_every=0)
-    for variant in (1, 3, 6, 8, 9):
+    for variant in (5, 8, 9):
         db = capi.DeviceBatch(hb, "cuda:0", want_cand=False, variant=variant)
         for _ in range(3): db.solve()
         ts = []

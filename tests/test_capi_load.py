@@ -95,14 +95,15 @@ def test_argument_checks_of_the_round_2_entry_points_need_no_device(gcs, built):
     arr = (C.POINTER(capi.CBatch) * 2)(C.pointer(cb), C.pointer(cb))
     assert lib.gcs_b200_solve_many(arr, 2, 0, None) == capi.GCS_E_INVALID    # host pointers
     assert b"device pointers" in lib.gcs_b200_last_error()
-    cb.variant = 10
+    cb.variant = 11
     assert lib.gcs_b200_solve_host(C.byref(cb), 0) == capi.GCS_E_INVALID and b"unknown variant" in lib.gcs_b200_last_error()
-    # kernel mapping a class resolves to: K4 and the 8-seed K1 take the sequential kernel
+    # kernel mapping a class resolves to: the bit-identical K4 and the 8-seed K1 take the sequential kernel, the contracted K4 the linear one
     R = lib.gcs_b200_resolve_variant
     assert R(capi.VARIANT_DEFAULT, 1, 1 << 19, 2) == capi.VARIANT_SORTED and R(capi.VARIANT_DEFAULT, 1, 1000, 2) == capi.VARIANT_STATIC
-    assert R(capi.VARIANT_DEFAULT, 4, 1 << 19, 2) == capi.VARIANT_SEQ and R(capi.VARIANT_CONTRACTED, 4, 1 << 19, 2) == capi.VARIANT_SEQ
+    assert R(capi.VARIANT_DEFAULT, 4, 1 << 19, 2) == capi.VARIANT_SEQ and R(capi.VARIANT_CONTRACTED, 4, 1 << 19, 2) == capi.VARIANT_CONTRACTED_LINEAR
     assert R(capi.VARIANT_CONTRACTED, 1, 1 << 19, 2) == capi.VARIANT_CONTRACTED_STATIC
     assert R(capi.VARIANT_CONTRACTED, 1, 1 << 19, 8) == capi.VARIANT_CONTRACTED_SEQ
+    assert R(capi.VARIANT_CONTRACTED, 4, 100, 8) == capi.VARIANT_CONTRACTED_LINEAR and R(capi.VARIANT_CONTRACTED_LINEAR, 1, 1 << 19, 2) == capi.VARIANT_CONTRACTED_STATIC
     assert R(capi.VARIANT_REFILL, 3, 5, 2) == capi.VARIANT_REFILL
     assert lib.gcs_b200_pcie_probe(0, 0, 1, 1, 0, 1, (C.c_double * 4)()) == capi.GCS_E_INVALID
 

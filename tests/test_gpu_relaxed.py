@@ -217,3 +217,120 @@ def test_contract_roots_next_to_a_centre(gpu, gcs, variant):
     worst = assert_batches_within_contract(hb, ref, f"needle triangles, variant {variant}")
     assert worst <= 1e-10  # the closed form is far inside the contract here, as the Cramer form was
     assert (ref.converged == 1).mean() > 0.99
+
+
+# ---- K4 in the contracted class: the linear kernel (GCS_VARIANT_CONTRACTED_LINEAR, newton_linear_kernel) ----
+LINEAR = 10
+
+
+def _k4_pair(gpu, gcs, n, mutate=None, guesses=None, **kw):
+    def make():
+        hb = gcs.synth.make(4, n, **kw)
+        if mutate is not None:
+            mutate(hb.cols, hb)
+        hb.guesses = guesses
+        return hb
+    hb = make()
+    hb.variant = LINEAR
+    gpu.solve_host(hb.alloc_outputs(), 0)
+    ref = O.solve(make().alloc_outputs())
+    return hb, ref
+
+
+@pytest.mark.parametrize("n_seeds", [2, 8])
+@pytest.mark.parametrize("n", [1, 2, 31, 64, 65, 127, 4099, 1 << 19])
+def test_linear_kernel_sizes_and_seed_counts(gpu, gcs, n, n_seeds):
+    """Includes the generator's parallel pairs (one row in 13: never converge, nearest-to-canvas) and
+    collinear codes: not certified, so they come out of the literal code bit for bit."""
+    import ctypes as C
+    lib, st = gcs.capi.load(), (C.c_uint64 * 8)()
+    lib.gcs_b200_contracted_stats_ex(0, st, 1)
+    hb, ref = _k4_pair(gpu, gcs, n, n_seeds=n_seeds)
+    lib.gcs_b200_contracted_stats_ex(0, st, 1)
+    worst = assert_batches_within_contract(hb, ref, f"K4 linear n {n} seeds {n_seeds}")
+    assert worst <= 1e-10
+    if n >= 4099:  # parallel pairs (one row in 13) and collinear codes cannot be certified: nearly all of the rest must be
+        hard = ((ref.iters != 2).any(axis=0) | ((hb.code & 0x30) != 0)).sum()
+        assert sum(st) <= (hard + 0.02 * n) * n_seeds, f"literal runs {list(st)} of {n * n_seeds}, {hard} hard rows"
+
+
+def test_linear_kernel_resolution(gpu, gcs):
+    R = gcs.capi.load().gcs_b200_resolve_variant
+    assert R(gcs.capi.VARIANT_CONTRACTED, 4, 17, 2) == LINEAR and R(LINEAR, 4, 1 << 20, 8) == LINEAR
+    hb = gcs.synth.make(1, 3000)  # any other kind: as VARIANT_CONTRACTED
+    hb.variant = LINEAR
+    gpu.solve_host(hb.alloc_outputs(), 0)
+    assert_batches_within_contract(hb, O.solve(gcs.synth.make(1, 3000).alloc_outputs()), "K1 through the linear variant id")
+
+
+@pytest.mark.parametrize("mode", ["box", "far", "near_root", "tiny", "mixed"])
+def test_linear_kernel_explicit_seeds(gpu, gcs, mode):
+    """Seeds the two certified decisions depend on: inside / astride the iteration-0 box, within a few
+    tolerances of the solution (the first update is then NOT longer than the threshold for certain),
+    and 1e7 .. 1e11 away (the second update - the landing's rounding error - straddles the threshold:
+    the case that found the w1 hole of the generic guards)."""
+    n = 1 << 16
+    rng = np.random.default_rng(808 + len(mode))
+    base = O.solve(gcs.synth.make(4, n, seed=0xB0B).alloc_outputs())
+    sol = np.stack([base.out[0], base.out[1]])  # [2, n]
+    if mode == "box":
+        g = rng.uniform(-3000, 3000, size=(2, 2, n))
+    elif mode == "far":
+        g = rng.uniform(-1.0, 1.0, size=(2, 2, n)) * 10.0 ** rng.uniform(7, 11, size=(2, 1, n))
+    elif mode == "near_root":
+        g = sol[None] + rng.normal(0, 1, size=(2, 2, n)) * 10.0 ** rng.uniform(-9, -3, size=(2, 1, n))
+    elif mode == "tiny":
+        g = rng.uniform(-3e-5, 3e-5, size=(2, 2, n))
+    else:
+        g = rng.uniform(-3000, 3000, size=(2, 2, n))
+        g[0, :, ::3] = rng.uniform(-9e-6, 9e-6, size=g[0, :, ::3].shape)     # seed 0 exits at i = 0, seed 1 does not
+        g[1, :, 1::3] = (sol + rng.normal(0, 3e-6, size=sol.shape))[:, 1::3]  # seed 1 starts within the tolerance of the solution
+    g = np.ascontiguousarray(np.where(np.isfinite(g), g, 1.0))
+    hb, ref = _k4_pair(gpu, gcs, n, guesses=g, seed=0xB0B)
+    assert_batches_within_contract(hb, ref, f"K4 linear, explicit seeds: {mode}")
+    if mode == "far":
+        assert len(np.unique(ref.iters)) >= 2  # some runs do need a third update: those must not have been certified
+
+
+def test_linear_kernel_degenerate_inputs(gpu, gcs):
+    """What no closed form may vouch for comes out of the literal code: bit-identical candidates."""
+    n = 4096
+
+    def mutate(c, hb):
+        c[0][0::16] = np.nan
+        c[5][1::16] = np.inf
+        c[2][2::16], c[3][2::16] = c[0][2::16], c[1][2::16]              # line 1 is a point
+        c[7][3::16] = c[5][3::16] + (c[2][3::16] - c[0][3::16])
+        c[8][3::16] = c[6][3::16] + (c[3][3::16] - c[1][3::16])          # parallel lines
+        c[5][4::16], c[6][4::16], c[7][4::16], c[8][4::16] = c[0][4::16], c[1][4::16], c[2][4::16], c[3][4::16]  # the same line twice
+        c[4][5::16] = 0.0                                                # s1 = 0: the orientation the selection tests is rounding noise
+        c[4][6::16] = 1e-13                                              # ... or next to it
+        c[0][7::16] = 1e300
+        c[7][8::16] = c[5][8::16] + (c[2][8::16] - c[0][8::16]) * (1 + 1e-9)
+        c[8][8::16] = c[6][8::16] + (c[3][8::16] - c[1][8::16]) * (1 - 1e-9)   # a hair off parallel: ill conditioned
+        for col in (0, 1, 2, 3, 5, 6, 7, 8):
+            c[col][9::16] *= 1e-7                                        # lines shorter than the tolerance, |cross| under the absolute epsilon
+        hb.code[10::16] |= gcs.capi.CODE_COLLINEAR
+        hb.code[11::16] |= gcs.capi.CODE_CANVAS_PARALLEL
+    hb, ref = _k4_pair(gpu, gcs, n, mutate=mutate, parallel_every=0)
+    assert_batches_within_contract(hb, ref, "K4 linear, degenerate inputs")
+    for o in (0, 1, 2, 3, 4, 5, 7, 10, 11):
+        a, b = hb.cand[..., o::16], ref.cand[..., o::16]
+        assert ((bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))).all(), f"row class {o} was certified"
+
+
+@pytest.mark.parametrize("scale", [1e-7, 1e-5, 1e-3, 1e3, 1e6])
+@pytest.mark.parametrize("ratio", [1.0, 1e-4])
+def test_linear_kernel_scales_and_mismatched_lengths(gpu, gcs, scale, ratio):
+    """Every length scaled (the thresholds are absolute), and line 2 made `ratio` times as long as
+    line 1 (|J|_F^2 / |det| grows with the mismatch: the bound on the second update must see it)."""
+    n = 1 << 17
+
+    def mutate(c, hb):
+        for col in range(12):
+            c[col] *= scale
+        mx, my = 0.5 * (c[5] + c[7]), 0.5 * (c[6] + c[8])
+        c[5][:], c[7][:] = mx + (c[5] - mx) * ratio, mx + (c[7] - mx) * ratio
+        c[6][:], c[8][:] = my + (c[6] - my) * ratio, my + (c[8] - my) * ratio
+    hb, ref = _k4_pair(gpu, gcs, n, mutate=mutate, parallel_every=0, seed=0xD1CE)
+    assert_batches_within_contract(hb, ref, f"K4 linear scale {scale} ratio {ratio}")
