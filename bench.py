@@ -649,6 +649,16 @@ def bench_kinds(ctx, steps=10):
         if "bit_identical" in dbs:
             same, worst = ctx.contract_check(dbs["line_variant"], dbs["bit_identical"])
             row["contract_check"] = {"iters_flags_roots_equal": same, "max_rel_coordinate_error": worst}
+        if kind == 4:  # the HBM-bound kind at a size where the launch's fixed cost no longer shows
+            del dbs, db
+            n4 = 1 << 22
+            db4 = capi.DeviceBatch(synth.make_pll(n4, parallel_every=0), ctx.dev, want_cand=False, variant=args.variant)
+            t4 = float(np.mean(ctx.time_launches([db4], steps, warmup=2)[0])) * 1e-3
+            b4 = db4.algorithmic_bytes()
+            row["at_4m"] = {"n": n4, "kernel": ctx.lib.gcs_b200_kernel_name(kind, 2, args.variant).decode(), "launch_ms": t4 * 1e3,
+                            "hbm_gbs": b4 / t4 / 1e9, "hbm_frac": b4 / t4 / 1e9 / peaks.get("hbm_gbs", 6650.0),
+                            "algorithmic_bytes_per_launch": b4}
+            del db4
         row["bound"] = "hbm" if kind == 4 else "fp64"
         out[f"K{kind}"] = row
     return out
@@ -933,8 +943,9 @@ def main():
         "algorithmic_flops_per_launch": w_k1,
         "algorithmic_flops_note": ("SURVEY.md 8d work model: (iters+1) * 64 flops per seed + selection, from the measured iteration "
                                    "counts - the reference algorithm's work (Householder QR counted at 44 flops per update).  The "
-                                   "contracted kernels reach the same iterates with a closed-form solve (~33 executed flops per update, "
-                                   "FMA = 2), so for them `achieved` is a rate of reference-algorithm work, not of executed flops; see "
+                                   "contracted kernels reach the same iterates with a closed-form landing and the scalar Newton map along the "
+                                   "constraint line (8 FP64 instructions per update), so for them `achieved` is a rate of "
+                                   "reference-algorithm work, not of executed flops; see "
                                    "executed_*" if fma_kernel else
                                    "SURVEY.md 8d work model from the measured iteration counts"),
         "executed_flops_per_launch": traffic.get(kernel_name, {}).get("executed_flops_per_launch"),

@@ -150,18 +150,21 @@ extern "C" {
 #define GCS_VARIANT_REFILL 2 /* persistent CTAs, TMA-staged tiles, warp-level lane refill */
 #define GCS_VARIANT_SORTED 3 /* CTA tiles; runs sorted by predicted update count, one lane finishes one run */
 #define GCS_VARIANT_PAIR 4 /* one lane per sub-system, its two seeds iterated in lockstep (2 seeds only; else static) */
-/* Tolerance-class arithmetic (csrc/newton_relaxed.cuh): closed-form 2x2 solve on fused
- * multiply-adds.  Contract: iteration counts, convergence flags and root indices equal to every
+/* Tolerance-class arithmetic (csrc/newton_relaxed.cuh): the update from the seed as a closed-form
+ * 2x2 solve on fused multiply-adds, the updates after it as the scalar Newton map along the line
+ * every equation pair of the path contains (the radical line for K1); K4, a linear pair, is solved
+ * in closed form with its iteration counts certified (CONTRACTED_LINEAR).  Contract: iteration counts, convergence flags and root indices equal to every
  * other variant's; coordinates within 1e-9 relative (the north star's tolerance) instead of bit
  * for bit.  The discrete half of the contract rests on guards (runs and selections whose decisions
  * could depend on the arithmetic are detected and redone with the literal device functions) whose
  * sufficiency is an error-analysis argument plus evidence - tests/test_gpu_relaxed.py,
- * tests/test_gpu_soak.py and the soaks of profiles/ (> 1e8 sub-systems without a difference; an
- * earlier soak did find one, which is why the carry term exists) - NOT a machine-checked proof.
+ * tests/test_gpu_soak.py and the soaks of profiles/ (> 1e8 sub-systems without a difference on the
+ * final arithmetic; earlier soaks did find two holes, which is why the carry term exists and why the
+ * line constants are formed from cancellation-free factors) - NOT a machine-checked proof.
  * Opt-in: DEFAULT never resolves to it, and the host mirror stays on the bit-identical kernels.
  * CONTRACTED = CONTRACTED_STATIC (measured fastest at every size) except the 8-seed K1, which takes
- * CONTRACTED_SEQ, and K4, which takes CONTRACTED_LINEAR; CONTRACTED_SORTED maps the same arithmetic
- * onto the sorted tiles. */
+ * CONTRACTED_SEQ, and K4, which takes CONTRACTED_LINEAR; CONTRACTED_SORTED runs the closed-form
+ * 2x2 solve for every update on the sorted tiles (its runs are handed from lane to lane mid-way). */
 #define GCS_VARIANT_CONTRACTED 5
 #define GCS_VARIANT_CONTRACTED_STATIC 6
 #define GCS_VARIANT_CONTRACTED_SORTED 7

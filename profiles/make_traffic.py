@@ -17,15 +17,24 @@ OUT = os.path.join(ROOT, "gpurun_out")
 def raw(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    return [dict(zip(rows[0], r)) for r in rows[2:]]
+    units = dict(zip(rows[0], rows[1]))  # ncu picks a unit per column and capture (Kbyte / Mbyte / Gbyte ...)
+    return [dict(zip(rows[0], r), _units=units) for r in rows[2:]]
 
 
 def f(x):
     return float(x.replace(",", ""))
 
 
+BYTES = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+
+
+def mbytes(d, key):
+    return f(d[key]) * BYTES[d["_units"][key]]
+
+
 def entry(d, src, alg):
-    rd, wr = f(d["dram__bytes_read.sum"]), f(d["dram__bytes_write.sum"])
+    rd, wr = mbytes(d, "dram__bytes_read.sum"), mbytes(d, "dram__bytes_write.sum")
+    assert d["_units"]["gpu__time_duration.sum"] in ("us", "usecond"), d["_units"]["gpu__time_duration.sum"]
     cyc = f(d["sm__cycles_elapsed.avg"])
     fl = (f(d["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed"])
           + f(d["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed"])
@@ -56,6 +65,9 @@ def main():
     k4 = raw(os.path.join(OUT, f"{P}_prof_seq_k4.ncu-rep"))
     name = "newton_seq_kernel<K4,2 seeds>" if "false" in k4[0]["Kernel Name"] or ", 0>" in k4[0]["Kernel Name"] else "newton_seq_kernel[contracted]<K4,2 seeds>"
     t[name] = entry(k4[0], f"profiles/{P}_ncu_seq_k4.md", "62.9 MB")
+    lin = os.path.join(OUT, f"{P}_prof_linear_k4.ncu-rep")
+    if os.path.exists(lin):
+        t["newton_linear_kernel[contracted]<K4,2 seeds>"] = entry(raw(lin)[0], f"profiles/{P}_ncu_linear_k4.md", "62.9 MB")
     k8 = raw(os.path.join(OUT, f"{P}_prof_seq_k1x8.ncu-rep"))
     t["newton_seq_kernel[contracted]<K1,8 seeds>"] = entry(k8[0], f"profiles/{P}_ncu_seq_k1x8.md", "2^20 x (48 + 1 + 16 + 1 + 24) B = 94.4 MB")
     json.dump(t, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
@@ -70,6 +82,9 @@ def main():
     summary(os.path.join(OUT, f"{P}_prof_seq_k4.ncu-rep"),
             f"Sequential kernel on K4 (newton_seq_kernel<4, 2, .>, 2^19 sub-systems without parallel line pairs), round 2\n\nlibrary: {lib}\n\n"
             f"command: `{cmd} -k regex:newton_seq_kernel -s 4 -c 1 python scratch/k4_hbm.py`", f"{P}_ncu_seq_k4.md")
+    if os.path.exists(lin):
+        summary(lin, f"Linear kernel on K4 (newton_linear_kernel<2>: GCS_VARIANT_CONTRACTED for K4; 2^19 sub-systems without parallel line pairs), round 2\n\nlibrary: {lib}\n\n"
+                f"command: `{cmd} -k regex:newton_linear_kernel -s 4 -c 1 python scratch/k4_hbm.py`", f"{P}_ncu_linear_k4.md")
     summary(os.path.join(OUT, f"{P}_prof_seq_k1x8.ncu-rep"),
             f"Sequential kernel on the 8-seed K1 (newton_seq_kernel<1, 8, true>, 2^20 sub-systems x 8 seeds: configs[2]), round 2\n\nlibrary: {lib}\n\n"
             f"command: `{cmd} -k regex:newton_seq_kernel -s 3 -c 1 python scratch/kbench.py 5 1 1048576 8`", f"{P}_ncu_seq_k1x8.md")

@@ -1,8 +1,12 @@
 set -x
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_relaxed.py -m gpu -x -q -k "linear or k4 or K4" > gpurun_out/r3g_pytest_linear.log 2>&1; tail -15 gpurun_out/r3g_pytest_linear.log
-python -m pytest tests/test_gpu_relaxed.py tests/test_gpu_soak.py tests/test_gpu_margins.py tests/test_capi_load.py -m gpu -x -q > gpurun_out/r3g_pytest.log 2>&1; tail -5 gpurun_out/r3g_pytest.log
-python scratch/k4_hbm.py > gpurun_out/r3g_k4.log 2>&1; cat gpurun_out/r3g_k4.log
-( time timeout 120 python scratch/soak_relaxed_guesses.py 1048576 ) > gpurun_out/r3g_soak2.log 2>&1; grep "K4\|violate" gpurun_out/r3g_soak2.log
-( time timeout 120 python scratch/soak_relaxed_scaled.py 1048576 ) > gpurun_out/r3g_soak3.log 2>&1; grep "K4\|violate" gpurun_out/r3g_soak3.log
-python scratch/kbench.py 5 1 1048576 8 > gpurun_out/r3g_kbench.log 2>&1; cat gpurun_out/r3g_kbench.log
+for L in "" build/alt_seq8.so build/alt_seq10.so; do
+  echo "== lib ${L:-default}" >> gpurun_out/r3h_seq.log
+  GCS_B200_LIB=${L:+$PWD/$L} python scratch/kbench.py 8 1,5 524288 2 >> gpurun_out/r3h_seq.log 2>&1
+  GCS_B200_LIB=${L:+$PWD/$L} python scratch/kbench.py 8 1,5 4194304 2 >> gpurun_out/r3h_seq.log 2>&1
+done
+cat gpurun_out/r3h_seq.log
+ncu --set full --clock-control none --import-source on -k regex:newton_seq_kernel -s 3 -c 1 -f -o gpurun_out/r3h_prof_seq_k1 python scratch/kbench.py 8 1 2097152 2 > gpurun_out/r3h_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:newton_seq_kernel -s 3 -c 1 -f -o gpurun_out/r3h_prof_seq_k5 python scratch/kbench.py 8 5 2097152 2 >> gpurun_out/r3h_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:newton_static_kernel -s 3 -c 1 -f -o gpurun_out/r3h_prof_static_k5 python scratch/kbench.py 5 5 2097152 2 >> gpurun_out/r3h_ncu.log 2>&1
+ls -la gpurun_out/r3h_prof*
