@@ -232,10 +232,13 @@ static __device__ __noinline__ RunOut literal_run_from_global(const BatchDev& p,
     return r;
 }
 
-// contracted: held to 80 registers (6 CTAs per SM); measured 8 / 6 / 5 CTAs: K1 55.3 / 51.7 / 50.7 us,
-// K3 80.4 / 73.7 / 74.8 us per 2^19
+// contracted: held to 64 registers (8 CTAs per SM).  With the Cramer form in the loop 80 registers
+// (6 CTAs) were the faster choice (8 / 6 / 5 CTAs: K1 55.3 / 51.7 / 50.7 us, K3 80.4 / 73.7 / 74.8 us per
+// 2^19); the line form's loop carries a fraction of that state, and the kernel - one dependent chain
+// per lane - wants the warps: 8 / 6 CTAs: K1 x 8 seeds 228 / 235 us per 2^20, K1 225.8 / 244.6 us, K5
+// 218.1 / 225.3 us per 2^22 with 2 seeds (10 CTAs = 48 registers: slower again)
 #ifndef GCS_SEQ_MINB
-#define GCS_SEQ_MINB 6
+#define GCS_SEQ_MINB 8
 #endif
 #ifndef GCS_SEQ_LIT_MINB
 #define GCS_SEQ_LIT_MINB 5
