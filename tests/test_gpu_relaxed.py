@@ -334,3 +334,64 @@ def test_linear_kernel_scales_and_mismatched_lengths(gpu, gcs, scale, ratio):
         c[6][:], c[8][:] = my + (c[6] - my) * ratio, my + (c[8] - my) * ratio
     hb, ref = _k4_pair(gpu, gcs, n, mutate=mutate, parallel_every=0, seed=0xD1CE)
     assert_batches_within_contract(hb, ref, f"K4 linear scale {scale} ratio {ratio}")
+
+
+# ---- degenerate inputs of the kinds whose runs take the line form through their own constants (K2, K3, K5) ----
+def _degenerate_rows(kind, c):
+    """Mutates the columns `c` of a generator batch, row class o = index % 16; returns the classes whose
+    candidates must come out of the literal code bit for bit (nothing a closed form may vouch for)."""
+    if kind == 3:  # circle (px, py, r) and the line at signed distance s from (xa, ya) -> (xb, yb)
+        ex, ey = c[5] - c[3], c[6] - c[4]
+        ln = np.hypot(ex, ey)
+        off = ((c[0] - c[3]) * ey - (c[1] - c[4]) * ex) / ln + c[7]   # the centre's offset from the line
+        c[2][0::16] = np.nan
+        c[3][1::16] = np.inf
+        c[5][2::16], c[6][2::16] = c[3][2::16], c[4][2::16]          # the line is a point
+        c[2][3::16] = 0.0                                            # zero radius
+        c[2][4::16] = np.abs(off)[4::16]                             # tangent line: a double root, linear convergence into det = 0
+        c[2][5::16] = 0.5 * np.abs(off)[5::16]                       # the line misses the circle: no real root
+        c[0][6::16] = 1e300
+        c[2][7::16] = np.abs(off)[7::16] * (1 + 1e-12)               # a hair inside tangency
+        c[7][8::16] -= off[8::16]                                    # the line through the centre: c = 0, h = r (well conditioned)
+        return (0, 1, 2, 6)
+    if kind == 2:  # dX x + dY y + (s1 - s2) = 0 and the unit circle
+        dX, dY = c[2] - c[0], c[3] - c[1]
+        ln = np.hypot(dX, dY)
+        c[4][0::16] = np.nan
+        c[0][1::16] = np.inf
+        c[2][2::16], c[3][2::16] = c[0][2::16], c[1][2::16]          # p2 = p1: no line
+        c[4][3::16], c[5][3::16] = ln[3::16], 0.0                    # |s1 - s2| = |p2 - p1|: tangent
+        c[4][4::16], c[5][4::16] = 2.0 * ln[4::16], 0.0              # |s1 - s2| > |p2 - p1|: no root
+        c[4][5::16] = c[5][5::16]                                    # s1 = s2: the line through the origin
+        c[2][6::16] = 1e300
+        c[4][7::16], c[5][7::16] = ln[7::16] * (1 - 1e-12), 0.0      # a hair inside tangency
+        return (0, 1, 2, 6)
+    assert kind == 5  # fdy x - fdx y = cosA |fd| and the unit circle
+    c[2][0::16] = np.nan
+    c[0][1::16] = np.inf
+    c[0][2::16], c[1][2::16] = 0.0, 0.0                              # no direction
+    c[2][3::16] = 1.0                                                # cosA = 1: tangent
+    c[2][4::16] = 1.5                                                # no root
+    c[2][5::16] = 0.0                                                # right angle: the line through the origin
+    c[0][6::16] = 1e300
+    c[2][7::16] = -1.0 + 1e-12                                       # a hair inside tangency
+    return (0, 1, 2, 6)
+
+
+@pytest.mark.parametrize("variant", [5, 6, 8])
+@pytest.mark.parametrize("kind", [2, 3, 5])
+def test_contract_degenerate_inputs_of_the_line_form_kinds(gpu, gcs, kind, variant):
+    n = 4096
+
+    def make():
+        hb = gcs.synth.make(kind, n, seed=0xDE6 + kind)
+        make.literal = _degenerate_rows(kind, hb.cols)
+        return hb
+    hb = make()
+    hb.variant = variant
+    gpu.solve_host(hb.alloc_outputs(), 0)
+    ref = O.solve(make().alloc_outputs())
+    assert_batches_within_contract(hb, ref, f"K{kind} variant {variant}, degenerate inputs")
+    for o in make.literal:
+        a, b = hb.cand[..., o::16], ref.cand[..., o::16]
+        assert ((bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))).all(), f"K{kind} row class {o} did not come out of the literal code"
