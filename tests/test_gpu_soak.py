@@ -117,3 +117,42 @@ def test_eight_seeds(gpu, gcs, offset, kind):
 def test_sorted_mapping_of_the_same_arithmetic(gpu, gcs, offset, kind):
     _check(gpu, lambda: gcs.synth.make(kind, 1 << 18, seed=0xABBA + offset), f"K{kind} contracted-sorted",
            variant=gpu.VARIANT_CONTRACTED_SORTED)
+
+
+@pytest.mark.parametrize("lo,hi", [(-6, -2), (-9, -5), (-3, 0)])
+def test_needle_triangles(gpu, gcs, offset, lo, hi):
+    """K1 with the free point 10^lo .. 10^hi from one of the centres: well conditioned, so the runs stay on
+    the closed-form path, and the line form's half chord has to come from cancellation-free factors
+    (tests/test_gpu_relaxed.py::test_contract_roots_next_to_a_centre is the fixed-seed regression test)."""
+    n = 1 << 18
+    rng = np.random.default_rng(7001 + offset + hi)
+    rho = 10.0 ** rng.uniform(lo, hi, size=n)
+    phi = rng.uniform(0.02, np.pi - 0.02, size=n) * np.where(rng.random(n) < 0.5, 1.0, -1.0)
+    near_b = rng.random(n) < 0.5
+
+    def make():
+        hb = gcs.synth.make(1, n, seed=0xBEE5 + offset)
+        ax, ay, ra, bx, by, rb = hb.cols
+        cx, cy = np.where(near_b, bx, ax), np.where(near_b, by, ay)
+        px, py = cx + rho * np.cos(phi), cy + rho * np.sin(phi)
+        ra[:] = np.hypot(px - ax, py - ay)
+        rb[:] = np.hypot(px - bx, py - by)
+        return hb
+    _check(gpu, make, f"K1 needles 1e{lo} .. 1e{hi}")
+
+
+@pytest.mark.parametrize("n_seeds", [2, 8])
+def test_linear_pairs(gpu, gcs, offset, n_seeds):
+    """K4 through newton_linear_kernel on fresh streams, lines of mismatched lengths (1 .. 1e-3)."""
+    n = 1 << 18
+    rng = np.random.default_rng(515 + offset + n_seeds)
+    ratio = 10.0 ** rng.uniform(-3, 0, size=n)
+
+    def make():
+        hb = gcs.synth.make(4, n, seed=0xF00D + offset, n_seeds=n_seeds)
+        c = hb.cols
+        mx, my = 0.5 * (c[5] + c[7]), 0.5 * (c[6] + c[8])
+        c[5][:], c[7][:] = mx + (c[5] - mx) * ratio, mx + (c[7] - mx) * ratio
+        c[6][:], c[8][:] = my + (c[6] - my) * ratio, my + (c[8] - my) * ratio
+        return hb
+    _check(gpu, make, f"K4 x {n_seeds} seeds, mismatched lengths")
