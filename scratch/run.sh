@@ -1,5 +1,9 @@
 set -x
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_soak.py -m gpu -x -q > gpurun_out/r3k_pytest.log 2>&1; tail -8 gpurun_out/r3k_pytest.log
-( time timeout 200 python scratch/soak_relaxed.py 2097152 0x9000 ) > gpurun_out/r3k_soak1.log 2>&1; tail -4 gpurun_out/r3k_soak1.log
-( time timeout 200 python scratch/soak_relaxed.py 2097152 0xA000 ) > gpurun_out/r3k_soak2.log 2>&1; tail -4 gpurun_out/r3k_soak2.log
+for L in "" build/alt_rlx6.so build/alt_rlx10.so build/alt_rlx12.so; do
+  echo "== lib ${L:-default}" >> gpurun_out/r3l_occ.log
+  GCS_B200_LIB=${L:+$PWD/$L} python scratch/kbench.py 5 1,5 524288 2 2>&1 | sed 's/literal re-runs.*//' >> gpurun_out/r3l_occ.log
+  GCS_B200_LIB=${L:+$PWD/$L} python scratch/kbench.py 5 1,5 4194304 2 2>&1 | sed 's/literal re-runs.*//' >> gpurun_out/r3l_occ.log
+  GCS_B200_LIB=${L:+$PWD/$L} python scratch/k4_hbm.py 2>&1 | grep "variant 5" >> gpurun_out/r3l_occ.log
+done
+cat gpurun_out/r3l_occ.log
