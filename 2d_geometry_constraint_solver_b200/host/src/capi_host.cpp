@@ -22,6 +22,7 @@
 #include <gcs/model/gcs_data_structures.hpp>
 #include <gcs/orchestration/geometric_constraint_system.hpp>
 
+#include "solving/bottom_up/merge3_batched.hpp"
 #include "solving/bottom_up/merge3_ppp_batched.hpp"
 #include "solving/bottom_up/merge3_solver_common.hpp"
 #include "solving/component_solver.hpp"
@@ -590,7 +591,20 @@ GCS_API double gcs_host_m3_score(int n_el, const int32_t* type, const double* ca
 // cluster c = 0..2 holds counts[c] elements (ids / pose4 concatenated, in insertion order).
 // Returns the size of the merged pose (0: no candidate; -1: error), out_ids ascending; stats[3] =
 // candidates solved, candidates scored, kernel launches; *score = the winning score.
+GCS_API int gcs_host_m3_merge(int which, int n_el, const int32_t* type, const double* canvas4, const int32_t* counts, const int32_t* ids,
+    const double* pose4, int32_t* out_ids, double* out_pose4, double* score, int64_t* stats);
+
 GCS_API int gcs_host_m3_ppp_merge(int n_el, const int32_t* type, const double* canvas4, const int32_t* counts, const int32_t* ids,
+    const double* pose4, int32_t* out_ids, double* out_pose4, double* score, int64_t* stats)
+{
+    return gcs_host_m3_merge(0, n_el, type, canvas4, counts, ids, pose4, out_ids, out_pose4, score, stats);
+}
+
+// The same for every Merge3 case (solving/bottom_up/merge3_batched.hpp): which = 0 PPP, 1 PLL, 2 LPP,
+// 3 LLP enumeration loop, 4 the rigid fallback, 5 the whole merge node (the reference's case order);
+// stats[4] = candidates solved, candidates scored, kernel launches, case that produced the pose
+// (Merge3Case; which itself unless which = 5).  Returns the size of the merged pose (0: none; -1: error).
+GCS_API int gcs_host_m3_merge(int which, int n_el, const int32_t* type, const double* canvas4, const int32_t* counts, const int32_t* ids,
     const double* pose4, int32_t* out_ids, double* out_pose4, double* score, int64_t* stats)
 {
     namespace Bu = Gcs::Solvers::BottomUp;
@@ -616,10 +630,36 @@ GCS_API int gcs_host_m3_ppp_merge(int n_el, const int32_t* type, const double* c
                 else
                     pose[c].emplace(node, Bu::LinePose { Vector2d(p[0], p[1]), Vector2d(p[2], p[3]) });
             }
-        Gcs::B200::Merge3PppReport rep;
-        const auto merged = Gcs::B200::solveMerge3Ppp(g, { &pose[0], &pose[1], &pose[2] }, 0, &rep);
-        if (stats) stats[0] = static_cast<int64_t>(rep.candidates), stats[1] = static_cast<int64_t>(rep.scored), stats[2] = static_cast<int64_t>(rep.launches);
-        if (score) *score = rep.bestScore;
+        const Gcs::B200::Merge3Children children { &pose[0], &pose[1], &pose[2] };
+        std::optional<Bu::ClusterPose> merged;
+        int64_t st[4] = { 0, 0, 0, which };
+        double best = 0.0;
+        if (which == 0) {
+            Gcs::B200::Merge3PppReport rep;
+            merged = Gcs::B200::solveMerge3Ppp(g, children, 0, &rep);
+            st[0] = static_cast<int64_t>(rep.candidates), st[1] = static_cast<int64_t>(rep.scored), st[2] = static_cast<int64_t>(rep.launches);
+            best = rep.bestScore;
+        } else if (which >= 1 && which <= 3) {
+            Gcs::B200::Merge3Report rep;
+            merged = which == 1 ? Gcs::B200::solveMerge3Pll(g, children, 0, &rep)
+                : which == 2    ? Gcs::B200::solveMerge3Lpp(g, children, 0, &rep)
+                                : Gcs::B200::solveMerge3Llp(g, children, 0, &rep);
+            st[0] = static_cast<int64_t>(rep.candidates), st[1] = static_cast<int64_t>(rep.scored), st[2] = static_cast<int64_t>(rep.launches);
+            best = rep.bestScore;
+        } else if (which == 4) {
+            merged = Gcs::B200::solveMerge3Fallback(children);
+        } else if (which == 5) {
+            Gcs::B200::Merge3NodeReport rep;
+            merged = Gcs::B200::solveMerge3Node(g, children, 0, &rep);
+            st[0] = static_cast<int64_t>(rep.candidates), st[1] = static_cast<int64_t>(rep.scored), st[2] = static_cast<int64_t>(rep.launches);
+            st[3] = static_cast<int64_t>(rep.solvedBy);
+            best = rep.bestScore;
+        } else {
+            throw std::invalid_argument("gcs_host_m3_merge: which must be 0..5");
+        }
+        if (stats) stats[0] = st[0], stats[1] = st[1], stats[2] = st[2];
+        if (stats && which != 0) stats[3] = st[3];  // the PPP entry point keeps its three-word layout
+        if (score) *score = best;
         if (!merged) return 0;
         int n = 0;
         for (int i = 0; i < n_el; ++i) {

@@ -24,6 +24,10 @@ CXX="${GCS_REF_CXX:-/usr/bin/g++}"
   "$ref/gui/src/constraint_model.cpp" \
   "$cs/src/solving/bottom_up/merge3_solver_common.cpp" \
   "$cs/src/solving/bottom_up/merge3_ppp_solver.cpp" \
+  "$cs/src/solving/bottom_up/merge3_pll_solver.cpp" \
+  "$cs/src/solving/bottom_up/merge3_lpp_solver.cpp" \
+  "$cs/src/solving/bottom_up/merge3_llp_solver.cpp" \
+  "$cs/src/solving/bottom_up/merge3_fallback_solver.cpp" \
   "$cs/src/model/elements.cpp" "$cs/src/model/constraints.cpp" \
   "$cs/src/solving/solvers/point_point_solvers.cpp" \
   "$cs/src/solving/solvers/point_line_solvers.cpp" \

@@ -9,6 +9,9 @@
 //   estimateRigidTransform / applyRigidTransform   :96-160, :162-178
 //   scoreMergedPose                       :411-456
 //   Merge3PppSolver::solve (the whole enumeration loop)   merge3_ppp_solver.cpp:18-214
+//   Merge3PllSolver / Merge3LppSolver / Merge3LlpSolver::solve   merge3_pll_solver.cpp:15-189, merge3_lpp_solver.cpp:15-208,
+//                                                                  merge3_llp_solver.cpp:15-190
+//   detectUnsolvableMerge3Lll, Merge3FallbackSolver::solve        merge3_fallback_solver.cpp:13-78
 // The point-from-two-points step is inlined in Merge3PppSolver::solve (merge3_ppp_solver.cpp:135-153);
 // gcs_ref_m3_point_pp repeats those three calls on the reference's own functions.
 // Third-party arithmetic (Eigen's JacobiSVD, ColPivHouseholderQR, autodiff) is the stand-ins'.
@@ -19,6 +22,10 @@
 #include <unordered_map>
 #include <vector>
 
+#include "solving/bottom_up/merge3_fallback_solver.hpp"
+#include "solving/bottom_up/merge3_llp_solver.hpp"
+#include "solving/bottom_up/merge3_lpp_solver.hpp"
+#include "solving/bottom_up/merge3_pll_solver.hpp"
 #include "solving/bottom_up/merge3_ppp_solver.hpp"
 #include "solving/bottom_up/merge3_solver_common.hpp"
 #include "solving/equations/equation_primitives.hpp"
@@ -120,12 +127,16 @@ REF_API double gcs_ref_m3_score(int n_el, const int32_t* type, const double* can
     return Bu::scoreMergedPose(g, merged);
 }
 
-// The reference's own Merge3PppSolver::solve on three child clusters of one sketch.
+// The reference's own Merge3 solver classes on three child clusters of one sketch.
 // Elements i = 0..n_el-1 (type 0 point: canvas x,y; 1 line: x1,y1,x2,y2).  Cluster c = 0..2 holds
 // counts[c] elements: ids / pose4 concatenated in the order they are inserted into the cluster's
-// pose map.  Returns the size of the merged pose (0: no candidate), out_ids ascending, out_pose4 per id.
-REF_API int gcs_ref_m3_ppp_merge(int n_el, const int32_t* type, const double* canvas4, const int32_t* counts, const int32_t* ids,
-    const double* pose4, int32_t* out_ids, double* out_pose4)
+// pose map.  which = 0 Merge3PppSolver, 1 Merge3PllSolver, 2 Merge3LppSolver, 3 Merge3LlpSolver,
+// 4 Merge3FallbackSolver, 5 the case order of a merge node (bottom_up_plan_solver.cpp:393-431: the
+// first of PPP, PLL, LPP, LLP that returns a pose; else nothing when detectUnsolvableMerge3Lll;
+// else the fallback) - *solved_by gets the case that produced the pose (5: none).
+// Returns the size of the merged pose (0: none), out_ids ascending, out_pose4 per id.
+REF_API int gcs_ref_m3_merge(int which, int n_el, const int32_t* type, const double* canvas4, const int32_t* counts, const int32_t* ids,
+    const double* pose4, int32_t* out_ids, double* out_pose4, int32_t* solved_by)
 {
     Gcs::ConstraintGraph g;
     std::vector<Gcs::ConstraintGraph::NodeIdType> nodes;
@@ -156,7 +167,29 @@ REF_API int gcs_ref_m3_ppp_merge(int n_el, const int32_t* type, const double* ca
     Gcs::PlanNode node { .kind = Gcs::PlanNodeKind::Merge3,
         .info = Gcs::Merge3Info { .output = Gcs::ClusterId { 9 }, .inputs = { Gcs::ClusterId { 1 }, Gcs::ClusterId { 2 }, Gcs::ClusterId { 3 } }, .outputElements = {} } };
     const Bu::Merge3Context context { .sourceGraph = g, .node = node, .children = children, .solvedNodePose = poses };
-    const auto merged = Bu::Merge3PppSolver::solve(context);
+    std::optional<Bu::ClusterPose> merged;
+    int by = which;
+    switch (which) {
+    case 0: merged = Bu::Merge3PppSolver::solve(context); break;
+    case 1: merged = Bu::Merge3PllSolver::solve(context); break;
+    case 2: merged = Bu::Merge3LppSolver::solve(context); break;
+    case 3: merged = Bu::Merge3LlpSolver::solve(context); break;
+    case 4: merged = Bu::Merge3FallbackSolver::solve(context); break;
+    default:
+        by = 0;
+        if ((merged = Bu::Merge3PppSolver::solve(context))) break;
+        by = 1;
+        if ((merged = Bu::Merge3PllSolver::solve(context))) break;
+        by = 2;
+        if ((merged = Bu::Merge3LppSolver::solve(context))) break;
+        by = 3;
+        if ((merged = Bu::Merge3LlpSolver::solve(context))) break;
+        by = 5;
+        if (Bu::detectUnsolvableMerge3Lll(context)) break;
+        merged = Bu::Merge3FallbackSolver::solve(context);
+        by = merged ? 4 : 5;
+    }
+    if (solved_by) *solved_by = by;
     if (!merged) return 0;
     int n = 0;
     for (int i = 0; i < n_el; ++i) {
@@ -174,4 +207,10 @@ REF_API int gcs_ref_m3_ppp_merge(int n_el, const int32_t* type, const double* ca
         ++n;
     }
     return n;
+}
+
+REF_API int gcs_ref_m3_ppp_merge(int n_el, const int32_t* type, const double* canvas4, const int32_t* counts, const int32_t* ids,
+    const double* pose4, int32_t* out_ids, double* out_pose4)
+{
+    return gcs_ref_m3_merge(0, n_el, type, canvas4, counts, ids, pose4, out_ids, out_pose4, nullptr);
 }

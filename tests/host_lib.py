@@ -49,6 +49,10 @@ def load():
             lib.gcs_host_m3_score.argtypes = [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                               C.POINTER(C.c_uint8)]
             lib.gcs_host_m3_score.restype = C.c_double
+        if hasattr(lib, "gcs_host_m3_merge"):
+            ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+            lib.gcs_host_m3_merge.restype = C.c_int
+            lib.gcs_host_m3_merge.argtypes = [C.c_int, C.c_int, ip, dp, ip, ip, dp, ip, dp, dp, C.POINTER(C.c_int64)]
         if hasattr(lib, "gcs_host_m3_ppp_merge"):
             ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
             lib.gcs_host_m3_ppp_merge.argtypes = [C.c_int, ip, dp, ip, ip, dp, ip, dp, dp, C.POINTER(C.c_int64)]
@@ -233,6 +237,20 @@ def m3_ppp_merge(types, canvas4, clusters):
     stats = (C.c_int64 * 3)()
     n = load().gcs_host_m3_ppp_merge(len(types), types.ctypes.data_as(ip), _dp(canvas4), counts.ctypes.data_as(ip), ids.ctypes.data_as(ip),
                                      _dp(pose4), out_ids.ctypes.data_as(ip), _dp(out_pose), C.byref(score), stats)
+    return n, out_ids[:max(n, 0)].copy(), out_pose[:max(n, 0)].copy(), score.value, tuple(stats)
+
+
+M3_CASES = {"ppp": 0, "pll": 1, "lpp": 2, "llp": 3, "fallback": 4, "node": 5}
+
+
+def m3_merge(which, types, canvas4, clusters):
+    """Gcs::B200::solveMerge3{Ppp,Pll,Lpp,Llp,Fallback,Node}.  Returns (n merged or 0 / -1, ids, pose4, score,
+    (candidates, scored, launches, case that produced the pose))."""
+    types, canvas4, counts, ids, pose4, out_ids, out_pose, ip = _m3_ppp_args(types, canvas4, clusters)
+    score = C.c_double()
+    stats = (C.c_int64 * 4)()
+    n = load().gcs_host_m3_merge(M3_CASES[which], len(types), types.ctypes.data_as(ip), _dp(canvas4), counts.ctypes.data_as(ip),
+                                 ids.ctypes.data_as(ip), _dp(pose4), out_ids.ctypes.data_as(ip), _dp(out_pose), C.byref(score), stats)
     return n, out_ids[:max(n, 0)].copy(), out_pose[:max(n, 0)].copy(), score.value, tuple(stats)
 
 

@@ -45,6 +45,10 @@ def load():
             lib.gcs_ref_m3_rigid_transform.argtypes = [C.c_int, dp, dp, dp]
             lib.gcs_ref_m3_score.argtypes = [C.c_int, C.POINTER(C.c_int32), dp, dp, bp]
             lib.gcs_ref_m3_score.restype = C.c_double
+        if hasattr(lib, "gcs_ref_m3_merge"):
+            ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+            lib.gcs_ref_m3_merge.restype = C.c_int
+            lib.gcs_ref_m3_merge.argtypes = [C.c_int, C.c_int, ip, dp, ip, ip, dp, ip, dp, ip]
         if hasattr(lib, "gcs_ref_m3_ppp_merge"):
             ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
             lib.gcs_ref_m3_ppp_merge.argtypes = [C.c_int, ip, dp, ip, ip, dp, ip, dp]
@@ -138,6 +142,17 @@ def m3_ppp_merge(types, canvas4, clusters):
     n = load().gcs_ref_m3_ppp_merge(len(types), types.ctypes.data_as(ip), _dp(canvas4), counts.ctypes.data_as(ip), ids.ctypes.data_as(ip),
                                     _dp(pose4), out_ids.ctypes.data_as(ip), _dp(out_pose))
     return n, out_ids[:max(n, 0)].copy(), out_pose[:max(n, 0)].copy()
+
+
+def m3_merge(which, types, canvas4, clusters):
+    """The reference's own Merge3{Ppp,Pll,Lpp,Llp,Fallback}Solver::solve, or ("node") the case order of a merge
+    node.  Returns (n merged or 0, ids, pose4, case that produced the pose).  Progress lines go to stderr."""
+    import host_lib as H
+    types, canvas4, counts, ids, pose4, out_ids, out_pose, ip = H._m3_ppp_args(types, canvas4, clusters)
+    by = C.c_int32(-1)
+    n = load().gcs_ref_m3_merge(H.M3_CASES[which], len(types), types.ctypes.data_as(ip), _dp(canvas4), counts.ctypes.data_as(ip),
+                                ids.ctypes.data_as(ip), _dp(pose4), out_ids.ctypes.data_as(ip), _dp(out_pose), C.byref(by))
+    return n, out_ids[:max(n, 0)].copy(), out_pose[:max(n, 0)].copy(), by.value
 
 
 def m3_rigid_transform(src, dst):

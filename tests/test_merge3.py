@@ -239,3 +239,178 @@ def test_ppp_merge_enumeration_loop_equals_the_reference_solver(gpu, host):
         os.close(devnull)
         os.close(saved)
     assert total > 500
+
+
+# ---- the Merge3 cases with a line in them, the fallback and the case order of a merge node ----
+def _m3_scenario(rng, spec, coincide=False, permute=True):
+    """Three solved clusters of one sketch.  spec: group -> (points, lines) for the groups r (reference only),
+    ra / rb (shared by the reference and moving cluster A / B), f (shared by A and B, outside the reference),
+    a / b (A / B only).  Every cluster holds the true layout under its own rigid motion, the canvas the true
+    layout under another motion with noise.  Returns (types, canvas4, [cluster 0, 1, 2] as (id, pose4) lists)."""
+    groups, types = {}, []
+    for name in ("r", "ra", "rb", "f", "a", "b"):
+        n_pt, n_ln = spec.get(name, (0, 0))
+        groups[name] = list(range(len(types), len(types) + n_pt + n_ln))
+        types += [0] * n_pt + [1] * n_ln
+    nid = len(types)
+    types = np.array(types, dtype=np.int32)
+    true = rng.uniform(-300, 300, size=(nid, 4))
+    for i in np.nonzero(types == 1)[0]:  # lines of a sensible length
+        d = rng.uniform(-1, 1, size=2)
+        true[i, 2:] = true[i, :2] + d / np.hypot(*d) * rng.uniform(60, 400)
+    if coincide and groups["f"] and groups["ra"]:  # a free point sitting on a fixed point of A
+        f0, a0 = groups["f"][0], groups["ra"][0]
+        if types[f0] == 0 and types[a0] == 0:
+            true[f0, :2] = true[a0, :2]
+
+    def motion():
+        th = rng.uniform(0, 2 * np.pi)
+        c, s = np.cos(th), np.sin(th)
+        t = rng.uniform(-500, 500, size=2)
+        return lambda p: np.array([c * p[0] - s * p[1] + t[0], s * p[0] + c * p[1] + t[1]])
+
+    def pose_of(ids, mv):
+        out = []
+        for i in ids:
+            p4 = np.zeros(4)
+            p4[:2] = mv(true[i, :2])
+            if types[i] == 1:
+                p4[2:] = mv(true[i, 2:])
+            out.append((int(i), p4))
+        return out
+
+    members = (groups["r"] + groups["ra"] + groups["rb"], groups["ra"] + groups["f"] + groups["a"], groups["rb"] + groups["f"] + groups["b"])
+    clusters = [pose_of(list(rng.permutation(ids)) if ids else [], motion()) for ids in members]
+    if permute:  # which child is the reference must not matter: the loops try all three
+        clusters = [clusters[k] for k in rng.permutation(3)]
+    cm = motion()
+    canvas4 = np.zeros((nid, 4))
+    for i in range(nid):
+        canvas4[i, :2] = cm(true[i, :2]) + rng.normal(0, 2.0, size=2)
+        if types[i] == 1:
+            canvas4[i, 2:] = cm(true[i, 2:]) + rng.normal(0, 2.0, size=2)
+    return types, canvas4, clusters
+
+
+P, L = (1, 0), (0, 1)
+M3_SHAPES = {
+    # two fixed points, a free line
+    "pll": [dict(r=(1, 1), ra=(2, 0), rb=(2, 0), f=(0, 2), a=(1, 0), b=(0, 1)), dict(ra=P, rb=P, f=L), dict(ra=(3, 0), rb=(2, 0), f=(0, 3), r=(2, 0)),
+            dict(ra=P, rb=P, f=(0, 0)), dict(ra=P, rb=(0, 0), f=L)],
+    # a fixed point in one moving cluster, a fixed line in the other, a free point
+    "lpp": [dict(r=(1, 0), ra=(2, 0), rb=(0, 2), f=(2, 0), a=(0, 1), b=(1, 0)), dict(ra=P, rb=L, f=P), dict(ra=(0, 2), rb=(3, 0), f=(3, 0), r=(1, 1)),
+            dict(ra=(1, 1), rb=(1, 1), f=(2, 0)), dict(ra=P, rb=L, f=(0, 0))],
+    # two fixed lines, a free point
+    "llp": [dict(r=(1, 0), ra=(0, 2), rb=(0, 2), f=(2, 0), a=(1, 0), b=(0, 1)), dict(ra=L, rb=L, f=P), dict(ra=(0, 3), rb=(0, 2), f=(3, 0), r=(0, 2)),
+            dict(ra=L, rb=L, f=(0, 0)), dict(ra=L, rb=(0, 0), f=P)],
+}
+
+
+def _quiet_stderr():
+    import contextlib
+
+    @contextlib.contextmanager
+    def cm():
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(2)
+        os.dup2(devnull, 2)  # the reference prints a line per candidate
+        try:
+            yield
+        finally:
+            os.dup2(saved, 2)
+            os.close(devnull)
+            os.close(saved)
+    return cm()
+
+
+def _need_ref_merge():
+    import ref_lib as R
+    if not R.available() or not hasattr(R.load(), "gcs_ref_m3_merge"):
+        pytest.skip("oracle/_ref (with the reference's Merge3 solver classes) not present on this box")
+    return R
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["pll", "lpp", "llp"])
+def test_line_case_enumeration_loops_equal_the_reference_solvers(gpu, host, case):
+    """Merge3PllSolver / Merge3LppSolver / Merge3LlpSolver::solve (merge3_pll_solver.cpp:15-189,
+    merge3_lpp_solver.cpp:15-208, merge3_llp_solver.cpp:15-190) against their batched forms: every candidate
+    of a merge through ONE kernel launch of its kind (K2 / K3 / K4), the merged pose bit for bit - over merges
+    with 1..36 candidates, passengers of both types, and merges without any candidate."""
+    R = _need_ref_merge()
+    rng = np.random.default_rng(90 + len(case) + ord(case[0]))
+    total = 0
+    with _quiet_stderr():
+        for rep in range(6):
+            for spec in M3_SHAPES[case]:
+                types, canvas4, clusters = _m3_scenario(rng, spec)
+                n_ref, ids_ref, pose_ref, _ = R.m3_merge(case, types, canvas4, clusters)
+                n, ids, pose, score, (cands, scored, launches, by) = H.m3_merge(case, types, canvas4, clusters)
+                assert n >= 0, H.last_error()
+                assert n == n_ref and np.array_equal(ids, ids_ref), (case, spec, n, n_ref)
+                assert same(pose, pose_ref).all(), (case, spec, pose, pose_ref)
+                assert launches == (1 if cands else 0), "every candidate of a merge goes through one launch"
+                total += cands
+    assert total > 150
+
+
+M3_NODE_SHAPES = [
+    ("ppp", dict(r=(1, 1), ra=(2, 0), rb=(2, 0), f=(2, 1), a=(1, 0), b=(0, 1))),   # points everywhere: the first case wins
+    ("ppp", dict(ra=(1, 1), rb=(1, 1), f=(1, 1))),                                  # every case has candidates: still PPP
+    ("pll", dict(ra=(2, 0), rb=(1, 0), f=(0, 2), r=(0, 1))),
+    ("pll", dict(ra=(1, 1), rb=(1, 1), f=(0, 1))),                                  # PLL before LLP-style lines
+    # a point, a line and a point shared pairwise: the LPP shape - and, seen from another child, the PLL shape
+    # (two points with the reference, a line between the moving clusters), which the case order tries first
+    ("pll", dict(ra=(1, 0), rb=(0, 1), f=(2, 0), a=(0, 1))),
+    ("pll", dict(ra=(0, 2), rb=(2, 0), f=(1, 0))),
+    ("llp", dict(ra=(0, 2), rb=(0, 1), f=(2, 0), r=(1, 0))),
+    ("unsolvable", dict(ra=(0, 1), rb=(0, 1), f=(0, 1))),                           # three lines: detectUnsolvableMerge3Lll
+    ("fallback", dict(ra=(2, 0), rb=(2, 0), f=(0, 0), a=(1, 0))),                   # nothing free: rigid fits over the shared points
+    ("fallback", dict(ra=(1, 1), rb=(0, 2), r=(1, 0))),
+    ("unsolvable", dict(r=(1, 0), a=(1, 0), b=(1, 0))),                             # nothing shared at all: the fallback has nothing to fit
+]
+
+
+@pytest.mark.gpu
+def test_merge_node_case_order_equals_the_reference(gpu, host):
+    """What a Merge3 plan node does (bottom_up_plan_solver.cpp:393-431): PPP, PLL, LPP, LLP in that order, the LLL
+    detector, the rigid fallback.  Gcs::B200::solveMerge3Node (PPP with its own launch; the three line cases
+    enumerated into ONE batch, at most a launch per kind) against the same sequence over the reference's own
+    classes: the same case decides and the merged pose is the same bit for bit."""
+    R = _need_ref_merge()
+    names = {0: "ppp", 1: "pll", 2: "lpp", 3: "llp", 4: "fallback", 5: "unsolvable"}
+    rng = np.random.default_rng(4711)
+    seen = set()
+    with _quiet_stderr():
+        for rep in range(5):
+            for expect, spec in M3_NODE_SHAPES:
+                types, canvas4, clusters = _m3_scenario(rng, spec, permute=(expect != "fallback"))
+                n_ref, ids_ref, pose_ref, by_ref = R.m3_merge("node", types, canvas4, clusters)
+                n, ids, pose, score, (cands, scored, launches, by) = H.m3_merge("node", types, canvas4, clusters)
+                assert n >= 0, H.last_error()
+                assert names[by] == names[by_ref] == expect, (expect, spec, names[by], names[by_ref])
+                assert n == n_ref and np.array_equal(ids, ids_ref), (expect, spec, n, n_ref)
+                assert same(pose, pose_ref).all(), (expect, spec)
+                assert launches <= 4
+                seen.add(expect)
+    assert seen == {"ppp", "pll", "llp", "fallback", "unsolvable"}  # LPP is shadowed by PLL in this order (see the shapes)
+
+
+def test_fallback_merge_equals_the_reference(host):
+    """Merge3FallbackSolver::solve (merge3_fallback_solver.cpp:61-78): child 1, then child 2, fitted onto child 0
+    over the elements they share - host arithmetic only, so this one runs without a device."""
+    R = _need_ref_merge()
+    rng = np.random.default_rng(31)
+    hits = 0
+    for rep in range(20):
+        for spec in (dict(ra=(2, 0), rb=(2, 0), a=(1, 1)), dict(ra=(1, 1), rb=(0, 2), r=(1, 0), b=(2, 0)), dict(ra=(3, 0), rb=(0, 0), f=(2, 0)),
+                     dict(r=(1, 0), a=(1, 0), b=(1, 0)), dict(ra=(0, 1), rb=(0, 1), f=(0, 1))):
+            types, canvas4, clusters = _m3_scenario(rng, spec, permute=bool(rep % 2))
+            n_ref, ids_ref, pose_ref, _ = R.m3_merge("fallback", types, canvas4, clusters)
+            n, ids, pose, score, stats = H.m3_merge("fallback", types, canvas4, clusters)
+            assert n >= 0, H.last_error()
+            assert n == n_ref and np.array_equal(ids, ids_ref), (spec, n, n_ref)
+            assert same(pose, pose_ref).all(), spec
+            assert stats[2] == 0  # no kernel launch
+            hits += n > 0
+    assert hits > 20
