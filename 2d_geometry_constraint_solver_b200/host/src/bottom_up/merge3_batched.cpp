@@ -7,6 +7,8 @@
 
 #include "solving/bottom_up/merge3_batched.hpp"
 
+#include "merge3_pass2.hpp"
+
 namespace Gcs::B200 {
 
 namespace Bu = Solvers::BottomUp;
@@ -196,38 +198,34 @@ void collectLlp(const ConstraintGraph& g, const Merge3Children& children, Merge3
 std::optional<Bu::ClusterPose> finish(
     const ConstraintGraph& g, const Merge3Children& children, const Merge3Batch& batch, const Enumeration& e, Merge3Report* report)
 {
-    std::optional<Bu::ClusterPose> bestMergedPose;
-    double bestScore = std::numeric_limits<double>::infinity();
-    std::size_t scored = 0;
-    for (const Candidate& c : e.candidates) {
+    const auto build = [&](std::size_t i) -> std::optional<Bu::ClusterPose> {
+        const Candidate& c = e.candidates[i];
         Bu::ElementPose solved;
         if (c.freeIsLine) {
             const auto line = batch.line(c.handle);
-            if (!line) continue;  // the helper's std::nullopt
+            if (!line) return std::nullopt;  // the helper's std::nullopt
             solved = *line;
         } else {
             const auto point = batch.point(c.handle);
-            if (!point) continue;
+            if (!point) return std::nullopt;
             solved = Bu::PointPose { *point };
         }
         const std::array<std::pair<NodeId, Bu::ElementPose>, 2> anchorsA { std::pair { c.fixedA, c.fixedAPose }, std::pair { c.free, solved } };
         const std::array<std::pair<NodeId, Bu::ElementPose>, 2> anchorsB { std::pair { c.fixedB, c.fixedBPose }, std::pair { c.free, solved } };
         const auto transformedA = Bu::transformClusterByAnchors(*children[c.movingA], anchorsA);
         const auto transformedB = Bu::transformClusterByAnchors(*children[c.movingB], anchorsB);
-        if (!transformedA || !transformedB) continue;
+        if (!transformedA || !transformedB) return std::nullopt;
         Bu::ClusterPose merged = *children[c.reference];
         merged[c.free] = solved;
         for (const auto& [elementId, pose] : *transformedA)
             if (!merged.contains(elementId)) merged.emplace(elementId, pose);
         for (const auto& [elementId, pose] : *transformedB)
             if (!merged.contains(elementId)) merged.emplace(elementId, pose);
-        ++scored;
-        const double score = Bu::scoreMergedPose(g, merged);
-        if (score < bestScore) {
-            bestScore = score;
-            bestMergedPose = std::move(merged);
-        }
-    }
+        return merged;
+    };
+    std::size_t scored = 0;
+    double bestScore = std::numeric_limits<double>::infinity();
+    auto bestMergedPose = detail::pickBestMergedPose(g, e.candidates.size(), build, scored, bestScore);  // on every host thread
     if (report) {
         report->candidates = e.candidates.size();
         report->scored = scored;

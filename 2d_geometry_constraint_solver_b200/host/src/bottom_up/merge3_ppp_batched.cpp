@@ -5,6 +5,8 @@
 
 #include "solving/bottom_up/merge3_ppp_batched.hpp"
 
+#include "merge3_pass2.hpp"
+
 namespace Gcs::B200 {
 
 namespace Bu = Solvers::BottomUp;
@@ -84,29 +86,25 @@ std::optional<Bu::ClusterPose> solveMerge3Ppp(const ConstraintGraph& sourceGraph
     // ---- every candidate's Newton solve + root selection: one launch ----
     if (!candidates.empty()) batch.solve(device);
 
-    // ---- pass 2: place, merge, score - in the enumeration's order, first best score wins ----
-    std::optional<Bu::ClusterPose> bestMergedPose;
-    double bestScore = std::numeric_limits<double>::infinity();
-    std::size_t scored = 0;
-    for (const Candidate& c : candidates) {
+    // ---- pass 2: place, merge, score - every candidate on its own (merge3_pass2.hpp), the first best score wins ----
+    const auto build = [&](std::size_t i) -> std::optional<Bu::ClusterPose> {
+        const Candidate& c = candidates[i];
         const Vector2d selectedFreePoint = batch.point(c.handle).value();
         const Bu::ClusterPose& referenceCluster = *children[c.reference];
         const auto transformedA = Bu::transformClusterByTwoPointAnchors(*children[c.movingA], c.fixedA, c.free, c.fixedAInGlobal, selectedFreePoint);
         const auto transformedB = Bu::transformClusterByTwoPointAnchors(*children[c.movingB], c.fixedB, c.free, c.fixedBInGlobal, selectedFreePoint);
-        if (!transformedA || !transformedB) continue;
+        if (!transformedA || !transformedB) return std::nullopt;
         Bu::ClusterPose merged = referenceCluster;  // :160-175
         merged[c.free] = Bu::PointPose { selectedFreePoint };
         for (const auto& [elementId, pose] : *transformedA)
             if (!merged.contains(elementId)) merged.emplace(elementId, pose);
         for (const auto& [elementId, pose] : *transformedB)
             if (!merged.contains(elementId)) merged.emplace(elementId, pose);
-        ++scored;
-        const double score = Bu::scoreMergedPose(sourceGraph, merged);
-        if (score < bestScore) {
-            bestScore = score;
-            bestMergedPose = std::move(merged);
-        }
-    }
+        return merged;
+    };
+    std::size_t scored = 0;
+    double bestScore = std::numeric_limits<double>::infinity();
+    std::optional<Bu::ClusterPose> bestMergedPose = detail::pickBestMergedPose(sourceGraph, candidates.size(), build, scored, bestScore);
     if (report) {
         report->candidates = candidates.size();
         report->scored = scored;
