@@ -26,6 +26,8 @@
 #include <array>
 #include <cstddef>
 #include <optional>
+#include <span>
+#include <vector>
 
 #include <gcs/export.hpp>
 #include <gcs/model/gcs_data_structures.hpp>
@@ -71,5 +73,23 @@ struct Merge3NodeReport {
 
 GCS_API std::optional<Solvers::BottomUp::ClusterPose> solveMerge3Node(
     const ConstraintGraph& sourceGraph, const Merge3Children& children, int device = 0, Merge3NodeReport* report = nullptr);
+
+// Every merge node of one level of a plan tree (nodes of a level do not depend on each other) through
+// ONE Merge3Batch: pass 1 of every node - PPP, and the three line cases where PPP has no candidate -
+// then at most one launch per equation-pair kind for the whole level, then pass 2 node by node in
+// the reference's case order.  Results are solveMerge3Node's; what changes is the number of launches:
+// 4 per level at most instead of up to 4 per node.  (A node whose PPP candidates all fail to place -
+// possible, never seen - falls back to its own batch for the line cases.)
+struct Merge3NodeInput {
+    const ConstraintGraph* sourceGraph = nullptr;
+    Merge3Children children {};
+};
+
+struct Merge3LevelReport {
+    std::size_t nodes = 0, candidates = 0, launches = 0;
+};
+
+GCS_API std::vector<std::optional<Solvers::BottomUp::ClusterPose>> solveMerge3Level(std::span<const Merge3NodeInput> nodes, int device = 0,
+    std::vector<Merge3NodeReport>* reports = nullptr, Merge3LevelReport* level = nullptr);
 
 }  // namespace Gcs::B200

@@ -7,6 +7,7 @@
 
 #include "solving/bottom_up/merge3_batched.hpp"
 
+#include "merge3_cases.hpp"
 #include "merge3_pass2.hpp"
 
 namespace Gcs::B200 {
@@ -329,6 +330,79 @@ std::optional<Bu::ClusterPose> solveMerge3Node(const ConstraintGraph& g, const M
     auto fallback = solveMerge3Fallback(children);
     r.solvedBy = fallback ? Merge3Case::Fallback : Merge3Case::Unsolvable;
     return fallback;
+}
+
+std::vector<std::optional<Bu::ClusterPose>> solveMerge3Level(
+    std::span<const Merge3NodeInput> nodes, int device, std::vector<Merge3NodeReport>* reports, Merge3LevelReport* level)
+{
+    struct NodeWork {
+        std::vector<detail::PppCandidate> ppp;
+        std::array<Enumeration, 3> line;  // PLL, LPP, LLP: collected only where PPP has no candidate
+        bool lineCollected = false;
+    };
+    Merge3Batch batch;
+    std::vector<NodeWork> work(nodes.size());
+    for (std::size_t k = 0; k < nodes.size(); ++k) {
+        const ConstraintGraph& g = *nodes[k].sourceGraph;
+        detail::collectPpp(g, nodes[k].children, batch, work[k].ppp);
+        if (!work[k].ppp.empty()) continue;
+        collectPll(g, nodes[k].children, batch, work[k].line[0]);
+        collectLpp(g, nodes[k].children, batch, work[k].line[1]);
+        collectLlp(g, nodes[k].children, batch, work[k].line[2]);
+        work[k].lineCollected = true;
+    }
+    if (batch.size() != 0) batch.solve(device);
+    std::size_t launches = batch.launches(), candidates = 0;
+
+    std::vector<std::optional<Bu::ClusterPose>> out(nodes.size());
+    std::vector<Merge3NodeReport> local(nodes.size());
+    for (std::size_t k = 0; k < nodes.size(); ++k) {
+        const ConstraintGraph& g = *nodes[k].sourceGraph;
+        const Merge3Children& children = nodes[k].children;
+        Merge3NodeReport& r = local[k];
+        r.candidates = work[k].ppp.size();
+        if (!work[k].ppp.empty()) {
+            std::size_t scored = 0;
+            double best = 0.0;
+            if ((out[k] = detail::finishPpp(g, children, batch, work[k].ppp, scored, best))) {
+                r.solvedBy = Merge3Case::Ppp, r.scored = scored, r.bestScore = best;
+                candidates += r.candidates;
+                continue;
+            }
+        }
+        const Merge3Batch* lineBatch = &batch;
+        Merge3Batch own;
+        if (!work[k].lineCollected) {  // PPP had candidates and none placed: this node's line cases on their own
+            collectPll(g, children, own, work[k].line[0]);
+            collectLpp(g, children, own, work[k].line[1]);
+            collectLlp(g, children, own, work[k].line[2]);
+            if (own.size() != 0) own.solve(device);
+            launches += own.launches();
+            lineBatch = &own;
+        }
+        bool done = false;
+        for (std::size_t c = 0; c < 3 && !done; ++c) {
+            Merge3Report one;
+            out[k] = finish(g, children, *lineBatch, work[k].line[c], &one);
+            r.candidates += one.candidates;
+            if (out[k]) {
+                r.solvedBy = static_cast<Merge3Case>(static_cast<int>(Merge3Case::Pll) + static_cast<int>(c));
+                r.scored = one.scored, r.bestScore = one.bestScore;
+                done = true;
+            }
+        }
+        candidates += r.candidates;
+        if (done) continue;
+        if (detectUnsolvableMerge3Lll(g, children)) {
+            r.solvedBy = Merge3Case::Unsolvable;
+            continue;
+        }
+        out[k] = solveMerge3Fallback(children);
+        r.solvedBy = out[k] ? Merge3Case::Fallback : Merge3Case::Unsolvable;
+    }
+    if (reports) *reports = std::move(local);
+    if (level) *level = { nodes.size(), candidates, launches };
+    return out;
 }
 
 }  // namespace Gcs::B200

@@ -5,6 +5,7 @@
 
 #include "solving/bottom_up/merge3_ppp_batched.hpp"
 
+#include "merge3_cases.hpp"
 #include "merge3_pass2.hpp"
 
 namespace Gcs::B200 {
@@ -13,25 +14,13 @@ namespace Bu = Solvers::BottomUp;
 using Eigen::Vector2d;
 using NodeId = ConstraintGraph::NodeIdType;
 
-namespace {
 
-// One candidate of the enumeration (merge3_ppp_solver.cpp:77-97): everything the second pass needs.
-struct Candidate {
-    std::size_t reference, movingA, movingB;
-    NodeId fixedA, fixedB, free;
-    Vector2d fixedAInGlobal, fixedBInGlobal;
-    Merge3Batch::Handle handle;
-};
+namespace detail {
 
-}  // namespace
-
-std::optional<Bu::ClusterPose> solveMerge3Ppp(const ConstraintGraph& sourceGraph, const std::array<const Bu::ClusterPose*, 3>& children,
-    int device, Merge3PppReport* report)
+// ---- pass 1: the reference's enumeration, collecting the equation pair of every candidate ----
+void collectPpp(const ConstraintGraph& sourceGraph, const std::array<const Bu::ClusterPose*, 3>& children, Merge3Batch& batch,
+    std::vector<PppCandidate>& candidates)
 {
-    Merge3Batch batch;
-    std::vector<Candidate> candidates;
-
-    // ---- pass 1: the reference's enumeration, collecting the equation pair of every candidate ----
     for (std::size_t referenceIndex = 0; referenceIndex < 3; ++referenceIndex) {
         std::array<std::size_t, 2> moving {};
         std::size_t at = 0;
@@ -83,12 +72,14 @@ std::optional<Bu::ClusterPose> solveMerge3Ppp(const ConstraintGraph& sourceGraph
         }
     }
 
-    // ---- every candidate's Newton solve + root selection: one launch ----
-    if (!candidates.empty()) batch.solve(device);
+}
 
-    // ---- pass 2: place, merge, score - every candidate on its own (merge3_pass2.hpp), the first best score wins ----
+// ---- pass 2: place, merge, score - every candidate on its own (merge3_pass2.hpp), the first best score wins ----
+std::optional<Bu::ClusterPose> finishPpp(const ConstraintGraph& sourceGraph, const std::array<const Bu::ClusterPose*, 3>& children,
+    const Merge3Batch& batch, const std::vector<PppCandidate>& candidates, std::size_t& scored, double& bestScore)
+{
     const auto build = [&](std::size_t i) -> std::optional<Bu::ClusterPose> {
-        const Candidate& c = candidates[i];
+        const PppCandidate& c = candidates[i];
         const Vector2d selectedFreePoint = batch.point(c.handle).value();
         const Bu::ClusterPose& referenceCluster = *children[c.reference];
         const auto transformedA = Bu::transformClusterByTwoPointAnchors(*children[c.movingA], c.fixedA, c.free, c.fixedAInGlobal, selectedFreePoint);
@@ -102,9 +93,21 @@ std::optional<Bu::ClusterPose> solveMerge3Ppp(const ConstraintGraph& sourceGraph
             if (!merged.contains(elementId)) merged.emplace(elementId, pose);
         return merged;
     };
+    return pickBestMergedPose(sourceGraph, candidates.size(), build, scored, bestScore);
+}
+
+}  // namespace detail
+
+std::optional<Bu::ClusterPose> solveMerge3Ppp(const ConstraintGraph& sourceGraph, const std::array<const Bu::ClusterPose*, 3>& children,
+    int device, Merge3PppReport* report)
+{
+    Merge3Batch batch;
+    std::vector<detail::PppCandidate> candidates;
+    detail::collectPpp(sourceGraph, children, batch, candidates);
+    if (!candidates.empty()) batch.solve(device);  // every candidate's Newton solve + root selection: one launch
     std::size_t scored = 0;
     double bestScore = std::numeric_limits<double>::infinity();
-    std::optional<Bu::ClusterPose> bestMergedPose = detail::pickBestMergedPose(sourceGraph, candidates.size(), build, scored, bestScore);
+    std::optional<Bu::ClusterPose> bestMergedPose = detail::finishPpp(sourceGraph, children, batch, candidates, scored, bestScore);
     if (report) {
         report->candidates = candidates.size();
         report->scored = scored;

@@ -682,6 +682,81 @@ GCS_API int gcs_host_m3_merge(int which, int n_el, const int32_t* type, const do
     }
 }
 
+// A level of merge nodes through ONE batch (Gcs::B200::solveMerge3Level).  Node k has n_el[k] elements; type /
+// canvas4 / out_ids / out_pose4 are concatenated over the nodes (n_el[k] slots each), counts holds 3 entries per
+// node, ids / pose4 the nodes' cluster members one node after the other.  out_n[k] = size of node k's merged pose
+// (0: none), solved_by[k] = Merge3Case; stats[3] = nodes, candidates solved, kernel launches.  Returns 0 or -1.
+GCS_API int gcs_host_m3_level(int n_nodes, const int32_t* n_el, const int32_t* type, const double* canvas4, const int32_t* counts,
+    const int32_t* ids, const double* pose4, int32_t* out_n, int32_t* out_ids, double* out_pose4, int32_t* solved_by, int64_t* stats)
+{
+    namespace Bu = Gcs::Solvers::BottomUp;
+    try {
+        struct Node {
+            Gcs::ConstraintGraph g;
+            std::vector<Gcs::ConstraintGraph::NodeIdType> nodes;
+            Bu::ClusterPose pose[3];
+        };
+        std::vector<std::unique_ptr<Node>> built;
+        std::vector<Gcs::B200::Merge3NodeInput> inputs;
+        std::size_t el0 = 0, at = 0;
+        for (int k = 0; k < n_nodes; ++k) {
+            auto nd = std::make_unique<Node>();
+            for (int i = 0; i < n_el[k]; ++i) {
+                const double* c = canvas4 + 4 * (el0 + static_cast<std::size_t>(i));
+                nd->nodes.push_back(nd->g.getGraph().addNode());
+                if (type[el0 + static_cast<std::size_t>(i)] == 0)
+                    nd->g.addElement(nd->nodes.back(), std::make_shared<Gcs::Element>(Gcs::Point(Vector2d(c[0], c[1]))));
+                else
+                    nd->g.addElement(nd->nodes.back(), std::make_shared<Gcs::Element>(Gcs::Line(Vector2d(c[0], c[1]), Vector2d(c[2], c[3]))));
+            }
+            for (int c = 0; c < 3; ++c)
+                for (int j = 0; j < counts[3 * k + c]; ++j, ++at) {
+                    const double* p = pose4 + 4 * at;
+                    const auto local = static_cast<std::size_t>(ids[at]);
+                    const auto node = nd->nodes.at(local);
+                    if (type[el0 + local] == 0)
+                        nd->pose[c].emplace(node, Bu::PointPose { Vector2d(p[0], p[1]) });
+                    else
+                        nd->pose[c].emplace(node, Bu::LinePose { Vector2d(p[0], p[1]), Vector2d(p[2], p[3]) });
+                }
+            inputs.push_back({ &nd->g, { &nd->pose[0], &nd->pose[1], &nd->pose[2] } });
+            built.push_back(std::move(nd));
+            el0 += static_cast<std::size_t>(n_el[k]);
+        }
+        std::vector<Gcs::B200::Merge3NodeReport> reports;
+        Gcs::B200::Merge3LevelReport level;
+        const auto merged = Gcs::B200::solveMerge3Level(inputs, 0, &reports, &level);
+        if (stats) stats[0] = static_cast<int64_t>(level.nodes), stats[1] = static_cast<int64_t>(level.candidates), stats[2] = static_cast<int64_t>(level.launches);
+        el0 = 0;
+        for (int k = 0; k < n_nodes; ++k) {
+            int n = 0;
+            if (solved_by) solved_by[k] = static_cast<int32_t>(reports[static_cast<std::size_t>(k)].solvedBy);
+            if (merged[static_cast<std::size_t>(k)]) {
+                const auto& m = *merged[static_cast<std::size_t>(k)];
+                for (int i = 0; i < n_el[k]; ++i) {
+                    const auto it = m.find(built[static_cast<std::size_t>(k)]->nodes[static_cast<std::size_t>(i)]);
+                    if (it == m.end()) continue;
+                    out_ids[el0 + static_cast<std::size_t>(n)] = i;
+                    double* o = out_pose4 + 4 * (el0 + static_cast<std::size_t>(n));
+                    o[0] = o[1] = o[2] = o[3] = 0.0;
+                    if (const auto* pp = std::get_if<Bu::PointPose>(&it->second))
+                        o[0] = pp->position.x(), o[1] = pp->position.y();
+                    else {
+                        const auto& l = std::get<Bu::LinePose>(it->second);
+                        o[0] = l.p1.x(), o[1] = l.p1.y(), o[2] = l.p2.x(), o[3] = l.p2.y();
+                    }
+                    ++n;
+                }
+            }
+            out_n[k] = n;
+            el0 += static_cast<std::size_t>(n_el[k]);
+        }
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail(ex);
+    }
+}
+
 // The step after the solve (gcs/b200/canvas_transform.hpp): elements with is_set != 0 carry solver
 // positions in pos; on return canvas holds the transformed sketch.  Returns 0 or -1.
 GCS_API int gcs_host_canvas_transform(int n_el, gcs_host_element* el)

@@ -254,6 +254,35 @@ def m3_merge(which, types, canvas4, clusters):
     return n, out_ids[:max(n, 0)].copy(), out_pose[:max(n, 0)].copy(), score.value, tuple(stats)
 
 
+def m3_level(nodes):
+    """Gcs::B200::solveMerge3Level over `nodes` = [(types, canvas4, clusters), ...].  Returns (rc, [(n, ids, pose4, case)],
+    (nodes, candidates, launches))."""
+    ip = C.POINTER(C.c_int32)
+    n_el = np.array([len(t) for t, _, _ in nodes], dtype=np.int32)
+    types = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int32) for t, _, _ in nodes]))
+    canvas4 = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, 4) for _, c, _ in nodes]))
+    counts = np.array([len(c) for _, _, cl in nodes for c in cl], dtype=np.int32)
+    ids = np.array([i for _, _, cl in nodes for c in cl for i, _ in c], dtype=np.int32)
+    pose4 = np.ascontiguousarray([p for _, _, cl in nodes for c in cl for _, p in c], dtype=np.float64).reshape(-1, 4)
+    out_n = np.zeros(len(nodes), dtype=np.int32)
+    out_ids = np.zeros(len(types), dtype=np.int32)
+    out_pose = np.zeros((len(types), 4))
+    by = np.zeros(len(nodes), dtype=np.int32)
+    stats = (C.c_int64 * 3)()
+    lib = load()
+    lib.gcs_host_m3_level.restype = C.c_int
+    lib.gcs_host_m3_level.argtypes = [C.c_int, ip, ip, C.POINTER(C.c_double), ip, ip, C.POINTER(C.c_double), ip, ip, C.POINTER(C.c_double), ip,
+                                      C.POINTER(C.c_int64)]
+    rc = lib.gcs_host_m3_level(len(nodes), n_el.ctypes.data_as(ip), types.ctypes.data_as(ip), _dp(canvas4), counts.ctypes.data_as(ip),
+                               ids.ctypes.data_as(ip), _dp(pose4), out_n.ctypes.data_as(ip), out_ids.ctypes.data_as(ip), _dp(out_pose),
+                               by.ctypes.data_as(ip), stats)
+    res, at = [], 0
+    for k, n in enumerate(out_n):
+        res.append((int(n), out_ids[at:at + n].copy(), out_pose[at:at + n].copy(), int(by[k])))
+        at += int(n_el[k])
+    return rc, res, tuple(stats)
+
+
 def canvas_transform(elements):
     """Solver -> canvas rigid motion over elements carrying is_set/pos.  Returns (rc, canvas list)."""
     els, _ = to_c(elements, [])

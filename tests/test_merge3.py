@@ -396,6 +396,26 @@ def test_merge_node_case_order_equals_the_reference(gpu, host):
     assert seen == {"ppp", "pll", "llp", "fallback", "unsolvable"}  # LPP is shadowed by PLL in this order (see the shapes)
 
 
+@pytest.mark.gpu
+def test_a_level_of_merge_nodes_shares_one_batch(gpu, host):
+    """Gcs::B200::solveMerge3Level: every merge node of a plan-tree level - all shapes mixed, 40 nodes - through ONE
+    Merge3Batch, at most one launch per equation-pair kind for the whole level; node by node the result is the
+    reference's case order over its own classes, bit for bit."""
+    R = _need_ref_merge()
+    rng = np.random.default_rng(2718)
+    shapes = [M3_NODE_SHAPES[k % len(M3_NODE_SHAPES)] for k in range(40)]
+    nodes = [_m3_scenario(rng, spec, permute=(expect != "fallback")) for expect, spec in shapes]
+    rc, got, (n_nodes, cands, launches) = H.m3_level(nodes)
+    assert rc == 0, H.last_error()
+    assert n_nodes == 40 and cands > 100
+    assert launches <= 4, "one launch per kind for the whole level"
+    with _quiet_stderr():
+        for (types, canvas4, clusters), (n, ids, pose, by) in zip(nodes, got):
+            n_ref, ids_ref, pose_ref, by_ref = R.m3_merge("node", types, canvas4, clusters)
+            assert by == by_ref and n == n_ref and np.array_equal(ids, ids_ref)
+            assert same(pose, pose_ref).all()
+
+
 def test_fallback_merge_equals_the_reference(host):
     """Merge3FallbackSolver::solve (merge3_fallback_solver.cpp:61-78): child 1, then child 2, fitted onto child 0
     over the elements they share - host arithmetic only, so this one runs without a device."""
