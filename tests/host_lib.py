@@ -259,11 +259,12 @@ def m3_level(nodes):
     (nodes, candidates, launches))."""
     ip = C.POINTER(C.c_int32)
     n_el = np.array([len(t) for t, _, _ in nodes], dtype=np.int32)
-    types = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int32) for t, _, _ in nodes]))
-    canvas4 = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, 4) for _, c, _ in nodes]))
+    types = np.ascontiguousarray(np.concatenate([np.zeros(0, dtype=np.int32)] + [np.asarray(t, dtype=np.int32) for t, _, _ in nodes]))
+    canvas4 = np.ascontiguousarray(np.concatenate([np.zeros((0, 4))] + [np.asarray(c, dtype=np.float64).reshape(-1, 4) for _, c, _ in nodes]))
     counts = np.array([len(c) for _, _, cl in nodes for c in cl], dtype=np.int32)
     ids = np.array([i for _, _, cl in nodes for c in cl for i, _ in c], dtype=np.int32)
     pose4 = np.ascontiguousarray([p for _, _, cl in nodes for c in cl for _, p in c], dtype=np.float64).reshape(-1, 4)
+    counts, ids = counts.astype(np.int32), ids.astype(np.int32)  # empty lists come out as float64
     out_n = np.zeros(len(nodes), dtype=np.int32)
     out_ids = np.zeros(len(types), dtype=np.int32)
     out_pose = np.zeros((len(types), 4))

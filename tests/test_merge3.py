@@ -434,3 +434,23 @@ def test_fallback_merge_equals_the_reference(host):
             assert stats[2] == 0  # no kernel launch
             hits += n > 0
     assert hits > 20
+
+
+def test_a_level_without_candidates_needs_no_device(host):
+    """solveMerge3Level on nodes that no enumeration has a candidate for (the fallback's and the unsolvable shapes,
+    and no node at all): nothing is packed, nothing is launched - so this runs without a device - and every node
+    is the reference's outcome."""
+    R = _need_ref_merge()
+    rc, got, stats = H.m3_level([])
+    assert rc == 0 and got == [] and stats == (0, 0, 0)
+    rng = np.random.default_rng(99)
+    shapes = [(e, s) for e, s in M3_NODE_SHAPES if e in ("fallback", "unsolvable")] * 5
+    nodes = [_m3_scenario(rng, spec, permute=(expect != "fallback")) for expect, spec in shapes]
+    rc, got, (n_nodes, cands, launches) = H.m3_level(nodes)
+    assert rc == 0, H.last_error()
+    assert (n_nodes, cands, launches) == (len(nodes), 0, 0)
+    names = {4: "fallback", 5: "unsolvable"}
+    for (expect, _), (types, canvas4, clusters), (n, ids, pose, by) in zip(shapes, nodes, got):
+        n_ref, ids_ref, pose_ref, by_ref = R.m3_merge("node", types, canvas4, clusters)
+        assert names[by] == names[by_ref] == expect
+        assert n == n_ref and np.array_equal(ids, ids_ref) and same(pose, pose_ref).all()
