@@ -454,3 +454,48 @@ def test_a_level_without_candidates_needs_no_device(host):
         n_ref, ids_ref, pose_ref, by_ref = R.m3_merge("node", types, canvas4, clusters)
         assert names[by] == names[by_ref] == expect
         assert n == n_ref and np.array_equal(ids, ids_ref) and same(pose, pose_ref).all()
+
+
+# ---- golden merge nodes: outputs of the reference's own solver classes, committed (oracle/make_golden_merge3_nodes.py) ----
+def _golden_nodes():
+    z = np.load(os.path.join(os.path.dirname(GOLD), "merge3_nodes.npz"))
+    names = {v: k for k, v in H.M3_CASES.items()}
+    el0 = mem0 = out0 = 0
+    for k in range(len(z["which"])):
+        n_el, counts, n = int(z["n_el"][k]), z["counts"][k], int(z["ref_n"][k])
+        types, canvas4 = z["types"][el0:el0 + n_el], z["canvas4"][el0:el0 + n_el]
+        clusters, at = [], mem0
+        for c in counts:
+            clusters.append([(int(i), p) for i, p in zip(z["ids"][at:at + c], z["pose4"][at:at + c])])
+            at += int(c)
+        yield names[int(z["which"][k])], types, canvas4, clusters, n, z["ref_ids"][out0:out0 + n], z["ref_pose4"][out0:out0 + n], int(z["ref_by"][k])
+        el0, mem0, out0 = el0 + n_el, at, out0 + n
+
+
+def test_golden_fallback_nodes(host):
+    """The committed reference outputs of Merge3FallbackSolver::solve: host arithmetic only, no device."""
+    seen = 0
+    for which, types, canvas4, clusters, n_ref, ids_ref, pose_ref, by_ref in _golden_nodes():
+        if which != "fallback":
+            continue
+        n, ids, pose, score, stats = H.m3_merge(which, types, canvas4, clusters)
+        assert n == n_ref and np.array_equal(ids, ids_ref) and same(pose, pose_ref).all()
+        seen += 1
+    assert seen >= 6
+
+
+@pytest.mark.gpu
+def test_golden_merge_nodes(gpu, host):
+    """Every committed scenario - the four enumeration loops, the fallback, the merge node - against what the
+    reference's own classes returned when the fixture was generated: merged pose bit for bit, same deciding case.
+    Needs no oracle/_ref at run time."""
+    seen = {}
+    for which, types, canvas4, clusters, n_ref, ids_ref, pose_ref, by_ref in _golden_nodes():
+        n, ids, pose, score, stats = H.m3_merge(which, types, canvas4, clusters)
+        assert n >= 0, H.last_error()
+        assert n == n_ref and np.array_equal(ids, ids_ref), (which, n, n_ref)
+        assert same(pose, pose_ref).all(), which
+        if which == "node":
+            assert stats[3] == by_ref
+        seen[which] = seen.get(which, 0) + 1
+    assert set(seen) == {"ppp", "pll", "lpp", "llp", "fallback", "node"} and sum(seen.values()) == 90
